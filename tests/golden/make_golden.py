@@ -1,0 +1,113 @@
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference on CPU.
+
+Run in the authoring container only:  python tests/golden/make_golden.py
+Inputs are regenerated from seeds by graspnerf_b200.synth (numpy PCG64), so only the
+reference's weights and OUTPUTS are stored.  Reference call sites exercised:
+  NeuralRayRenderer.sample_volume  (renderer.py:164-199)  -> volume + stage intermediates
+  NeuralRayRenderer.render_impl    (renderer.py:152-162)  -> coarse+fine RGB head (eval)
+"""
+import os
+import sys
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+from ref_harness import build_reference_net            # noqa: E402
+from graspnerf_b200.synth import make_scene, make_query  # noqa: E402
+
+HOT_PREFIXES = ('agg_net.', 'fine_agg_net.', 'dist_decoder.', 'fine_dist_decoder.')
+
+from cases import VOLUME_CASES, RENDER_CASES  # noqa: E402
+
+
+def to_torch(d):
+    return {k: (torch.from_numpy(v) if isinstance(v, np.ndarray) else v) for k, v in d.items()}
+
+
+def hot_state_dict(nr):
+    return {k: v.detach().clone() for k, v in nr.state_dict().items() if k.startswith(HOT_PREFIXES)}
+
+
+def run_volume_case(nr, kw, n_probe=512):
+    from network.render_ops import project_points_dict
+    from utils.field_utils import TSDF_SAMPLE_POINTS
+    scene = make_scene(**kw)
+    ref = to_torch(scene)
+    out = {}
+    with torch.no_grad():
+        vol = nr.sample_volume(ref)
+        out['volume'] = vol[0, 0].numpy()
+        # re-run the stages one by one (same calls sample_volume makes) to record intermediates
+        res = 40
+        que_pts = (torch.from_numpy(TSDF_SAMPLE_POINTS) + torch.tensor(ref['bbox3d'][0])).reshape(1, res * res, res, 3)
+        que_pts = torch.flip(que_pts, (2,))
+        prj = project_points_dict(ref, que_pts)
+        prj = nr.get_img_feats(ref, prj)
+        prj = nr.predict_proj_ray_prob(prj, ref, torch.empty(0), False)
+        que_dir = torch.tensor([0, 0, 1]).reshape(1, 1, 1, 3).repeat(1, res * res, res, 1)
+        feats, emb, dir_diff, vmask = nr.agg_net._get_embedding(prj, que_dir)
+        outs, _ = nr.agg_net.agg_impl(feats, emb, dir_diff, vmask, que_pts)
+        assert torch.equal(outs[..., 3].reshape(1, 1, res, res, res).flip(-1), vol)
+    V = ref['imgs'].shape[0]
+    N = res ** 3
+
+    def nv(t):  # [V,1,rn,dn,C] -> [N,V,C]
+        return t.reshape(V, N, -1).permute(1, 0, 2)
+    rng = np.random.default_rng(1234)
+    probe = np.sort(rng.choice(N, n_probe, replace=False))
+    out['mask'] = nv(prj['mask'])[..., 0].numpy().astype(np.uint8)            # full [N,V] index table
+    out['probe'] = probe.astype(np.int64)
+    for k in ('pts', 'depth', 'dir', 'rgb', 'ray_feats', 'img_feats', 'hit_prob', 'vis', 'alpha'):
+        out['p_' + ('uv' if k == 'pts' else k)] = nv(prj[k])[probe].numpy()
+    out['p_prob_emb'] = emb.reshape(N, V, -1)[probe].numpy()
+    out['p_dir_diff'] = dir_diff.reshape(N, V, -1)[probe].numpy()
+    out['valid_ratio'] = np.float32(prj['mask'].mean().item())
+    return out
+
+
+def run_render_case(nr, case):
+    scene = make_scene(**case['scene'])
+    ref = to_torch(scene)
+    q = make_query(scene, case['num_rays'], case['qseed'])
+    que = to_torch(q)
+    # torch.autograd.grad inside the reference needs grad mode on; eval = is_train False
+    res = nr.render_impl(que, ref, False)
+    keep = ['pixel_colors_nr', 'alpha_values', 'hit_prob_nr', 'sdf_values', 'colors_nr', 'render_depth',
+            'ray_mask', 'sdf_gradient_error', 'pixel_colors_gt', 's']
+    out = {}
+    for k in keep:
+        for sfx in ('', '_fine'):
+            if k + sfx in res:
+                out[k + sfx] = res[k + sfx].detach().numpy()
+    # the fine pass's own inputs, recomputed with the reference's samplers (eval => deterministic)
+    from network.render_ops import sample_depth, sample_fine_depth
+    with torch.no_grad():
+        depth, _ = sample_depth(que['depth_range'], que['coords'], nr.cfg['depth_sample_num'], False)
+        fd = sample_fine_depth(depth, res['hit_prob_nr'].detach(), que['depth_range'],
+                               nr.cfg['fine_depth_sample_num'], False)
+        out['depth'] = depth.numpy()
+        out['fine_depth_unsorted'] = fd.numpy()
+        out['depth_fine'] = torch.sort(fd, -1)[0].numpy()
+    return out
+
+
+def main():
+    cfg, net = build_reference_net(0)
+    nr = net.nr_net
+    sd = hot_state_dict(nr)
+    np.savez_compressed(os.path.join(HERE, 'weights_seed0.npz'), **{k: v.numpy() for k, v in sd.items()})
+    print('weights', len(sd), sum(v.numel() for v in sd.values()))
+    for name, kw in VOLUME_CASES.items():
+        out = run_volume_case(nr, kw)
+        np.savez_compressed(os.path.join(HERE, f'volume_{name}.npz'), **out)
+        print(name, 'valid_ratio', out['valid_ratio'], 'vol mean/std', out['volume'].mean(), out['volume'].std())
+    for name, case in RENDER_CASES.items():
+        out = run_render_case(nr, case)
+        np.savez_compressed(os.path.join(HERE, f'render_{name}.npz'), **out)
+        print(name, {k: v.shape for k, v in out.items()})
+
+
+if __name__ == '__main__':
+    main()
