@@ -1,0 +1,90 @@
+"""ctypes binding of libgraspnerf_b200.so (include/graspnerf_b200.h).
+
+There is NO fallback: if the library is missing or a struct size disagrees the import of the product path fails.
+"""
+import ctypes as C
+import os
+
+from .build import LIBPATH
+
+c_float_p = C.POINTER(C.c_float)
+
+
+class GnRayDirFc(C.Structure):
+    _fields_ = [('w0', C.c_float * 4 * 16), ('b0', C.c_float * 16), ('w1', C.c_float * 16 * 36), ('b1', C.c_float * 36)]
+
+
+class GnK1Params(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ('imgs', 'img_feats', 'ray_feats', 'KRt', 'cam', 'axis', 'bbox_min', 'pts',
+                                          'que_dir', 'rec', 'pt', 'dbg_feat_idx')] + \
+               [(n, C.c_int) for n in ('B', 'V', 'H', 'W', 'fh', 'fw', 'R', 'N', 'dn', 'S', 'volume_mode',
+                                       'tiles_per_scene')] + [('rdfc', GnRayDirFc)]
+
+
+class GnK2aParams(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ('rec', 'pt', 'weights', 'depth_range', 'que_dists', 'pooled', 'colors',
+                                          'dbg_rows')] + [(n, C.c_int) for n in ('B', 'N', 'V', 'S', 'dn')]
+
+
+class GnK2bParams(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ('pooled', 'weights', 'axis', 'bbox_min', 'pts', 'pos_table', 'sdf', 'grad')] + \
+               [(n, C.c_int) for n in ('B', 'N', 'dn', 'R', 'volume_mode')]
+
+
+class GnK3Params(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ('sdf', 'grad', 'colors', 'que_dir', 'depth')] + \
+               [('inv_s', C.c_float), ('cos_anneal_ratio', C.c_float)] + \
+               [(n, C.c_void_p) for n in ('alpha', 'hit_prob', 'pixel_colors', 'render_depth', 'eik_partial')] + \
+               [(n, C.c_int) for n in ('B', 'rn', 'dn')]
+
+
+_lib = None
+
+
+def load():
+    """Loads the library (once) and declares the prototypes.  Raises if it is absent or inconsistent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIBPATH):
+        raise RuntimeError(
+            f'{LIBPATH} not found: build it with `python -m graspnerf_b200.build` (or __graft_entry__.build()). '
+            'graspnerf_b200 has no CPU / PyTorch fallback for its CUDA kernels.')
+    lib = C.CDLL(LIBPATH)
+    lib.gn_version.restype = C.c_char_p
+    for name, st in (('gn_k1_forward', GnK1Params), ('gn_k2a_forward', GnK2aParams), ('gn_k2b_forward', GnK2bParams),
+                     ('gn_k3_composite', GnK3Params)):
+        fn = getattr(lib, name)
+        fn.restype = C.c_int
+        fn.argtypes = [C.POINTER(st), C.c_void_p]
+    lib.gn_k3_coarse_depths.restype = C.c_int
+    lib.gn_k3_coarse_depths.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    lib.gn_k3_fine_depths.restype = C.c_int
+    lib.gn_k3_fine_depths.argtypes = [C.c_void_p] * 6 + [C.c_int] * 4 + [C.c_void_p]
+    lib.gn_weight_entry.restype = C.c_int
+    lib.gn_weight_entry.argtypes = [C.c_int, C.POINTER(C.c_char_p)] + [C.POINTER(C.c_int)] * 4
+    for name, st in (('gn_sizeof_k1_params', GnK1Params), ('gn_sizeof_k2a_params', GnK2aParams),
+                     ('gn_sizeof_k2b_params', GnK2bParams), ('gn_sizeof_k3_params', GnK3Params)):
+        got = getattr(lib, name)()
+        if got != C.sizeof(st):
+            raise RuntimeError(f'{name}: library says {got} bytes, ctypes mirror has {C.sizeof(st)}')
+    _lib = lib
+    return lib
+
+
+def weight_table():
+    """[(name, offset, rows, cols, cols_padded)] as enumerated by the library."""
+    lib = load()
+    out = []
+    for i in range(lib.gn_weight_entry_count()):
+        name = C.c_char_p()
+        off, rows, cols, cp = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        rc = lib.gn_weight_entry(i, C.byref(name), C.byref(off), C.byref(rows), C.byref(cols), C.byref(cp))
+        assert rc == 0
+        out.append((name.value.decode(), off.value, rows.value, cols.value, cp.value))
+    return out
+
+
+def check(rc, what):
+    if rc != 0:
+        raise RuntimeError(f'{what} failed with code {rc}' + (' (argument error)' if rc < 0 else ' (cudaError_t)'))

@@ -1,0 +1,60 @@
+// Common device helpers for the graspnerf_b200 sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define GN_FEAT_C 32          // channels of img_feats / ray_feats (renderer.py:53, init_net.py:24)
+#define GN_REC_VOL 72         // floats per (point,view) record, volume mode
+#define GN_REC_RAY 76         // ... RGB-head mode (adds dir_diff[4])
+#define GN_PT_STRIDE 72       // floats per point: mean[36] | var[36]
+#define GN_POOL_STRIDE 68     // floats per point written by K2a: mean32 | var32 | wmean, nvalid, 0, 0
+
+// record layout (floats), see DESIGN.md "Data layout in HBM"
+#define GN_REC_RAYF 0         // [0,32)  ray_feats * mask
+#define GN_REC_FIMG 32        // [32,64) img_feats*mask + dir-feature (channels 3..34 of the reference's rgb_feat)
+#define GN_REC_FRGB 64        // [64,67) rgb*mask + dir-feature (channels 0..2) ; [67] mask
+#define GN_REC_MASK 67
+#define GN_REC_DEPTH 68       // [68] projection depth ; [69,72) rgb*mask (rgb_in of ibrnet.py:458)
+#define GN_REC_RGBIN 69
+#define GN_REC_DD 72          // [72,76) dir_diff (RGB-head mode only)
+
+__device__ __forceinline__ float gn_elu(float x) {
+    // nn.ELU (alpha 1): x>0 ? x : exp(x)-1.  __expf = ex2.approx(x*log2e): rel. err ~2^-21.
+    return x > 0.f ? x : (__expf(x) - 1.f);
+}
+__device__ __forceinline__ float gn_sigmoid(float x) { return 1.f / (1.f + __expf(-x)); }
+__device__ __forceinline__ float gn_softplus(float x) {
+    // nn.Softplus(beta=1, threshold=20)
+    return x > 20.f ? x : log1pf(__expf(x));
+}
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+// streaming store: the record is written once and read once by the next kernel
+__device__ __forceinline__ void st4_cs(float* p, float4 v) { __stcs(reinterpret_cast<float4*>(p), v); }
+
+__device__ __forceinline__ float4 f4_fma(float4 a, float w, float4 acc) {
+    acc.x = fmaf(a.x, w, acc.x); acc.y = fmaf(a.y, w, acc.y);
+    acc.z = fmaf(a.z, w, acc.z); acc.w = fmaf(a.w, w, acc.w);
+    return acc;
+}
+__device__ __forceinline__ float4 f4_mul(float4 a, float w) { return make_float4(a.x * w, a.y * w, a.z * w, a.w * w); }
+__device__ __forceinline__ float4 f4_add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+
+// ---- bilinear tap arithmetic, FIXED op order without FMA (mirrors oracle/nr_oracle.py:bilinear_coords;
+// reference ops.py:29-30 + F.grid_sample(padding_mode='border')).
+struct GnTap1D { int i0, i1; float w0, w1; };
+__device__ __forceinline__ GnTap1D gn_tap1d(float u, int size_img, int size_map, bool align_corners) {
+    float xn = __fsub_rn(__fmul_rn(__fdiv_rn(u, (float)(size_img - 1)), 2.f), 1.f);
+    float ix;
+    if (align_corners) ix = __fmul_rn(__fdiv_rn(__fadd_rn(xn, 1.f), 2.f), (float)(size_map - 1));
+    else               ix = __fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(xn, 1.f), (float)size_map), 1.f), 2.f);
+    ix = fminf(fmaxf(ix, 0.f), (float)(size_map - 1));
+    float f0 = floorf(ix);
+    GnTap1D t;
+    t.w1 = __fsub_rn(ix, f0);
+    t.w0 = __fsub_rn(__fadd_rn(f0, 1.f), ix);
+    t.i0 = (int)f0;
+    t.i1 = min(t.i0 + 1, size_map - 1);
+    return t;
+}

@@ -1,0 +1,150 @@
+// K3: NeuS alpha, alpha compositing and the depth samplers of the RGB head (latency-bound, one thread per ray).
+//
+//   gn_k3_composite     _get_alpha_from_sdf (aggregate_net.py:105-123), alpha_values2hit_prob (render_ops.py:72-80),
+//                       pixel colour / depth sums (renderer.py:105-106,136), eikonal partial sums (aggregate_net.py:139)
+//   gn_k3_coarse_depths sample_depth, deterministic branch (render_ops.py:146-170)
+//   gn_k3_fine_depths   sample_fine_depth (render_ops.py:172-229) + the sort of renderer.py:148.
+// Sums and scans run left to right in fp32 (the order oracle/nr_oracle.py states), so the searchsorted index table is
+// bit-exact against the oracle.
+#include "gn_common.cuh"
+#include "../../include/graspnerf_b200.h"
+
+__device__ __forceinline__ float k3_sigmoid(float x) { return __fdiv_rn(1.f, 1.f + expf(-x)); }
+
+__global__ void gn_k3_composite_kernel(const GnK3Params p)
+{
+    const long long ray = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ray >= (long long)p.B * p.rn) return;
+    const int dn = p.dn;
+    const float* sdf = p.sdf + ray * dn;
+    const float* grad = p.grad + ray * dn * 3;
+    const float* col = p.colors + ray * dn * 4;
+    const float* dep = p.depth + ray * dn;
+    const float qx = p.que_dir[ray * 3], qy = p.que_dir[ray * 3 + 1], qz = p.que_dir[ray * 3 + 2];
+    const float car = p.cos_anneal_ratio;
+    float T = 1.f, c0 = 0.f, c1 = 0.f, c2 = 0.f, rd = 0.f, eik = 0.f;
+    for (int d = 0; d < dn; ++d) {
+        const float gx = grad[d * 3], gy = grad[d * 3 + 1], gz = grad[d * 3 + 2];
+        const float dist = (d + 1 < dn) ? __fsub_rn(dep[d + 1], dep[d]) : 1e6f;      // depth2dists render_ops.py:41-44
+        const float true_cos = ((-qx * gx) + (-qy * gy)) + (-qz * gz);
+        const float iter_cos = -(fmaxf(-true_cos * 0.5f + 0.5f, 0.f) * (1.f - car) + fmaxf(-true_cos, 0.f) * car);
+        const float s = sdf[d];
+        const float nxt = s + iter_cos * dist * 0.5f, prv = s - iter_cos * dist * 0.5f;
+        const float pc = k3_sigmoid(prv * p.inv_s), nc = k3_sigmoid(nxt * p.inv_s);
+        const float alpha = fminf(fmaxf(__fdiv_rn((pc - nc) + 1e-5f, pc + 1e-5f), 0.f), 1.f);
+        const float hit = alpha * T;                                                 // render_ops.py:77-79
+        T *= (1.f - alpha) + 1e-10f;
+        p.alpha[ray * dn + d] = alpha;
+        p.hit_prob[ray * dn + d] = hit;
+        c0 = fmaf(hit, col[d * 4], c0); c1 = fmaf(hit, col[d * 4 + 1], c1); c2 = fmaf(hit, col[d * 4 + 2], c2);
+        rd = fmaf(hit, dep[d], rd);
+        const float gn = sqrtf(gx * gx + gy * gy + gz * gz) - 1.f;
+        eik = fmaf(gn, gn, eik);
+    }
+    p.pixel_colors[ray * 3] = c0; p.pixel_colors[ray * 3 + 1] = c1; p.pixel_colors[ray * 3 + 2] = c2;
+    p.render_depth[ray] = rd;
+    p.eik_partial[ray] = eik;
+}
+
+extern "C" int gn_k3_composite(const GnK3Params* hp, void* stream)
+{
+    const GnK3Params& p = *hp;
+    if (p.B < 1 || p.rn < 1 || p.dn < 1) return -1;
+    const long long rays = (long long)p.B * p.rn;
+    const int threads = 128;
+    gn_k3_composite_kernel<<<(unsigned)((rays + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(p);
+    return (int)cudaGetLastError();
+}
+
+__global__ void gn_k3_coarse_kernel(const float* __restrict__ depth_range, float* __restrict__ depth, int B, int rn, int dn)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)B * rn * dn) return;
+    const int d = (int)(i % dn);
+    const int b = (int)(i / ((long long)rn * dn));
+    const float near = depth_range[b * 2], far = depth_range[b * 2 + 1];
+    const float inear = __fdiv_rn(1.f, near), span = __fsub_rn(__fdiv_rn(1.f, far), inear);
+    const float interval = __fdiv_rn(span, (float)(dn - 1));
+    float tick;
+    if (d == 0) tick = 0.f;
+    else if (d == dn - 1) tick = span;
+    else tick = __fmul_rn(interval, (float)d);
+    depth[i] = __fdiv_rn(1.f, __fadd_rn(inear, tick));
+}
+
+extern "C" int gn_k3_coarse_depths(const float* depth_range, float* depth, int B, int rn, int dn, void* stream)
+{
+    if (B < 1 || rn < 1 || dn < 3) return -1;
+    const long long n = (long long)B * rn * dn;
+    gn_k3_coarse_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(depth_range, depth, B, rn, dn);
+    return (int)cudaGetLastError();
+}
+
+#define K3F_THREADS 64
+__global__ void gn_k3_fine_kernel(const float* __restrict__ depth, const float* __restrict__ hit_prob,
+                                  const float* __restrict__ depth_range, const float* __restrict__ u,
+                                  float* __restrict__ fine_depth, long long* __restrict__ inds,
+                                  int B, int rn, int dn, int fdn)
+{
+    extern __shared__ float k3s[];
+    const int per = 2 * (dn + 1) + fdn;
+    float* cdf = k3s + threadIdx.x * per;
+    float* centre = cdf + dn + 1;
+    float* out = centre + dn + 1;
+    const long long ray = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ray >= (long long)B * rn) return;
+    const int b = (int)(ray / rn);
+    const float near = __fdiv_rn(-1.f, depth_range[b * 2]), far = __fdiv_rn(-1.f, depth_range[b * 2 + 1]);
+    const float span = __fsub_rn(far, near);
+    const float* dep = depth + ray * dn;
+    const float* hp = hit_prob + ray * dn;
+    float prev = 0.f, sum = 0.f;
+    for (int i = 0; i < dn; ++i) {
+        const float di = __fdiv_rn(__fsub_rn(__fdiv_rn(-1.f, dep[i]), near), span);
+        if (i == 0) centre[0] = di;
+        else centre[i] = __fdiv_rn(__fadd_rn(di, prev), 2.f);
+        prev = di;
+        const float h = __fadd_rn(hp[i], 1e-5f);
+        sum = (i == 0) ? h : __fadd_rn(sum, h);
+    }
+    centre[dn] = prev;
+    cdf[0] = 0.f;
+    float run = 0.f;
+    for (int i = 0; i < dn; ++i) {
+        const float pdf = __fdiv_rn(__fadd_rn(hp[i], 1e-5f), sum);
+        run = (i == 0) ? pdf : __fadd_rn(run, pdf);
+        cdf[i + 1] = run;
+    }
+    for (int j = 0; j < fdn; ++j) {
+        const float uj = u[ray * fdn + j];
+        int idx = 0;                                         // searchsorted(right=True): first i with cdf[i] > u
+        while (idx <= dn && !(cdf[idx] > uj)) ++idx;
+        const int below = max(idx - 1, 0), above = min(idx, dn);
+        const float c0 = cdf[below], c1 = cdf[above], b0 = centre[below], b1 = centre[above];
+        float denom = __fsub_rn(c1, c0);
+        if (denom < 1e-5f) denom = 1.f;
+        const float tt = __fdiv_rn(__fsub_rn(uj, c0), denom);
+        float fd = __fadd_rn(b0, __fmul_rn(tt, __fsub_rn(b1, b0)));
+        fd = __fdiv_rn(-1.f, __fadd_rn(__fmul_rn(fd, span), near));
+        if (inds) inds[ray * fdn + j] = idx;
+        // insertion sort (ascending), renderer.py:148
+        int k = j;
+        while (k > 0 && out[k - 1] > fd) { out[k] = out[k - 1]; --k; }
+        out[k] = fd;
+    }
+    for (int j = 0; j < fdn; ++j) fine_depth[ray * fdn + j] = out[j];
+}
+
+extern "C" int gn_k3_fine_depths(const float* depth, const float* hit_prob, const float* depth_range, const float* u,
+                                 float* fine_depth, int64_t* inds, int B, int rn, int dn, int fdn, void* stream)
+{
+    if (B < 1 || rn < 1 || dn < 2 || fdn < 1) return -1;
+    const size_t smem = (size_t)K3F_THREADS * (2 * (dn + 1) + fdn) * sizeof(float);
+    if (smem > 227 * 1024) return -5;
+    cudaError_t e = cudaFuncSetAttribute(gn_k3_fine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    const long long rays = (long long)B * rn;
+    gn_k3_fine_kernel<<<(unsigned)((rays + K3F_THREADS - 1) / K3F_THREADS), K3F_THREADS, smem, (cudaStream_t)stream>>>(
+        depth, hit_prob, depth_range, u, fine_depth, (long long*)inds, B, rn, dn, fdn);
+    return (int)cudaGetLastError();
+}

@@ -1,0 +1,230 @@
+"""Torch-tensor front end of the C ABI (include/graspnerf_b200.h).
+
+PyTorch is plumbing here: it owns device memory and the current stream; every computation below is one of the
+hand-written sm_100a kernels.  Nothing in this module has a CPU or eager-PyTorch fallback - without a CUDA device and the
+built library these functions raise.
+"""
+import ctypes as C
+import numpy as np
+import torch
+
+from . import _lib
+from .weights import pack_blob, pack_ray_dir_fc, positional_table, voxel_axis_table
+
+REC_VOL, REC_RAY, PT_STRIDE, POOL_STRIDE = 72, 76, 72, 68
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _f32c(t, device):
+    if not torch.is_tensor(t):
+        t = torch.as_tensor(np.asarray(t, dtype=np.float32))
+    return t.to(device=device, dtype=torch.float32).contiguous()
+
+
+def _require_cuda(t, what):
+    if not t.is_cuda:
+        raise RuntimeError(f'{what} must live on a CUDA device: graspnerf_b200 has no CPU path')
+
+
+class HeadWeights:
+    """Device-resident packed weights of one (agg_net, dist_decoder) pair + kernel constants.
+
+    `refresh(sd)` re-packs when any source tensor changed (training); inference packs once."""
+
+    def __init__(self, sd, agg_prefix='agg_net.', dd_prefix='dist_decoder.', device='cuda'):
+        self.agg_prefix, self.dd_prefix, self.device = agg_prefix, dd_prefix, torch.device(device)
+        self._versions = None
+        self._pos = {}
+        self._axis = {}
+        self.refresh(sd)
+
+    def _keys(self, sd):
+        return [k for k in sd if k.startswith(self.agg_prefix) or k.startswith(self.dd_prefix)]
+
+    def refresh(self, sd):
+        vers = tuple((k, sd[k]._version, sd[k].data_ptr()) for k in self._keys(sd))
+        if vers == self._versions:
+            return
+        self.blob = torch.from_numpy(pack_blob(sd, self.agg_prefix, self.dd_prefix)).to(self.device)
+        self.rdfc = pack_ray_dir_fc(sd, self.agg_prefix)
+        var = sd.get(self.agg_prefix + 'deviation_network.variance')
+        self.variance = float(var) if var is not None else 0.3
+        self._versions = vers
+
+    def pos_table(self, dn):
+        if dn not in self._pos:
+            self._pos[dn] = torch.from_numpy(positional_table(dn)).to(self.device)
+        return self._pos[dn]
+
+    def axis(self, resolution, volume_size=0.3):
+        key = (resolution, volume_size)
+        if key not in self._axis:
+            self._axis[key] = torch.from_numpy(voxel_axis_table(resolution, volume_size)).to(self.device)
+        return self._axis[key]
+
+
+def camera_matrices(poses, Ks):
+    """[B,V,3,4] K@[R|t] and [B,V,3] camera centres -R^T t; 6 tiny matmuls, done with torch exactly as the reference
+    does (render_ops.py:94,112) so that the fp32 values entering the kernel are the reference's."""
+    KRt = Ks @ poses
+    cam = (-poses[..., :3].transpose(-1, -2) @ poses[..., 3:])[..., 0]
+    return KRt.contiguous(), cam.contiguous()
+
+
+def to_channels_last_maps(fmap):
+    """[B,V,C,fh,fw] (any strides) -> contiguous [B,V,fh,fw,C]; free when the encoder already produced channels_last."""
+    return fmap.permute(0, 1, 3, 4, 2).contiguous()
+
+
+class Scene:
+    """Batched device-side inputs of the hot path (B scenes x V views)."""
+
+    def __init__(self, imgs, img_feats, ray_feats, poses, Ks, depth_range, feats_channels_last=False):
+        # accept single-scene [V,...] tensors like the reference's ref_imgs_info
+        if imgs.dim() == 4:
+            imgs, img_feats, ray_feats = imgs[None], img_feats[None], ray_feats[None]
+            poses, Ks, depth_range = poses[None], Ks[None], depth_range[None]
+        _require_cuda(imgs, 'imgs')
+        dev = imgs.device
+        self.device = dev
+        self.imgs = _f32c(imgs, dev)
+        if feats_channels_last:       # already [B,V,fh,fw,32]
+            self.img_feats, self.ray_feats = _f32c(img_feats, dev), _f32c(ray_feats, dev)
+        else:                         # logical [B,V,32,fh,fw]; a channels_last-strided tensor converts without a copy
+            self.img_feats = to_channels_last_maps(img_feats.to(dev, torch.float32))
+            self.ray_feats = to_channels_last_maps(ray_feats.to(dev, torch.float32))
+        self.B, self.V, _, self.H, self.W = self.imgs.shape
+        _, _, self.fh, self.fw, c = self.img_feats.shape
+        if c != 32 or self.ray_feats.shape != self.img_feats.shape:
+            raise ValueError('feature maps must be [B,V,fh,fw,32]')
+        self.KRt, self.cam = camera_matrices(_f32c(poses, dev), _f32c(Ks, dev))
+        self.depth_range = _f32c(depth_range, dev)
+
+
+def k1_forward(scene, hw, *, resolution=None, bbox_min=None, volume_size=0.3, pts=None, que_dir=None, dn=None,
+               debug_idx=False):
+    """K1 launch.  Volume mode: resolution + bbox_min [B,3].  Ray mode: pts [B,N,3], que_dir [B,N/dn,3], dn."""
+    lib = _lib.load()
+    dev = scene.device
+    p = _lib.GnK1Params()
+    vol = pts is None
+    if vol:
+        R = int(resolution)
+        N, dn_, S = R * R * R, R, REC_VOL
+        bbox_min = _f32c(bbox_min, dev).reshape(scene.B, 3)
+        axis = hw.axis(R, volume_size)
+        p.axis, p.bbox_min, p.R = _ptr(axis).value, _ptr(bbox_min).value, R
+    else:
+        pts = _f32c(pts, dev)
+        que_dir = _f32c(que_dir, dev)
+        N, dn_, S = pts.shape[1], int(dn), REC_RAY
+        p.pts, p.que_dir, p.R = _ptr(pts).value, _ptr(que_dir).value, 0
+    rec = torch.empty((scene.B, N, scene.V, S), device=dev, dtype=torch.float32)
+    pt = torch.empty((scene.B, N, PT_STRIDE), device=dev, dtype=torch.float32)
+    dbg = torch.zeros((scene.B, N, scene.V, 2), device=dev, dtype=torch.int32) if debug_idx else None
+    p.imgs, p.img_feats, p.ray_feats = _ptr(scene.imgs).value, _ptr(scene.img_feats).value, _ptr(scene.ray_feats).value
+    p.KRt, p.cam = _ptr(scene.KRt).value, _ptr(scene.cam).value
+    p.rec, p.pt, p.dbg_feat_idx = _ptr(rec).value, _ptr(pt).value, _ptr(dbg).value
+    p.B, p.V, p.H, p.W, p.fh, p.fw = scene.B, scene.V, scene.H, scene.W, scene.fh, scene.fw
+    p.N, p.dn, p.S, p.volume_mode = N, dn_, S, 1 if vol else 0
+    p.rdfc = hw.rdfc
+    _lib.check(lib.gn_k1_forward(C.byref(p), _stream()), 'gn_k1_forward')
+    return (rec, pt, dbg) if debug_idx else (rec, pt)
+
+
+def k2a_forward(rec, pt, hw, depth_range, *, que_dists=None, dn=1, want_colors=False, debug=False):
+    lib = _lib.load()
+    B, N, V, S = rec.shape
+    dev = rec.device
+    pooled = torch.empty((B, N, POOL_STRIDE), device=dev, dtype=torch.float32)
+    colors = torch.empty((B, N, 4), device=dev, dtype=torch.float32) if want_colors else None
+    dbg = torch.zeros((B, N, V, 8), device=dev, dtype=torch.float32) if debug else None
+    p = _lib.GnK2aParams()
+    p.rec, p.pt, p.weights, p.depth_range = _ptr(rec).value, _ptr(pt).value, _ptr(hw.blob).value, _ptr(depth_range).value
+    if que_dists is not None:
+        que_dists = _f32c(que_dists, dev)
+    p.que_dists, p.pooled, p.colors, p.dbg_rows = _ptr(que_dists).value, _ptr(pooled).value, _ptr(colors).value, _ptr(dbg).value
+    p.B, p.N, p.V, p.S, p.dn = B, N, V, S, int(dn)
+    _lib.check(lib.gn_k2a_forward(C.byref(p), _stream()), 'gn_k2a_forward')
+    return pooled, colors, dbg
+
+
+def k2b_forward(pooled, hw, *, dn, resolution=None, bbox_min=None, volume_size=0.3, pts=None, want_grad=False):
+    lib = _lib.load()
+    B, N, _ = pooled.shape
+    dev = pooled.device
+    p = _lib.GnK2bParams()
+    vol = pts is None
+    if vol:
+        R = int(resolution)
+        bbox_min = _f32c(bbox_min, dev).reshape(B, 3)
+        axis = hw.axis(R, volume_size)
+        out = torch.empty((B, 1, R, R, R), device=dev, dtype=torch.float32)
+        p.axis, p.bbox_min, p.R = _ptr(axis).value, _ptr(bbox_min).value, R
+    else:
+        pts = _f32c(pts, dev)
+        out = torch.empty((B, N), device=dev, dtype=torch.float32)
+        p.pts, p.R = _ptr(pts).value, 0
+    grad = torch.empty((B, N, 3), device=dev, dtype=torch.float32) if want_grad else None
+    pos = hw.pos_table(int(dn))
+    p.pooled, p.weights, p.pos_table, p.sdf, p.grad = _ptr(pooled).value, _ptr(hw.blob).value, _ptr(pos).value, _ptr(out).value, _ptr(grad).value
+    p.B, p.N, p.dn, p.volume_mode = B, N, int(dn), 1 if vol else 0
+    _lib.check(lib.gn_k2b_forward(C.byref(p), _stream()), 'gn_k2b_forward')
+    return out, grad
+
+
+def k3_composite(sdf, grad, colors, que_dir, depth, inv_s, cos_anneal_ratio=1.0):
+    """sdf [B,rn,dn]; grad [B,rn,dn,3]; colors [B,rn,dn,4]; que_dir [B,rn,3]; depth [B,rn,dn]."""
+    lib = _lib.load()
+    B, rn, dn = sdf.shape
+    dev = sdf.device
+    alpha = torch.empty((B, rn, dn), device=dev, dtype=torch.float32)
+    hit = torch.empty_like(alpha)
+    pix = torch.empty((B, rn, 3), device=dev, dtype=torch.float32)
+    rdepth = torch.empty((B, rn), device=dev, dtype=torch.float32)
+    eik = torch.empty((B, rn), device=dev, dtype=torch.float32)
+    p = _lib.GnK3Params()
+    p.sdf, p.grad, p.colors, p.que_dir, p.depth = _ptr(sdf).value, _ptr(grad).value, _ptr(colors).value, _ptr(que_dir).value, _ptr(depth).value
+    p.inv_s, p.cos_anneal_ratio = float(inv_s), float(cos_anneal_ratio)
+    p.alpha, p.hit_prob, p.pixel_colors, p.render_depth, p.eik_partial = _ptr(alpha).value, _ptr(hit).value, _ptr(pix).value, _ptr(rdepth).value, _ptr(eik).value
+    p.B, p.rn, p.dn = B, rn, dn
+    _lib.check(lib.gn_k3_composite(C.byref(p), _stream()), 'gn_k3_composite')
+    return alpha, hit, pix, rdepth, eik
+
+
+def k3_coarse_depths(depth_range_q, rn, dn):
+    """depth_range_q [B,2] -> [B,rn,dn]  (sample_depth, render_ops.py:146-170, deterministic)."""
+    lib = _lib.load()
+    B = depth_range_q.shape[0]
+    out = torch.empty((B, rn, dn), device=depth_range_q.device, dtype=torch.float32)
+    _lib.check(lib.gn_k3_coarse_depths(_ptr(depth_range_q), _ptr(out), B, rn, dn, _stream()), 'gn_k3_coarse_depths')
+    return out
+
+
+def k3_fine_depths(depth, hit_prob, depth_range_q, u, want_inds=False):
+    """-> sorted fine depths [B,rn,fdn] (+ int64 searchsorted indices)."""
+    lib = _lib.load()
+    B, rn, dn = depth.shape
+    fdn = u.shape[-1]
+    out = torch.empty((B, rn, fdn), device=depth.device, dtype=torch.float32)
+    inds = torch.empty((B, rn, fdn), device=depth.device, dtype=torch.int64) if want_inds else None
+    _lib.check(lib.gn_k3_fine_depths(_ptr(depth), _ptr(hit_prob), _ptr(depth_range_q), _ptr(u), _ptr(out), _ptr(inds),
+                                     B, rn, dn, fdn, _stream()), 'gn_k3_fine_depths')
+    return out, inds
+
+
+def sample_volume(scene, hw, bbox_min, resolution=40, volume_size=0.3, debug=None):
+    """NeuralRayRenderer.sample_volume (renderer.py:164-199) for B scenes: K1 -> K2a -> K2b.  Returns [B,1,R,R,R]."""
+    rec, pt = k1_forward(scene, hw, resolution=resolution, bbox_min=bbox_min, volume_size=volume_size)
+    pooled, _, dbg = k2a_forward(rec, pt, hw, scene.depth_range, debug=debug is not None)
+    vol, _ = k2b_forward(pooled, hw, dn=resolution, resolution=resolution, bbox_min=bbox_min, volume_size=volume_size)
+    if debug is not None:
+        debug.update(rec=rec, pt=pt, pooled=pooled, rows=dbg)
+    return vol

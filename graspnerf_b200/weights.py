@@ -1,0 +1,117 @@
+"""Packs the reference's state_dict tensors into the fp32 blob the K2 kernels read.
+
+The blob layout (entry names, offsets, padded shapes) is owned by the native library and enumerated through the C ABI
+(gn_weight_entry); this module only knows which reference tensor feeds which entry and how to permute it.  Key names
+are the reference's, so a `model_best.pth` packs unchanged.
+"""
+import ctypes as C
+import numpy as np
+import torch
+
+from . import _lib
+
+# record channel order of the 35-wide "rgb_feat": [img_feats 32 | rgb 3]; reference order is [rgb 3 | img_feats 32]
+# (ibrnet.py:458-459, aggregate_net.py:67)
+PERM35 = list(range(3, 35)) + [0, 1, 2]
+
+
+def _np(t):
+    return t.detach().to('cpu', torch.float32).numpy()
+
+
+def _entries(sd, agg_prefix, dd_prefix):
+    A = agg_prefix + 'agg_impl.'
+    e = {}
+
+    def lin(dst_w, dst_b, key, vector=False):
+        w = _np(sd[key + '.weight'])
+        e[dst_w] = w if vector else w.T
+        if dst_b is not None:
+            e[dst_b] = _np(sd[key + '.bias'])[None, :]
+    for short, name in (('mean', 'mean_decoder'), ('var', 'var_decoder'), ('aw', 'aw_decoder')):
+        lin(f'dd.{short}.w0', f'dd.{short}.b0', f'{dd_prefix}{name}.0')
+        lin(f'dd.{short}.w2', f'dd.{short}.b2', f'{dd_prefix}{name}.2')
+        lin(f'dd.{short}.w4', f'dd.{short}.b4', f'{dd_prefix}{name}.4')
+    lin('pe.w0', 'pe.b0', agg_prefix + 'prob_embed.0')
+    lin('pe.w2', 'pe.b2', agg_prefix + 'prob_embed.2')
+    lin('nf.w0', 'nf.b0', A + 'neuray_fc.0')
+    lin('nf.w2', 'nf.b2', A + 'neuray_fc.2', vector=True)
+    w = _np(sd[A + 'base_fc.0.weight'])                       # [64, 207]
+    wg = np.zeros((144, 64), np.float32)
+    for q in range(4):                                         # mean0 | var0 | mean1 | var1
+        wg[q * 36:q * 36 + 35] = w[:, [q * 35 + c for c in PERM35]].T
+    wf = np.zeros((36, 64), np.float32)
+    wf[:35] = w[:, [140 + c for c in PERM35]].T
+    e['bf.wg'], e['bf.wf'], e['bf.wp'] = wg, wf, w[:, 175:207].T
+    e['bf.b0'] = _np(sd[A + 'base_fc.0.bias'])[None, :]
+    lin('bf.w2', 'bf.b2', A + 'base_fc.2')
+    lin('vf.w0', 'vf.b0', A + 'vis_fc.0')
+    lin('vf.w2', 'vf.b2', A + 'vis_fc.2')
+    lin('v2.w0', 'v2.b0', A + 'vis_fc2.0')
+    lin('v2.w2', 'v2.b2', A + 'vis_fc2.2', vector=True)
+    lin('rf.w0', 'rf.b0', A + 'rgb_fc.0')
+    lin('rf.w2', 'rf.b2', A + 'rgb_fc.2')
+    lin('rf.w4', 'rf.b4', A + 'rgb_fc.4', vector=True)
+    lin('gf.w0', 'gf.b0', A + 'geometry_fc.0')
+    lin('gf.w2', 'gf.b2', A + 'geometry_fc.2')
+    for dst, src in (('at.wq', 'w_qs'), ('at.wk', 'w_ks'), ('at.wv', 'w_vs'), ('at.fc', 'fc')):
+        e[dst] = _np(sd[f'{A}ray_attention.{src}.weight']).T
+    e['at.ln_w'] = _np(sd[A + 'ray_attention.layer_norm.weight'])[None, :]
+    e['at.ln_b'] = _np(sd[A + 'ray_attention.layer_norm.bias'])[None, :]
+    lin('og.w0', 'og.b0', A + 'out_geometry_fc.0')
+    lin('og.w1', 'og.b1', A + 'out_geometry_fc.1', vector=True)
+    return e
+
+
+def pack_blob(sd, agg_prefix='agg_net.', dd_prefix='dist_decoder.'):
+    """-> np.float32 [gn_weight_blob_floats()]"""
+    lib = _lib.load()
+    table = _lib.weight_table()
+    ent = _entries(sd, agg_prefix, dd_prefix)
+    blob = np.zeros(lib.gn_weight_blob_floats(), np.float32)
+    seen = set()
+    for name, off, rows, cols, cp in table:
+        a = ent[name]
+        a = a.reshape(rows, cols) if a.ndim == 1 else a
+        if a.shape[0] < rows:                                   # row-padded entries keep their trailing zero rows
+            a = np.concatenate([a, np.zeros((rows - a.shape[0], a.shape[1]), np.float32)], 0)
+        assert a.shape == (rows, cols), (name, a.shape, (rows, cols))
+        view = blob[off:off + rows * cp].reshape(rows, cp)
+        view[:, :cols] = a
+        seen.add(name)
+    assert seen == set(ent), set(ent) ^ seen
+    return blob
+
+
+def pack_ray_dir_fc(sd, agg_prefix='agg_net.'):
+    """-> GnRayDirFc ctypes struct (K1 kernel-parameter constants)."""
+    A = agg_prefix + 'agg_impl.'
+    s = _lib.GnRayDirFc()
+    w0 = np.ascontiguousarray(_np(sd[A + 'ray_dir_fc.0.weight']))          # [16,4]
+    b0 = np.ascontiguousarray(_np(sd[A + 'ray_dir_fc.0.bias']))
+    w1 = np.zeros((36, 16), np.float32)
+    b1 = np.zeros(36, np.float32)
+    w1[:35] = _np(sd[A + 'ray_dir_fc.2.weight'])[PERM35]
+    b1[:35] = _np(sd[A + 'ray_dir_fc.2.bias'])[PERM35]
+    C.memmove(C.addressof(s.w0), w0.ctypes.data, w0.nbytes)
+    C.memmove(C.addressof(s.b0), b0.ctypes.data, b0.nbytes)
+    C.memmove(C.addressof(s.w1), w1.ctypes.data, w1.nbytes)
+    C.memmove(C.addressof(s.b1), b1.ctypes.data, b1.nbytes)
+    return s
+
+
+def positional_table(n_samples, d_hid=16):
+    """Sinusoid table of IBRNetWithNeuRayNeus.posenc (ibrnet.py:437-445), [n_samples, 16] fp32; the reference builds it
+    in float64 numpy and casts, so it is host-side constant data rather than kernel arithmetic."""
+    pos = np.arange(n_samples, dtype=np.float64)[:, None]
+    j = np.arange(d_hid)[None, :]
+    ang = pos / np.power(10000.0, 2 * (j // 2) / d_hid)
+    tab = np.where(j % 2 == 0, np.sin(ang), np.cos(ang))
+    return tab.astype(np.float32)
+
+
+def voxel_axis_table(resolution, volume_size=0.3):
+    """utils/field_utils.py:12-25: (i * VOXEL + HALF) in python double, cast to fp32."""
+    voxel = volume_size / resolution
+    half = voxel / 2
+    return np.array([i * voxel + half for i in range(resolution)]).astype(np.float32)

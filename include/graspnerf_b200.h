@@ -1,0 +1,148 @@
+/* graspnerf_b200 C ABI  --  libgraspnerf_b200.so
+ *
+ * Drop-in boundary for GraspNeRF's generalizable-NeRF volumetric TSDF hot path (reference: PKU-EPIC/GraspNeRF,
+ * src/nr/network).  The reference has NO native/FFI layer for this path (it is pure PyTorch);
+ * these entry points are what a binding for the path binds: each one replaces a chain of reference torch ops,
+ * cited per function.  The reference-side binding (ctypes) is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to fp32 unless stated; the caller owns all buffers (kernels never allocate);
+ *   - all launches go to the caller's `stream` (a cudaStream_t passed as void*), no host synchronisation;
+ *   - return value: 0 = ok, <0 = argument error, >0 = cudaError_t of the launch; no exceptions cross the ABI;
+ *   - re-entrant, no global state; one process per GPU under data parallelism.
+ *
+ * Data layout in HBM:
+ *   feature maps  : channels-last  [B, V, fh, fw, 32]
+ *   images        : planar         [B, V, 3, H, W]
+ *   record  `rec` : [B, N, V, S]   S = 72 (volume) or 76 (RGB head); n = ray*dn + sample
+ *   per-point `pt`: [B, N, 72]     mean[img32,rgb3], nvalid | var[img32,rgb3], 0
+ *   `pooled`      : [B, N, 68]     K2a output: mean32 | var32 | mean_v(w), nvalid, 0, 0
+ */
+#ifndef GRASPNERF_B200_H
+#define GRASPNERF_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ray_dir_fc weights (ibrnet.py:382-385), passed by value inside GnK1Params (kernel constant bank).
+ * w1/b1 rows are in the record's channel order: rows 0..31 = reference outputs 3..34 (img_feats channels),
+ * rows 32..34 = reference outputs 0..2 (rgb), row 35 = 0. */
+typedef struct GnRayDirFc {
+    float w0[16][4];
+    float b0[16];
+    float w1[36][16];
+    float b1[36];
+} GnRayDirFc;
+
+/* K1: fused project - sample - aggregate.
+ * Replaces project_points_dict (render_ops.py:82-144), get_img_feats (renderer.py:80-88), get_dir_diff
+ * (aggregate_net.py:11-17), ray_dir_fc + add (ibrnet.py:457-459) and the mask-weighted mean/var
+ * (ibrnet.py:466,471).  volume_mode=1: points are the voxel centres of utils/field_utils.py:12-27 plus bbox_min,
+ * in sample_volume's order (renderer.py:166-170).  volume_mode=0: explicit points (RGB head, render_ops.py:27-39). */
+typedef struct GnK1Params {
+    const float* imgs;        /* [B,V,3,H,W] */
+    const float* img_feats;   /* [B,V,fh,fw,32] channels-last */
+    const float* ray_feats;   /* [B,V,fh,fw,32] channels-last */
+    const float* KRt;         /* [B,V,3,4]  K @ [R|t]  (render_ops.py:94) */
+    const float* cam;         /* [B,V,3]    camera centres -R^T t (render_ops.py:112) */
+    const float* axis;        /* [R] voxel-centre table (volume mode) */
+    const float* bbox_min;    /* [B,3] (volume mode) */
+    const float* pts;         /* [B,N,3] (ray mode) */
+    const float* que_dir;     /* [B,N/dn,3] unit query direction per ray (ray mode) */
+    float* rec;               /* out [B,N,V,S] */
+    float* pt;                /* out [B,N,72] */
+    int* dbg_feat_idx;        /* optional out [B,N,V,2] int32 (x0,y0) feature-map corner indices, or NULL */
+    int B, V, H, W, fh, fw;
+    int R;                    /* grid resolution (volume mode) */
+    int N;                    /* points per scene */
+    int dn;                   /* samples per ray */
+    int S;                    /* record stride in floats: 72 or 76 */
+    int volume_mode;
+    int tiles_per_scene;      /* filled in by the launcher */
+    GnRayDirFc rdfc;
+} GnK1Params;
+
+int gn_k1_forward(const GnK1Params* params, void* stream);
+
+/* K2 weight blob: all head weights packed k-major ([in][out_padded]) in one fp32 buffer.  The table of entries is
+ * owned by the library; the host packer enumerates it (so offsets can never disagree). */
+int gn_weight_entry_count(void);
+int gn_weight_entry(int idx, const char** name, int* offset, int* rows, int* cols, int* cols_padded);
+int gn_weight_blob_floats(void);
+
+/* K2a: per-(point,view) head + cross-view pooling.
+ * Replaces MixtureLogisticsDistDecoder.forward + compute_prob (dist_decoder.py:99-142, via predict_proj_ray_prob
+ * renderer.py:62-78), prob_embed (aggregate_net.py:47-54) and IBRNetWithNeuRayNeus.forward lines 466-484 + 507-511
+ * (ibrnet.py): neuray_fc, weighted mean/var, base_fc, vis_fc, vis_fc2, pooling, and (with_rgb) rgb_fc + softmax blend.
+ * que_dists: NULL -> fixed +-0.005 interval (volume mode, dist_decoder.py:121-124); else [B,N] normalised
+ * inverse-depth spacings (render_ops.py:46-52). */
+typedef struct GnK2aParams {
+    const float* rec;          /* [B,N,V,S] */
+    const float* pt;           /* [B,N,72] */
+    const float* weights;      /* blob */
+    const float* depth_range;  /* [B,V,2] */
+    const float* que_dists;    /* [B,N] or NULL */
+    float* pooled;             /* out [B,N,68] */
+    float* colors;             /* out [B,N,4] (rgb, 0) or NULL */
+    float* dbg_rows;           /* optional out [B,N,V,8]: hit, vis, w0, vis2, x0, x1, pe0, pe1 ; or NULL */
+    int B, N, V, S, dn;
+} GnK2aParams;
+int gn_k2a_forward(const GnK2aParams* params, void* stream);
+
+/* K2b: per-ray geometry head.
+ * Replaces ibrnet.py:485-495: embed (neus.py:21-66), geometry_fc, + pos_encoding (ibrnet.py:437-445), MultiHeadAttention
+ * over the dn samples (ibrnet.py:52-102, query-row mask), LayerNorm, out_geometry_fc, clip(-1,1), invalid -> 1.0.
+ * volume_mode=1: writes volume[B,R,R,R] with the final z flip of renderer.py:198 fused; else sdf[B,N].
+ * grad (optional, [B,N,3]): d(sum sdf)/d pts  (ibrnet.py:497-504), hand-derived reverse pass. */
+typedef struct GnK2bParams {
+    const float* pooled;       /* [B,N,68] */
+    const float* weights;      /* blob */
+    const float* axis;         /* [R] (volume mode) */
+    const float* bbox_min;     /* [B,3] (volume mode) */
+    const float* pts;          /* [B,N,3] (ray mode) */
+    const float* pos_table;    /* [dn,16] sinusoid table (ibrnet.py:437-445) */
+    float* sdf;                /* out: volume [B,R,R,R] or sdf [B,N] */
+    float* grad;               /* out [B,N,3] or NULL */
+    int B, N, dn, R, volume_mode;
+} GnK2bParams;
+int gn_k2b_forward(const GnK2bParams* params, void* stream);
+
+/* K3: NeuS alpha + alpha compositing for the RGB head.
+ * Replaces _get_alpha_from_sdf (aggregate_net.py:105-123), alpha_values2hit_prob (render_ops.py:72-80), the colour /
+ * depth sums (renderer.py:105-106,136) and the eikonal partial sums (aggregate_net.py:139). */
+typedef struct GnK3Params {
+    const float* sdf;          /* [B,rn,dn] */
+    const float* grad;         /* [B,rn,dn,3] */
+    const float* colors;       /* [B,rn,dn,4] */
+    const float* que_dir;      /* [B,rn,3] */
+    const float* depth;        /* [B,rn,dn] */
+    float inv_s;               /* exp(10*variance) clipped (aggregate_net.py:107) */
+    float cos_anneal_ratio;
+    float* alpha;              /* out [B,rn,dn] */
+    float* hit_prob;           /* out [B,rn,dn] */
+    float* pixel_colors;       /* out [B,rn,3] */
+    float* render_depth;       /* out [B,rn] */
+    float* eik_partial;        /* out [B,rn]: sum_d (|grad|-1)^2 */
+    int B, rn, dn;
+} GnK3Params;
+int gn_k3_composite(const GnK3Params* params, void* stream);
+
+/* K3 samplers (index tables bit-exact): sample_depth (render_ops.py:146-170, deterministic branch) and
+ * sample_fine_depth (render_ops.py:172-229; u supplied by the caller: midpoints in eval, uniform randoms in train). */
+int gn_k3_coarse_depths(const float* depth_range /*[B,2]*/, float* depth /*[B,rn,dn]*/, int B, int rn, int dn, void* stream);
+int gn_k3_fine_depths(const float* depth /*[B,rn,dn]*/, const float* hit_prob /*[B,rn,dn]*/, const float* depth_range /*[B,2]*/,
+                      const float* u /*[B,rn,fdn]*/, float* fine_depth /*[B,rn,fdn] sorted*/, int64_t* inds /*[B,rn,fdn] or NULL*/,
+                      int B, int rn, int dn, int fdn, void* stream);
+
+const char* gn_version(void);
+int gn_sizeof_k1_params(void);
+int gn_sizeof_k2a_params(void);
+int gn_sizeof_k2b_params(void);
+int gn_sizeof_k3_params(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

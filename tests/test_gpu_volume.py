@@ -1,0 +1,95 @@
+"""GPU parity: the CUDA volume path (K1 -> K2a -> K2b through the C ABI) against the CPU oracle and the committed
+reference outputs.  Tolerance recipe: |a-b| <= 1e-4*|b| + 1e-4*max|b| for fp32 values, bit-exact
+for index tables (masks, voxel order, bilinear corner indices)."""
+import os
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import load_golden, golden_weights, assert_close, ROOT
+from tests.golden.cases import VOLUME_CASES
+from graspnerf_b200.synth import make_scene
+
+pytestmark = pytest.mark.gpu
+
+
+def _scene_t(kw):
+    sc = make_scene(**kw)
+    return {k: (torch.from_numpy(v) if isinstance(v, np.ndarray) else v) for k, v in sc.items()}
+
+
+def _dump(name, **arrs):
+    d = os.path.join(ROOT, 'gpurun_out')
+    if os.environ.get('GN_DUMP') and os.path.isdir(d):
+        np.savez_compressed(os.path.join(d, name + '.npz'), **{k: np.asarray(v) for k, v in arrs.items()})
+
+
+@pytest.mark.parametrize('name', list(VOLUME_CASES))
+def test_volume_path_vs_oracle_and_golden(name):
+    from graspnerf_b200 import ops
+    from oracle import nr_oracle as O
+    g = load_golden(f'volume_{name}.npz')
+    sd = golden_weights()
+    sc = _scene_t(VOLUME_CASES[name])
+    dev = torch.device('cuda:0')
+    hw = ops.HeadWeights(sd, 'agg_net.', 'dist_decoder.', dev)
+    scene = ops.Scene(sc['imgs'].to(dev), sc['img_feats'].to(dev), sc['ray_feats'].to(dev), sc['poses'].to(dev),
+                      sc['Ks'].to(dev), sc['depth_range'].to(dev))
+    bbox_min = torch.tensor([sc['bbox3d'][0]], device=dev)
+    rec, pt, idx = ops.k1_forward(scene, hw, resolution=40, bbox_min=bbox_min, debug_idx=True)
+    pooled, _, rows = ops.k2a_forward(rec, pt, hw, scene.depth_range, debug=True)
+    vol, _ = ops.k2b_forward(pooled, hw, dn=40, resolution=40, bbox_min=bbox_min)
+    torch.cuda.synchronize()
+    rec, pt, idx, pooled, rows, vol = [t.cpu() for t in (rec, pt, idx, pooled, rows, vol)]
+
+    ovol, orec, oagg = O.sample_volume(sd, sc, with_intermediates=True)
+    _dump(f'volume_{name}', rec=rec[0, ::97].numpy(), pt=pt[0].numpy(), pooled=pooled[0].numpy(), rows=rows[0, ::7].numpy(),
+          vol=vol[0, 0].numpy())
+    # ---- index tables: bit exact
+    mask = rec[0, :, :, 67]
+    assert torch.equal(mask, orec['mask']), f"{(mask != orec['mask']).sum().item()} mask flips vs oracle"
+    assert np.array_equal(mask.numpy().astype(np.uint8), g['mask']), 'mask differs from the reference golden table'
+    assert torch.equal(idx[0, :, :, 0].long(), orec['feat_idx'][0]), 'bilinear x0 corner indices differ'
+    assert torch.equal(idx[0, :, :, 1].long(), orec['feat_idx'][1]), 'bilinear y0 corner indices differ'
+    assert torch.equal(pt[0, :, 35], orec['mask'].sum(1)), 'nvalid'
+    # ---- K1 record
+    assert_close(rec[0, :, :, 0:32], orec['ray_feats'], what='rec.ray_feats')
+    assert_close(rec[0, :, :, 32:64], oagg['f'][..., 3:35], what='rec.f_img')
+    assert_close(rec[0, :, :, 64:67], oagg['f'][..., 0:3], what='rec.f_rgb')
+    assert_close(rec[0, :, :, 68], orec['depth'], what='rec.depth')
+    assert_close(rec[0, :, :, 69:72], orec['rgb'], what='rec.rgb_in')
+    assert_close(pt[0, :, 0:32], oagg['mean1'][:, 3:35], what='pt.mean_img')
+    assert_close(pt[0, :, 32:35], oagg['mean1'][:, 0:3], what='pt.mean_rgb')
+    assert_close(pt[0, :, 36:68], oagg['var1'][:, 3:35], what='pt.var_img')
+    assert_close(pt[0, :, 68:71], oagg['var1'][:, 0:3], what='pt.var_rgb')
+    # ---- K2a rows and pooled
+    assert_close(rows[0, :, :, 0], orec['hit_prob'], what='hit_prob')
+    assert_close(rows[0, :, :, 1], orec['vis'], what='vis')
+    assert_close(rows[0, :, :, 2], oagg['w0'], what='w0')
+    assert_close(rows[0, :, :, 6:8], oagg['prob_emb'][..., 0:2], what='prob_emb[0:2]')
+    assert_close(rows[0, :, :, 4:6], oagg['x'][..., 0:2], what='x[0:2]')
+    assert_close(rows[0, :, :, 3], oagg['vis2'], what='vis2')
+    assert_close(pooled[0, :, 0:65], oagg['pooled'], what='pooled')
+    # ---- volume: vs oracle and vs the reference's own output
+    rel = assert_close(vol[0, 0], ovol[0, 0], what='volume vs oracle')
+    rel_g = assert_close(vol[0, 0], g['volume'], what='volume vs reference golden')
+    assert rel < 1e-5 and rel_g < 1e-5, (rel, rel_g)
+
+
+def test_volume_batch_equals_loop():
+    """B scenes in one launch == B single-scene launches (bit exact: same kernels, same arithmetic)."""
+    from graspnerf_b200 import ops
+    sd = golden_weights()
+    dev = torch.device('cuda:0')
+    hw = ops.HeadWeights(sd, 'agg_net.', 'dist_decoder.', dev)
+    scs = [_scene_t(dict(seed=s, num_views=4, h=96, w=160, radius=0.45)) for s in (11, 12, 13)]
+
+    def stack(k):
+        return torch.stack([s[k] for s in scs]).to(dev)
+    scene = ops.Scene(stack('imgs'), stack('img_feats'), stack('ray_feats'), stack('poses'), stack('Ks'), stack('depth_range'))
+    bbox = torch.tensor([s['bbox3d'][0] for s in scs], device=dev)
+    vol_b = ops.sample_volume(scene, hw, bbox, 40)
+    for i, s in enumerate(scs):
+        sc1 = ops.Scene(*[s[k].to(dev) for k in ('imgs', 'img_feats', 'ray_feats', 'poses', 'Ks', 'depth_range')])
+        v1 = ops.sample_volume(sc1, hw, bbox[i:i + 1], 40)
+        assert torch.equal(v1[0], vol_b[i])
