@@ -1,0 +1,256 @@
+#!/usr/bin/env python
+"""bench.py - TSDF-volumes/sec of the GraspNeRF volumetric hot path on B200 (see DESIGN.md "Measurement").
+
+  python bench.py --gpus N --steps K --warmup W            # our CUDA path (one rank per GPU under torchrun)
+  python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host cores (oracle port)
+
+A "step" = one pass of the hot path (NeuralRayRenderer.sample_volume given the encoders' feature maps: K1 -> K2a -> K2b)
+over one scene of BASELINE.json configs[1] (6 views 288x512, 40^3 grid).  Steps cycle through a pool of 8 different
+synthetic scenes (8 x 24.8 MB of inputs > the 126 MB L2), so no step finds its inputs in L2.
+  value : volumes/s with inputs resident in HBM (device-timed, max over ranks, all ranks' volumes counted)
+  e2e   : the same through graspnerf_b200.engine.VolumeEngine with pinned HOST inputs (H2D + kernels + D2H per step)
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'TSDF-volumes/sec (6-view 288x512, 40^3 grid)'
+V, H, W, R = 6, 288, 512, 40
+POOL = 8
+K1_BYTES = 4 * V * (3 * H * W + 2 * 32 * (H // 4) * (W // 4)) + 4 * R ** 3 * (V * 72 + 70)   # 153,284,608
+K2_FLOPS = 2 * R ** 3 * (V * 28464 + 9104)                                                  # ~23.2 GFLOP
+
+
+def load_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {'hbm_gbs': d['hbm_gbs'], 'tf_burst': d['bf16_tflops'], 'tf_sustained': d.get('bf16_tflops_sustained', d['bf16_tflops']),
+                'source': 'measured'}
+    return {'hbm_gbs': 6650.0, 'tf_burst': 1590.0, 'tf_sustained': 1400.0, 'source': 'fallback'}
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}', '--format=csv,noheader,nounits'],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(',')])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        if not self.rows:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unsampled']}
+        sm = sorted(float(r[0]) for r in self.rows)
+        reasons = [n for i, n in enumerate(['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'])
+                   if any(r[2 + i].lower().startswith('active') for r in self.rows)]
+        return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': float(self.rows[0][1]), 'reasons': reasons, 'samples': len(self.rows)}
+
+
+def make_pool(n, seed0=0):
+    from graspnerf_b200.synth import make_scene
+    return [make_scene(seed=seed0 + s, num_views=V, h=H, w=W) for s in range(n)]
+
+
+def cpu_reference_volumes(n_volumes, warmup=1):
+    """The reference algorithm for the path on the host cores: oracle/nr_oracle.sample_volume (a torch-CPU restatement
+    of renderer.py:164-199, pinned to the real reference by tests/golden).  The reference itself is Python and cannot
+    travel to the GPU box, so kind = "port"."""
+    from oracle import nr_oracle as O
+    from tests.helpers import golden_weights
+    torch.set_num_threads(os.cpu_count())
+    sd = golden_weights()
+    sc = make_pool(1)[0]
+    sct = {k: (torch.from_numpy(v) if isinstance(v, np.ndarray) else v) for k, v in sc.items()}
+    with torch.no_grad():
+        for _ in range(warmup):
+            O.sample_volume(sd, sct)
+        t0 = time.perf_counter()
+        for _ in range(n_volumes):
+            O.sample_volume(sd, sct)
+        dt = time.perf_counter() - t0
+    return n_volumes / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    vps, dt = cpu_reference_volumes(args.steps, max(args.warmup, 1))
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': vps, 'unit': 'volumes/s', 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': 1e3 / vps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'configs[1]: 1 scene, 6x288x512, 40^3 grid, sample_volume given feature maps'},
+        'cpu_baseline': {'value': vps, 'unit': 'volumes/s', 'cores': torch.get_num_threads(), 'kind': 'port',
+                         'sample': f'{args.steps} volumes of the workload, oracle/nr_oracle.sample_volume, torch CPU fp32'},
+        'e2e': {'value': vps, 'unit': 'volumes/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--warmup', type=int, default=10)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--cpu-volumes', type=int, default=12, help='size of the bounded CPU-baseline sample')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        return run_reference(args)
+
+    from graspnerf_b200 import ops
+    from graspnerf_b200.engine import VolumeEngine, HostScene
+    from tests.helpers import golden_weights
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device: graspnerf_b200 has no CPU path (use --impl reference for the CPU arm)')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=dev)
+    W_ = max(args.warmup, 3)
+    K = args.steps
+
+    sd = golden_weights()              # random init of the reference architecture under torch.manual_seed(0)
+    hw = ops.HeadWeights(sd, 'agg_net.', 'dist_decoder.', dev)
+    pool = make_pool(POOL, seed0=100 * rank)
+    scenes, bboxes, hosts = [], [], []
+    for sc in pool:
+        t = {k: torch.from_numpy(v).to(dev) for k, v in sc.items() if isinstance(v, np.ndarray)}
+        s = ops.Scene(t['imgs'], t['img_feats'], t['ray_feats'], t['poses'], t['Ks'], t['depth_range'])
+        scenes.append(s)
+        bboxes.append(torch.tensor([sc['bbox3d'][0]], device=dev))
+        hosts.append(HostScene(sc['imgs'], s.img_feats[0].cpu(), s.ray_feats[0].cpu(), sc['poses'], sc['Ks'], sc['depth_range'],
+                               np.asarray(sc['bbox3d'][0], np.float32)))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(i, evs=None):
+        s, bb = scenes[i % POOL], bboxes[i % POOL]
+        if evs is not None:
+            evs[0].record()
+        rec, pt = ops.k1_forward(s, hw, resolution=R, bbox_min=bb)
+        if evs is not None:
+            evs[1].record()
+        pooled, _, _ = ops.k2a_forward(rec, pt, hw, s.depth_range)
+        if evs is not None:
+            evs[2].record()
+        vol, _ = ops.k2b_forward(pooled, hw, dn=R, resolution=R, bbox_min=bb)
+        if evs is not None:
+            evs[3].record()
+        return vol
+
+    # ---------------- device-resident timing ----------------
+    for i in range(W_):
+        step(i)
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(K)]
+    ev0.record()
+    for i in range(K):
+        step(W_ + i, kev[i])
+    ev1.record()
+    barrier()
+    sampler.stop_flag = True
+    total_ms = ev0.elapsed_time(ev1)
+    kt = np.array([[e[j].elapsed_time(e[j + 1]) for j in range(3)] for e in kev]).mean(0)     # ms per launch: K1, K2a, K2b
+
+    # ---------------- end-to-end timing (pinned host in, pinned host out) ----------------
+    eng = VolumeEngine(hw, hosts[0], R, slots=3, device=dev)
+    for i in range(W_):
+        eng.submit(hosts[i % POOL])
+    eng.drain()
+    barrier()
+    t0 = time.perf_counter()
+    checksum = 0.0
+    for i in range(K):
+        _, fin = eng.submit(hosts[(W_ + i) % POOL], tag=i)
+        if fin is not None:
+            checksum += float(fin[1][0, 0, 0, 0, 0])
+    for _, out in eng.drain():
+        checksum += float(out[0, 0, 0, 0, 0])
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+
+    times = torch.tensor([total_ms, e2e_ms], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms = times.tolist()
+    sampler.join(timeout=2)
+    if rank == 0:
+        peaks = load_peaks()
+        value = world * K / (total_ms / 1e3)
+        k1_gbs = K1_BYTES / (kt[0] * 1e-3) / 1e9
+        k2_tfs = K2_FLOPS / ((kt[1] + kt[2]) * 1e-3) / 1e12
+        dominant_k2 = (kt[1] + kt[2]) >= kt[0]
+        roof_k1 = {'kernel': 'gn_k1_kernel', 'bound': 'hbm', 'achieved': k1_gbs, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
+                   'frac': k1_gbs / peaks['hbm_gbs'], 'traffic': None, 'us_per_launch': kt[0] * 1e3, 'peak_source': peaks['source']}
+        roof_k2 = {'kernel': 'gn_k2a_simt_kernel+gn_k2b_kernel', 'bound': 'tensor', 'achieved': k2_tfs, 'peak': peaks['tf_sustained'],
+                   'unit': 'TFLOP/s', 'frac': k2_tfs / peaks['tf_sustained'], 'traffic': None,
+                   'us_per_launch': (kt[1] + kt[2]) * 1e3, 'peak_source': peaks['source'],
+                   'note': 'fp32 SIMT head (no tensor cores yet); algorithmic FLOPs = SURVEY 8d reference-semantics count'}
+        line = {
+            'metric': METRIC, 'value': value, 'unit': 'volumes/s', 'n_gpus': world, 'steps': K, 'warmup': W_,
+            'ms_per_step': total_ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+            'data': 'synthetic',
+            'config': {'workload': 'configs[1]: 1 scene/step, 6x288x512, 40^3 grid, sample_volume given feature maps',
+                       'l2': f'inputs cycle through {POOL} scenes x 24.8 MB (> 126 MB L2); no flush kernel in the timed region',
+                       'parallelism': f'replicas x{world} (scenes sharded, no data-path collective)'},
+            'roofline': roof_k2 if dominant_k2 else roof_k1,
+            'roofline_k1': roof_k1, 'roofline_k2': roof_k2,
+            'kernel_us': {'k1': kt[0] * 1e3, 'k2a': kt[1] * 1e3, 'k2b': kt[2] * 1e3},
+            'e2e': {'value': world * K / (e2e_ms / 1e3), 'unit': 'volumes/s', 'h2d_bytes_per_step': eng.h2d_bytes,
+                    'd2h_bytes_per_step': eng.d2h_bytes, 'api': 'graspnerf_b200.engine.VolumeEngine.submit (pinned host buffers)'},
+            'gpu_launches': 3 * K,
+            'clocks': sampler.summary(),
+            'checksum': checksum,
+        }
+        if world == 1:
+            vps, dt = cpu_reference_volumes(args.cpu_volumes, 2)
+            line['cpu_baseline'] = {'value': vps, 'unit': 'volumes/s', 'cores': torch.get_num_threads(), 'kind': 'port',
+                                    'sample': f'{args.cpu_volumes} volumes of the same workload in {dt:.1f} s '
+                                              '(oracle/nr_oracle.sample_volume, torch CPU fp32, all host threads)'}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

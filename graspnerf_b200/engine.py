@@ -1,0 +1,85 @@
+"""Host-buffer front end of the hot path: pinned host scenes in, TSDF volumes out, copies overlapped with compute.
+
+This is the reference-facing call for the `sample_volume` path when the inputs live in HOST memory (what
+GraspNeRFPlanner.core hands to the network, src/nr/main.py:225-247): H2D of the step's inputs, K1 -> K2a -> K2b, D2H of
+the volume.  Three slots are kept in flight so the PCIe copies of step i+1 run under the kernels of step i
+(one copy stream + one compute stream, ordered by CUDA events; no host synchronisation inside the loop except when a
+slot is recycled).
+"""
+import torch
+
+from . import ops
+
+
+class HostScene:
+    """Pinned host buffers of one scene (the layout K1 consumes: channels-last feature maps)."""
+
+    def __init__(self, imgs, img_feats_cl, ray_feats_cl, poses, Ks, depth_range, bbox_min):
+        def pin(x):
+            t = torch.as_tensor(x, dtype=torch.float32).contiguous()
+            return t.pin_memory() if torch.cuda.is_available() else t
+        self.imgs, self.img_feats, self.ray_feats = pin(imgs), pin(img_feats_cl), pin(ray_feats_cl)
+        self.poses, self.Ks, self.depth_range, self.bbox_min = pin(poses), pin(Ks), pin(depth_range), pin(bbox_min)
+
+    @property
+    def nbytes(self):
+        return sum(t.numel() * 4 for t in (self.imgs, self.img_feats, self.ray_feats, self.poses, self.Ks,
+                                           self.depth_range, self.bbox_min))
+
+
+class _Slot:
+    def __init__(self, hs, resolution, device):
+        def dev(t):
+            return torch.empty(t.shape, dtype=torch.float32, device=device)
+        self.imgs, self.img_feats, self.ray_feats = dev(hs.imgs)[None], dev(hs.img_feats)[None], dev(hs.ray_feats)[None]
+        self.poses, self.Ks, self.depth_range = dev(hs.poses)[None], dev(hs.Ks)[None], dev(hs.depth_range)[None]
+        self.bbox_min = dev(hs.bbox_min).reshape(1, 3)
+        self.out_host = torch.empty((1, 1, resolution, resolution, resolution), dtype=torch.float32).pin_memory()
+        self.ev_in = torch.cuda.Event()
+        self.ev_done = torch.cuda.Event()
+        self.busy = False
+        self.tag = None
+
+
+class VolumeEngine:
+    def __init__(self, head_weights, example, resolution=40, volume_size=0.3, slots=3, device='cuda'):
+        self.hw, self.R, self.vs = head_weights, resolution, volume_size
+        self.device = torch.device(device)
+        self.copy_stream = torch.cuda.Stream(self.device)
+        self.compute_stream = torch.cuda.Stream(self.device)
+        self.slots = [_Slot(example, resolution, self.device) for _ in range(slots)]
+        self.next = 0
+        self.h2d_bytes = example.nbytes
+        self.d2h_bytes = resolution ** 3 * 4
+
+    def submit(self, hs, tag=None):
+        """Queues one scene; returns the slot index.  If the slot is still in flight its result is returned first via
+        `collect`."""
+        i = self.next
+        self.next = (self.next + 1) % len(self.slots)
+        s = self.slots[i]
+        finished = self.collect(i) if s.busy else None
+        with torch.cuda.stream(self.copy_stream):
+            for dst, src in ((s.imgs, hs.imgs), (s.img_feats, hs.img_feats), (s.ray_feats, hs.ray_feats),
+                             (s.poses, hs.poses), (s.Ks, hs.Ks), (s.depth_range, hs.depth_range)):
+                dst[0].copy_(src, non_blocking=True)
+            s.bbox_min.copy_(hs.bbox_min.reshape(1, 3), non_blocking=True)
+            s.ev_in.record(self.copy_stream)
+        with torch.cuda.stream(self.compute_stream):
+            self.compute_stream.wait_event(s.ev_in)
+            scene = ops.Scene(s.imgs, s.img_feats, s.ray_feats, s.poses, s.Ks, s.depth_range, feats_channels_last=True)
+            vol = ops.sample_volume(scene, self.hw, s.bbox_min, self.R, self.vs)
+            s.out_host.copy_(vol, non_blocking=True)
+            s.ev_done.record(self.compute_stream)
+        s.busy, s.tag = True, tag
+        return i, finished
+
+    def collect(self, i):
+        """Blocks until slot i finished; returns (tag, pinned host volume [1,1,R,R,R])."""
+        s = self.slots[i]
+        s.ev_done.synchronize()
+        s.busy = False
+        return s.tag, s.out_host
+
+    def drain(self):
+        return [self.collect(i) for i, s in enumerate(self.slots) if s.busy]

@@ -1,0 +1,78 @@
+"""CPU: the C-ABI library builds for sm_100a, loads, and exports every symbol include/graspnerf_b200.h declares;
+host-side packing logic is consistent with the library's own weight table.  No compute calls (no GPU here)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import ROOT, golden_weights
+
+
+@pytest.fixture(scope='module')
+def lib():
+    from graspnerf_b200.build import build_library
+    from graspnerf_b200 import _lib
+    build_library()
+    return _lib.load()
+
+
+def test_every_declared_symbol_is_exported(lib):
+    hdr = open(os.path.join(ROOT, 'include', 'graspnerf_b200.h')).read()
+    names = set(re.findall(r'\b(gn_[a-z0-9_]+)\s*\(', hdr))
+    assert len(names) >= 12
+    for n in sorted(names):
+        assert hasattr(lib, n), f'{n} declared in the header but not exported'
+    assert b'sm_100a' in lib.gn_version()
+
+
+def test_struct_sizes_match(lib):
+    from graspnerf_b200 import _lib
+    assert lib.gn_sizeof_k1_params() == ctypes.sizeof(_lib.GnK1Params)
+    assert lib.gn_sizeof_k2a_params() == ctypes.sizeof(_lib.GnK2aParams)
+    assert lib.gn_sizeof_k2b_params() == ctypes.sizeof(_lib.GnK2bParams)
+    assert lib.gn_sizeof_k3_params() == ctypes.sizeof(_lib.GnK3Params)
+
+
+def test_weight_table_is_dense_and_aligned(lib):
+    from graspnerf_b200 import _lib
+    tab = _lib.weight_table()
+    off = 0
+    for name, o, rows, cols, cp in tab:
+        assert o == off and o % 4 == 0 and cp % 4 == 0 and cp >= cols, name
+        off += rows * cp
+    assert off == lib.gn_weight_blob_floats()
+
+
+def test_pack_blob_roundtrip(lib):
+    """Every reference tensor lands where the table says, k-major, with the [rgb|img] -> [img|rgb] permutation."""
+    from graspnerf_b200 import _lib
+    from graspnerf_b200.weights import pack_blob, pack_ray_dir_fc, PERM35
+    sd = golden_weights()
+    blob = pack_blob(sd, 'fine_agg_net.', 'fine_dist_decoder.')
+    tab = {n: (o, r, c, cp) for n, o, r, c, cp in _lib.weight_table()}
+
+    def entry(n):
+        o, r, c, cp = tab[n]
+        return blob[o:o + r * cp].reshape(r, cp)[:, :c]
+    A = 'fine_agg_net.agg_impl.'
+    w = sd[A + 'base_fc.0.weight'].numpy()
+    assert np.array_equal(entry('bf.wp'), w[:, 175:].T)
+    wg = entry('bf.wg')
+    assert np.array_equal(wg[36 + 0], w[:, 35 + 3]) and np.array_equal(wg[36 + 32], w[:, 35 + 0]) and not wg[35].any()
+    assert np.array_equal(entry('dd.var.w4'), sd['fine_dist_decoder.var_decoder.4.weight'].numpy().T)
+    assert np.array_equal(entry('at.fc'), sd[A + 'ray_attention.fc.weight'].numpy().T)
+    assert np.array_equal(entry('og.w1'), sd[A + 'out_geometry_fc.1.weight'].numpy())
+    r = pack_ray_dir_fc(sd, 'fine_agg_net.')
+    w1 = np.ctypeslib.as_array(r.w1)
+    assert np.array_equal(w1[:35], sd[A + 'ray_dir_fc.2.weight'].numpy()[PERM35]) and not w1[35].any()
+
+
+def test_product_path_refuses_cpu():
+    """No CPU fallback: the torch front end raises on host tensors."""
+    from graspnerf_b200 import ops
+    t = torch.zeros(2, 3, 8, 8)
+    with pytest.raises(RuntimeError):
+        ops.Scene(t, torch.zeros(2, 32, 2, 2), torch.zeros(2, 32, 2, 2), torch.zeros(2, 3, 4), torch.zeros(2, 3, 3), torch.zeros(2, 2))
