@@ -10,20 +10,16 @@ from .build import LIBPATH
 c_float_p = C.POINTER(C.c_float)
 
 
-class GnRayDirFc(C.Structure):
-    _fields_ = [('w0', C.c_float * 4 * 16), ('b0', C.c_float * 16), ('w1', C.c_float * 16 * 36), ('b1', C.c_float * 36)]
-
-
 class GnK1Params(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ('imgs', 'img_feats', 'ray_feats', 'KRt', 'cam', 'axis', 'bbox_min', 'pts',
                                           'que_dir', 'rec', 'pt', 'dbg_feat_idx')] + \
-               [(n, C.c_int) for n in ('B', 'V', 'H', 'W', 'fh', 'fw', 'R', 'N', 'dn', 'S', 'volume_mode',
-                                       'tiles_per_scene')] + [('rdfc', GnRayDirFc)]
+               [(n, C.c_int) for n in ('B', 'V', 'H', 'W', 'fh', 'fw', 'R', 'N', 'dn', 'volume_mode',
+                                       'tiles_per_scene')]
 
 
 class GnK2aParams(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ('rec', 'pt', 'weights', 'depth_range', 'que_dists', 'pooled', 'colors',
-                                          'dbg_rows')] + [(n, C.c_int) for n in ('B', 'N', 'V', 'S', 'dn')]
+                                          'dbg_rows')] + [(n, C.c_int) for n in ('B', 'N', 'V', 'dn', 'with_rgb')]
 
 
 class GnK2bParams(C.Structure):

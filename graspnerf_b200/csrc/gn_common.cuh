@@ -4,19 +4,16 @@
 #include <stdint.h>
 
 #define GN_FEAT_C 32          // channels of img_feats / ray_feats (renderer.py:53, init_net.py:24)
-#define GN_REC_VOL 72         // floats per (point,view) record, volume mode
-#define GN_REC_RAY 76         // ... RGB-head mode (adds dir_diff[4])
-#define GN_PT_STRIDE 72       // floats per point: mean[36] | var[36]
+#define GN_REC_STRIDE 72      // floats per (point,view) record
+#define GN_PT_STRIDE 2        // floats per point written by K1: nvalid, view bit mask (uint32 bits)
 #define GN_POOL_STRIDE 68     // floats per point written by K2a: mean32 | var32 | wmean, nvalid, 0, 0
 
 // record layout (floats), see DESIGN.md "Data layout in HBM"
 #define GN_REC_RAYF 0         // [0,32)  ray_feats * mask
-#define GN_REC_FIMG 32        // [32,64) img_feats*mask + dir-feature (channels 3..34 of the reference's rgb_feat)
-#define GN_REC_FRGB 64        // [64,67) rgb*mask + dir-feature (channels 0..2) ; [67] mask
-#define GN_REC_MASK 67
-#define GN_REC_DEPTH 68       // [68] projection depth ; [69,72) rgb*mask (rgb_in of ibrnet.py:458)
-#define GN_REC_RGBIN 69
-#define GN_REC_DD 72          // [72,76) dir_diff (RGB-head mode only)
+#define GN_REC_IMGF 32        // [32,64) img_feats * mask
+#define GN_REC_RGB 64         // [64,67) rgb * mask ; [67] projection depth
+#define GN_REC_DEPTH 67
+#define GN_REC_DD 68          // [68,72) dir_diff = (dir - que_dir, dir . que_dir)   (aggregate_net.py:11-17)
 
 __device__ __forceinline__ float gn_elu(float x) {
     // nn.ELU (alpha 1): x>0 ? x : exp(x)-1.  __expf = ex2.approx(x*log2e): rel. err ~2^-21.

@@ -9,6 +9,8 @@ struct GnWEntry { const char* name; int rows; int cols; int cols_pad; };
 // (graspnerf_b200/weights.py) performs the permutation.
 //   f35 order here  : [img_feats 32 | rgb 3]           (reference ibrnet.py:458-459: [rgb 3 | img_feats 32])
 #define GN_W_TABLE(X) \
+    /* ray_dir_fc (ibrnet.py:382-385): 4 -> 16 -> 35, output columns in record order [img 32 | rgb 3 | pad] */ \
+    X(RD_W0, "rd.w0", 4, 16, 16) X(RD_B0, "rd.b0", 1, 16, 16) X(RD_W1, "rd.w1", 16, 35, 36) X(RD_B1, "rd.b1", 1, 35, 36) \
     X(DD_MEAN_W0, "dd.mean.w0", 32, 32, 32) X(DD_MEAN_B0, "dd.mean.b0", 1, 32, 32) \
     X(DD_MEAN_W2, "dd.mean.w2", 32, 32, 32) X(DD_MEAN_B2, "dd.mean.b2", 1, 32, 32) \
     X(DD_MEAN_W4, "dd.mean.w4", 32, 2, 4)   X(DD_MEAN_B4, "dd.mean.b4", 1, 2, 4)   \

@@ -1,26 +1,25 @@
-// K1: fused project - sample - aggregate kernel (HBM-bound).
+// K1: fused project - sample kernel (HBM-bound).
 //
 // Replaces, per (point, view), the reference op chain
 //   project_points_dict        render_ops.py:82-144   (K@Rt projection, validity mask, view dirs,
 //                                                      bilinear taps of ray_feats and imgs)
 //   get_img_feats              renderer.py:80-88      (bilinear tap of img_feats)
 //   get_dir_diff               aggregate_net.py:11-17
-//   ray_dir_fc + add           ibrnet.py:457-459
-//   mask-weighted mean/var     ibrnet.py:466,471 (mean1,var1), fused_mean_variance ibrnet.py:112-116
-// and writes one 288-byte record per (point, view) plus one 288-byte record per point.
+//   num_valid_obs / mask       ibrnet.py:466,490      (per-point valid count + view bit mask)
+// and writes one 288-byte record per (point, view) plus 8 bytes per point.  (ray_dir_fc and the weighted
+// mean/variance poolings of ibrnet.py:457-471 are GEMM / epilogue work and live in K2a: with them inside this
+// kernel it was issue-bound at 25 % of the HBM roofline, see profiles/.)
 //
 // Work decomposition (one CTA = 256 threads = one tile of 32 points x V views):
-//   phase A  thread <-> (point, view): projection, mask, view direction, dir_diff, ray_dir_fc (4->16->35),
-//            bilinear tap offsets/weights; results parked in shared memory.
+//   phase A  thread <-> (point, view): projection, mask, view direction, dir_diff, bilinear tap offsets/weights;
+//            results parked in shared memory.
 //   phase B  8 lanes <-> one point, lane j <-> channels 4j..4j+3: each bilinear tap is ONE 128-byte line of
-//            the channels-last feature map (8 x LDG.128), records leave as coalesced float4 stores, the
-//            cross-view weighted mean/variance is accumulated in registers over the view loop.
+//            the channels-last feature map (8 x LDG.128), records leave as coalesced float4 streaming stores.
 #include "gn_common.cuh"
 #include "../../include/graspnerf_b200.h"
 
 #define K1_THREADS 256
 #define K1_TILE_P 32
-#define K1_PAIR_F 36          // floats of dir-feature per pair in smem: [img 32 | rgb 3 | pad]
 
 struct K1PairInfo {           // 64 bytes, written in phase A, read (broadcast) in phase B
     int   fo[4];              // feature-map tap offsets (floats) within the view's [fh,fw,32] map
@@ -36,9 +35,7 @@ gn_k1_kernel(const __grid_constant__ GnK1Params p)
     const int V = p.V;
     const int npair = K1_TILE_P * V;
     K1PairInfo* s_info = reinterpret_cast<K1PairInfo*>(smem_raw);                    // [npair]
-    float* s_dfeat = reinterpret_cast<float*>(s_info + npair);                       // [npair][36]
-    float* s_f     = s_dfeat + npair * K1_PAIR_F;                                    // [npair][36] stash of f for the variance pass
-    float* s_misc  = s_f + npair * K1_PAIR_F;                                        // [npair][8]: mask, depth, dd0..3, pad
+    float* s_misc  = reinterpret_cast<float*>(s_info + npair);                       // [npair][8]: dd0..3, mask, depth, pad
 
     const int tiles_per_scene = p.tiles_per_scene;
     const int b = blockIdx.x / tiles_per_scene;
@@ -96,25 +93,6 @@ gn_k1_kernel(const __grid_constant__ GnK1Params p)
         // aggregate_net.py:13-15
         float dd[4] = { ex - qx, ey - qy, ez - qz, (ex * qx + ey * qy) + ez * qz };
 
-        // ray_dir_fc: Linear(4,16) ELU Linear(16,35) ELU   (ibrnet.py:382-385,457)
-        float hid[16];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            float a = p.rdfc.b0[k];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) a = fmaf(p.rdfc.w0[k][i], dd[i], a);
-            hid[k] = gn_elu(a);
-        }
-        float* df = s_dfeat + pair * K1_PAIR_F;
-#pragma unroll
-        for (int c = 0; c < 35; ++c) {          // output order permuted on the host: [img 32 | rgb 3]
-            float a = p.rdfc.b1[c];
-#pragma unroll
-            for (int k = 0; k < 16; ++k) a = fmaf(p.rdfc.w1[c][k], hid[k], a);
-            df[c] = gn_elu(a);
-        }
-        df[35] = 0.f;
-
         // bilinear taps.  feature maps: align_corners=False (map size != image size), images: True
         // (render_ops.py:64-68); both normalised by the IMAGE size (ops.py:29-30); border padding.
         K1PairInfo inf;
@@ -144,7 +122,8 @@ gn_k1_kernel(const __grid_constant__ GnK1Params p)
         }
         s_info[pair] = inf;
         float* ms = s_misc + pair * 8;
-        ms[0] = mask; ms[1] = depth; ms[2] = dd[0]; ms[3] = dd[1]; ms[4] = dd[2]; ms[5] = dd[3];
+        st4(ms, make_float4(dd[0], dd[1], dd[2], dd[3]));
+        ms[4] = mask; ms[5] = depth;
     }
     __syncthreads();
 
@@ -164,21 +143,25 @@ gn_k1_kernel(const __grid_constant__ GnK1Params p)
         n = min(n, p.N - 1);
     }
     float nvalid = 0.f;
-    for (int v = 0; v < V; ++v) nvalid += s_misc[(pl * V + v) * 8];
-    const float wden = nvalid + 1e-8f;             // ibrnet.py:466
-    const int S = p.S;
-    float* rec = p.rec + ((size_t)b * p.N + n) * V * S;
+    unsigned bits = 0u;
+    for (int v = 0; v < V; ++v) {
+        const float m = s_misc[(pl * V + v) * 8 + 4];
+        nvalid += m;
+        bits |= (m != 0.f ? 1u : 0u) << v;
+    }
+    float* rec = p.rec + ((size_t)b * p.N + n) * V * GN_REC_STRIDE;
     const size_t fmap_sz = (size_t)p.fh * p.fw * GN_FEAT_C;
     const size_t plane = (size_t)p.H * p.W;
+    const float* rf_base = p.ray_feats + (size_t)b * V * fmap_sz + 4 * j;
+    const float* if_base = p.img_feats + (size_t)b * V * fmap_sz + 4 * j;
+    const float* im_base = p.imgs + ((size_t)b * V * 3 + (j < 3 ? j : 0)) * plane;
 
-    float4 m_img = make_float4(0.f, 0.f, 0.f, 0.f);
-    float m_rgb = 0.f;
     for (int v = 0; v < V; ++v) {
         const int pair = pl * V + v;
         const int4 fo = *reinterpret_cast<const int4*>(s_info[pair].fo);
         const float4 fwt = *reinterpret_cast<const float4*>(s_info[pair].fw_);
-        const float* rf = p.ray_feats + ((size_t)b * V + v) * fmap_sz + 4 * j;
-        const float* imf = p.img_feats + ((size_t)b * V + v) * fmap_sz + 4 * j;
+        const float* rf = rf_base + (size_t)v * fmap_sz;
+        const float* imf = if_base + (size_t)v * fmap_sz;
         // issue all eight 128-bit gathers before use
         const float4 r0 = ldg4(rf + fo.x), r1 = ldg4(rf + fo.y), r2 = ldg4(rf + fo.z), r3 = ldg4(rf + fo.w);
         const float4 g0 = ldg4(imf + fo.x), g1 = ldg4(imf + fo.y), g2 = ldg4(imf + fo.z), g3 = ldg4(imf + fo.w);
@@ -186,62 +169,27 @@ gn_k1_kernel(const __grid_constant__ GnK1Params p)
         if (j < 3) {
             const int4 io = *reinterpret_cast<const int4*>(s_info[pair].io);
             const float4 iw = *reinterpret_cast<const float4*>(s_info[pair].iw);
-            const float* im = p.imgs + (((size_t)b * V + v) * 3 + j) * plane;
+            const float* im = im_base + (size_t)v * 3 * plane;
             rgbv = __ldg(im + io.x) * iw.x;
             rgbv = fmaf(__ldg(im + io.y), iw.y, rgbv);
             rgbv = fmaf(__ldg(im + io.z), iw.z, rgbv);
             rgbv = fmaf(__ldg(im + io.w), iw.w, rgbv);
         }
-        const float mask = s_misc[pair * 8], depth = s_misc[pair * 8 + 1];
-        const float wv = __fdiv_rn(mask, wden);
         float4 ray = f4_mul(r0, fwt.x); ray = f4_fma(r1, fwt.y, ray); ray = f4_fma(r2, fwt.z, ray); ray = f4_fma(r3, fwt.w, ray);
         float4 img = f4_mul(g0, fwt.x); img = f4_fma(g1, fwt.y, img); img = f4_fma(g2, fwt.z, img); img = f4_fma(g3, fwt.w, img);
-        const float4 dfe = *reinterpret_cast<const float4*>(s_dfeat + pair * K1_PAIR_F + 4 * j);
-        const float4 fimg = f4_add(img, dfe);                                  // ibrnet.py:459
-        const float frgb = rgbv + s_dfeat[pair * K1_PAIR_F + 32 + (j < 3 ? j : 3)];
-        float* row = rec + (size_t)v * S;
+        float* row = rec + (size_t)v * GN_REC_STRIDE;
+        // tail chunks: lane 0 <- (rgb0, rgb1, rgb2, depth), lane 1 <- dir_diff
+        const float c1 = __shfl_sync(0xffffffffu, rgbv, gbase + 1), c2 = __shfl_sync(0xffffffffu, rgbv, gbase + 2);
         if (live) {
             st4_cs(row + GN_REC_RAYF + 4 * j, ray);
-            st4_cs(row + GN_REC_FIMG + 4 * j, fimg);
-        }
-        st4(s_f + pair * K1_PAIR_F + 4 * j, fimg);
-        if (j < 3) s_f[pair * K1_PAIR_F + 32 + j] = frgb;
-        m_img = f4_fma(fimg, wv, m_img);
-        m_rgb = fmaf(frgb, wv, m_rgb);
-        // tail chunks: lane 0 <- (frgb0,frgb1,frgb2,mask), lane 1 <- (depth, rgb0, rgb1, rgb2)
-        const float f1 = __shfl_sync(0xffffffffu, frgb, gbase + 1), f2 = __shfl_sync(0xffffffffu, frgb, gbase + 2);
-        const float c0 = __shfl_sync(0xffffffffu, rgbv, gbase + 0), c2 = __shfl_sync(0xffffffffu, rgbv, gbase + 2);
-        if (live) {
-            if (j == 0) st4_cs(row + GN_REC_FRGB, make_float4(frgb, f1, f2, mask));
-            else if (j == 1) st4_cs(row + GN_REC_DEPTH, make_float4(depth, c0, rgbv, c2));
-            else if (j == 2 && S > GN_REC_DD) st4_cs(row + GN_REC_DD, *reinterpret_cast<const float4*>(s_misc + pair * 8 + 2));
+            st4_cs(row + GN_REC_IMGF + 4 * j, img);
+            if (j == 0) st4_cs(row + GN_REC_RGB, make_float4(rgbv, c1, c2, s_misc[pair * 8 + 5]));
+            else if (j == 1) st4_cs(row + GN_REC_DD, *reinterpret_cast<const float4*>(s_misc + pair * 8));
         }
     }
-    __syncwarp();
-    // variance pass over the stashed f (ibrnet.py:115: sum_v w * (x - mean)^2)
-    float4 v_img = make_float4(0.f, 0.f, 0.f, 0.f);
-    float v_rgb = 0.f;
-    for (int v = 0; v < V; ++v) {
-        const int pair = pl * V + v;
-        const float wv = __fdiv_rn(s_misc[pair * 8], wden);
-        const float4 f = *reinterpret_cast<const float4*>(s_f + pair * K1_PAIR_F + 4 * j);
-        float d;
-        d = f.x - m_img.x; v_img.x = fmaf(wv * d, d, v_img.x);
-        d = f.y - m_img.y; v_img.y = fmaf(wv * d, d, v_img.y);
-        d = f.z - m_img.z; v_img.z = fmaf(wv * d, d, v_img.z);
-        d = f.w - m_img.w; v_img.w = fmaf(wv * d, d, v_img.w);
-        if (j < 3) { d = s_f[pair * K1_PAIR_F + 32 + j] - m_rgb; v_rgb = fmaf(wv * d, d, v_rgb); }
-    }
-    const float mr1 = __shfl_sync(0xffffffffu, m_rgb, gbase + 1), mr2 = __shfl_sync(0xffffffffu, m_rgb, gbase + 2);
-    const float vr1 = __shfl_sync(0xffffffffu, v_rgb, gbase + 1), vr2 = __shfl_sync(0xffffffffu, v_rgb, gbase + 2);
-    if (live) {
-        float* pt = p.pt + ((size_t)b * p.N + n) * GN_PT_STRIDE;
-        st4_cs(pt + 4 * j, m_img);
-        st4_cs(pt + 36 + 4 * j, v_img);
-        if (j == 0) {
-            st4_cs(pt + 32, make_float4(m_rgb, mr1, mr2, nvalid));
-            st4_cs(pt + 68, make_float4(v_rgb, vr1, vr2, 0.f));
-        }
+    if (live && j == 0) {
+        float2 o; o.x = nvalid; o.y = __uint_as_float(bits);
+        *reinterpret_cast<float2*>(p.pt + ((size_t)b * p.N + n) * GN_PT_STRIDE) = o;
     }
 }
 
@@ -249,7 +197,6 @@ extern "C" int gn_k1_forward(const GnK1Params* hp, void* stream)
 {
     GnK1Params p = *hp;
     if (p.V < 1 || p.V > 32 || p.B < 1 || p.N < 1) return -1;
-    if (p.S != GN_REC_VOL && p.S != GN_REC_RAY) return -2;
     if (p.volume_mode) {
         if ((p.R % 8) != 0 || p.N != p.R * p.R * p.R || !p.axis || !p.bbox_min) return -3;
         p.tiles_per_scene = (p.R / 2) * (p.R / 2) * (p.R / 8);
@@ -258,7 +205,7 @@ extern "C" int gn_k1_forward(const GnK1Params* hp, void* stream)
         p.tiles_per_scene = (p.N + K1_TILE_P - 1) / K1_TILE_P;
     }
     const int npair = K1_TILE_P * p.V;
-    const size_t smem = (size_t)npair * (sizeof(K1PairInfo) + (2 * K1_PAIR_F + 8) * sizeof(float));
+    const size_t smem = (size_t)npair * (sizeof(K1PairInfo) + 8 * sizeof(float));
     if (smem > 227 * 1024) return -5;
     cudaError_t e = cudaFuncSetAttribute(gn_k1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;

@@ -6,6 +6,7 @@
 // ibrnet.py:470-471,484 and the softmax of 509-510) is a short warp-shuffle loop.
 //
 // Reference op chain replaced (per row):
+//   ray_dir_fc + add, mean1/var1            ibrnet.py:457-459,471
 //   dist_decoder MLPs + compute_prob       dist_decoder.py:99-142, 6-51   (via renderer.py:62-78)
 //   prob_embed                             aggregate_net.py:47-54
 //   neuray_fc, weight0, mean0/var0         ibrnet.py:469-470
@@ -85,7 +86,7 @@ gn_k2a_simt_kernel(const __grid_constant__ GnK2aParams p, int num_tiles, int G)
         *reinterpret_cast<float4*>(sw + i) = ldg4(p.weights + i);
     __syncthreads();
 
-    const int V = p.V, S = p.S;
+    const int V = p.V;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool lane_active = lane < G * V;
     const int g = lane_active ? lane / V : 0;
@@ -101,13 +102,13 @@ gn_k2a_simt_kernel(const __grid_constant__ GnK2aParams p, int num_tiles, int G)
         pidx = pidx < total_pts ? pidx : total_pts - 1;
         const int b = (int)(pidx / p.N);
         const int n = (int)(pidx - (long long)b * p.N);
-        const float* row = p.rec + ((size_t)pidx * V + v) * S;
-        const float* ptr = p.pt + (size_t)pidx * GN_PT_STRIDE;
+        const float* row = p.rec + ((size_t)pidx * V + v) * GN_REC_STRIDE;
+        const float2 ptv = __ldg(reinterpret_cast<const float2*>(p.pt + (size_t)pidx * GN_PT_STRIDE));
 
-        const float4 tail = ldg4(row + GN_REC_FRGB);           // frgb0..2, mask
-        const float mask = valid ? tail.w : 0.f;
-        const float depth = __ldg(row + GN_REC_DEPTH);
-        const float nvalid = __ldg(ptr + 35);
+        const float4 tail = ldg4(row + GN_REC_RGB);            // rgb0..2 (masked), depth
+        const float mask = (valid && ((__float_as_uint(ptv.y) >> v) & 1u)) ? 1.f : 0.f;
+        const float depth = tail.w;
+        const float nvalid = ptv.x;
         const float wgt = __fdiv_rn(mask, nvalid + 1e-8f);      // ibrnet.py:466
 
         float pe[32];
@@ -168,49 +169,68 @@ gn_k2a_simt_kernel(const __grid_constant__ GnK2aParams p, int num_tiles, int G)
             const float s = dot_row<8>(sw + GN_OFF(NF_W2), t, sw[GN_OFF(NF_B2)]);
             w0 = gn_sigmoid(s) * wgt;
         }
-        // ---- f (record order: img 32 | rgb 3), mean0/var0 over views (ibrnet.py:470)
+        // ---- ray_dir_fc (ibrnet.py:457) and f = [img_feats | rgb] + direction feature (ibrnet.py:459), record order
+        const float4 ddv = ldg4(row + GN_REC_DD);
         float f[36];
+        {
+            const float dd[4] = { ddv.x, ddv.y, ddv.z, ddv.w };
+            float hid[16];
+            load_bias<16>(sw + GN_OFF(RD_B0), hid);
+            mv_acc<4, 16>(sw + GN_OFF(RD_W0), dd, hid);
+            elu_inplace<16>(hid);
+            load_bias<36>(sw + GN_OFF(RD_B1), f);
+            mv_acc<16, 36>(sw + GN_OFF(RD_W1), hid, f);
 #pragma unroll
-        for (int c = 0; c < 32; c += 4) {
-            const float4 t = ldg4(row + GN_REC_FIMG + c);
-            f[c] = t.x; f[c + 1] = t.y; f[c + 2] = t.z; f[c + 3] = t.w;
+            for (int c = 0; c < 32; c += 4) {
+                const float4 t = ldg4(row + GN_REC_IMGF + c);
+                f[c] = gn_elu(f[c]) + t.x; f[c + 1] = gn_elu(f[c + 1]) + t.y;
+                f[c + 2] = gn_elu(f[c + 2]) + t.z; f[c + 3] = gn_elu(f[c + 3]) + t.w;
+            }
+            f[32] = gn_elu(f[32]) + tail.x; f[33] = gn_elu(f[33]) + tail.y; f[34] = gn_elu(f[34]) + tail.z; f[35] = 0.f;
         }
-        f[32] = tail.x; f[33] = tail.y; f[34] = tail.z; f[35] = 0.f;
 
         float y[64];
         {
             // view-invariant part of base_fc.0: 144 inputs [mean0|var0|mean1|var1] (each 36 wide, pad row = 0 weight).
             // Lane (g,v) computes outputs n = v, v+V, ... and parks them in shared memory for its group.
-            float gq[36];                                  // mean0 first, then overwritten in place by var0
+            float g0[36], g1[36];                          // means first, then overwritten in place by the variances
 #pragma unroll
-            for (int c = 0; c < 35; ++c) {
-                const float t = w0 * f[c];
-                float s = 0.f;
-                for (int jv = 0; jv < V; ++jv) s += __shfl_sync(FULL, t, (gb + jv) & 31);
-                gq[c] = s;
+            for (int c = 0; c < 35; ++c) {                 // ibrnet.py:470-471
+                const float t0 = w0 * f[c], t1 = wgt * f[c];
+                float s0 = 0.f, s1 = 0.f;
+                for (int jv = 0; jv < V; ++jv) {
+                    s0 += __shfl_sync(FULL, t0, (gb + jv) & 31);
+                    s1 += __shfl_sync(FULL, t1, (gb + jv) & 31);
+                }
+                g0[c] = s0; g1[c] = s1;
             }
-            gq[35] = 0.f;
+            g0[35] = 0.f; g1[35] = 0.f;
             const float* wg = sw + GN_OFF(BF_WG);
-            for (int nn = v; nn < 64; nn += V) {            // rows 0..35 (mean0), 72..143 (mean1|var1 from the pt record)
+            for (int nn = v; nn < 64; nn += V) {            // rows 0..35 (mean0), 72..107 (mean1)
                 float acc = 0.f;
 #pragma unroll
-                for (int c = 0; c < 36; ++c) acc = fmaf(gq[c], wg[c * 64 + nn], acc);
-#pragma unroll 8
-                for (int c = 0; c < 72; ++c) acc = fmaf(__ldg(ptr + c), wg[(72 + c) * 64 + nn], acc);
+                for (int c = 0; c < 36; ++c) acc = fmaf(g0[c], wg[c * 64 + nn], acc);
+#pragma unroll
+                for (int c = 0; c < 36; ++c) acc = fmaf(g1[c], wg[(72 + c) * 64 + nn], acc);
                 if (lane_active) ypart[nn] = acc;
             }
 #pragma unroll
             for (int c = 0; c < 35; ++c) {
-                const float dlt = f[c] - gq[c];
-                const float t = w0 * dlt * dlt;
-                float s = 0.f;
-                for (int jv = 0; jv < V; ++jv) s += __shfl_sync(FULL, t, (gb + jv) & 31);
-                gq[c] = s;
+                const float d0 = f[c] - g0[c], d1 = f[c] - g1[c];
+                const float t0 = w0 * d0 * d0, t1 = wgt * d1 * d1;
+                float s0 = 0.f, s1 = 0.f;
+                for (int jv = 0; jv < V; ++jv) {
+                    s0 += __shfl_sync(FULL, t0, (gb + jv) & 31);
+                    s1 += __shfl_sync(FULL, t1, (gb + jv) & 31);
+                }
+                g0[c] = s0; g1[c] = s1;
             }
-            for (int nn = v; nn < 64; nn += V) {            // rows 36..71 (var0)
+            for (int nn = v; nn < 64; nn += V) {            // rows 36..71 (var0), 108..143 (var1)
                 float acc = 0.f;
 #pragma unroll
-                for (int c = 0; c < 36; ++c) acc = fmaf(gq[c], wg[(36 + c) * 64 + nn], acc);
+                for (int c = 0; c < 36; ++c) acc = fmaf(g0[c], wg[(36 + c) * 64 + nn], acc);
+#pragma unroll
+                for (int c = 0; c < 36; ++c) acc = fmaf(g1[c], wg[(108 + c) * 64 + nn], acc);
                 if (lane_active) ypart[nn] += acc;
             }
             __syncwarp();
@@ -294,13 +314,12 @@ gn_k2a_simt_kernel(const __grid_constant__ GnK2aParams p, int num_tiles, int G)
         }
 
         // ---- rgb_fc + masked softmax over views (ibrnet.py:507-511)
-        if (p.colors) {
+        if (p.with_rgb && p.colors) {
             float in[40], r16[16], r8[8];
 #pragma unroll
             for (int c = 0; c < 32; ++c) in[c] = x[c];
             in[32] = vis2;
-            const float4 dd = (S > GN_REC_DD) ? ldg4(row + GN_REC_DD) : make_float4(0.f, 0.f, 0.f, 0.f);
-            in[33] = dd.x; in[34] = dd.y; in[35] = dd.z; in[36] = dd.w;
+            in[33] = ddv.x; in[34] = ddv.y; in[35] = ddv.z; in[36] = ddv.w;
             load_bias<16>(sw + GN_OFF(RF_B0), r16);
             mv_acc<37, 16>(sw + GN_OFF(RF_W0), in, r16);
             elu_inplace<16>(r16);
@@ -315,12 +334,11 @@ gn_k2a_simt_kernel(const __grid_constant__ GnK2aParams p, int num_tiles, int G)
             float es = 0.f;
             for (int jv = 0; jv < V; ++jv) es += __shfl_sync(FULL, e, (gb + jv) & 31);
             const float bw = __fdiv_rn(e, es);
-            const float4 rgbin = ldg4(row + GN_REC_DEPTH);     // depth, rgb0..2
-            float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+            float c0 = 0.f, c1 = 0.f, c2 = 0.f;                // rgb_in = rgb * mask (ibrnet.py:458)
             for (int jv = 0; jv < V; ++jv) {
-                c0 += __shfl_sync(FULL, bw * rgbin.y, (gb + jv) & 31);
-                c1 += __shfl_sync(FULL, bw * rgbin.z, (gb + jv) & 31);
-                c2 += __shfl_sync(FULL, bw * rgbin.w, (gb + jv) & 31);
+                c0 += __shfl_sync(FULL, bw * tail.x, (gb + jv) & 31);
+                c1 += __shfl_sync(FULL, bw * tail.y, (gb + jv) & 31);
+                c2 += __shfl_sync(FULL, bw * tail.z, (gb + jv) & 31);
             }
             if (writer) st4(p.colors + (size_t)pidx * 4, make_float4(c0, c1, c2, 0.f));
         }
@@ -331,7 +349,6 @@ extern "C" int gn_k2a_forward(const GnK2aParams* hp, void* stream)
 {
     const GnK2aParams& p = *hp;
     if (p.V < 1 || p.V > 32 || p.B < 1 || p.N < 1) return -1;
-    if (p.S != GN_REC_VOL && p.S != GN_REC_RAY) return -2;
     if (p.que_dists && (p.dn < 1 || (p.N % p.dn) != 0)) return -4;
     const int G = 32 / p.V;
     const long long total = (long long)p.B * p.N;

@@ -9,9 +9,9 @@ import numpy as np
 import torch
 
 from . import _lib
-from .weights import pack_blob, pack_ray_dir_fc, positional_table, voxel_axis_table
+from .weights import pack_blob, positional_table, voxel_axis_table
 
-REC_VOL, REC_RAY, PT_STRIDE, POOL_STRIDE = 72, 76, 72, 68
+REC_STRIDE, PT_STRIDE, POOL_STRIDE = 72, 2, 68
 
 
 def _stream():
@@ -53,7 +53,6 @@ class HeadWeights:
         if vers == self._versions:
             return
         self.blob = torch.from_numpy(pack_blob(sd, self.agg_prefix, self.dd_prefix)).to(self.device)
-        self.rdfc = pack_ray_dir_fc(sd, self.agg_prefix)
         var = sd.get(self.agg_prefix + 'deviation_network.variance')
         self.variance = float(var) if var is not None else 0.3
         self._versions = vers
@@ -117,31 +116,30 @@ def k1_forward(scene, hw, *, resolution=None, bbox_min=None, volume_size=0.3, pt
     vol = pts is None
     if vol:
         R = int(resolution)
-        N, dn_, S = R * R * R, R, REC_VOL
+        N, dn_ = R * R * R, R
         bbox_min = _f32c(bbox_min, dev).reshape(scene.B, 3)
         axis = hw.axis(R, volume_size)
         p.axis, p.bbox_min, p.R = _ptr(axis).value, _ptr(bbox_min).value, R
     else:
         pts = _f32c(pts, dev)
         que_dir = _f32c(que_dir, dev)
-        N, dn_, S = pts.shape[1], int(dn), REC_RAY
+        N, dn_ = pts.shape[1], int(dn)
         p.pts, p.que_dir, p.R = _ptr(pts).value, _ptr(que_dir).value, 0
-    rec = torch.empty((scene.B, N, scene.V, S), device=dev, dtype=torch.float32)
+    rec = torch.empty((scene.B, N, scene.V, REC_STRIDE), device=dev, dtype=torch.float32)
     pt = torch.empty((scene.B, N, PT_STRIDE), device=dev, dtype=torch.float32)
     dbg = torch.zeros((scene.B, N, scene.V, 2), device=dev, dtype=torch.int32) if debug_idx else None
     p.imgs, p.img_feats, p.ray_feats = _ptr(scene.imgs).value, _ptr(scene.img_feats).value, _ptr(scene.ray_feats).value
     p.KRt, p.cam = _ptr(scene.KRt).value, _ptr(scene.cam).value
     p.rec, p.pt, p.dbg_feat_idx = _ptr(rec).value, _ptr(pt).value, _ptr(dbg).value
     p.B, p.V, p.H, p.W, p.fh, p.fw = scene.B, scene.V, scene.H, scene.W, scene.fh, scene.fw
-    p.N, p.dn, p.S, p.volume_mode = N, dn_, S, 1 if vol else 0
-    p.rdfc = hw.rdfc
+    p.N, p.dn, p.volume_mode = N, dn_, 1 if vol else 0
     _lib.check(lib.gn_k1_forward(C.byref(p), _stream()), 'gn_k1_forward')
     return (rec, pt, dbg) if debug_idx else (rec, pt)
 
 
 def k2a_forward(rec, pt, hw, depth_range, *, que_dists=None, dn=1, want_colors=False, debug=False):
     lib = _lib.load()
-    B, N, V, S = rec.shape
+    B, N, V, _ = rec.shape
     dev = rec.device
     pooled = torch.empty((B, N, POOL_STRIDE), device=dev, dtype=torch.float32)
     colors = torch.empty((B, N, 4), device=dev, dtype=torch.float32) if want_colors else None
@@ -151,7 +149,7 @@ def k2a_forward(rec, pt, hw, depth_range, *, que_dists=None, dn=1, want_colors=F
     if que_dists is not None:
         que_dists = _f32c(que_dists, dev)
     p.que_dists, p.pooled, p.colors, p.dbg_rows = _ptr(que_dists).value, _ptr(pooled).value, _ptr(colors).value, _ptr(dbg).value
-    p.B, p.N, p.V, p.S, p.dn = B, N, V, S, int(dn)
+    p.B, p.N, p.V, p.dn, p.with_rgb = B, N, V, int(dn), 1 if want_colors else 0
     _lib.check(lib.gn_k2a_forward(C.byref(p), _stream()), 'gn_k2a_forward')
     return pooled, colors, dbg
 

@@ -4,7 +4,6 @@ The blob layout (entry names, offsets, padded shapes) is owned by the native lib
 (gn_weight_entry); this module only knows which reference tensor feeds which entry and how to permute it.  Key names
 are the reference's, so a `model_best.pth` packs unchanged.
 """
-import ctypes as C
 import numpy as np
 import torch
 
@@ -28,6 +27,10 @@ def _entries(sd, agg_prefix, dd_prefix):
         e[dst_w] = w if vector else w.T
         if dst_b is not None:
             e[dst_b] = _np(sd[key + '.bias'])[None, :]
+    w = _np(sd[A + 'ray_dir_fc.0.weight'])                      # [16,4]
+    e['rd.w0'], e['rd.b0'] = w.T, _np(sd[A + 'ray_dir_fc.0.bias'])[None, :]
+    e['rd.w1'] = _np(sd[A + 'ray_dir_fc.2.weight'])[PERM35].T   # [16,35], columns in record order
+    e['rd.b1'] = _np(sd[A + 'ray_dir_fc.2.bias'])[PERM35][None, :]
     for short, name in (('mean', 'mean_decoder'), ('var', 'var_decoder'), ('aw', 'aw_decoder')):
         lin(f'dd.{short}.w0', f'dd.{short}.b0', f'{dd_prefix}{name}.0')
         lin(f'dd.{short}.w2', f'dd.{short}.b2', f'{dd_prefix}{name}.2')
@@ -81,23 +84,6 @@ def pack_blob(sd, agg_prefix='agg_net.', dd_prefix='dist_decoder.'):
         seen.add(name)
     assert seen == set(ent), set(ent) ^ seen
     return blob
-
-
-def pack_ray_dir_fc(sd, agg_prefix='agg_net.'):
-    """-> GnRayDirFc ctypes struct (K1 kernel-parameter constants)."""
-    A = agg_prefix + 'agg_impl.'
-    s = _lib.GnRayDirFc()
-    w0 = np.ascontiguousarray(_np(sd[A + 'ray_dir_fc.0.weight']))          # [16,4]
-    b0 = np.ascontiguousarray(_np(sd[A + 'ray_dir_fc.0.bias']))
-    w1 = np.zeros((36, 16), np.float32)
-    b1 = np.zeros(36, np.float32)
-    w1[:35] = _np(sd[A + 'ray_dir_fc.2.weight'])[PERM35]
-    b1[:35] = _np(sd[A + 'ray_dir_fc.2.bias'])[PERM35]
-    C.memmove(C.addressof(s.w0), w0.ctypes.data, w0.nbytes)
-    C.memmove(C.addressof(s.b0), b0.ctypes.data, b0.nbytes)
-    C.memmove(C.addressof(s.w1), w1.ctypes.data, w1.nbytes)
-    C.memmove(C.addressof(s.b1), b1.ctypes.data, b1.nbytes)
-    return s
 
 
 def positional_table(n_samples, d_hid=16):

@@ -14,8 +14,8 @@
  * Data layout in HBM:
  *   feature maps  : channels-last  [B, V, fh, fw, 32]
  *   images        : planar         [B, V, 3, H, W]
- *   record  `rec` : [B, N, V, S]   S = 72 (volume) or 76 (RGB head); n = ray*dn + sample
- *   per-point `pt`: [B, N, 72]     mean[img32,rgb3], nvalid | var[img32,rgb3], 0
+ *   record  `rec` : [B, N, V, 72]  ray_feats32 | img_feats32 | rgb3, depth | dir_diff4 ; n = ray*dn + sample
+ *   per-point `pt`: [B, N, 2]      nvalid, view bit mask
  *   `pooled`      : [B, N, 68]     K2a output: mean32 | var32 | mean_v(w), nvalid, 0, 0
  */
 #ifndef GRASPNERF_B200_H
@@ -26,20 +26,9 @@
 extern "C" {
 #endif
 
-/* ray_dir_fc weights (ibrnet.py:382-385), passed by value inside GnK1Params (kernel constant bank).
- * w1/b1 rows are in the record's channel order: rows 0..31 = reference outputs 3..34 (img_feats channels),
- * rows 32..34 = reference outputs 0..2 (rgb), row 35 = 0. */
-typedef struct GnRayDirFc {
-    float w0[16][4];
-    float b0[16];
-    float w1[36][16];
-    float b1[36];
-} GnRayDirFc;
-
-/* K1: fused project - sample - aggregate.
+/* K1: fused project - sample.
  * Replaces project_points_dict (render_ops.py:82-144), get_img_feats (renderer.py:80-88), get_dir_diff
- * (aggregate_net.py:11-17), ray_dir_fc + add (ibrnet.py:457-459) and the mask-weighted mean/var
- * (ibrnet.py:466,471).  volume_mode=1: points are the voxel centres of utils/field_utils.py:12-27 plus bbox_min,
+ * (aggregate_net.py:11-17) and the per-point valid-view count / mask (ibrnet.py:466,490).  volume_mode=1: points are the voxel centres of utils/field_utils.py:12-27 plus bbox_min,
  * in sample_volume's order (renderer.py:166-170).  volume_mode=0: explicit points (RGB head, render_ops.py:27-39). */
 typedef struct GnK1Params {
     const float* imgs;        /* [B,V,3,H,W] */
@@ -51,17 +40,15 @@ typedef struct GnK1Params {
     const float* bbox_min;    /* [B,3] (volume mode) */
     const float* pts;         /* [B,N,3] (ray mode) */
     const float* que_dir;     /* [B,N/dn,3] unit query direction per ray (ray mode) */
-    float* rec;               /* out [B,N,V,S] */
-    float* pt;                /* out [B,N,72] */
+    float* rec;               /* out [B,N,V,72] */
+    float* pt;                /* out [B,N,2]: nvalid (float), view bit mask (uint32 bits) */
     int* dbg_feat_idx;        /* optional out [B,N,V,2] int32 (x0,y0) feature-map corner indices, or NULL */
     int B, V, H, W, fh, fw;
     int R;                    /* grid resolution (volume mode) */
     int N;                    /* points per scene */
     int dn;                   /* samples per ray */
-    int S;                    /* record stride in floats: 72 or 76 */
     int volume_mode;
     int tiles_per_scene;      /* filled in by the launcher */
-    GnRayDirFc rdfc;
 } GnK1Params;
 
 int gn_k1_forward(const GnK1Params* params, void* stream);
@@ -73,21 +60,22 @@ int gn_weight_entry(int idx, const char** name, int* offset, int* rows, int* col
 int gn_weight_blob_floats(void);
 
 /* K2a: per-(point,view) head + cross-view pooling.
- * Replaces MixtureLogisticsDistDecoder.forward + compute_prob (dist_decoder.py:99-142, via predict_proj_ray_prob
+ * Replaces ray_dir_fc + add and the mask-weighted mean/var (ibrnet.py:457-471), MixtureLogisticsDistDecoder.forward + compute_prob (dist_decoder.py:99-142, via predict_proj_ray_prob
  * renderer.py:62-78), prob_embed (aggregate_net.py:47-54) and IBRNetWithNeuRayNeus.forward lines 466-484 + 507-511
  * (ibrnet.py): neuray_fc, weighted mean/var, base_fc, vis_fc, vis_fc2, pooling, and (with_rgb) rgb_fc + softmax blend.
  * que_dists: NULL -> fixed +-0.005 interval (volume mode, dist_decoder.py:121-124); else [B,N] normalised
  * inverse-depth spacings (render_ops.py:46-52). */
 typedef struct GnK2aParams {
-    const float* rec;          /* [B,N,V,S] */
-    const float* pt;           /* [B,N,72] */
+    const float* rec;          /* [B,N,V,72] */
+    const float* pt;           /* [B,N,2] */
     const float* weights;      /* blob */
     const float* depth_range;  /* [B,V,2] */
     const float* que_dists;    /* [B,N] or NULL */
     float* pooled;             /* out [B,N,68] */
     float* colors;             /* out [B,N,4] (rgb, 0) or NULL */
     float* dbg_rows;           /* optional out [B,N,V,8]: hit, vis, w0, vis2, x0, x1, pe0, pe1 ; or NULL */
-    int B, N, V, S, dn;
+    int B, N, V, dn;
+    int with_rgb;              /* 1: also evaluate rgb_fc + blend into `colors` */
 } GnK2aParams;
 int gn_k2a_forward(const GnK2aParams* params, void* stream);
 

@@ -49,7 +49,7 @@ def test_weight_table_is_dense_and_aligned(lib):
 def test_pack_blob_roundtrip(lib):
     """Every reference tensor lands where the table says, k-major, with the [rgb|img] -> [img|rgb] permutation."""
     from graspnerf_b200 import _lib
-    from graspnerf_b200.weights import pack_blob, pack_ray_dir_fc, PERM35
+    from graspnerf_b200.weights import pack_blob, PERM35
     sd = golden_weights()
     blob = pack_blob(sd, 'fine_agg_net.', 'fine_dist_decoder.')
     tab = {n: (o, r, c, cp) for n, o, r, c, cp in _lib.weight_table()}
@@ -65,9 +65,8 @@ def test_pack_blob_roundtrip(lib):
     assert np.array_equal(entry('dd.var.w4'), sd['fine_dist_decoder.var_decoder.4.weight'].numpy().T)
     assert np.array_equal(entry('at.fc'), sd[A + 'ray_attention.fc.weight'].numpy().T)
     assert np.array_equal(entry('og.w1'), sd[A + 'out_geometry_fc.1.weight'].numpy())
-    r = pack_ray_dir_fc(sd, 'fine_agg_net.')
-    w1 = np.ctypeslib.as_array(r.w1)
-    assert np.array_equal(w1[:35], sd[A + 'ray_dir_fc.2.weight'].numpy()[PERM35]) and not w1[35].any()
+    assert np.array_equal(entry('rd.w1'), sd[A + 'ray_dir_fc.2.weight'].numpy()[PERM35].T)
+    assert np.array_equal(entry('rd.w0'), sd[A + 'ray_dir_fc.0.weight'].numpy().T)
 
 
 def test_product_path_refuses_cpu():

@@ -46,22 +46,19 @@ def test_volume_path_vs_oracle_and_golden(name):
     _dump(f'volume_{name}', rec=rec[0, ::97].numpy(), pt=pt[0].numpy(), pooled=pooled[0].numpy(), rows=rows[0, ::7].numpy(),
           vol=vol[0, 0].numpy())
     # ---- index tables: bit exact
-    mask = rec[0, :, :, 67]
+    bits = pt[0, :, 1].contiguous().view(torch.int32)
+    mask = torch.stack([((bits >> v) & 1).float() for v in range(rec.shape[2])], 1)
     assert torch.equal(mask, orec['mask']), f"{(mask != orec['mask']).sum().item()} mask flips vs oracle"
     assert np.array_equal(mask.numpy().astype(np.uint8), g['mask']), 'mask differs from the reference golden table'
     assert torch.equal(idx[0, :, :, 0].long(), orec['feat_idx'][0]), 'bilinear x0 corner indices differ'
     assert torch.equal(idx[0, :, :, 1].long(), orec['feat_idx'][1]), 'bilinear y0 corner indices differ'
-    assert torch.equal(pt[0, :, 35], orec['mask'].sum(1)), 'nvalid'
+    assert torch.equal(pt[0, :, 0], orec['mask'].sum(1)), 'nvalid'
     # ---- K1 record
     assert_close(rec[0, :, :, 0:32], orec['ray_feats'], what='rec.ray_feats')
-    assert_close(rec[0, :, :, 32:64], oagg['f'][..., 3:35], what='rec.f_img')
-    assert_close(rec[0, :, :, 64:67], oagg['f'][..., 0:3], what='rec.f_rgb')
-    assert_close(rec[0, :, :, 68], orec['depth'], what='rec.depth')
-    assert_close(rec[0, :, :, 69:72], orec['rgb'], what='rec.rgb_in')
-    assert_close(pt[0, :, 0:32], oagg['mean1'][:, 3:35], what='pt.mean_img')
-    assert_close(pt[0, :, 32:35], oagg['mean1'][:, 0:3], what='pt.mean_rgb')
-    assert_close(pt[0, :, 36:68], oagg['var1'][:, 3:35], what='pt.var_img')
-    assert_close(pt[0, :, 68:71], oagg['var1'][:, 0:3], what='pt.var_rgb')
+    assert_close(rec[0, :, :, 32:64], orec['img_feats'], what='rec.img_feats')
+    assert_close(rec[0, :, :, 64:67], orec['rgb'], what='rec.rgb')
+    assert_close(rec[0, :, :, 67], orec['depth'], what='rec.depth')
+    assert_close(rec[0, :, :, 68:72], oagg['dir_diff'], what='rec.dir_diff')
     # ---- K2a rows and pooled
     assert_close(rows[0, :, :, 0], orec['hit_prob'], what='hit_prob')
     assert_close(rows[0, :, :, 1], orec['vis'], what='vis')
