@@ -137,7 +137,10 @@ def k1_forward(scene, hw, *, resolution=None, bbox_min=None, volume_size=0.3, pt
     return (rec, pt, dbg) if debug_idx else (rec, pt)
 
 
-def k2a_forward(rec, pt, hw, depth_range, *, que_dists=None, dn=1, want_colors=False, debug=False):
+K2A_IMPL = 'tc'      # 'tc' (tcgen05, default) or 'simt' (fp32 CUDA-core implementation kept as the on-GPU cross-check)
+
+
+def k2a_forward(rec, pt, hw, depth_range, *, que_dists=None, dn=1, want_colors=False, debug=False, impl=None):
     lib = _lib.load()
     B, N, V, _ = rec.shape
     dev = rec.device
@@ -150,7 +153,9 @@ def k2a_forward(rec, pt, hw, depth_range, *, que_dists=None, dn=1, want_colors=F
         que_dists = _f32c(que_dists, dev)
     p.que_dists, p.pooled, p.colors, p.dbg_rows = _ptr(que_dists).value, _ptr(pooled).value, _ptr(colors).value, _ptr(dbg).value
     p.B, p.N, p.V, p.dn, p.with_rgb = B, N, V, int(dn), 1 if want_colors else 0
-    _lib.check(lib.gn_k2a_forward(C.byref(p), _stream()), 'gn_k2a_forward')
+    impl = impl or K2A_IMPL
+    fn = lib.gn_k2a_forward_tc if impl == 'tc' else lib.gn_k2a_forward
+    _lib.check(fn(C.byref(p), _stream()), f'gn_k2a_forward[{impl}]')
     return pooled, colors, dbg
 
 

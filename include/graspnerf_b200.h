@@ -77,7 +77,8 @@ typedef struct GnK2aParams {
     int B, N, V, dn;
     int with_rgb;              /* 1: also evaluate rgb_fc + blend into `colors` */
 } GnK2aParams;
-int gn_k2a_forward(const GnK2aParams* params, void* stream);
+int gn_k2a_forward(const GnK2aParams* params, void* stream);      /* fp32 SIMT implementation (reference for the TC path) */
+int gn_k2a_forward_tc(const GnK2aParams* params, void* stream);   /* tcgen05 / TMEM implementation (fp16 hi/lo split, 3 MMAs per product) */
 
 /* K2b: per-ray geometry head.
  * Replaces ibrnet.py:485-495: embed (neus.py:21-66), geometry_fc, + pos_encoding (ibrnet.py:437-445), MultiHeadAttention

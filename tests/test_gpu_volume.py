@@ -24,8 +24,9 @@ def _dump(name, **arrs):
         np.savez_compressed(os.path.join(d, name + '.npz'), **{k: np.asarray(v) for k, v in arrs.items()})
 
 
+@pytest.mark.parametrize('impl', ['simt', 'tc'])
 @pytest.mark.parametrize('name', list(VOLUME_CASES))
-def test_volume_path_vs_oracle_and_golden(name):
+def test_volume_path_vs_oracle_and_golden(name, impl):
     from graspnerf_b200 import ops
     from oracle import nr_oracle as O
     g = load_golden(f'volume_{name}.npz')
@@ -37,14 +38,13 @@ def test_volume_path_vs_oracle_and_golden(name):
                       sc['Ks'].to(dev), sc['depth_range'].to(dev))
     bbox_min = torch.tensor([sc['bbox3d'][0]], device=dev)
     rec, pt, idx = ops.k1_forward(scene, hw, resolution=40, bbox_min=bbox_min, debug_idx=True)
-    pooled, _, rows = ops.k2a_forward(rec, pt, hw, scene.depth_range, debug=True)
+    pooled, _, rows = ops.k2a_forward(rec, pt, hw, scene.depth_range, debug=True, impl=impl)
     vol, _ = ops.k2b_forward(pooled, hw, dn=40, resolution=40, bbox_min=bbox_min)
     torch.cuda.synchronize()
     rec, pt, idx, pooled, rows, vol = [t.cpu() for t in (rec, pt, idx, pooled, rows, vol)]
 
     ovol, orec, oagg = O.sample_volume(sd, sc, with_intermediates=True)
-    _dump(f'volume_{name}', rec=rec[0, ::97].numpy(), pt=pt[0].numpy(), pooled=pooled[0].numpy(), rows=rows[0, ::7].numpy(),
-          vol=vol[0, 0].numpy())
+    _dump(f'volume_{name}_{impl}', pooled=pooled[0, ::5].numpy(), rows=rows[0, ::5].numpy(), vol=vol[0, 0].numpy())
     # ---- index tables: bit exact
     bits = pt[0, :, 1].contiguous().view(torch.int32)
     mask = torch.stack([((bits >> v) & 1).float() for v in range(rec.shape[2])], 1)

@@ -11,6 +11,7 @@ from tests.helpers import golden_weights
 def main():
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 1
     iters = int(sys.argv[2]) if len(sys.argv) > 2 else 20
+    ops.K2A_IMPL = sys.argv[3] if len(sys.argv) > 3 else 'tc'
     dev = torch.device('cuda:0')
     sd = golden_weights()
     hw = ops.HeadWeights(sd, 'agg_net.', 'dist_decoder.', dev)
@@ -35,7 +36,7 @@ def main():
         if it >= 3:
             acc += [ev[i].elapsed_time(ev[i + 1]) for i in range(3)]
     acc /= iters
-    print(f'B={B}: K1 {acc[0]*1e3:.1f} us  K2a {acc[1]*1e3:.1f} us  K2b {acc[2]*1e3:.1f} us  total {acc.sum()*1e3:.1f} us '
+    print(f'[{ops.K2A_IMPL}] B={B}: K1 {acc[0]*1e3:.1f} us  K2a {acc[1]*1e3:.1f} us  K2b {acc[2]*1e3:.1f} us  total {acc.sum()*1e3:.1f} us '
           f'-> {B/acc.sum()*1e3:.1f} volumes/s; K1 roofline bytes/vol 153284608 -> {153284608*B/acc[0]/1e6:.1f} GB/s')
 
 
