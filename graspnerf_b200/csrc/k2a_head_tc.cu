@@ -40,8 +40,10 @@ __host__ __device__ constexpr int tc_img_off(int i) {          // offset in halv
     return o;
 }
 constexpr int TC_IMG_HALVES = tc_img_off(L_COUNT);
-constexpr int TC_F32_FLOATS = GN_W_K2A_FLOATS;                    // the fp32 blob (biases + CUDA-core weights are read from it)
-constexpr size_t TC_SMEM_BYTES = (size_t)TC_IMG_HALVES * 2 + (size_t)TC_F32_FLOATS * 4 + 64;
+// biases and the few CUDA-core weights (third dist-decoder layers, neuray_fc.2, vis_fc2.2, rgb_fc) are read straight from
+// the fp32 blob in global memory: warp-uniform addresses, a couple of KB that stay in L1.
+constexpr size_t TC_SMEM_BYTES = (size_t)TC_IMG_HALVES * 2 + 64;
+static_assert(TC_SMEM_BYTES <= 227 * 1024, "K2a-TC shared memory budget");
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -170,14 +172,13 @@ gn_k2a_tc_kernel(const __grid_constant__ GnK2aParams p, int num_tiles, int G)
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __half* s_img = reinterpret_cast<__half*>(smem_raw);
-    float* sw = reinterpret_cast<float*>(smem_raw + (size_t)TC_IMG_HALVES * 2);            // fp32 blob copy
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(sw + TC_F32_FLOATS);                     // [2]
+    const float* __restrict__ sw = p.weights;                                              // fp32 blob (global, L1-resident constants)
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)TC_IMG_HALVES * 2);   // [2]
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + TC_SLOTS);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int slot = warp >> 2;
     // ---- one-time setup: fp32 blob copy, fp16 images, TMEM, mbarriers
-    for (int i = tid * 4; i < TC_F32_FLOATS; i += TC_THREADS * 4) *reinterpret_cast<float4*>(sw + i) = ldg4(p.weights + i);
     for (int i = tid; i < TC_IMG_HALVES / 2; i += TC_THREADS) reinterpret_cast<uint32_t*>(s_img)[i] = 0u;
     __syncthreads();
     {
@@ -569,7 +570,6 @@ extern "C" int gn_k2a_forward_tc(const GnK2aParams* hp, void* stream)
     const long long per_tile = 4LL * G;
     const long long tiles = (total + per_tile - 1) / per_tile;
     if (tiles > 0x7fffffffLL) return -6;
-    if (TC_SMEM_BYTES > 227 * 1024) return -5;
     cudaError_t e = cudaFuncSetAttribute(gn_k2a_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     int dev = 0, sms = 148;
