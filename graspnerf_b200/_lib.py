@@ -19,11 +19,12 @@ class GnK1Params(C.Structure):
 
 class GnK2aParams(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ('rec', 'pt', 'weights', 'depth_range', 'que_dists', 'pooled', 'colors',
-                                          'dbg_rows')] + [(n, C.c_int) for n in ('B', 'N', 'V', 'dn', 'with_rgb')]
+                                          'dbg_rows', 'tc_const', 'tok', 'axis', 'bbox_min', 'pts')] + \
+               [(n, C.c_int) for n in ('B', 'N', 'V', 'dn', 'with_rgb', 'R', 'volume_mode')]
 
 
 class GnK2bParams(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in ('pooled', 'weights', 'axis', 'bbox_min', 'pts', 'pos_table', 'sdf', 'grad')] + \
+    _fields_ = [(n, C.c_void_p) for n in ('pooled', 'tok', 'weights', 'axis', 'bbox_min', 'pts', 'pos_table', 'sdf', 'grad')] + \
                [(n, C.c_int) for n in ('B', 'N', 'dn', 'R', 'volume_mode')]
 
 
@@ -57,6 +58,8 @@ def load():
     lib.gn_k3_coarse_depths.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
     lib.gn_k3_fine_depths.restype = C.c_int
     lib.gn_k3_fine_depths.argtypes = [C.c_void_p] * 6 + [C.c_int] * 4 + [C.c_void_p]
+    lib.gn_k2a_tc_prepare.restype = C.c_int
+    lib.gn_k2a_tc_prepare.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.gn_weight_entry.restype = C.c_int
     lib.gn_weight_entry.argtypes = [C.c_int, C.POINTER(C.c_char_p)] + [C.POINTER(C.c_int)] * 4
     for name, st in (('gn_sizeof_k1_params', GnK1Params), ('gn_sizeof_k2a_params', GnK2aParams),

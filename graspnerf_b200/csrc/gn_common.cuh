@@ -7,6 +7,7 @@
 #define GN_REC_STRIDE 72      // floats per (point,view) record
 #define GN_PT_STRIDE 2        // floats per point written by K1: nvalid, view bit mask (uint32 bits)
 #define GN_POOL_STRIDE 68     // floats per point written by K2a: mean32 | var32 | wmean, nvalid, 0, 0
+#define GN_TOK_STRIDE 20      // floats per point written by K2a (tensor-core path): geometry_fc output 16 | nvalid, 0, 0, 0
 
 // record layout (floats), see DESIGN.md "Data layout in HBM"
 #define GN_REC_RAYF 0         // [0,32)  ray_feats * mask

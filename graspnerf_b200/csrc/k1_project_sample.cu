@@ -14,7 +14,8 @@
 //   phase A  thread <-> (point, view): projection, mask, view direction, dir_diff, bilinear tap offsets/weights;
 //            results parked in shared memory.
 //   phase B  8 lanes <-> one point, lane j <-> channels 4j..4j+3: each bilinear tap is ONE 128-byte line of
-//            the channels-last feature map (8 x LDG.128), records leave as coalesced float4 streaming stores.
+//            the channels-last feature map (8 x LDG.128), the 4 image taps are 4 RGBA texels on lanes 0..3, records leave
+//            as coalesced float4 streaming stores.
 #include "gn_common.cuh"
 #include "../../include/graspnerf_b200.h"
 
@@ -28,7 +29,7 @@ struct K1PairInfo {           // 64 bytes, written in phase A, read (broadcast) 
     float iw[4];              // image tap weights * mask
 };
 
-__global__ void __launch_bounds__(K1_THREADS, 3)
+__global__ void __launch_bounds__(K1_THREADS, 4)
 gn_k1_kernel(const __grid_constant__ GnK1Params p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -154,7 +155,7 @@ gn_k1_kernel(const __grid_constant__ GnK1Params p)
     const size_t plane = (size_t)p.H * p.W;
     const float* rf_base = p.ray_feats + (size_t)b * V * fmap_sz + 4 * j;
     const float* if_base = p.img_feats + (size_t)b * V * fmap_sz + 4 * j;
-    const float* im_base = p.imgs + ((size_t)b * V * 3 + (j < 3 ? j : 0)) * plane;
+    const float* im_base = p.imgs + (size_t)b * V * plane * 4;            // RGBA-interleaved [B,V,H,W,4]
 
     for (int v = 0; v < V; ++v) {
         const int pair = pl * V + v;
@@ -165,25 +166,25 @@ gn_k1_kernel(const __grid_constant__ GnK1Params p)
         // issue all eight 128-bit gathers before use
         const float4 r0 = ldg4(rf + fo.x), r1 = ldg4(rf + fo.y), r2 = ldg4(rf + fo.z), r3 = ldg4(rf + fo.w);
         const float4 g0 = ldg4(imf + fo.x), g1 = ldg4(imf + fo.y), g2 = ldg4(imf + fo.z), g3 = ldg4(imf + fo.w);
-        float rgbv = 0.f;
-        if (j < 3) {
-            const int4 io = *reinterpret_cast<const int4*>(s_info[pair].io);
-            const float4 iw = *reinterpret_cast<const float4*>(s_info[pair].iw);
-            const float* im = im_base + (size_t)v * 3 * plane;
-            rgbv = __ldg(im + io.x) * iw.x;
-            rgbv = fmaf(__ldg(im + io.y), iw.y, rgbv);
-            rgbv = fmaf(__ldg(im + io.z), iw.z, rgbv);
-            rgbv = fmaf(__ldg(im + io.w), iw.w, rgbv);
+        // image taps: lane j<4 fetches tap j as one RGBA texel (LDG.128) and scales it; the 4 partial colours are
+        // summed over lanes 0..3 of the group with two xor-shuffles (order (t0+t1)+(t2+t3))
+        float cr = 0.f, cg = 0.f, cb = 0.f;
+        if (j < 4) {
+            const int io = s_info[pair].io[j];
+            const float iw = s_info[pair].iw[j];
+            const float4 px = ldg4(im_base + ((size_t)v * plane + io) * 4);
+            cr = px.x * iw; cg = px.y * iw; cb = px.z * iw;
         }
         float4 ray = f4_mul(r0, fwt.x); ray = f4_fma(r1, fwt.y, ray); ray = f4_fma(r2, fwt.z, ray); ray = f4_fma(r3, fwt.w, ray);
         float4 img = f4_mul(g0, fwt.x); img = f4_fma(g1, fwt.y, img); img = f4_fma(g2, fwt.z, img); img = f4_fma(g3, fwt.w, img);
         float* row = rec + (size_t)v * GN_REC_STRIDE;
         // tail chunks: lane 0 <- (rgb0, rgb1, rgb2, depth), lane 1 <- dir_diff
-        const float c1 = __shfl_sync(0xffffffffu, rgbv, gbase + 1), c2 = __shfl_sync(0xffffffffu, rgbv, gbase + 2);
+        cr += __shfl_xor_sync(0xffffffffu, cr, 1); cg += __shfl_xor_sync(0xffffffffu, cg, 1); cb += __shfl_xor_sync(0xffffffffu, cb, 1);
+        cr += __shfl_xor_sync(0xffffffffu, cr, 2); cg += __shfl_xor_sync(0xffffffffu, cg, 2); cb += __shfl_xor_sync(0xffffffffu, cb, 2);
         if (live) {
             st4_cs(row + GN_REC_RAYF + 4 * j, ray);
             st4_cs(row + GN_REC_IMGF + 4 * j, img);
-            if (j == 0) st4_cs(row + GN_REC_RGB, make_float4(rgbv, c1, c2, s_misc[pair * 8 + 5]));
+            if (j == 0) st4_cs(row + GN_REC_RGB, make_float4(cr, cg, cb, s_misc[pair * 8 + 5]));
             else if (j == 1) st4_cs(row + GN_REC_DD, *reinterpret_cast<const float4*>(s_misc + pair * 8));
         }
     }

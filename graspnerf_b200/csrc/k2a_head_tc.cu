@@ -1,16 +1,19 @@
-// K2a (tensor-core version): per-(point,view) head + cross-view pooling on tcgen05 / TMEM.
+// K2a (tensor-core version): per-(point,view) head + cross-view pooling (+ geometry_fc) on tcgen05 / TMEM.
 //
-// Same reference op chain and same math as k2a_head_simt.cu (ibrnet.py:457-484,507-511; dist_decoder.py:99-142;
+// Same reference op chain and same math as k2a_head_simt.cu (ibrnet.py:457-489,507-511; dist_decoder.py:99-142;
 // aggregate_net.py:47-54), re-organised as a chain of small GEMMs D[128 x N] = A[128 x K] * W[N x K]^T:
 //   * a tile is 128 rows = 4 warps x (G points x V views); thread t owns row t = TMEM lane t for the whole chain;
 //   * the A operand of every layer lives in TENSOR MEMORY (tcgen05.mma "TS" form): the epilogue of layer i writes
 //     the activated output straight back with tcgen05.st, it never touches shared memory;
 //   * every fp32 operand is split into fp16 hi + lo (a = hi + lo to ~2^-22) and each product is three MMAs
 //     (lo*hi + hi*lo + hi*hi, fp32 accumulation in TMEM) - kind::f16, K = 16 per instruction;
-//   * weights are converted once per CTA into K-major SWIZZLE_NONE fp16 images in shared memory (B operand);
+//   * weights: K-major SWIZZLE_NONE fp16 hi/lo images + the small fp32 constants, prepared ONCE per weight update by
+//     gn_k2a_tc_prepare_kernel into a global buffer that each CTA copies verbatim into shared memory;
 //   * two tiles ("slots", 4 warps each) are in flight per CTA so one slot's MMAs run under the other slot's epilogue;
-//   * cross-view poolings are warp-shuffle loops exactly as in the SIMT kernel.
-// Operand layouts were validated on B200 with tools/tc_probe.cu (see profiles/tc_probe_r01.txt).
+//   * cross-view poolings go through a per-warp shared-memory scratch (write 36 values, V-strided partial sums, read back);
+//   * optionally (tok != NULL) geometry_fc (ibrnet.py:487-489: 86 -> 64 -> 16 on [mean, var, mean_v(w), embed(pts)]) runs
+//     as two more GEMMs on the pooled rows, so the per-ray kernel K2b only does attention + LayerNorm + output MLP.
+// Operand layouts were validated on B200 with tools/tc_probe.cu (profiles/tc_probe_r01.txt).
 #include "gn_common.cuh"
 #include "gn_weights.cuh"
 #include "../../include/graspnerf_b200.h"
@@ -27,12 +30,13 @@
 
 // ---- shared-memory B images (fp16, element (n,k) at (k/8)*(N*8) + n*8 + k%8) ------------------------------------
 struct TcLayer { int N, K; };
-enum { L_DD1, L_DD2M, L_DD2V, L_DD2A, L_PE0, L_PE2, L_NF0, L_RD0, L_RD1, L_BF0A, L_BF0B, L_BF2, L_VF0, L_VF2, L_V20, L_COUNT };
+enum { L_DD1, L_DD2M, L_DD2V, L_DD2A, L_PE0, L_PE2, L_NF0, L_RD0, L_RD1, L_BF0A, L_BF0B, L_BF2, L_VF0, L_VF2, L_V20, L_GF0, L_GF2, L_COUNT };
 __host__ __device__ constexpr TcLayer tc_layer(int i) {
     return i == L_DD1 ? TcLayer{96, 32} : i == L_DD2M ? TcLayer{32, 32} : i == L_DD2V ? TcLayer{32, 32} : i == L_DD2A ? TcLayer{32, 32}
          : i == L_PE0 ? TcLayer{32, 48} : i == L_PE2 ? TcLayer{32, 32} : i == L_NF0 ? TcLayer{16, 32} : i == L_RD0 ? TcLayer{16, 16}
          : i == L_RD1 ? TcLayer{48, 16} : i == L_BF0A ? TcLayer{64, 80} : i == L_BF0B ? TcLayer{64, 144} : i == L_BF2 ? TcLayer{32, 64}
-         : i == L_VF0 ? TcLayer{32, 32} : i == L_VF2 ? TcLayer{48, 32} : TcLayer{32, 32};
+         : i == L_VF0 ? TcLayer{32, 32} : i == L_VF2 ? TcLayer{48, 32} : i == L_V20 ? TcLayer{32, 32}
+         : i == L_GF0 ? TcLayer{64, 96} : TcLayer{16, 64};
 }
 __host__ __device__ constexpr int tc_img_off(int i) {          // offset in halves of the HI image; LO follows at +N*K
     int o = 0;
@@ -40,10 +44,30 @@ __host__ __device__ constexpr int tc_img_off(int i) {          // offset in halv
     return o;
 }
 constexpr int TC_IMG_HALVES = tc_img_off(L_COUNT);
-// biases and the few CUDA-core weights (third dist-decoder layers, neuray_fc.2, vis_fc2.2, rgb_fc) are read straight from
-// the fp32 blob in global memory: warp-uniform addresses, a couple of KB that stay in L1.
-constexpr size_t TC_SMEM_BYTES = (size_t)TC_IMG_HALVES * 2 + 64;
-static_assert(TC_SMEM_BYTES <= 227 * 1024, "K2a-TC shared memory budget");
+
+// ---- small fp32 constants (biases + the CUDA-core layers), stored right after the images --------------------------
+constexpr int kTcSmall[] = {
+    GN_W_DD_MEAN_B0, GN_W_DD_VAR_B0, GN_W_DD_AW_B0, GN_W_DD_MEAN_B2, GN_W_DD_VAR_B2, GN_W_DD_AW_B2,
+    GN_W_DD_MEAN_W4, GN_W_DD_VAR_W4, GN_W_DD_AW_W4, GN_W_DD_MEAN_B4, GN_W_DD_VAR_B4, GN_W_DD_AW_B4,
+    GN_W_PE_B0, GN_W_PE_B2, GN_W_NF_B0, GN_W_NF_W2, GN_W_NF_B2, GN_W_RD_B0, GN_W_RD_B1, GN_W_BF_B0, GN_W_BF_B2,
+    GN_W_VF_B0, GN_W_VF_B2, GN_W_V2_B0, GN_W_V2_W2, GN_W_V2_B2,
+    GN_W_RF_W0, GN_W_RF_B0, GN_W_RF_W2, GN_W_RF_B2, GN_W_RF_W4, GN_W_RF_B4, GN_W_GF_B0, GN_W_GF_B2 };
+constexpr int kTcSmallCount = sizeof(kTcSmall) / sizeof(int);
+constexpr int ts_off_idx(int j) { int o = 0; for (int i = 0; i < j; ++i) o += gn_w_size(kTcSmall[i]); return o; }
+constexpr int ts_find(int id) { for (int i = 0; i < kTcSmallCount; ++i) if (kTcSmall[i] == id) return i; return -1; }
+template <int ID> struct TsOffT {
+    static_assert(ts_find(ID) >= 0, "entry is not in the small-constant list");
+    static constexpr int value = ts_off_idx(ts_find(ID));
+};
+constexpr int TC_SMALL_FLOATS = ts_off_idx(kTcSmallCount);
+#define TS(id) (TsOffT<GN_W_##id>::value)
+constexpr int TC_CONST_BYTES = TC_IMG_HALVES * 2 + TC_SMALL_FLOATS * 4;      // global "tc_const" buffer == its smem image
+static_assert(TC_CONST_BYTES % 16 == 0, "tc_const must be copyable with 16-byte loads");
+#define TC_POOL_STRIDE 44                                                     // floats per row of the pooling scratch
+__host__ __device__ constexpr size_t tc_smem_bytes(int G) {
+    return (size_t)TC_CONST_BYTES + (size_t)(TC_THREADS / 32) * (32 + G) * TC_POOL_STRIDE * 4 + 64;
+}
+static_assert(tc_smem_bytes(5) <= 227 * 1024, "K2a-TC shared memory budget at V = 6");
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -70,18 +94,26 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         if (it > (1u << 24)) __trap();
     }
 }
-__device__ __forceinline__ void tm_ld16(uint32_t taddr, float* y) {
-    uint32_t r[16];
+__device__ __forceinline__ void tm_ld16_issue(uint32_t taddr, uint32_t* r) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
                    "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]) : "r"(taddr));
+}
+__device__ __forceinline__ void tm_ld16_fence(uint32_t* r) {
+    // ties the loaded registers to a point AFTER tcgen05.wait::ld so no use can be scheduled above the wait
+    asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                      "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]) :: "memory");
+}
+// N accumulator columns -> registers: all loads in flight, ONE wait
+template <int N> __device__ __forceinline__ void tm_ld(uint32_t taddr, float* y) {
+    uint32_t r[N];
+#pragma unroll
+    for (int c = 0; c < N; c += 16) tm_ld16_issue(taddr + c, r + c);
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-    for (int i = 0; i < 16; ++i) y[i] = __uint_as_float(r[i]);
-}
-template <int N> __device__ __forceinline__ void tm_ld(uint32_t taddr, float* y) {
+    for (int c = 0; c < N; c += 16) tm_ld16_fence(r + c);
 #pragma unroll
-    for (int c = 0; c < N; c += 16) tm_ld16(taddr + c, y + c);
+    for (int i = 0; i < N; ++i) y[i] = __uint_as_float(r[i]);
 }
 __device__ __forceinline__ void tm_st8(uint32_t taddr, const uint32_t* r) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
@@ -103,6 +135,27 @@ template <int K> __device__ __forceinline__ void tm_store_a(uint32_t slot_lane_a
         }
         tm_st8(slot_lane_addr + TM_AHI + k0 / 2 + c, hi);
         tm_st8(slot_lane_addr + TM_ALO + k0 / 2 + c, lo);
+    }
+}
+// ELU with one MUFU: ex2.approx.ftz (rel. err 2^-22)
+__device__ __forceinline__ float tc_elu(float x) {
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 1.4426950408889634f));
+    return x > 0.f ? x : e - 1.f;
+}
+// y = elu(y + b)
+template <int N> __device__ __forceinline__ void bias_elu(const float* __restrict__ b, float* y) {
+#pragma unroll
+    for (int n = 0; n < N; n += 4) {
+        const float4 w = *reinterpret_cast<const float4*>(b + n);
+        y[n] = tc_elu(y[n] + w.x); y[n + 1] = tc_elu(y[n + 1] + w.y); y[n + 2] = tc_elu(y[n + 2] + w.z); y[n + 3] = tc_elu(y[n + 3] + w.w);
+    }
+}
+template <int N> __device__ __forceinline__ void add_bias(const float* __restrict__ b, float* y) {
+#pragma unroll
+    for (int n = 0; n < N; n += 4) {
+        const float4 w = *reinterpret_cast<const float4*>(b + n);
+        y[n] += w.x; y[n + 1] += w.y; y[n + 2] += w.z; y[n + 3] += w.w;
     }
 }
 
@@ -145,9 +198,32 @@ __device__ __forceinline__ void tc_issue(const TcCtx& cx, int d_col, int a_k0, b
     mbar_wait((cx).bar, (cx).parity); (cx).parity ^= 1u;                             \
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-// fp32 (k-major blob) -> fp16 hi/lo image block: rows [k_dst, k_dst+ksrc), cols [n_dst, n_dst+nsrc)
+// Cross-view sum of 36 per-row values through the warp's scratch: out[c] = sum over the V rows of my point of vals[c].
+// (summation order v = 0..V-1, like the shuffle loops of the SIMT kernel)
+__device__ __forceinline__ void pool36(float* scr, int lane, int g, int v, int gb, int V, bool lane_active, const float* vals, float* out)
+{
+    float* mine = scr + lane * TC_POOL_STRIDE;
+#pragma unroll
+    for (int c = 0; c < 36; c += 4) st4(mine + c, make_float4(vals[c], vals[c + 1], vals[c + 2], vals[c + 3]));
+    __syncwarp();
+    float* sums = scr + (32 + g) * TC_POOL_STRIDE;
+    for (int c = v; c < 36; c += V) {
+        float s = 0.f;
+        for (int jv = 0; jv < V; ++jv) s += scr[(gb + jv) * TC_POOL_STRIDE + c];
+        if (lane_active) sums[c] = s;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < 36; c += 4) {
+        const float4 t = *reinterpret_cast<const float4*>(sums + c);
+        out[c] = t.x; out[c + 1] = t.y; out[c + 2] = t.z; out[c + 3] = t.w;
+    }
+    __syncwarp();
+}
+
+// ---- prepare: fp32 blob -> [fp16 hi/lo images | small fp32 constants] in global memory ---------------------------------
 __device__ void tc_fill(__half* img, int N, int K, const float* __restrict__ src, int ksrc, int nsrc, int cp, int k_dst, int n_dst) {
-    for (int i = threadIdx.x; i < ksrc * nsrc; i += TC_THREADS) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ksrc * nsrc; i += gridDim.x * blockDim.x) {
         const int k = i / nsrc, n = i - k * nsrc;
         const float w = __ldg(src + k * cp + n);
         const __half hi = __float2half_rn(w);
@@ -158,13 +234,44 @@ __device__ void tc_fill(__half* img, int N, int K, const float* __restrict__ src
         img[N * K + off] = lo;
     }
 }
-
-template <int N> __device__ __forceinline__ void add_bias(const float* __restrict__ b, float* y) {
-#pragma unroll
-    for (int n = 0; n < N; n += 4) {
-        const float4 w = *reinterpret_cast<const float4*>(b + n);
-        y[n] += w.x; y[n + 1] += w.y; y[n + 2] += w.z; y[n + 3] += w.w;
-    }
+struct TcSmallPlan { int src[kTcSmallCount], n[kTcSmallCount], dst[kTcSmallCount]; };
+__global__ void gn_k2a_tc_prepare_kernel(const float* __restrict__ W, unsigned char* __restrict__ out, const TcSmallPlan plan)
+{
+    __half* s_img = reinterpret_cast<__half*>(out);               // caller zero-fills `out` first
+#define IMG(L) (s_img + tc_img_off(L))
+    tc_fill(IMG(L_DD1), 96, 32, W + GN_OFF(DD_MEAN_W0), 32, 32, 32, 0, 0);
+    tc_fill(IMG(L_DD1), 96, 32, W + GN_OFF(DD_VAR_W0), 32, 32, 32, 0, 32);
+    tc_fill(IMG(L_DD1), 96, 32, W + GN_OFF(DD_AW_W0), 32, 32, 32, 0, 64);
+    tc_fill(IMG(L_DD2M), 32, 32, W + GN_OFF(DD_MEAN_W2), 32, 32, 32, 0, 0);
+    tc_fill(IMG(L_DD2V), 32, 32, W + GN_OFF(DD_VAR_W2), 32, 32, 32, 0, 0);
+    tc_fill(IMG(L_DD2A), 32, 32, W + GN_OFF(DD_AW_W2), 32, 32, 32, 0, 0);
+    tc_fill(IMG(L_PE0), 32, 48, W + GN_OFF(PE_W0), 34, 32, 32, 0, 0);
+    tc_fill(IMG(L_PE2), 32, 32, W + GN_OFF(PE_W2), 32, 32, 32, 0, 0);
+    tc_fill(IMG(L_NF0), 16, 32, W + GN_OFF(NF_W0), 32, 8, 8, 0, 0);
+    tc_fill(IMG(L_RD0), 16, 16, W + GN_OFF(RD_W0), 4, 16, 16, 0, 0);
+    tc_fill(IMG(L_RD1), 48, 16, W + GN_OFF(RD_W1), 16, 36, 36, 0, 0);
+    tc_fill(IMG(L_BF0A), 64, 80, W + GN_OFF(BF_WF), 36, 64, 64, 0, 0);
+    tc_fill(IMG(L_BF0A), 64, 80, W + GN_OFF(BF_WP), 32, 64, 64, 48, 0);
+    // bf.wg rows are [mean0 36 | var0 36 | mean1 36 | var1 36]; image k order: m0[0..31] m1[0..31] v0[0..31] v1[0..31] tails
+    tc_fill(IMG(L_BF0B), 64, 144, W + GN_OFF(BF_WG) + 0 * 64, 32, 64, 64, 0, 0);
+    tc_fill(IMG(L_BF0B), 64, 144, W + GN_OFF(BF_WG) + 72 * 64, 32, 64, 64, 32, 0);
+    tc_fill(IMG(L_BF0B), 64, 144, W + GN_OFF(BF_WG) + 36 * 64, 32, 64, 64, 64, 0);
+    tc_fill(IMG(L_BF0B), 64, 144, W + GN_OFF(BF_WG) + 108 * 64, 32, 64, 64, 96, 0);
+    tc_fill(IMG(L_BF0B), 64, 144, W + GN_OFF(BF_WG) + 32 * 64, 3, 64, 64, 128, 0);
+    tc_fill(IMG(L_BF0B), 64, 144, W + GN_OFF(BF_WG) + 104 * 64, 3, 64, 64, 131, 0);
+    tc_fill(IMG(L_BF0B), 64, 144, W + GN_OFF(BF_WG) + 68 * 64, 3, 64, 64, 134, 0);
+    tc_fill(IMG(L_BF0B), 64, 144, W + GN_OFF(BF_WG) + 140 * 64, 3, 64, 64, 137, 0);
+    tc_fill(IMG(L_BF2), 32, 64, W + GN_OFF(BF_W2), 64, 32, 32, 0, 0);
+    tc_fill(IMG(L_VF0), 32, 32, W + GN_OFF(VF_W0), 32, 32, 32, 0, 0);
+    tc_fill(IMG(L_VF2), 48, 32, W + GN_OFF(VF_W2), 32, 36, 36, 0, 0);
+    tc_fill(IMG(L_V20), 32, 32, W + GN_OFF(V2_W0), 32, 32, 32, 0, 0);
+    tc_fill(IMG(L_GF0), 64, 96, W + GN_OFF(GF_W0), 86, 64, 64, 0, 0);
+    tc_fill(IMG(L_GF2), 16, 64, W + GN_OFF(GF_W2), 64, 16, 16, 0, 0);
+#undef IMG
+    float* small = reinterpret_cast<float*>(out + (size_t)TC_IMG_HALVES * 2);
+    for (int e = 0; e < kTcSmallCount; ++e)
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < plan.n[e]; i += gridDim.x * blockDim.x)
+            small[plan.dst[e] + i] = __ldg(W + plan.src[e] + i);
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -172,45 +279,18 @@ gn_k2a_tc_kernel(const __grid_constant__ GnK2aParams p, int num_tiles, int G)
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __half* s_img = reinterpret_cast<__half*>(smem_raw);
-    const float* __restrict__ sw = p.weights;                                              // fp32 blob (global, L1-resident constants)
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)TC_IMG_HALVES * 2);   // [2]
+    const float* sw = reinterpret_cast<const float*>(smem_raw + (size_t)TC_IMG_HALVES * 2);   // small fp32 constants, index with TS()
+    float* s_pool = reinterpret_cast<float*>(smem_raw + TC_CONST_BYTES);                       // [8 warps][(32+G)][44]
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_pool + (TC_THREADS / 32) * (32 + G) * TC_POOL_STRIDE);
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + TC_SLOTS);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int slot = warp >> 2;
-    // ---- one-time setup: fp32 blob copy, fp16 images, TMEM, mbarriers
-    for (int i = tid; i < TC_IMG_HALVES / 2; i += TC_THREADS) reinterpret_cast<uint32_t*>(s_img)[i] = 0u;
-    __syncthreads();
+    // ---- one-time setup: constants copy, TMEM, mbarriers
     {
-        const float* W = p.weights;
-#define IMG(L) (s_img + tc_img_off(L))
-        tc_fill(IMG(L_DD1), 96, 32, W + GN_OFF(DD_MEAN_W0), 32, 32, 32, 0, 0);
-        tc_fill(IMG(L_DD1), 96, 32, W + GN_OFF(DD_VAR_W0), 32, 32, 32, 0, 32);
-        tc_fill(IMG(L_DD1), 96, 32, W + GN_OFF(DD_AW_W0), 32, 32, 32, 0, 64);
-        tc_fill(IMG(L_DD2M), 32, 32, W + GN_OFF(DD_MEAN_W2), 32, 32, 32, 0, 0);
-        tc_fill(IMG(L_DD2V), 32, 32, W + GN_OFF(DD_VAR_W2), 32, 32, 32, 0, 0);
-        tc_fill(IMG(L_DD2A), 32, 32, W + GN_OFF(DD_AW_W2), 32, 32, 32, 0, 0);
-        tc_fill(IMG(L_PE0), 32, 48, W + GN_OFF(PE_W0), 34, 32, 32, 0, 0);
-        tc_fill(IMG(L_PE2), 32, 32, W + GN_OFF(PE_W2), 32, 32, 32, 0, 0);
-        tc_fill(IMG(L_NF0), 16, 32, W + GN_OFF(NF_W0), 32, 8, 8, 0, 0);
-        tc_fill(IMG(L_RD0), 16, 16, W + GN_OFF(RD_W0), 4, 16, 16, 0, 0);
-        tc_fill(IMG(L_RD1), 48, 16, W + GN_OFF(RD_W1), 16, 36, 36, 0, 0);
-        tc_fill(IMG(L_BF0A), 64, 80, W + GN_OFF(BF_WF), 36, 64, 64, 0, 0);
-        tc_fill(IMG(L_BF0A), 64, 80, W + GN_OFF(BF_WP), 32, 64, 64, 48, 0);
-        // bf.wg rows are [mean0 36 | var0 36 | mean1 36 | var1 36]; image k order: m0[0..31] m1[0..31] v0[0..31] v1[0..31] tails
-        tc_fill(IMG(L_BF0B), 64, 144, W + GN_OFF(BF_WG) + 0 * 64, 32, 64, 64, 0, 0);
-        tc_fill(IMG(L_BF0B), 64, 144, W + GN_OFF(BF_WG) + 72 * 64, 32, 64, 64, 32, 0);
-        tc_fill(IMG(L_BF0B), 64, 144, W + GN_OFF(BF_WG) + 36 * 64, 32, 64, 64, 64, 0);
-        tc_fill(IMG(L_BF0B), 64, 144, W + GN_OFF(BF_WG) + 108 * 64, 32, 64, 64, 96, 0);
-        tc_fill(IMG(L_BF0B), 64, 144, W + GN_OFF(BF_WG) + 32 * 64, 3, 64, 64, 128, 0);
-        tc_fill(IMG(L_BF0B), 64, 144, W + GN_OFF(BF_WG) + 104 * 64, 3, 64, 64, 131, 0);
-        tc_fill(IMG(L_BF0B), 64, 144, W + GN_OFF(BF_WG) + 68 * 64, 3, 64, 64, 134, 0);
-        tc_fill(IMG(L_BF0B), 64, 144, W + GN_OFF(BF_WG) + 140 * 64, 3, 64, 64, 137, 0);
-        tc_fill(IMG(L_BF2), 32, 64, W + GN_OFF(BF_W2), 64, 32, 32, 0, 0);
-        tc_fill(IMG(L_VF0), 32, 32, W + GN_OFF(VF_W0), 32, 32, 32, 0, 0);
-        tc_fill(IMG(L_VF2), 48, 32, W + GN_OFF(VF_W2), 32, 36, 36, 0, 0);
-        tc_fill(IMG(L_V20), 32, 32, W + GN_OFF(V2_W0), 32, 32, 32, 0, 0);
-#undef IMG
+        const uint4* src = reinterpret_cast<const uint4*>(p.tc_const);
+        uint4* dst = reinterpret_cast<uint4*>(smem_raw);
+        for (int i = tid; i < TC_CONST_BYTES / 16; i += TC_THREADS) dst[i] = __ldg(src + i);
     }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(s_tmem)), "r"(512));
@@ -242,6 +322,7 @@ gn_k2a_tc_kernel(const __grid_constant__ GnK2aParams p, int num_tiles, int G)
     const int gb = g * V;
     const long long total_pts = (long long)p.B * p.N;
     const unsigned FULL = 0xffffffffu;
+    float* scr = s_pool + warp * (32 + G) * TC_POOL_STRIDE;
 
     for (int tile = blockIdx.x * TC_SLOTS + slot; tile < num_tiles; tile += gridDim.x * TC_SLOTS) {
         long long pidx = ((long long)tile * 4 + (warp & 3)) * G + g;
@@ -272,18 +353,9 @@ gn_k2a_tc_kernel(const __grid_constant__ GnK2aParams p, int num_tiles, int G)
         // ================= S2: second layers (block diagonal: three N=32,K=32 GEMMs) =====================
         {
             float h[32];
-            tm_ld<32>(cx.lane_addr + TM_D + 0, h);  add_bias<32>(sw + GN_OFF(DD_MEAN_B0), h);
-#pragma unroll
-            for (int c = 0; c < 32; ++c) h[c] = gn_elu(h[c]);
-            tm_store_a<32>(cx.lane_addr, 48, h);
-            tm_ld<32>(cx.lane_addr + TM_D + 32, h); add_bias<32>(sw + GN_OFF(DD_VAR_B0), h);
-#pragma unroll
-            for (int c = 0; c < 32; ++c) h[c] = gn_elu(h[c]);
-            tm_store_a<32>(cx.lane_addr, 80, h);
-            tm_ld<32>(cx.lane_addr + TM_D + 64, h); add_bias<32>(sw + GN_OFF(DD_AW_B0), h);
-#pragma unroll
-            for (int c = 0; c < 32; ++c) h[c] = gn_elu(h[c]);
-            tm_store_a<32>(cx.lane_addr, 112, h);
+            tm_ld<32>(cx.lane_addr + TM_D + 0, h);  bias_elu<32>(sw + TS(DD_MEAN_B0), h);  tm_store_a<32>(cx.lane_addr, 48, h);
+            tm_ld<32>(cx.lane_addr + TM_D + 32, h); bias_elu<32>(sw + TS(DD_VAR_B0), h);   tm_store_a<32>(cx.lane_addr, 80, h);
+            tm_ld<32>(cx.lane_addr + TM_D + 64, h); bias_elu<32>(sw + TS(DD_AW_B0), h);    tm_store_a<32>(cx.lane_addr, 112, h);
         }
         TC_GEMM_BEGIN(cx)
             tc_issue<L_DD2M>(cx, 0, 48, false); tc_issue<L_DD2V>(cx, 32, 80, false); tc_issue<L_DD2A>(cx, 64, 112, false);
@@ -291,30 +363,22 @@ gn_k2a_tc_kernel(const __grid_constant__ GnK2aParams p, int num_tiles, int G)
         // ================= third layers on CUDA cores, compute_prob (dist_decoder.py:109-142) ============
         float hit, vis;
         {
-            float h[32], om[4], ov[4], oa[4];
-            tm_ld<32>(cx.lane_addr + TM_D + 0, h);  add_bias<32>(sw + GN_OFF(DD_MEAN_B2), h);
+            float h[32], om0, om1, ov0, ov1, oa;
+            tm_ld<32>(cx.lane_addr + TM_D + 0, h);  bias_elu<32>(sw + TS(DD_MEAN_B2), h);
+            om0 = sw[TS(DD_MEAN_B4)]; om1 = sw[TS(DD_MEAN_B4) + 1];
 #pragma unroll
-            for (int c = 0; c < 32; ++c) h[c] = gn_elu(h[c]);
+            for (int k = 0; k < 32; ++k) { const float2 w = *reinterpret_cast<const float2*>(sw + TS(DD_MEAN_W4) + k * 4); om0 = fmaf(h[k], w.x, om0); om1 = fmaf(h[k], w.y, om1); }
+            tm_ld<32>(cx.lane_addr + TM_D + 32, h); bias_elu<32>(sw + TS(DD_VAR_B2), h);
+            ov0 = sw[TS(DD_VAR_B4)]; ov1 = sw[TS(DD_VAR_B4) + 1];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) om[q] = sw[GN_OFF(DD_MEAN_B4) + q];
+            for (int k = 0; k < 32; ++k) { const float2 w = *reinterpret_cast<const float2*>(sw + TS(DD_VAR_W4) + k * 4); ov0 = fmaf(h[k], w.x, ov0); ov1 = fmaf(h[k], w.y, ov1); }
+            tm_ld<32>(cx.lane_addr + TM_D + 64, h); bias_elu<32>(sw + TS(DD_AW_B2), h);
+            oa = sw[TS(DD_AW_B4)];
 #pragma unroll
-            for (int k = 0; k < 32; ++k) { const float4 w = *reinterpret_cast<const float4*>(sw + GN_OFF(DD_MEAN_W4) + k * 4); om[0] = fmaf(h[k], w.x, om[0]); om[1] = fmaf(h[k], w.y, om[1]); }
-            tm_ld<32>(cx.lane_addr + TM_D + 32, h); add_bias<32>(sw + GN_OFF(DD_VAR_B2), h);
-#pragma unroll
-            for (int c = 0; c < 32; ++c) h[c] = gn_elu(h[c]);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) ov[q] = sw[GN_OFF(DD_VAR_B4) + q];
-#pragma unroll
-            for (int k = 0; k < 32; ++k) { const float4 w = *reinterpret_cast<const float4*>(sw + GN_OFF(DD_VAR_W4) + k * 4); ov[0] = fmaf(h[k], w.x, ov[0]); ov[1] = fmaf(h[k], w.y, ov[1]); }
-            tm_ld<32>(cx.lane_addr + TM_D + 64, h); add_bias<32>(sw + GN_OFF(DD_AW_B2), h);
-#pragma unroll
-            for (int c = 0; c < 32; ++c) h[c] = gn_elu(h[c]);
-            oa[0] = sw[GN_OFF(DD_AW_B4)];
-#pragma unroll
-            for (int k = 0; k < 32; ++k) oa[0] = fmaf(h[k], sw[GN_OFF(DD_AW_W4) + k * 4], oa[0]);
-            const float mean0 = gn_softplus(om[0]), mean1 = gn_softplus(om[1]);
-            const float var0 = gn_softplus(ov[0]) + 0.05f, var1 = gn_softplus(ov[1]) + 0.05f;
-            const float aw = gn_sigmoid(oa[0]);
+            for (int k = 0; k < 32; ++k) oa = fmaf(h[k], sw[TS(DD_AW_W4) + k * 4], oa);
+            const float mean0 = gn_softplus(om0), mean1 = gn_softplus(om1);
+            const float var0 = gn_softplus(ov0) + 0.05f, var1 = gn_softplus(ov1) + 0.05f;
+            const float aw = gn_sigmoid(oa);
             const float* dr = p.depth_range + ((size_t)b * V + v) * 2;
             const float rnear = __fdiv_rn(-1.f, __ldg(dr)), rfar = __fdiv_rn(-1.f, __ldg(dr + 1));
             float d = __fdiv_rn(-1.f, fmaxf(depth, 1e-5f));
@@ -346,7 +410,7 @@ gn_k2a_tc_kernel(const __grid_constant__ GnK2aParams p, int num_tiles, int G)
         // ================= S4: prob_embed.2 ===============================================================
         {
             float e1[32];
-            tm_ld<32>(cx.lane_addr + TM_D, e1); add_bias<32>(sw + GN_OFF(PE_B0), e1);
+            tm_ld<32>(cx.lane_addr + TM_D, e1); add_bias<32>(sw + TS(PE_B0), e1);
 #pragma unroll
             for (int c = 0; c < 32; ++c) e1[c] = fmaxf(e1[c], 0.f);
             tm_store_a<32>(cx.lane_addr, 80, e1);
@@ -356,7 +420,7 @@ gn_k2a_tc_kernel(const __grid_constant__ GnK2aParams p, int num_tiles, int G)
         float pe01[2];
         {
             float pe[32];
-            tm_ld<32>(cx.lane_addr + TM_D, pe); add_bias<32>(sw + GN_OFF(PE_B2), pe);
+            tm_ld<32>(cx.lane_addr + TM_D, pe); add_bias<32>(sw + TS(PE_B2), pe);
             pe01[0] = pe[0]; pe01[1] = pe[1];
             tm_store_a<32>(cx.lane_addr, 48, pe);               // stays at k 48..79 for base_fc (S7a)
             float dd[16];
@@ -371,38 +435,36 @@ gn_k2a_tc_kernel(const __grid_constant__ GnK2aParams p, int num_tiles, int G)
         {
             float t[32];
             tm_ld<32>(cx.lane_addr + TM_D, t);
-            float s = sw[GN_OFF(NF_B2)];
+            float s = sw[TS(NF_B2)];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) s = fmaf(gn_elu(t[k] + sw[GN_OFF(NF_B0) + k]), sw[GN_OFF(NF_W2) + k], s);
+            for (int k = 0; k < 8; ++k) s = fmaf(tc_elu(t[k] + sw[TS(NF_B0) + k]), sw[TS(NF_W2) + k], s);
             w0 = gn_sigmoid(s) * wgt;                           // ibrnet.py:469
             float hid[16];
 #pragma unroll
-            for (int k = 0; k < 16; ++k) hid[k] = gn_elu(t[16 + k] + sw[GN_OFF(RD_B0) + k]);
+            for (int k = 0; k < 16; ++k) hid[k] = tc_elu(t[16 + k] + sw[TS(RD_B0) + k]);
             tm_store_a<16>(cx.lane_addr, 128, hid);
         }
         TC_GEMM_BEGIN(cx) tc_issue<L_RD1>(cx, 0, 128, false); TC_GEMM_END(cx)
-        // ================= f = feats + direction feature; mean/var poolings; S7a ==========================
-        float g0[36], g1[36];
+        // ================= f = feats + direction feature; mean/var poolings; S7a, S7b =======================
         {
-            float f[48];
-            tm_ld<48>(cx.lane_addr + TM_D, f); add_bias<36>(sw + GN_OFF(RD_B1), f);
+            float f[48], g0[36], g1[36], tmp[36];
+            tm_ld<48>(cx.lane_addr + TM_D, f); bias_elu<36>(sw + TS(RD_B1), f);
 #pragma unroll
             for (int c = 0; c < 32; c += 4) {
                 const float4 t = ldg4(row + GN_REC_IMGF + c);
-                f[c] = gn_elu(f[c]) + t.x; f[c + 1] = gn_elu(f[c + 1]) + t.y; f[c + 2] = gn_elu(f[c + 2]) + t.z; f[c + 3] = gn_elu(f[c + 3]) + t.w;
+                f[c] += t.x; f[c + 1] += t.y; f[c + 2] += t.z; f[c + 3] += t.w;     // ibrnet.py:459
             }
-            f[32] = gn_elu(f[32]) + tail.x; f[33] = gn_elu(f[33]) + tail.y; f[34] = gn_elu(f[34]) + tail.z;
+            f[32] += tail.x; f[33] += tail.y; f[34] += tail.z;
 #pragma unroll
             for (int c = 35; c < 48; ++c) f[c] = 0.f;
             tm_store_a<48>(cx.lane_addr, 0, f);                 // A[k 0..47] = f (ray_feats no longer needed)
+            // ibrnet.py:470-471 means
 #pragma unroll
-            for (int c = 0; c < 35; ++c) {                      // ibrnet.py:470-471 means
-                const float t0 = w0 * f[c], t1 = wgt * f[c];
-                float s0 = 0.f, s1 = 0.f;
-                for (int jv = 0; jv < V; ++jv) { s0 += __shfl_sync(FULL, t0, (gb + jv) & 31); s1 += __shfl_sync(FULL, t1, (gb + jv) & 31); }
-                g0[c] = s0; g1[c] = s1;
-            }
-            g0[35] = 0.f; g1[35] = 0.f;
+            for (int c = 0; c < 36; ++c) tmp[c] = w0 * f[c];
+            pool36(scr, lane, g, v, gb, V, lane_active, tmp, g0);
+#pragma unroll
+            for (int c = 0; c < 36; ++c) tmp[c] = wgt * f[c];
+            pool36(scr, lane, g, v, gb, V, lane_active, tmp, g1);
             TC_GEMM_BEGIN(cx) tc_issue<L_BF0A>(cx, 0, 0, false); TC_GEMM_END(cx)
             // S7b operand, k layout: mean0[0..31] | mean1[0..31] | var0[0..31] | var1[0..31] | tails (channels 32..34 of the four)
             tm_store_a<32>(cx.lane_addr, 0, g0);
@@ -411,13 +473,11 @@ gn_k2a_tc_kernel(const __grid_constant__ GnK2aParams p, int num_tiles, int G)
 #pragma unroll
             for (int c = 0; c < 3; ++c) { tl[c] = g0[32 + c]; tl[3 + c] = g1[32 + c]; }
 #pragma unroll
-            for (int c = 0; c < 35; ++c) {                      // variances in place (ibrnet.py:115)
-                const float d0 = f[c] - g0[c], d1 = f[c] - g1[c];
-                const float t0 = w0 * d0 * d0, t1 = wgt * d1 * d1;
-                float s0 = 0.f, s1 = 0.f;
-                for (int jv = 0; jv < V; ++jv) { s0 += __shfl_sync(FULL, t0, (gb + jv) & 31); s1 += __shfl_sync(FULL, t1, (gb + jv) & 31); }
-                g0[c] = s0; g1[c] = s1;
-            }
+            for (int c = 0; c < 36; ++c) { const float d0 = f[c] - g0[c]; tmp[c] = w0 * d0 * d0; }      // ibrnet.py:115
+            pool36(scr, lane, g, v, gb, V, lane_active, tmp, g0);
+#pragma unroll
+            for (int c = 0; c < 36; ++c) { const float d1 = f[c] - g1[c]; tmp[c] = wgt * d1 * d1; }
+            pool36(scr, lane, g, v, gb, V, lane_active, tmp, g1);
             tm_store_a<32>(cx.lane_addr, 64, g0);
             tm_store_a<32>(cx.lane_addr, 96, g1);
 #pragma unroll
@@ -429,17 +489,14 @@ gn_k2a_tc_kernel(const __grid_constant__ GnK2aParams p, int num_tiles, int G)
         // ================= S8: base_fc.2 ====================================================================
         {
             float y[64];
-            tm_ld<64>(cx.lane_addr + TM_D, y); add_bias<64>(sw + GN_OFF(BF_B0), y);
-#pragma unroll
-            for (int c = 0; c < 64; ++c) y[c] = gn_elu(y[c]);
+            tm_ld<64>(cx.lane_addr + TM_D, y); bias_elu<64>(sw + TS(BF_B0), y);
             tm_store_a<64>(cx.lane_addr, 0, y);
         }
         TC_GEMM_BEGIN(cx) tc_issue<L_BF2>(cx, 0, 0, false); TC_GEMM_END(cx)
         // ================= S9/S10: vis_fc ====================================================================
-        float x[32];
-        tm_ld<32>(cx.lane_addr + TM_D, x); add_bias<32>(sw + GN_OFF(BF_B2), x);
-#pragma unroll
-        for (int c = 0; c < 32; ++c) x[c] = gn_elu(x[c]);
+        float x[36];
+        tm_ld<32>(cx.lane_addr + TM_D, x); bias_elu<32>(sw + TS(BF_B2), x);
+        x[32] = 0.f; x[33] = 0.f; x[34] = 0.f; x[35] = 0.f;
         {
             float xi[32];
 #pragma unroll
@@ -449,19 +506,16 @@ gn_k2a_tc_kernel(const __grid_constant__ GnK2aParams p, int num_tiles, int G)
         TC_GEMM_BEGIN(cx) tc_issue<L_VF0>(cx, 0, 64, false); TC_GEMM_END(cx)
         {
             float t[32];
-            tm_ld<32>(cx.lane_addr + TM_D, t); add_bias<32>(sw + GN_OFF(VF_B0), t);
-#pragma unroll
-            for (int c = 0; c < 32; ++c) t[c] = gn_elu(t[c]);
+            tm_ld<32>(cx.lane_addr + TM_D, t); bias_elu<32>(sw + TS(VF_B0), t);
             tm_store_a<32>(cx.lane_addr, 96, t);
         }
         TC_GEMM_BEGIN(cx) tc_issue<L_VF2>(cx, 0, 96, false); TC_GEMM_END(cx)
-        float visw;
         {
             float xv[48];
-            tm_ld<48>(cx.lane_addr + TM_D, xv); add_bias<36>(sw + GN_OFF(VF_B2), xv);
+            tm_ld<48>(cx.lane_addr + TM_D, xv); bias_elu<36>(sw + TS(VF_B2), xv);
 #pragma unroll
-            for (int c = 0; c < 32; ++c) x[c] += gn_elu(xv[c]);
-            visw = gn_sigmoid(gn_elu(xv[32])) * mask;           // ibrnet.py:478-479
+            for (int c = 0; c < 32; ++c) x[c] += xv[c];
+            const float visw = gn_sigmoid(xv[32]) * mask;       // ibrnet.py:478-479
             float xi[32];
 #pragma unroll
             for (int c = 0; c < 32; ++c) xi[c] = x[c] * visw;
@@ -472,10 +526,10 @@ gn_k2a_tc_kernel(const __grid_constant__ GnK2aParams p, int num_tiles, int G)
         float vis2;
         {
             float t[32];
-            tm_ld<32>(cx.lane_addr + TM_D, t); add_bias<32>(sw + GN_OFF(V2_B0), t);
-            float s = sw[GN_OFF(V2_B2)];
+            tm_ld<32>(cx.lane_addr + TM_D, t); bias_elu<32>(sw + TS(V2_B0), t);
+            float s = sw[TS(V2_B2)];
 #pragma unroll
-            for (int k = 0; k < 32; ++k) s = fmaf(gn_elu(t[k]), sw[GN_OFF(V2_W2) + k], s);
+            for (int k = 0; k < 32; ++k) s = fmaf(t[k], sw[TS(V2_W2) + k], s);
             vis2 = gn_sigmoid(s) * mask;
         }
         // ================= final pooling (ibrnet.py:482-484,487) ===============================================
@@ -484,60 +538,104 @@ gn_k2a_tc_kernel(const __grid_constant__ GnK2aParams p, int num_tiles, int G)
         const float w2 = __fdiv_rn(vis2, ssum + 1e-8f);
         float w2sum = 0.f;
         for (int jv = 0; jv < V; ++jv) w2sum += __shfl_sync(FULL, w2, (gb + jv) & 31);
-        float* out = p.pooled + (size_t)pidx * GN_POOL_STRIDE;
+        const float wmean = w2sum / (float)V;
         const bool writer = valid && v == 0;
+        float mu[36], vr[36];
+        {
+            float tmp[36];
 #pragma unroll
-        for (int c = 0; c < 32; c += 4) {
-            float mu[4], vr[4];
+            for (int c = 0; c < 36; ++c) tmp[c] = w2 * x[c];
+            pool36(scr, lane, g, v, gb, V, lane_active, tmp, mu);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const float t = w2 * x[c + q];
-                float s = 0.f;
-                for (int jv = 0; jv < V; ++jv) s += __shfl_sync(FULL, t, (gb + jv) & 31);
-                mu[q] = s;
-                const float dlt = x[c + q] - s;
-                const float t2 = w2 * dlt * dlt;
-                float s2 = 0.f;
-                for (int jv = 0; jv < V; ++jv) s2 += __shfl_sync(FULL, t2, (gb + jv) & 31);
-                vr[q] = s2;
-            }
-            if (writer) {
-                st4(out + c, make_float4(mu[0], mu[1], mu[2], mu[3]));
-                st4(out + 32 + c, make_float4(vr[0], vr[1], vr[2], vr[3]));
-            }
+            for (int c = 0; c < 36; ++c) { const float dl = x[c] - mu[c]; tmp[c] = w2 * dl * dl; }
+            pool36(scr, lane, g, v, gb, V, lane_active, tmp, vr);
         }
-        if (writer) st4(out + 64, make_float4(w2sum / (float)V, nvalid, 0.f, 0.f));
+        if (p.pooled && writer) {
+            float* out = p.pooled + (size_t)pidx * GN_POOL_STRIDE;
+#pragma unroll
+            for (int c = 0; c < 32; c += 4) {
+                st4(out + c, make_float4(mu[c], mu[c + 1], mu[c + 2], mu[c + 3]));
+                st4(out + 32 + c, make_float4(vr[c], vr[c + 1], vr[c + 2], vr[c + 3]));
+            }
+            st4(out + 64, make_float4(wmean, nvalid, 0.f, 0.f));
+        }
         if (p.dbg_rows && valid) {
             float* dr = p.dbg_rows + ((size_t)pidx * V + v) * 8;
             st4(dr, make_float4(hit, vis, w0, vis2));
             st4(dr + 4, make_float4(x[0], x[1], pe01[0], pe01[1]));
         }
+        // ================= geometry_fc on the pooled rows (ibrnet.py:487-489) -> per-point token =================
+        if (p.tok) {            // uniform branch
+            tm_store_a<32>(cx.lane_addr, 0, mu);
+            tm_store_a<32>(cx.lane_addr, 32, vr);
+            {
+                float e[32];
+                float px, py, pz;
+                if (p.volume_mode) {   // same arithmetic as K1 (field_utils.py:17-27 + bbox3d[0]); n = (i*R+j)*R + (R-1-k)
+                    const int R = p.R;
+                    const int r = n / R, dsm = n - r * R;
+                    const int i = r / R, j = r - i * R, k = R - 1 - dsm;
+                    px = __fadd_rn(__ldg(p.axis + i), __ldg(p.bbox_min + b * 3 + 0));
+                    py = __fadd_rn(__ldg(p.axis + j), __ldg(p.bbox_min + b * 3 + 1));
+                    pz = __fadd_rn(__ldg(p.axis + k), __ldg(p.bbox_min + b * 3 + 2));
+                } else {
+                    const float* q = p.pts + (size_t)pidx * 3;
+                    px = __ldg(q); py = __ldg(q + 1); pz = __ldg(q + 2);
+                }
+                const float pv[3] = { px, py, pz };
+                e[0] = wmean; e[1] = px; e[2] = py; e[3] = pz;                 // k 64 | embed (neus.py:21-66): p, sin/cos(p*{1,2,4})
+#pragma unroll
+                for (int q = 0; q < 3; ++q)
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) sincosf(pv[a] * (float)(1 << q), &e[4 + 6 * q + a], &e[4 + 6 * q + 3 + a]);
+#pragma unroll
+                for (int c = 22; c < 32; ++c) e[c] = 0.f;
+                tm_store_a<32>(cx.lane_addr, 64, e);
+            }
+            TC_GEMM_BEGIN(cx) tc_issue<L_GF0>(cx, 0, 0, false); TC_GEMM_END(cx)
+            {
+                float y[64];
+                tm_ld<64>(cx.lane_addr + TM_D, y); bias_elu<64>(sw + TS(GF_B0), y);
+                tm_store_a<64>(cx.lane_addr, 0, y);
+            }
+            TC_GEMM_BEGIN(cx) tc_issue<L_GF2>(cx, 0, 0, false); TC_GEMM_END(cx)
+            {
+                float t[16];
+                tm_ld<16>(cx.lane_addr + TM_D, t); bias_elu<16>(sw + TS(GF_B2), t);
+                if (writer) {
+                    float* out = p.tok + (size_t)pidx * GN_TOK_STRIDE;
+                    st4(out, make_float4(t[0], t[1], t[2], t[3]));       st4(out + 4, make_float4(t[4], t[5], t[6], t[7]));
+                    st4(out + 8, make_float4(t[8], t[9], t[10], t[11])); st4(out + 12, make_float4(t[12], t[13], t[14], t[15]));
+                    st4(out + 16, make_float4(nvalid, 0.f, 0.f, 0.f));
+                }
+            }
+        }
         // ================= rgb_fc + masked softmax over views (ibrnet.py:507-511), CUDA cores ================
         if (p.with_rgb && p.colors) {
             float r16[16], r8[8];
 #pragma unroll
-            for (int c = 0; c < 16; ++c) r16[c] = sw[GN_OFF(RF_B0) + c];
+            for (int c = 0; c < 16; ++c) r16[c] = sw[TS(RF_B0) + c];
             const float dd4[5] = { vis2, ddv.x, ddv.y, ddv.z, ddv.w };
 #pragma unroll
             for (int k = 0; k < 37; ++k) {
                 const float xk = k < 32 ? x[k] : dd4[k - 32];
 #pragma unroll
                 for (int c = 0; c < 16; c += 4) {
-                    const float4 w = *reinterpret_cast<const float4*>(sw + GN_OFF(RF_W0) + k * 16 + c);
+                    const float4 w = *reinterpret_cast<const float4*>(sw + TS(RF_W0) + k * 16 + c);
                     r16[c] = fmaf(xk, w.x, r16[c]); r16[c + 1] = fmaf(xk, w.y, r16[c + 1]); r16[c + 2] = fmaf(xk, w.z, r16[c + 2]); r16[c + 3] = fmaf(xk, w.w, r16[c + 3]);
                 }
             }
 #pragma unroll
-            for (int c = 0; c < 8; ++c) r8[c] = sw[GN_OFF(RF_B2) + c];
+            for (int c = 0; c < 8; ++c) r8[c] = sw[TS(RF_B2) + c];
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
-                const float xk = gn_elu(r16[k]);
+                const float xk = tc_elu(r16[k]);
 #pragma unroll
-                for (int c = 0; c < 8; ++c) r8[c] = fmaf(xk, sw[GN_OFF(RF_W2) + k * 8 + c], r8[c]);
+                for (int c = 0; c < 8; ++c) r8[c] = fmaf(xk, sw[TS(RF_W2) + k * 8 + c], r8[c]);
             }
-            float logit = sw[GN_OFF(RF_B4)];
+            float logit = sw[TS(RF_B4)];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) logit = fmaf(gn_elu(r8[k]), sw[GN_OFF(RF_W4) + k], logit);
+            for (int k = 0; k < 8; ++k) logit = fmaf(tc_elu(r8[k]), sw[TS(RF_W4) + k], logit);
             if (mask == 0.f) logit = -1e9f;
             float mx = -INFINITY;
             for (int jv = 0; jv < V; ++jv) mx = fmaxf(mx, __shfl_sync(FULL, logit, (gb + jv) & 31));
@@ -560,23 +658,42 @@ gn_k2a_tc_kernel(const __grid_constant__ GnK2aParams p, int num_tiles, int G)
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(*s_tmem), "r"(512));
 }
 
+extern "C" int gn_k2a_tc_const_bytes(void) { return TC_CONST_BYTES; }
+
+extern "C" int gn_k2a_tc_prepare(const float* weights, void* tc_const, void* stream)
+{
+    cudaError_t e = cudaMemsetAsync(tc_const, 0, TC_CONST_BYTES, (cudaStream_t)stream);
+    if (e != cudaSuccess) return (int)e;
+    TcSmallPlan plan;
+    for (int i = 0; i < kTcSmallCount; ++i) { plan.src[i] = gn_w_off(kTcSmall[i]); plan.n[i] = gn_w_size(kTcSmall[i]); plan.dst[i] = ts_off_idx(i); }
+    gn_k2a_tc_prepare_kernel<<<32, 256, 0, (cudaStream_t)stream>>>(weights, reinterpret_cast<unsigned char*>(tc_const), plan);
+    return (int)cudaGetLastError();
+}
+
 extern "C" int gn_k2a_forward_tc(const GnK2aParams* hp, void* stream)
 {
     const GnK2aParams& p = *hp;
-    if (p.V < 1 || p.V > 32 || p.B < 1 || p.N < 1) return -1;
+    if (p.V < 2 || p.V > 32 || p.B < 1 || p.N < 1) return -1;
     if (p.que_dists && (p.dn < 1 || (p.N % p.dn) != 0)) return -4;
+    if (!p.tc_const) return -7;
+    if (p.tok) {
+        if (p.volume_mode && (p.R < 1 || p.N != p.R * p.R * p.R || !p.axis || !p.bbox_min)) return -3;
+        if (!p.volume_mode && !p.pts) return -4;
+    }
     const int G = 32 / p.V;
     const long long total = (long long)p.B * p.N;
     const long long per_tile = 4LL * G;
     const long long tiles = (total + per_tile - 1) / per_tile;
     if (tiles > 0x7fffffffLL) return -6;
-    cudaError_t e = cudaFuncSetAttribute(gn_k2a_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES);
+    const size_t smem = tc_smem_bytes(G);
+    if (smem > 227 * 1024) return -5;
+    cudaError_t e = cudaFuncSetAttribute(gn_k2a_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long long want = (tiles + TC_SLOTS - 1) / TC_SLOTS;
     const int grid = (int)(want < sms ? want : sms);
-    gn_k2a_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, (cudaStream_t)stream>>>(p, (int)tiles, G);
+    gn_k2a_tc_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(p, (int)tiles, G);
     return (int)cudaGetLastError();
 }

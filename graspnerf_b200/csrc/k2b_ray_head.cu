@@ -348,16 +348,159 @@ gn_k2b_kernel(const __grid_constant__ GnK2bParams p, int rpb)
     }
 }
 
+// Attention-only variant: the geometry_fc output (post-ELU, before the positional table) arrives from K2a's GEMM chain
+// as tok[B,N,20]; this kernel does +pos, q/k/v, 4-head attention over the ray's samples, fc + residual, LayerNorm,
+// out_geometry_fc, clip and the invalid fill (ibrnet.py:491-495).  No gradient path (volume mode / sdf_only).
+#define K2B_AT_OFF (GN_OFF(AT_WQ) - GN_W_K2B_OFF)
+#define K2B_AT_FLOATS (GN_W_K2B_FLOATS - K2B_AT_OFF)
+#define WA(id) (GN_OFF(id) - GN_OFF(AT_WQ))
+__global__ void __launch_bounds__(K2B_THREADS, 4)
+gn_k2b_attn_kernel(const __grid_constant__ GnK2bParams p, int rpb)
+{
+    __shared__ __align__(16) float sw[K2B_AT_FLOATS];
+    __shared__ __align__(16) float sK[K2B_THREADS * 16];
+    __shared__ __align__(16) float sV[K2B_THREADS * 16];
+    for (int i = threadIdx.x * 4; i < K2B_AT_FLOATS; i += K2B_THREADS * 4)
+        *reinterpret_cast<float4*>(sw + i) = ldg4(p.weights + GN_OFF(AT_WQ) + i);
+    const int t = threadIdx.x;
+    const int dn = p.dn;
+    const int rn = p.N / dn;
+    const int rl = t / dn, d = t - rl * dn;
+    const long long ray = (long long)blockIdx.x * rpb + rl;
+    const bool valid = (rl < rpb) && (ray < (long long)p.B * rn);
+    const long long rayc = valid ? ray : 0;
+    const int b = (int)(rayc / rn), r = (int)(rayc - (long long)b * rn);
+    const size_t pidx = (size_t)b * p.N + (size_t)r * dn + d;
+    const int t0 = (rl < rpb) ? rl * dn : 0;
+    float tok[16];
+    float nvalid;
+    {
+        const float* tp = p.tok + pidx * GN_TOK_STRIDE;
+#pragma unroll
+        for (int c = 0; c < 16; c += 4) {
+            const float4 q = ldg4(tp + c);
+            const float4 ps = ldg4(p.pos_table + d * 16 + c);
+            tok[c] = q.x + ps.x; tok[c + 1] = q.y + ps.y; tok[c + 2] = q.z + ps.z; tok[c + 3] = q.w + ps.w;   // ibrnet.py:491
+        }
+        nvalid = __ldg(tp + 16);
+    }
+    __syncthreads();
+    float q[16], kk[16], vv[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) { q[c] = 0.f; kk[c] = 0.f; vv[c] = 0.f; }
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const float xk = tok[k];
+#pragma unroll
+        for (int c = 0; c < 16; c += 4) {
+            const float4 wq = *reinterpret_cast<const float4*>(sw + WA(AT_WQ) + k * 16 + c);
+            const float4 wk = *reinterpret_cast<const float4*>(sw + WA(AT_WK) + k * 16 + c);
+            const float4 wv = *reinterpret_cast<const float4*>(sw + WA(AT_WV) + k * 16 + c);
+            q[c] = fmaf(xk, wq.x, q[c]); q[c + 1] = fmaf(xk, wq.y, q[c + 1]); q[c + 2] = fmaf(xk, wq.z, q[c + 2]); q[c + 3] = fmaf(xk, wq.w, q[c + 3]);
+            kk[c] = fmaf(xk, wk.x, kk[c]); kk[c + 1] = fmaf(xk, wk.y, kk[c + 1]); kk[c + 2] = fmaf(xk, wk.z, kk[c + 2]); kk[c + 3] = fmaf(xk, wk.w, kk[c + 3]);
+            vv[c] = fmaf(xk, wv.x, vv[c]); vv[c + 1] = fmaf(xk, wv.y, vv[c + 1]); vv[c + 2] = fmaf(xk, wv.z, vv[c + 2]); vv[c + 3] = fmaf(xk, wv.w, vv[c + 3]);
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 16; c += 4) {
+        q[c] = q[c] / 2.0f; q[c + 1] = q[c + 1] / 2.0f; q[c + 2] = q[c + 2] / 2.0f; q[c + 3] = q[c + 3] / 2.0f;     // temperature d_k^0.5 = 2
+        st4(sK + t * 16 + c, make_float4(kk[c], kk[c + 1], kk[c + 2], kk[c + 3]));
+        st4(sV + t * 16 + c, make_float4(vv[c], vv[c + 1], vv[c + 2], vv[c + 3]));
+    }
+    __syncthreads();
+    const bool qmask = nvalid > 1.f;
+    float o[16];
+    const float puni = 1.0f / (float)dn;
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        if (!qmask) {
+            for (int jj = 0; jj < dn; ++jj) {
+                const float4 vj = *reinterpret_cast<const float4*>(sV + (t0 + jj) * 16 + 4 * h);
+                a0 = fmaf(puni, vj.x, a0); a1 = fmaf(puni, vj.y, a1); a2 = fmaf(puni, vj.z, a2); a3 = fmaf(puni, vj.w, a3);
+            }
+        } else {
+            float m = -INFINITY;
+            for (int jj = 0; jj < dn; ++jj) {
+                const float4 kj = *reinterpret_cast<const float4*>(sK + (t0 + jj) * 16 + 4 * h);
+                m = fmaxf(m, fmaf(q[4 * h + 3], kj.w, fmaf(q[4 * h + 2], kj.z, fmaf(q[4 * h + 1], kj.y, q[4 * h] * kj.x))));
+            }
+            float z = 0.f;
+            for (int jj = 0; jj < dn; ++jj) {
+                const float4 kj = *reinterpret_cast<const float4*>(sK + (t0 + jj) * 16 + 4 * h);
+                const float4 vj = *reinterpret_cast<const float4*>(sV + (t0 + jj) * 16 + 4 * h);
+                const float s = fmaf(q[4 * h + 3], kj.w, fmaf(q[4 * h + 2], kj.z, fmaf(q[4 * h + 1], kj.y, q[4 * h] * kj.x)));
+                const float e = __expf(s - m);
+                z += e;
+                a0 = fmaf(e, vj.x, a0); a1 = fmaf(e, vj.y, a1); a2 = fmaf(e, vj.z, a2); a3 = fmaf(e, vj.w, a3);
+            }
+            const float iz = 1.f / z;
+            a0 *= iz; a1 *= iz; a2 *= iz; a3 *= iz;
+        }
+        o[4 * h] = a0; o[4 * h + 1] = a1; o[4 * h + 2] = a2; o[4 * h + 3] = a3;
+    }
+    float a[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) a[c] = tok[c];
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+#pragma unroll
+        for (int c = 0; c < 16; c += 4) {
+            const float4 w = *reinterpret_cast<const float4*>(sw + WA(AT_FC) + k * 16 + c);
+            a[c] = fmaf(o[k], w.x, a[c]); a[c + 1] = fmaf(o[k], w.y, a[c + 1]); a[c + 2] = fmaf(o[k], w.z, a[c + 2]); a[c + 3] = fmaf(o[k], w.w, a[c + 3]);
+        }
+    float mu = 0.f;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) mu += a[c];
+    mu *= (1.f / 16.f);
+    float var = 0.f;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) { const float dl = a[c] - mu; var = fmaf(dl, dl, var); }
+    var *= (1.f / 16.f);
+    const float rstd = rsqrtf(var + 1e-6f);
+    float ln[16], z16[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) ln[c] = fmaf((a[c] - mu) * rstd, sw[WA(AT_LNW) + c], sw[WA(AT_LNB) + c]);
+#pragma unroll
+    for (int c = 0; c < 16; ++c) z16[c] = sw[WA(OG_B0) + c];
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+#pragma unroll
+        for (int c = 0; c < 16; c += 4) {
+            const float4 w = *reinterpret_cast<const float4*>(sw + WA(OG_W0) + k * 16 + c);
+            z16[c] = fmaf(ln[k], w.x, z16[c]); z16[c + 1] = fmaf(ln[k], w.y, z16[c + 1]); z16[c + 2] = fmaf(ln[k], w.z, z16[c + 2]); z16[c + 3] = fmaf(ln[k], w.w, z16[c + 3]);
+        }
+    float s = sw[WA(OG_B1)];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) s = fmaf(z16[c], sw[WA(OG_W1) + c], s);
+    float sdf = fminf(fmaxf(s, -1.f), 1.f);
+    if (nvalid < 1.f) sdf = 1.f;
+    if (valid) {
+        if (p.volume_mode) {
+            const int R = p.R;
+            p.sdf[(size_t)b * p.N + (size_t)r * R + (R - 1 - d)] = sdf;
+        } else {
+            p.sdf[pidx] = sdf;
+        }
+    }
+}
+
 extern "C" int gn_k2b_forward(const GnK2bParams* hp, void* stream)
 {
     const GnK2bParams& p = *hp;
     if (p.B < 1 || p.N < 1 || p.dn < 1 || p.dn > K2B_THREADS || (p.N % p.dn) != 0) return -1;
-    if (p.volume_mode && (p.N != p.R * p.R * p.R || p.dn != p.R || !p.axis || !p.bbox_min)) return -3;
-    if (!p.volume_mode && !p.pts) return -4;
     const int rpb = K2B_THREADS / p.dn;
     const long long rays = (long long)p.B * (p.N / p.dn);
     const long long grid = (rays + rpb - 1) / rpb;
     if (grid > 0x7fffffffLL) return -6;
+    if (!p.pooled) {                       // attention-only path on K2a's tokens
+        if (!p.tok || p.grad) return -2;
+        if (p.volume_mode && (p.N != p.R * p.R * p.R || p.dn != p.R)) return -3;
+        gn_k2b_attn_kernel<<<(unsigned)grid, K2B_THREADS, 0, (cudaStream_t)stream>>>(p, rpb);
+        return (int)cudaGetLastError();
+    }
+    if (p.volume_mode && (p.N != p.R * p.R * p.R || p.dn != p.R || !p.axis || !p.bbox_min)) return -3;
+    if (!p.volume_mode && !p.pts) return -4;
     const bool wg = p.grad != nullptr;
     size_t smem = ((size_t)GN_W_K2B_FLOATS + 2 * K2B_THREADS * 16) * sizeof(float);
     if (wg) smem += (size_t)K2B_THREADS * (16 + 16 + 12 + 65) * sizeof(float);

@@ -11,7 +11,7 @@ import torch
 from . import _lib
 from .weights import pack_blob, positional_table, voxel_axis_table
 
-REC_STRIDE, PT_STRIDE, POOL_STRIDE = 72, 2, 68
+REC_STRIDE, PT_STRIDE, POOL_STRIDE, TOK_STRIDE = 72, 2, 68, 20
 
 
 def _stream():
@@ -53,6 +53,11 @@ class HeadWeights:
         if vers == self._versions:
             return
         self.blob = torch.from_numpy(pack_blob(sd, self.agg_prefix, self.dd_prefix)).to(self.device)
+        # tensor-core operand images (fp16 hi/lo, K-major) + small constants, built on the device from the fp32 blob
+        lib = _lib.load()
+        self.tc_const = torch.empty(lib.gn_k2a_tc_const_bytes(), dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(lib.gn_k2a_tc_prepare(_ptr(self.blob), _ptr(self.tc_const), _stream()), 'gn_k2a_tc_prepare')
         var = sd.get(self.agg_prefix + 'deviation_network.variance')
         self.variance = float(var) if var is not None else 0.3
         self._versions = vers
@@ -93,13 +98,15 @@ class Scene:
         _require_cuda(imgs, 'imgs')
         dev = imgs.device
         self.device = dev
-        self.imgs = _f32c(imgs, dev)
+        imgs = _f32c(imgs, dev)                                                     # [B,V,3,H,W] as the reference holds them
+        self.B, self.V, _, self.H, self.W = imgs.shape
+        # RGBA-interleaved copy [B,V,H,W,4]: one bilinear tap = one 16-byte texel (layout change only, like channels-last)
+        self.imgs = torch.cat([imgs.permute(0, 1, 3, 4, 2), imgs.new_zeros(self.B, self.V, self.H, self.W, 1)], -1).contiguous()
         if feats_channels_last:       # already [B,V,fh,fw,32]
             self.img_feats, self.ray_feats = _f32c(img_feats, dev), _f32c(ray_feats, dev)
         else:                         # logical [B,V,32,fh,fw]; a channels_last-strided tensor converts without a copy
             self.img_feats = to_channels_last_maps(img_feats.to(dev, torch.float32))
             self.ray_feats = to_channels_last_maps(ray_feats.to(dev, torch.float32))
-        self.B, self.V, _, self.H, self.W = self.imgs.shape
         _, _, self.fh, self.fw, c = self.img_feats.shape
         if c != 32 or self.ray_feats.shape != self.img_feats.shape:
             raise ValueError('feature maps must be [B,V,fh,fw,32]')
@@ -140,31 +147,55 @@ def k1_forward(scene, hw, *, resolution=None, bbox_min=None, volume_size=0.3, pt
 K2A_IMPL = 'tc'      # 'tc' (tcgen05, default) or 'simt' (fp32 CUDA-core implementation kept as the on-GPU cross-check)
 
 
-def k2a_forward(rec, pt, hw, depth_range, *, que_dists=None, dn=1, want_colors=False, debug=False, impl=None):
+def k2a_forward(rec, pt, hw, depth_range, *, que_dists=None, dn=1, want_colors=False, debug=False, impl=None,
+                want_pooled=True, want_tok=False, resolution=None, bbox_min=None, volume_size=0.3, pts=None):
+    """K2a launch.  impl 'tc' (tcgen05) or 'simt'.  want_tok (tc only): also run geometry_fc and emit per-point tokens
+    [B,N,20] for the attention-only K2b; needs the points: (resolution, bbox_min) in volume mode or pts [B,N,3]."""
     lib = _lib.load()
+    impl = impl or K2A_IMPL
     B, N, V, _ = rec.shape
     dev = rec.device
-    pooled = torch.empty((B, N, POOL_STRIDE), device=dev, dtype=torch.float32)
+    pooled = torch.empty((B, N, POOL_STRIDE), device=dev, dtype=torch.float32) if want_pooled else None
     colors = torch.empty((B, N, 4), device=dev, dtype=torch.float32) if want_colors else None
     dbg = torch.zeros((B, N, V, 8), device=dev, dtype=torch.float32) if debug else None
+    tok = None
     p = _lib.GnK2aParams()
     p.rec, p.pt, p.weights, p.depth_range = _ptr(rec).value, _ptr(pt).value, _ptr(hw.blob).value, _ptr(depth_range).value
     if que_dists is not None:
         que_dists = _f32c(que_dists, dev)
     p.que_dists, p.pooled, p.colors, p.dbg_rows = _ptr(que_dists).value, _ptr(pooled).value, _ptr(colors).value, _ptr(dbg).value
     p.B, p.N, p.V, p.dn, p.with_rgb = B, N, V, int(dn), 1 if want_colors else 0
-    impl = impl or K2A_IMPL
+    if impl == 'tc':
+        p.tc_const = _ptr(hw.tc_const).value
+        if want_tok:
+            tok = torch.empty((B, N, TOK_STRIDE), device=dev, dtype=torch.float32)
+            p.tok = _ptr(tok).value
+            if pts is None:
+                R = int(resolution)
+                bbox_min = _f32c(bbox_min, dev).reshape(B, 3)
+                axis = hw.axis(R, volume_size)
+                p.axis, p.bbox_min, p.R, p.volume_mode = _ptr(axis).value, _ptr(bbox_min).value, R, 1
+            else:
+                pts = _f32c(pts, dev)
+                p.pts, p.R, p.volume_mode = _ptr(pts).value, 0, 0
+    elif want_tok or not want_pooled:
+        raise ValueError("tokens are produced by the tensor-core K2a only")
     fn = lib.gn_k2a_forward_tc if impl == 'tc' else lib.gn_k2a_forward
     _lib.check(fn(C.byref(p), _stream()), f'gn_k2a_forward[{impl}]')
+    if want_tok:
+        return pooled, colors, dbg, tok
     return pooled, colors, dbg
 
 
-def k2b_forward(pooled, hw, *, dn, resolution=None, bbox_min=None, volume_size=0.3, pts=None, want_grad=False):
+def k2b_forward(pooled, hw, *, dn, resolution=None, bbox_min=None, volume_size=0.3, pts=None, want_grad=False, tok=None):
+    """K2b launch.  pooled [B,N,68] -> full head (embed, geometry_fc, attention; grad optional);
+    tok [B,N,20] (pooled=None) -> attention-only kernel on K2a-TC's tokens."""
     lib = _lib.load()
-    B, N, _ = pooled.shape
-    dev = pooled.device
+    src = pooled if pooled is not None else tok
+    B, N, _ = src.shape
+    dev = src.device
     p = _lib.GnK2bParams()
-    vol = pts is None
+    vol = resolution is not None
     if vol:
         R = int(resolution)
         bbox_min = _f32c(bbox_min, dev).reshape(B, 3)
@@ -172,12 +203,13 @@ def k2b_forward(pooled, hw, *, dn, resolution=None, bbox_min=None, volume_size=0
         out = torch.empty((B, 1, R, R, R), device=dev, dtype=torch.float32)
         p.axis, p.bbox_min, p.R = _ptr(axis).value, _ptr(bbox_min).value, R
     else:
-        pts = _f32c(pts, dev)
         out = torch.empty((B, N), device=dev, dtype=torch.float32)
+        if pts is not None:
+            pts = _f32c(pts, dev)
         p.pts, p.R = _ptr(pts).value, 0
     grad = torch.empty((B, N, 3), device=dev, dtype=torch.float32) if want_grad else None
     pos = hw.pos_table(int(dn))
-    p.pooled, p.weights, p.pos_table, p.sdf, p.grad = _ptr(pooled).value, _ptr(hw.blob).value, _ptr(pos).value, _ptr(out).value, _ptr(grad).value
+    p.pooled, p.tok, p.weights, p.pos_table, p.sdf, p.grad = _ptr(pooled).value, _ptr(tok).value, _ptr(hw.blob).value, _ptr(pos).value, _ptr(out).value, _ptr(grad).value
     p.B, p.N, p.dn, p.volume_mode = B, N, int(dn), 1 if vol else 0
     _lib.check(lib.gn_k2b_forward(C.byref(p), _stream()), 'gn_k2b_forward')
     return out, grad
@@ -223,11 +255,76 @@ def k3_fine_depths(depth, hit_prob, depth_range_q, u, want_inds=False):
     return out, inds
 
 
-def sample_volume(scene, hw, bbox_min, resolution=40, volume_size=0.3, debug=None):
-    """NeuralRayRenderer.sample_volume (renderer.py:164-199) for B scenes: K1 -> K2a -> K2b.  Returns [B,1,R,R,R]."""
+def sample_volume(scene, hw, bbox_min, resolution=40, volume_size=0.3, debug=None, impl=None):
+    """NeuralRayRenderer.sample_volume (renderer.py:164-199) for B scenes: K1 -> K2a -> K2b.  Returns [B,1,R,R,R].
+    impl 'tc' (default): tcgen05 K2a emits per-point tokens, K2b is attention-only.  'simt': fp32 CUDA-core K2a + full K2b."""
+    impl = impl or K2A_IMPL
     rec, pt = k1_forward(scene, hw, resolution=resolution, bbox_min=bbox_min, volume_size=volume_size)
-    pooled, _, dbg = k2a_forward(rec, pt, hw, scene.depth_range, debug=debug is not None)
-    vol, _ = k2b_forward(pooled, hw, dn=resolution, resolution=resolution, bbox_min=bbox_min, volume_size=volume_size)
+    if impl == 'tc':
+        pooled, _, dbg, tok = k2a_forward(rec, pt, hw, scene.depth_range, debug=debug is not None, impl='tc',
+                                          want_pooled=debug is not None, want_tok=True, resolution=resolution,
+                                          bbox_min=bbox_min, volume_size=volume_size)
+        vol, _ = k2b_forward(None, hw, dn=resolution, resolution=resolution, bbox_min=bbox_min, volume_size=volume_size, tok=tok)
+    else:
+        pooled, _, dbg = k2a_forward(rec, pt, hw, scene.depth_range, debug=debug is not None, impl='simt')
+        vol, _ = k2b_forward(pooled, hw, dn=resolution, resolution=resolution, bbox_min=bbox_min, volume_size=volume_size)
     if debug is not None:
         debug.update(rec=rec, pt=pt, pooled=pooled, rows=dbg)
     return vol
+
+
+# ------------------------------------------------------------------------------------------------ RGB head
+def query_rays(coords, poses, Ks):
+    """coords2rays (render_ops.py:4-25) for B query views: coords [B,rn,2] pixel (x,y) -> centre [B,3], un-normalised
+    directions [B,rn,3].  A 3x3 inverse and two tiny matmuls per view: done with torch like the reference."""
+    rot_t = poses[:, :, :3].transpose(1, 2)
+    centre = -(rot_t @ poses[:, :, 3:])[..., 0]
+    hom = torch.cat([coords, torch.ones_like(coords[..., :1])], -1)
+    cam = torch.inverse(Ks) @ hom.transpose(1, 2)
+    world = (rot_t @ cam + centre[:, :, None]).transpose(1, 2)
+    return centre, world - centre[:, None]
+
+
+def render_by_depth(scene, hw, que, que_depth, ray_mask_view_num=2, ray_mask_point_num=8):
+    """render_by_depth + network_rendering (renderer.py:90-138), eval mode, for B query views.
+    que: dict coords [B,rn,2], poses [B,3,4], Ks [B,3,3], depth_range [B,2] (device tensors); que_depth [B,rn,dn]."""
+    B, rn, dn = que_depth.shape
+    dr = que['depth_range']
+    near, far = (-1 / dr[:, 0])[:, None, None], (-1 / dr[:, 1])[:, None, None]
+    dinv = (-1 / que_depth - near) / (far - near)                                   # depth2inv_dists render_ops.py:46-52
+    inv_dists = torch.cat([dinv[..., 1:] - dinv[..., :-1], torch.full_like(dinv[..., :1], 1e6)], -1)
+    centre, dirs = query_rays(que['coords'], que['poses'], que['Ks'])
+    pts = (centre[:, None, None] + dirs[:, :, None] * que_depth[..., None]).reshape(B, rn * dn, 3)   # depth2points 27-39
+    que_dir = (-dirs / torch.norm(dirs, dim=2, keepdim=True)).contiguous()
+    rec, pt = k1_forward(scene, hw, pts=pts, que_dir=que_dir, dn=dn)
+    pooled, colors, _ = k2a_forward(rec, pt, hw, scene.depth_range, que_dists=inv_dists.reshape(B, rn * dn), dn=dn,
+                                    want_colors=True)
+    sdf, grad = k2b_forward(pooled, hw, dn=dn, pts=pts, want_grad=True)
+    import math
+    inv_s = min(max(math.exp(hw.variance * 10.0), 1e-6), 1e6)                        # neus.py:19, aggregate_net.py:107
+    alpha, hit, pix, rdepth, eik = k3_composite(sdf.reshape(B, rn, dn), grad.reshape(B, rn, dn, 3),
+                                                colors.reshape(B, rn, dn, 4), que_dir, que_depth.contiguous(), inv_s)
+    nvalid = pt[..., 0].reshape(B, rn, dn)
+    out = {'alpha_values': alpha, 'sdf_values': sdf.reshape(B, rn, dn), 'colors_nr': colors.reshape(B, rn, dn, 4)[..., :3],
+           'hit_prob_nr': hit, 'pixel_colors_nr': pix, 'render_depth': rdepth,
+           'sdf_gradient_error': (eik.sum(1) / (rn * dn)).reshape(B, 1),
+           'ray_mask': (nvalid > ray_mask_view_num).sum(-1) > ray_mask_point_num,             # renderer.py:129-132
+           'sdf_grad': grad.reshape(B, rn, dn, 3)}
+    return out
+
+
+def render_rays(scene, hw_coarse, hw_fine, que, dn=40, fdn=40, u=None):
+    """render_impl + fine_render_impl (renderer.py:140-162), hierarchical sampling on.  u: [B,rn,fdn] uniform randoms
+    (training) or None -> stratified midpoints (eval, render_ops.py:197-200)."""
+    B, rn = que['coords'].shape[:2]
+    depth = k3_coarse_depths(que['depth_range'], rn, dn)
+    out = render_by_depth(scene, hw_coarse, que, depth)
+    if u is None:
+        u = (0.5 / fdn + torch.arange(fdn, device=depth.device, dtype=torch.float32) / fdn).expand(B, rn, fdn).contiguous()
+    fdepth, inds = k3_fine_depths(depth, out['hit_prob_nr'], que['depth_range'], u, want_inds=True)
+    fine = render_by_depth(scene, hw_fine, que, fdepth)
+    out['depth'] = depth
+    for k, v in fine.items():
+        out[k + '_fine'] = v
+    out['depth_fine'], out['fine_inds'] = fdepth, inds
+    return out

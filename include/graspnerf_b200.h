@@ -13,7 +13,7 @@
  *
  * Data layout in HBM:
  *   feature maps  : channels-last  [B, V, fh, fw, 32]
- *   images        : planar         [B, V, 3, H, W]
+ *   images        : RGBA-interleaved [B, V, H, W, 4] (one bilinear tap = one 16-byte texel)
  *   record  `rec` : [B, N, V, 72]  ray_feats32 | img_feats32 | rgb3, depth | dir_diff4 ; n = ray*dn + sample
  *   per-point `pt`: [B, N, 2]      nvalid, view bit mask
  *   `pooled`      : [B, N, 68]     K2a output: mean32 | var32 | mean_v(w), nvalid, 0, 0
@@ -31,7 +31,7 @@ extern "C" {
  * (aggregate_net.py:11-17) and the per-point valid-view count / mask (ibrnet.py:466,490).  volume_mode=1: points are the voxel centres of utils/field_utils.py:12-27 plus bbox_min,
  * in sample_volume's order (renderer.py:166-170).  volume_mode=0: explicit points (RGB head, render_ops.py:27-39). */
 typedef struct GnK1Params {
-    const float* imgs;        /* [B,V,3,H,W] */
+    const float* imgs;        /* [B,V,H,W,4] RGBA-interleaved (A unused) */
     const float* img_feats;   /* [B,V,fh,fw,32] channels-last */
     const float* ray_feats;   /* [B,V,fh,fw,32] channels-last */
     const float* KRt;         /* [B,V,3,4]  K @ [R|t]  (render_ops.py:94) */
@@ -74,11 +74,20 @@ typedef struct GnK2aParams {
     float* pooled;             /* out [B,N,68] */
     float* colors;             /* out [B,N,4] (rgb, 0) or NULL */
     float* dbg_rows;           /* optional out [B,N,V,8]: hit, vis, w0, vis2, x0, x1, pe0, pe1 ; or NULL */
+    /* tensor-core path only: */
+    const void* tc_const;      /* buffer of gn_k2a_tc_const_bytes() bytes filled by gn_k2a_tc_prepare() */
+    float* tok;                /* optional out [B,N,20]: geometry_fc output (ibrnet.py:487-489) 16 | nvalid,0,0,0 ; or NULL */
+    const float* axis;         /* [R]   (tok, volume mode) */
+    const float* bbox_min;     /* [B,3] (tok, volume mode) */
+    const float* pts;          /* [B,N,3] (tok, ray mode) */
     int B, N, V, dn;
     int with_rgb;              /* 1: also evaluate rgb_fc + blend into `colors` */
+    int R, volume_mode;        /* (tok) */
 } GnK2aParams;
 int gn_k2a_forward(const GnK2aParams* params, void* stream);      /* fp32 SIMT implementation (reference for the TC path) */
 int gn_k2a_forward_tc(const GnK2aParams* params, void* stream);   /* tcgen05 / TMEM implementation (fp16 hi/lo split, 3 MMAs per product) */
+int gn_k2a_tc_const_bytes(void);
+int gn_k2a_tc_prepare(const float* weights, void* tc_const, void* stream);   /* fp32 blob -> fp16 hi/lo operand images + small constants */
 
 /* K2b: per-ray geometry head.
  * Replaces ibrnet.py:485-495: embed (neus.py:21-66), geometry_fc, + pos_encoding (ibrnet.py:437-445), MultiHeadAttention
@@ -86,7 +95,8 @@ int gn_k2a_forward_tc(const GnK2aParams* params, void* stream);   /* tcgen05 / T
  * volume_mode=1: writes volume[B,R,R,R] with the final z flip of renderer.py:198 fused; else sdf[B,N].
  * grad (optional, [B,N,3]): d(sum sdf)/d pts  (ibrnet.py:497-504), hand-derived reverse pass. */
 typedef struct GnK2bParams {
-    const float* pooled;       /* [B,N,68] */
+    const float* pooled;       /* [B,N,68]  (full path: embed + geometry_fc + attention; required when grad != NULL) */
+    const float* tok;          /* [B,N,20]  (attention-only path: geometry_fc already done by K2a-TC); used when pooled == NULL */
     const float* weights;      /* blob */
     const float* axis;         /* [R] (volume mode) */
     const float* bbox_min;     /* [B,3] (volume mode) */

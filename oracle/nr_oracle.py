@@ -404,8 +404,16 @@ def fine_depths(depth, hit_prob, depth_range_q, fdn, u=None):
     centre = (dinv[..., 1:] + dinv[..., :-1]) / 2
     centre = torch.cat([dinv[..., 0:1], centre, dinv[..., -1:]], -1)        # [rn,dn+1]
     hp = hit_prob + 1e-5
-    pdf = hp / torch.sum(hp, -1, keepdim=True)
-    cdf = torch.cumsum(pdf, -1)
+    # fixed left-to-right fp32 order for the normaliser and the running sum (torch.sum / torch.cumsum leave the order
+    # to the backend; the CUDA sampler follows THIS order so its searchsorted table can be compared bit-exactly)
+    tot = hp[..., 0]
+    for i in range(1, hp.shape[-1]):
+        tot = tot + hp[..., i]
+    pdf = hp / tot[..., None]
+    run = [pdf[..., 0]]
+    for i in range(1, pdf.shape[-1]):
+        run.append(run[-1] + pdf[..., i])
+    cdf = torch.stack(run, -1)
     cdf = torch.cat([torch.zeros_like(cdf[..., :1]), cdf], -1)              # [rn,dn+1]
     if u is None:
         interval = 1 / fdn

@@ -38,9 +38,17 @@ def test_volume_path_vs_oracle_and_golden(name, impl):
                       sc['Ks'].to(dev), sc['depth_range'].to(dev))
     bbox_min = torch.tensor([sc['bbox3d'][0]], device=dev)
     rec, pt, idx = ops.k1_forward(scene, hw, resolution=40, bbox_min=bbox_min, debug_idx=True)
-    pooled, _, rows = ops.k2a_forward(rec, pt, hw, scene.depth_range, debug=True, impl=impl)
-    vol, _ = ops.k2b_forward(pooled, hw, dn=40, resolution=40, bbox_min=bbox_min)
+    if impl == 'tc':      # tensor-core K2a: pooled (checked below) AND per-point tokens -> attention-only K2b
+        pooled, _, rows, tok = ops.k2a_forward(rec, pt, hw, scene.depth_range, debug=True, impl='tc', want_tok=True,
+                                               resolution=40, bbox_min=bbox_min)
+        vol, _ = ops.k2b_forward(None, hw, dn=40, resolution=40, bbox_min=bbox_min, tok=tok)
+        vol_full, _ = ops.k2b_forward(pooled, hw, dn=40, resolution=40, bbox_min=bbox_min)     # full K2b on the same pooled rows
+    else:
+        pooled, _, rows = ops.k2a_forward(rec, pt, hw, scene.depth_range, debug=True, impl='simt')
+        vol, _ = ops.k2b_forward(pooled, hw, dn=40, resolution=40, bbox_min=bbox_min)
+        vol_full = vol
     torch.cuda.synchronize()
+    vol_full = vol_full.cpu()
     rec, pt, idx, pooled, rows, vol = [t.cpu() for t in (rec, pt, idx, pooled, rows, vol)]
 
     ovol, orec, oagg = O.sample_volume(sd, sc, with_intermediates=True)
@@ -68,6 +76,7 @@ def test_volume_path_vs_oracle_and_golden(name, impl):
     assert_close(rows[0, :, :, 3], oagg['vis2'], what='vis2')
     assert_close(pooled[0, :, 0:65], oagg['pooled'], what='pooled')
     # ---- volume: vs oracle and vs the reference's own output
+    assert_close(vol_full[0, 0], ovol[0, 0], what='volume (full K2b) vs oracle')
     rel = assert_close(vol[0, 0], ovol[0, 0], what='volume vs oracle')
     rel_g = assert_close(vol[0, 0], g['volume'], what='volume vs reference golden')
     assert rel < 1e-5 and rel_g < 1e-5, (rel, rel_g)
@@ -86,6 +95,9 @@ def test_volume_batch_equals_loop():
     scene = ops.Scene(stack('imgs'), stack('img_feats'), stack('ray_feats'), stack('poses'), stack('Ks'), stack('depth_range'))
     bbox = torch.tensor([s['bbox3d'][0] for s in scs], device=dev)
     vol_b = ops.sample_volume(scene, hw, bbox, 40)
+    vol_s = ops.sample_volume(scene, hw, bbox, 40, impl='simt')
+    from tests.helpers import assert_close as _ac
+    _ac(vol_b.cpu(), vol_s.cpu(), what='tensor-core path vs fp32 SIMT path')
     for i, s in enumerate(scs):
         sc1 = ops.Scene(*[s[k].to(dev) for k in ('imgs', 'img_feats', 'ray_feats', 'poses', 'Ks', 'depth_range')])
         v1 = ops.sample_volume(sc1, hw, bbox[i:i + 1], 40)
