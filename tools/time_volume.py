@@ -28,16 +28,21 @@ def main():
         ev[0].record()
         rec, pt = ops.k1_forward(scene, hw, resolution=40, bbox_min=bbox)
         ev[1].record()
-        pooled, _, _ = ops.k2a_forward(rec, pt, hw, scene.depth_range)
-        ev[2].record()
-        vol, _ = ops.k2b_forward(pooled, hw, dn=40, resolution=40, bbox_min=bbox)
+        if ops.K2A_IMPL == 'tc':
+            _, _, _, tok = ops.k2a_forward(rec, pt, hw, scene.depth_range, want_pooled=False, want_tok=True, resolution=40, bbox_min=bbox)
+            ev[2].record()
+            vol, _ = ops.k2b_forward(None, hw, dn=40, resolution=40, bbox_min=bbox, tok=tok)
+        else:
+            pooled, _, _ = ops.k2a_forward(rec, pt, hw, scene.depth_range)
+            ev[2].record()
+            vol, _ = ops.k2b_forward(pooled, hw, dn=40, resolution=40, bbox_min=bbox)
         ev[3].record()
         torch.cuda.synchronize()
         if it >= 3:
             acc += [ev[i].elapsed_time(ev[i + 1]) for i in range(3)]
     acc /= iters
     print(f'[{ops.K2A_IMPL}] B={B}: K1 {acc[0]*1e3:.1f} us  K2a {acc[1]*1e3:.1f} us  K2b {acc[2]*1e3:.1f} us  total {acc.sum()*1e3:.1f} us '
-          f'-> {B/acc.sum()*1e3:.1f} volumes/s; K1 roofline bytes/vol 153284608 -> {153284608*B/acc[0]/1e6:.1f} GB/s')
+          f'-> {B/acc.sum()*1e3:.1f} volumes/s; K1 bytes/vol 135876608 -> {135876608*B/acc[0]/1e6:.1f} GB/s')
 
 
 if __name__ == '__main__':
