@@ -22,12 +22,15 @@
 #define K1_THREADS 256
 #define K1_TILE_P 32
 
-struct K1PairInfo {           // 64 bytes, written in phase A, read (broadcast) in phase B
+struct K1PairInfo {           // written in phase A, read (broadcast within an 8-lane group) in phase B.  80-byte stride: the four
+                              // groups of a warp read pairs V apart; 64 B (and 32 B for s_misc) strides put them on the same banks
     int   fo[4];              // feature-map tap offsets (floats) within the view's [fh,fw,32] map
     float fw_[4];             // feature tap weights * mask   (nw, ne, sw, se)
     int   io[4];              // image tap offsets (pixels) within one H*W plane
     float iw[4];              // image tap weights * mask
+    float pad[4];
 };
+#define K1_MISC 12            // floats per pair in s_misc: dd0..3, mask, depth, pad
 
 __global__ void __launch_bounds__(K1_THREADS, 4)
 gn_k1_kernel(const __grid_constant__ GnK1Params p)
@@ -36,7 +39,7 @@ gn_k1_kernel(const __grid_constant__ GnK1Params p)
     const int V = p.V;
     const int npair = K1_TILE_P * V;
     K1PairInfo* s_info = reinterpret_cast<K1PairInfo*>(smem_raw);                    // [npair]
-    float* s_misc  = reinterpret_cast<float*>(s_info + npair);                       // [npair][8]: dd0..3, mask, depth, pad
+    float* s_misc  = reinterpret_cast<float*>(s_info + npair);                       // [npair][12]: dd0..3, mask, depth, pad
 
     const int tiles_per_scene = p.tiles_per_scene;
     const int b = blockIdx.x / tiles_per_scene;
@@ -121,8 +124,11 @@ gn_k1_kernel(const __grid_constant__ GnK1Params p)
             inf.iw[0] = __fmul_rn(tx.w0, ty.w0) * mask; inf.iw[1] = __fmul_rn(tx.w1, ty.w0) * mask;
             inf.iw[2] = __fmul_rn(tx.w0, ty.w1) * mask; inf.iw[3] = __fmul_rn(tx.w1, ty.w1) * mask;
         }
-        s_info[pair] = inf;
-        float* ms = s_misc + pair * 8;
+        *reinterpret_cast<int4*>(s_info[pair].fo) = *reinterpret_cast<const int4*>(inf.fo);
+        *reinterpret_cast<float4*>(s_info[pair].fw_) = *reinterpret_cast<const float4*>(inf.fw_);
+        *reinterpret_cast<int4*>(s_info[pair].io) = *reinterpret_cast<const int4*>(inf.io);
+        *reinterpret_cast<float4*>(s_info[pair].iw) = *reinterpret_cast<const float4*>(inf.iw);
+        float* ms = s_misc + pair * K1_MISC;
         st4(ms, make_float4(dd[0], dd[1], dd[2], dd[3]));
         ms[4] = mask; ms[5] = depth;
     }
@@ -146,7 +152,7 @@ gn_k1_kernel(const __grid_constant__ GnK1Params p)
     float nvalid = 0.f;
     unsigned bits = 0u;
     for (int v = 0; v < V; ++v) {
-        const float m = s_misc[(pl * V + v) * 8 + 4];
+        const float m = s_misc[(pl * V + v) * K1_MISC + 4];
         nvalid += m;
         bits |= (m != 0.f ? 1u : 0u) << v;
     }
@@ -184,8 +190,11 @@ gn_k1_kernel(const __grid_constant__ GnK1Params p)
         if (live) {
             st4_cs(row + GN_REC_RAYF + 4 * j, ray);
             st4_cs(row + GN_REC_IMGF + 4 * j, img);
-            if (j == 0) st4_cs(row + GN_REC_RGB, make_float4(cr, cg, cb, s_misc[pair * 8 + 5]));
-            else if (j == 1) st4_cs(row + GN_REC_DD, *reinterpret_cast<const float4*>(s_misc + pair * 8));
+            // tail: lanes 0 and 1 write the two adjacent 16-byte chunks [64,68) and [68,72) with ONE store instruction
+            if (j < 2) {
+                const float4 ddq = *reinterpret_cast<const float4*>(s_misc + pair * K1_MISC);
+                st4_cs(row + GN_REC_RGB + 4 * j, j == 0 ? make_float4(cr, cg, cb, s_misc[pair * K1_MISC + 5]) : ddq);
+            }
         }
     }
     if (live && j == 0) {
@@ -206,7 +215,7 @@ extern "C" int gn_k1_forward(const GnK1Params* hp, void* stream)
         p.tiles_per_scene = (p.N + K1_TILE_P - 1) / K1_TILE_P;
     }
     const int npair = K1_TILE_P * p.V;
-    const size_t smem = (size_t)npair * (sizeof(K1PairInfo) + 8 * sizeof(float));
+    const size_t smem = (size_t)npair * (sizeof(K1PairInfo) + K1_MISC * sizeof(float));
     if (smem > 227 * 1024) return -5;
     cudaError_t e = cudaFuncSetAttribute(gn_k1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;

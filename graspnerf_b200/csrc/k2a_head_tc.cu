@@ -75,13 +75,22 @@ __device__ __forceinline__ uint64_t tc_desc(uint32_t saddr, uint32_t lbo, uint32
     // tcgen05 shared-memory matrix descriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), SWIZZLE_NONE
     return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46);
 }
-__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                 "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-                 :: "r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint32_t a_tmem, uint32_t bdesc_lo, uint32_t idesc, uint32_t acc, uint32_t elected) {
+    // executed by the whole issuing warp with warp-uniform operands; only the elected lane issues (CUTLASS idiom), so the
+    // operands live in uniform registers.  High descriptor word is constant: SBO = 128 B (>>4 = 8), version 1 (bit 46).
+    asm volatile("{\n\t.reg .pred p, q;\n\t.reg .b64 bd;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+                 "mov.b64 bd, {%2, %6};\n\t"
+                 "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], bd, %3, p;\n\t}"
+                 :: "r"(d_tmem), "r"(a_tmem), "r"(bdesc_lo), "r"(idesc), "r"(acc), "r"(elected), "n"(0x4008) : "memory");
 }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+__device__ __forceinline__ void tc_commit(uint32_t bar, uint32_t elected) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
+                 "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" :: "r"(bar), "r"(elected) : "memory");
+}
+__device__ __forceinline__ uint32_t elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred;
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     // try_wait suspends the thread for a HW-bounded time per attempt; the attempt counter turns a lost arrival
@@ -159,30 +168,80 @@ template <int N> __device__ __forceinline__ void add_bias(const float* __restric
     }
 }
 
+// Generic layer epilogue, shared by every "plain" layer (NOT inlined: one copy of the code serves ~60 % of all
+// activations, which keeps the kernel's instruction footprint cache-friendly):
+//   A[k0 + 0 .. 16*nchunk) = act(D[d_col + 0 .. 16*nchunk) + bias),  ACT 0 none, 1 ELU, 2 ReLU.
+// The tcgen05.ld of chunk c+1 is in flight while chunk c is activated, split and stored.
+template <int ACT>
+__device__ __noinline__ void tc_epilogue(uint32_t lane_addr, int d_col, int nchunk, const float* __restrict__ bias, int k0)
+{
+    uint32_t r[16];
+    tm_ld16_issue(lane_addr + TM_D + d_col, r);
+#pragma unroll 1
+    for (int c = 0; c < nchunk; ++c) {
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        tm_ld16_fence(r);
+        float y[16];
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) {
+            const float4 w = *reinterpret_cast<const float4*>(bias + c * 16 + i);
+            y[i] = __uint_as_float(r[i]) + w.x; y[i + 1] = __uint_as_float(r[i + 1]) + w.y;
+            y[i + 2] = __uint_as_float(r[i + 2]) + w.z; y[i + 3] = __uint_as_float(r[i + 3]) + w.w;
+        }
+        if (c + 1 < nchunk) tm_ld16_issue(lane_addr + TM_D + d_col + (c + 1) * 16, r);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) y[i] = ACT == 1 ? tc_elu(y[i]) : (ACT == 2 ? fmaxf(y[i], 0.f) : y[i]);
+        tm_store_a<16>(lane_addr, k0 + c * 16, y);
+    }
+}
+
+// Cross-view sums of the 36 values every lane has parked in its scratch row: sums row of group g <- sum over its V rows.
+// (summation order v = 0..V-1, like the shuffle loops of the SIMT kernel)
+__device__ __noinline__ void tc_pool_rows(float* scr, int g, int v, int gb, int V, bool lane_active)
+{
+    __syncwarp();
+    float* sums = scr + (32 + g) * TC_POOL_STRIDE;
+    const float* base = scr + gb * TC_POOL_STRIDE;
+#pragma unroll 1
+    for (int c = v; c < 36; c += V) {
+        float s = 0.f;
+        const float* q = base + c;
+#pragma unroll 2
+        for (int jv = 0; jv < V; ++jv) s += q[jv * TC_POOL_STRIDE];
+        if (lane_active) sums[c] = s;
+    }
+    __syncwarp();
+}
+
 struct TcCtx {
     uint32_t tmem_slot;       // TMEM base of this slot (lane 0)
     uint32_t lane_addr;       // tmem_slot + (warp%4 * 32 << 16)
-    uint32_t img_base;        // shared address of the image area
+    uint32_t img_base16;      // (shared address of the image area) >> 4
     uint32_t bar;             // shared address of this slot's mbarrier
     uint32_t parity;
     int bar_id;               // named barrier id of this slot
-    bool leader;
+    bool issuer;              // this warp issues the slot's MMAs (warp-uniform)
+    uint32_t elected;         // 1 on the one lane of the issuing warp that actually issues
 };
 
-// One GEMM (three fp16 passes).  Issued by the slot leader only.
+// One GEMM (three fp16 passes).  Executed by the slot's issuing warp; one elected lane issues.
 template <int LAYER>
 __device__ __forceinline__ void tc_issue(const TcCtx& cx, int d_col, int a_k0, bool accumulate) {
     constexpr int N = tc_layer(LAYER).N, K = tc_layer(LAYER).K;
     constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // F32 accum, F16 x F16, M=128
-    const uint32_t bhi = cx.img_base + tc_img_off(LAYER) * 2, blo = bhi + N * K * 2;
+    // low descriptor word = (start address >> 4) | (LBO >> 4) << 16 with LBO = N*16 B (k-chunk stride); the start address of
+    // every image / k-step is the (runtime) image base plus a compile-time constant, so each MMA costs one add
+    constexpr uint32_t lbo_field = (uint32_t)((N * 16) >> 4) << 16;
+    constexpr uint32_t hi_off = (uint32_t)(tc_img_off(LAYER) * 2) >> 4, lo_off = hi_off + (uint32_t)((N * K * 2) >> 4);
     uint32_t acc = accumulate ? 1u : 0u;
 #pragma unroll
     for (int pass = 0; pass < 3; ++pass) {                 // small terms first: lo*hi, hi*lo, hi*hi
         const uint32_t a_col = (pass == 0 ? TM_ALO : TM_AHI) + a_k0 / 2;
-        const uint32_t b = (pass == 1) ? blo : bhi;
+        const uint32_t boff = (pass == 1) ? lo_off : hi_off;
 #pragma unroll
         for (int ks = 0; ks < K / 16; ++ks) {
-            tc_mma(cx.tmem_slot + TM_D + d_col, cx.tmem_slot + a_col + ks * 8, tc_desc(b + ks * 2 * (N * 16), N * 16, 128), idesc, acc);
+            tc_mma(cx.tmem_slot + TM_D + d_col, cx.tmem_slot + a_col + ks * 8,
+                   cx.img_base16 + (boff + (uint32_t)(ks * 2 * N) + lbo_field), idesc, acc, cx.elected);
             acc = 1u;
         }
     }
@@ -192,27 +251,20 @@ __device__ __forceinline__ void tc_issue(const TcCtx& cx, int d_col, int a_k0, b
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");                     \
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");                 \
     asm volatile("bar.sync %0, 128;" :: "r"((cx).bar_id) : "memory");                \
-    if ((cx).leader) { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if ((cx).issuer) { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #define TC_GEMM_END(cx)                                                              \
-        tc_commit((cx).bar); }                                                       \
+        tc_commit((cx).bar, (cx).elected); __syncwarp(); }                                                     \
     mbar_wait((cx).bar, (cx).parity); (cx).parity ^= 1u;                             \
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
 // Cross-view sum of 36 per-row values through the warp's scratch: out[c] = sum over the V rows of my point of vals[c].
-// (summation order v = 0..V-1, like the shuffle loops of the SIMT kernel)
 __device__ __forceinline__ void pool36(float* scr, int lane, int g, int v, int gb, int V, bool lane_active, const float* vals, float* out)
 {
     float* mine = scr + lane * TC_POOL_STRIDE;
 #pragma unroll
     for (int c = 0; c < 36; c += 4) st4(mine + c, make_float4(vals[c], vals[c + 1], vals[c + 2], vals[c + 3]));
-    __syncwarp();
-    float* sums = scr + (32 + g) * TC_POOL_STRIDE;
-    for (int c = v; c < 36; c += V) {
-        float s = 0.f;
-        for (int jv = 0; jv < V; ++jv) s += scr[(gb + jv) * TC_POOL_STRIDE + c];
-        if (lane_active) sums[c] = s;
-    }
-    __syncwarp();
+    tc_pool_rows(scr, g, v, gb, V, lane_active);
+    const float* sums = scr + (32 + g) * TC_POOL_STRIDE;
 #pragma unroll
     for (int c = 0; c < 36; c += 4) {
         const float4 t = *reinterpret_cast<const float4*>(sums + c);
@@ -284,7 +336,8 @@ gn_k2a_tc_kernel(const __grid_constant__ GnK2aParams p, int num_tiles, int G)
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_pool + (TC_THREADS / 32) * (32 + G) * TC_POOL_STRIDE);
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + TC_SLOTS);
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);          // warp-uniform by construction
     const int slot = warp >> 2;
     // ---- one-time setup: constants copy, TMEM, mbarriers
     {
@@ -309,11 +362,12 @@ gn_k2a_tc_kernel(const __grid_constant__ GnK2aParams p, int num_tiles, int G)
     TcCtx cx;
     cx.tmem_slot = *s_tmem + slot * TM_SLOT;
     cx.lane_addr = cx.tmem_slot + ((uint32_t)((warp & 3) * 32) << 16);
-    cx.img_base = smem_u32(s_img);
+    cx.img_base16 = smem_u32(s_img) >> 4;
     cx.bar = smem_u32(&s_bar[slot]);
     cx.parity = 0u;
     cx.bar_id = 1 + slot;
-    cx.leader = (tid & 127) == 0;
+    cx.issuer = (warp & 3) == 0;
+    cx.elected = cx.issuer ? elect_one() : 0u;
 
     const int V = p.V;
     const bool lane_active = lane < G * V;
@@ -351,12 +405,8 @@ gn_k2a_tc_kernel(const __grid_constant__ GnK2aParams p, int num_tiles, int G)
         }
         TC_GEMM_BEGIN(cx) tc_issue<L_DD1>(cx, 0, 0, false); TC_GEMM_END(cx)
         // ================= S2: second layers (block diagonal: three N=32,K=32 GEMMs) =====================
-        {
-            float h[32];
-            tm_ld<32>(cx.lane_addr + TM_D + 0, h);  bias_elu<32>(sw + TS(DD_MEAN_B0), h);  tm_store_a<32>(cx.lane_addr, 48, h);
-            tm_ld<32>(cx.lane_addr + TM_D + 32, h); bias_elu<32>(sw + TS(DD_VAR_B0), h);   tm_store_a<32>(cx.lane_addr, 80, h);
-            tm_ld<32>(cx.lane_addr + TM_D + 64, h); bias_elu<32>(sw + TS(DD_AW_B0), h);    tm_store_a<32>(cx.lane_addr, 112, h);
-        }
+        static_assert(TS(DD_VAR_B0) == TS(DD_MEAN_B0) + 32 && TS(DD_AW_B0) == TS(DD_MEAN_B0) + 64, "dist-decoder biases must be contiguous");
+        tc_epilogue<1>(cx.lane_addr, 0, 6, sw + TS(DD_MEAN_B0), 48);      // D[0..95] -> ELU -> A[k 48..143]
         TC_GEMM_BEGIN(cx)
             tc_issue<L_DD2M>(cx, 0, 48, false); tc_issue<L_DD2V>(cx, 32, 80, false); tc_issue<L_DD2A>(cx, 64, 112, false);
         TC_GEMM_END(cx)
@@ -392,8 +442,9 @@ gn_k2a_tc_kernel(const __grid_constant__ GnK2aParams p, int num_tiles, int G)
                 const float h_prev = smp > 0 ? __ldg(qd - 1) * 0.5f : h_cur;
                 nearp = d - h_prev; farp = d + h_cur;
             }
-            const float c00 = 0.5f + 0.5f * tanhf((nearp - mean0) * var0), c10 = 0.5f + 0.5f * tanhf((farp - mean0) * var0);
-            const float c01 = 0.5f + 0.5f * tanhf((nearp - mean1) * var1), c11 = 0.5f + 0.5f * tanhf((farp - mean1) * var1);
+            // 0.5 + 0.5*tanh(d) == sigmoid(2d)   (dist_decoder.py:129-130)
+            const float c00 = gn_sigmoid(2.f * ((nearp - mean0) * var0)), c10 = gn_sigmoid(2.f * ((farp - mean0) * var0));
+            const float c01 = gn_sigmoid(2.f * ((nearp - mean1) * var1)), c11 = gn_sigmoid(2.f * ((farp - mean1) * var1));
             const float mix1 = 1.f - aw;
             vis = ((1.f - c00) * aw + (1.f - c01) * mix1) * mask;
             hit = ((c10 - c00) * aw + (c11 - c01) * mix1) * mask;
@@ -408,21 +459,17 @@ gn_k2a_tc_kernel(const __grid_constant__ GnK2aParams p, int num_tiles, int G)
         }
         TC_GEMM_BEGIN(cx) tc_issue<L_PE0>(cx, 0, 0, false); TC_GEMM_END(cx)
         // ================= S4: prob_embed.2 ===============================================================
-        {
-            float e1[32];
-            tm_ld<32>(cx.lane_addr + TM_D, e1); add_bias<32>(sw + TS(PE_B0), e1);
-#pragma unroll
-            for (int c = 0; c < 32; ++c) e1[c] = fmaxf(e1[c], 0.f);
-            tm_store_a<32>(cx.lane_addr, 80, e1);
-        }
+        tc_epilogue<2>(cx.lane_addr, 0, 2, sw + TS(PE_B0), 80);           // ReLU (aggregate_net.py:31)
         TC_GEMM_BEGIN(cx) tc_issue<L_PE2>(cx, 0, 80, false); TC_GEMM_END(cx)
         // ================= S5: neuray_fc.0 on prob_emb, ray_dir_fc.0 on dir_diff ==========================
-        float pe01[2];
+        float pe01[2] = { 0.f, 0.f };
+        if (p.dbg_rows) {                                        // debug only: first two prob_embed outputs
+            float t16[16];
+            tm_ld<16>(cx.lane_addr + TM_D, t16);
+            pe01[0] = t16[0] + sw[TS(PE_B2)]; pe01[1] = t16[1] + sw[TS(PE_B2) + 1];
+        }
+        tc_epilogue<0>(cx.lane_addr, 0, 2, sw + TS(PE_B2), 48);           // prob_embed stays at k 48..79 for base_fc (S7a)
         {
-            float pe[32];
-            tm_ld<32>(cx.lane_addr + TM_D, pe); add_bias<32>(sw + TS(PE_B2), pe);
-            pe01[0] = pe[0]; pe01[1] = pe[1];
-            tm_store_a<32>(cx.lane_addr, 48, pe);               // stays at k 48..79 for base_fc (S7a)
             float dd[16];
 #pragma unroll
             for (int c = 0; c < 16; ++c) dd[c] = 0.f;
@@ -433,17 +480,14 @@ gn_k2a_tc_kernel(const __grid_constant__ GnK2aParams p, int num_tiles, int G)
         // ================= S6: ray_dir_fc.2 ; weight0 =======================================================
         float w0;
         {
-            float t[32];
-            tm_ld<32>(cx.lane_addr + TM_D, t);
+            float t[16];
+            tm_ld<16>(cx.lane_addr + TM_D, t);
             float s = sw[TS(NF_B2)];
 #pragma unroll
             for (int k = 0; k < 8; ++k) s = fmaf(tc_elu(t[k] + sw[TS(NF_B0) + k]), sw[TS(NF_W2) + k], s);
             w0 = gn_sigmoid(s) * wgt;                           // ibrnet.py:469
-            float hid[16];
-#pragma unroll
-            for (int k = 0; k < 16; ++k) hid[k] = tc_elu(t[16 + k] + sw[TS(RD_B0) + k]);
-            tm_store_a<16>(cx.lane_addr, 128, hid);
         }
+        tc_epilogue<1>(cx.lane_addr, 16, 1, sw + TS(RD_B0), 128);       // ray_dir_fc hidden: D[16..31] -> ELU -> A[k 128..143]
         TC_GEMM_BEGIN(cx) tc_issue<L_RD1>(cx, 0, 128, false); TC_GEMM_END(cx)
         // ================= f = feats + direction feature; mean/var poolings; S7a, S7b =======================
         {
@@ -487,11 +531,7 @@ gn_k2a_tc_kernel(const __grid_constant__ GnK2aParams p, int num_tiles, int G)
         }
         TC_GEMM_BEGIN(cx) tc_issue<L_BF0B>(cx, 0, 0, true); TC_GEMM_END(cx)
         // ================= S8: base_fc.2 ====================================================================
-        {
-            float y[64];
-            tm_ld<64>(cx.lane_addr + TM_D, y); bias_elu<64>(sw + TS(BF_B0), y);
-            tm_store_a<64>(cx.lane_addr, 0, y);
-        }
+        tc_epilogue<1>(cx.lane_addr, 0, 4, sw + TS(BF_B0), 0);
         TC_GEMM_BEGIN(cx) tc_issue<L_BF2>(cx, 0, 0, false); TC_GEMM_END(cx)
         // ================= S9/S10: vis_fc ====================================================================
         float x[36];
@@ -504,11 +544,7 @@ gn_k2a_tc_kernel(const __grid_constant__ GnK2aParams p, int num_tiles, int G)
             tm_store_a<32>(cx.lane_addr, 64, xi);
         }
         TC_GEMM_BEGIN(cx) tc_issue<L_VF0>(cx, 0, 64, false); TC_GEMM_END(cx)
-        {
-            float t[32];
-            tm_ld<32>(cx.lane_addr + TM_D, t); bias_elu<32>(sw + TS(VF_B0), t);
-            tm_store_a<32>(cx.lane_addr, 96, t);
-        }
+        tc_epilogue<1>(cx.lane_addr, 0, 2, sw + TS(VF_B0), 96);
         TC_GEMM_BEGIN(cx) tc_issue<L_VF2>(cx, 0, 96, false); TC_GEMM_END(cx)
         {
             float xv[48];
@@ -587,17 +623,13 @@ gn_k2a_tc_kernel(const __grid_constant__ GnK2aParams p, int num_tiles, int G)
 #pragma unroll
                 for (int q = 0; q < 3; ++q)
 #pragma unroll
-                    for (int a = 0; a < 3; ++a) sincosf(pv[a] * (float)(1 << q), &e[4 + 6 * q + a], &e[4 + 6 * q + 3 + a]);
+                    for (int a = 0; a < 3; ++a) __sincosf(pv[a] * (float)(1 << q), &e[4 + 6 * q + a], &e[4 + 6 * q + 3 + a]);   // |arg| < 4: abs err ~1e-6
 #pragma unroll
                 for (int c = 22; c < 32; ++c) e[c] = 0.f;
                 tm_store_a<32>(cx.lane_addr, 64, e);
             }
             TC_GEMM_BEGIN(cx) tc_issue<L_GF0>(cx, 0, 0, false); TC_GEMM_END(cx)
-            {
-                float y[64];
-                tm_ld<64>(cx.lane_addr + TM_D, y); bias_elu<64>(sw + TS(GF_B0), y);
-                tm_store_a<64>(cx.lane_addr, 0, y);
-            }
+            tc_epilogue<1>(cx.lane_addr, 0, 4, sw + TS(GF_B0), 0);
             TC_GEMM_BEGIN(cx) tc_issue<L_GF2>(cx, 0, 0, false); TC_GEMM_END(cx)
             {
                 float t[16];

@@ -54,7 +54,7 @@ def test_render_coarse_and_fine(name, impl):
         fd, inds = ops.k3_fine_depths(torch.from_numpy(g['depth']).to(dev), hp, que['depth_range'], u.to(dev), want_inds=True)
         ofd, oinds = O.fine_depths(torch.from_numpy(g['depth'][0]), torch.from_numpy(g['hit_prob_nr'][0]), oq['depth_range'], 40)
         assert torch.equal(inds[0].cpu(), oinds), 'searchsorted index table differs from the oracle'
-        assert_close(fd[0].cpu(), torch.sort(ofd, -1)[0], rtol=1e-6, atol_scale=1e-7, what='fine depths vs oracle')
+        assert_close(fd[0].cpu(), torch.sort(ofd, -1)[0], rtol=1e-5, atol_scale=1e-6, what='fine depths vs oracle')
         assert_close(fd.cpu(), g['depth_fine'], what='fine depths vs reference')
         # ---- fine pass on the reference's fine depths
         fine = ops.render_by_depth(scene, hw_f, que, torch.from_numpy(g['depth_fine']).to(dev))
