@@ -160,7 +160,9 @@ def main():
 
     sd = golden_weights()              # random init of the reference architecture under torch.manual_seed(0)
     hw = ops.HeadWeights(sd, 'agg_net.', 'dist_decoder.', dev)
-    pool = make_pool(POOL, seed0=100 * rank)
+    from graspnerf_b200.shard import shard_scenes, max_over_ranks
+    # every rank owns its own shard of the global scene stream (rank r takes scenes r, r+W, ...): no data-path collective
+    pool = [make_pool(1, seed0=s)[0] for s in shard_scenes(POOL * world, rank, world)]
     scenes, bboxes, hosts = [], [], []
     for sc in pool:
         t = {k: torch.from_numpy(v).to(dev) for k, v in sc.items() if isinstance(v, np.ndarray)}
@@ -225,10 +227,7 @@ def main():
     torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - t0) * 1e3
 
-    times = torch.tensor([total_ms, e2e_ms], device=dev, dtype=torch.float64)
-    if dist is not None:
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms = times.tolist()
+    total_ms, e2e_ms = max_over_ranks([total_ms, e2e_ms], dist, dev)
     sampler.join(timeout=2)
     if rank == 0:
         peaks = load_peaks()

@@ -1,0 +1,170 @@
+"""2-D feature encoders and the VGN 3-D head: plain PyTorch/cuDNN modules (out of the CUDA hot path),
+re-stated here only so that the boundary class owns every parameter of the reference checkpoint under the reference's
+key names.  Architectures follow src/nr/network/ops.py:78-230, init_net.py:8-35, vis_encoder.py:6-21 and
+src/gd/networks.py:39-97; the key/shape table is pinned by tests/golden/state_dict_keys.json."""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+def _inorm(c):
+    return nn.InstanceNorm2d(c, track_running_stats=False, affine=True)
+
+
+def _c3(cin, cout, stride=1):
+    return nn.Conv2d(cin, cout, 3, stride, 1, bias=False, padding_mode='reflect')
+
+
+def _c1(cin, cout, stride=1):
+    return nn.Conv2d(cin, cout, 1, stride, bias=False, padding_mode='reflect')
+
+
+class BasicBlock(nn.Module):                      # ops.py:86-125
+    def __init__(self, cin, cout, stride=1, downsample=None):
+        super().__init__()
+        self.conv1, self.bn1 = _c3(cin, cout, stride), _inorm(cout)
+        self.relu = nn.ReLU(inplace=True)
+        self.conv2, self.bn2 = _c3(cout, cout), _inorm(cout)
+        self.downsample = downsample
+
+    def forward(self, x):
+        y = self.relu(self.bn1(self.conv1(x)))
+        y = self.bn2(self.conv2(y))
+        return self.relu(y + (x if self.downsample is None else self.downsample(x)))
+
+
+class ConvNormELU(nn.Module):                     # ops.py `conv` 127-140
+    def __init__(self, cin, cout, k, stride):
+        super().__init__()
+        self.conv = nn.Conv2d(cin, cout, k, stride, (k - 1) // 2, padding_mode='reflect')
+        self.bn = _inorm(cout)
+
+    def forward(self, x):
+        return F.elu(self.bn(self.conv(x)))
+
+
+class UpConv(nn.Module):                          # ops.py `upconv` 142-150
+    def __init__(self, cin, cout, k, scale):
+        super().__init__()
+        self.scale = scale
+        self.conv = ConvNormELU(cin, cout, k, 1)
+
+    def forward(self, x):
+        return self.conv(F.interpolate(x, scale_factor=self.scale, mode='bilinear', align_corners=True))
+
+
+class ResUNetLight(nn.Module):                    # ops.py:150-230
+    def __init__(self, in_dim=3, layers=(2, 3, 6, 3), out_dim=32, inplanes=32):
+        super().__init__()
+        self.inplanes = inplanes
+        self.conv1 = nn.Conv2d(in_dim, inplanes, 7, 2, 3, bias=False, padding_mode='reflect')
+        self.bn1 = _inorm(inplanes)
+        self.relu = nn.ReLU(inplace=True)
+        self.layer1 = self._stage(32, layers[0])
+        self.layer2 = self._stage(64, layers[1])
+        self.layer3 = self._stage(128, layers[2])
+        self.upconv3 = UpConv(128, 64, 3, 2)
+        self.iconv3 = ConvNormELU(128, 64, 3, 1)
+        self.upconv2 = UpConv(64, 32, 3, 2)
+        self.iconv2 = ConvNormELU(64, 32, 3, 1)
+        self.out_conv = nn.Conv2d(32, out_dim, 1, 1)
+
+    def _stage(self, planes, blocks):
+        down = nn.Sequential(_c1(self.inplanes, planes, 2), _inorm(planes))     # stride 2 on every stage
+        mods = [BasicBlock(self.inplanes, planes, 2, down)]
+        self.inplanes = planes
+        mods += [BasicBlock(planes, planes) for _ in range(1, blocks)]
+        return nn.Sequential(*mods)
+
+    @staticmethod
+    def _skip(skip, x):
+        dy, dx = x.shape[2] - skip.shape[2], x.shape[3] - skip.shape[3]
+        skip = F.pad(skip, (dx // 2, dx - dx // 2, dy // 2, dy - dy // 2))
+        return torch.cat([x, skip], 1)
+
+    def forward(self, x):
+        x = self.relu(self.bn1(self.conv1(x)))
+        x1 = self.layer1(x)
+        x2 = self.layer2(x1)
+        x3 = self.layer3(x2)
+        x = self.iconv3(self._skip(x2, self.upconv3(x3)))
+        x = self.iconv2(self._skip(x1, self.upconv2(x)))
+        return self.out_conv(x)
+
+
+class ResidualBlock(nn.Module):                   # ops.py:43-76 (use_norm branch)
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.conv = nn.Sequential(_inorm(cin), nn.ReLU(True), nn.Conv2d(cin, cout, 3, 1, 1, bias=False, padding_mode='reflect'),
+                                  _inorm(cout), nn.ReLU(True), nn.Conv2d(cout, cout, 3, 1, 1, bias=False, padding_mode='reflect'))
+        self.short_cut = None if cin == cout else nn.Conv2d(cin, cout, 1, 1)
+
+    def forward(self, x):
+        y = self.conv(x)
+        return y + (x if self.short_cut is None else self.short_cut(x))
+
+
+class CostVolumeInitNet(nn.Module):               # init_net.py:8-35 (no cost volume despite the name)
+    default_cfg = {'cost_volume_sn': 64}
+
+    def __init__(self, cfg):
+        super().__init__()
+        self.cfg = {**self.default_cfg, **cfg}
+        self.register_buffer('imagenet_mean', torch.tensor([0.485, 0.456, 0.406])[None, :, None, None])
+        self.register_buffer('imagenet_std', torch.tensor([0.229, 0.224, 0.225])[None, :, None, None])
+        self.res_net = ResUNetLight(out_dim=32)
+        self.out_conv = nn.Sequential(_c3(32, 32), ResidualBlock(32, 32), _c1(32, 32))
+
+    def forward(self, ref_imgs_info, src_imgs_info, is_train):
+        return self.out_conv(self.res_net(ref_imgs_info['imgs']))
+
+
+class DefaultVisEncoder(nn.Module):               # vis_encoder.py:6-21
+    def __init__(self, cfg):
+        super().__init__()
+        self.cfg = dict(cfg)
+        self.out_conv = nn.Sequential(_c3(64, 32), ResidualBlock(32, 32), ResidualBlock(32, 32), _c1(32, 32))
+
+    def forward(self, ray_feats, imgs_feats):
+        return self.out_conv(torch.cat([imgs_feats, ray_feats], 1))
+
+
+name2init_net = {'cost_volume': CostVolumeInitNet}
+name2vis_encoder = {'default': DefaultVisEncoder}
+
+
+class _VgnEncoder(nn.Module):                     # gd/networks.py:57-74
+    def __init__(self):
+        super().__init__()
+        self.conv1 = nn.Conv3d(1, 16, 5, stride=2, padding=2)
+        self.conv2 = nn.Conv3d(16, 32, 3, stride=2, padding=1)
+        self.conv3 = nn.Conv3d(32, 64, 3, stride=2, padding=1)
+
+    def forward(self, x):
+        return F.relu(self.conv3(F.relu(self.conv2(F.relu(self.conv1(x))))))
+
+
+class _VgnDecoder(nn.Module):                     # gd/networks.py:77-97 (hard-coded 10/20/40 grids)
+    def __init__(self):
+        super().__init__()
+        self.conv1 = nn.Conv3d(64, 64, 3, padding=1)
+        self.conv2 = nn.Conv3d(64, 32, 3, padding=1)
+        self.conv3 = nn.Conv3d(32, 16, 5, padding=2)
+
+    def forward(self, x):
+        x = F.interpolate(F.relu(self.conv1(x)), 10)
+        x = F.interpolate(F.relu(self.conv2(x)), 20)
+        return F.interpolate(F.relu(self.conv3(x)), 40)
+
+
+class VgnConvNet(nn.Module):                      # gd/networks.py:39-54
+    def __init__(self):
+        super().__init__()
+        self.encoder, self.decoder = _VgnEncoder(), _VgnDecoder()
+        self.conv_qual = nn.Conv3d(16, 1, 5, padding=2)
+        self.conv_rot = nn.Conv3d(16, 4, 5, padding=2)
+        self.conv_width = nn.Conv3d(16, 1, 5, padding=2)
+
+    def forward(self, x):
+        x = self.decoder(self.encoder(x))
+        return torch.sigmoid(self.conv_qual(x)), F.normalize(self.conv_rot(x), dim=1), self.conv_width(x)

@@ -1,0 +1,179 @@
+"""Drop-in mirror of the reference's model API (src/nr/network/renderer.py:13-335): same class names, ctor cfg handling,
+`forward(data)` signature, output-dict keys and `state_dict` keys, so `Trainer` / `GraspNeRFPlanner` can construct
+`name2network['grasp_nerf'](cfg)` and load `model_best.pth` unchanged.
+
+What runs where:
+  * 2-D encoders, depth-mean head, VGN 3-D conv: PyTorch/cuDNN (out of the CUDA hot path);
+  * sample_volume and the RGB head (render): the sm_100a kernels through graspnerf_b200.ops - no torch fallback.
+Round-1 limitation: the CUDA hot path is forward-only (no autograd), so training through this class is not possible yet;
+`forward` raises if gradients are required of it."""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import ops
+from .encoders import ResUNetLight, VgnConvNet, name2init_net, name2vis_encoder
+from .heads import name2agg_net, name2dist_decoder
+
+
+class NeuralRayRenderer(nn.Module):
+    base_cfg = {                                              # renderer.py:14-47
+        'vis_encoder_type': 'default', 'vis_encoder_cfg': {},
+        'dist_decoder_type': 'mixture_logistics', 'dist_decoder_cfg': {},
+        'agg_net_type': 'default', 'agg_net_cfg': {},
+        'use_hierarchical_sampling': False, 'fine_agg_net_cfg': {}, 'fine_dist_decoder_cfg': {},
+        'fine_depth_sample_num': 64, 'fine_depth_use_all': False,
+        'ray_batch_num': 2048, 'depth_sample_num': 64, 'alpha_value_ground_state': -15,
+        'use_dr_prediction': False, 'use_nr_color_for_dr': False, 'use_self_hit_prob': False,
+        'use_ray_mask': True, 'ray_mask_view_num': 2, 'ray_mask_point_num': 8,
+        'render_depth': False, 'disable_view_dir': False, 'render_rgb': False,
+        'init_net_type': 'depth', 'init_net_cfg': {}, 'depth_loss_coords_num': 8192,
+    }
+
+    def __init__(self, cfg):
+        super().__init__()
+        self.cfg = {**self.base_cfg, **cfg}
+        if self.cfg['agg_net_type'] != 'neus':
+            raise NotImplementedError("only agg_net_type 'neus' (the shipped nrvgn_sdf.yaml) is implemented")
+        self.vis_encoder = name2vis_encoder[self.cfg['vis_encoder_type']](self.cfg['vis_encoder_cfg'])
+        self.dist_decoder = name2dist_decoder[self.cfg['dist_decoder_type']](self.cfg['dist_decoder_cfg'])
+        self.image_encoder = ResUNetLight(3, [1, 2, 6, 4], 32, inplanes=16)
+        self.init_net = name2init_net[self.cfg['init_net_type']](self.cfg['init_net_cfg'])
+        self.agg_net = name2agg_net[self.cfg['agg_net_type']](self.cfg['agg_net_cfg'])
+        if self.cfg['use_hierarchical_sampling']:
+            self.fine_dist_decoder = name2dist_decoder[self.cfg['dist_decoder_type']](self.cfg['fine_dist_decoder_cfg'])
+            self.fine_agg_net = name2agg_net[self.cfg['agg_net_type']](self.cfg['fine_agg_net_cfg'])
+        self.use_sdf = True
+        self._hw = {}
+
+    # ------------------------------------------------------------------------------------------------ plumbing
+    def _head_weights(self, fine=False):
+        key = 'fine' if fine else 'coarse'
+        agg, dd = ('fine_agg_net.', 'fine_dist_decoder.') if fine else ('agg_net.', 'dist_decoder.')
+        sd = {k: v for k, v in self.named_parameters() if k.startswith(agg) or k.startswith(dd)}
+        dev = next(self.parameters()).device
+        if key not in self._hw or self._hw[key].device != dev:
+            self._hw[key] = ops.HeadWeights(sd, agg, dd, dev)
+        else:
+            self._hw[key].refresh(sd)
+        return self._hw[key]
+
+    @staticmethod
+    def _scene(ref_imgs_info):
+        return ops.Scene(ref_imgs_info['imgs'], ref_imgs_info['img_feats'], ref_imgs_info['ray_feats'],
+                         ref_imgs_info['poses'], ref_imgs_info['Ks'], ref_imgs_info['depth_range'])
+
+    # ------------------------------------------------------------------------------------------------ hot path
+    def sample_volume(self, ref_imgs_info):
+        """renderer.py:164-199 (volume_type ['sdf']): K1 -> K2a -> K2b; returns [1,1,R,R,R]."""
+        if any(m != 'sdf' for m in self.cfg['volume_type']):
+            raise NotImplementedError("volume_type other than ['sdf'] is not implemented")
+        scene = self._scene(ref_imgs_info)
+        # bbox3d is a python list in training (train_dataset.py) and an fp32 tensor [2,3] in inference (main.py:231)
+        bbox_min = torch.as_tensor(ref_imgs_info['bbox3d'][0], dtype=torch.float32).to(scene.device).reshape(1, 3)
+        return ops.sample_volume(scene, self._head_weights(False), bbox_min, self.cfg['volume_resolution'])
+
+    def render(self, que_imgs_info, ref_imgs_info, is_train):
+        """renderer.py:201-220: chunk the query rays by ray_batch_num, coarse + fine pass per chunk (render_impl 152-162)."""
+        scene = self._scene(ref_imgs_info)
+        coords = que_imgs_info['coords']
+        dn, fdn = self.cfg['depth_sample_num'], self.cfg['fine_depth_sample_num']
+        hw_c = self._head_weights(False)
+        hw_f = self._head_weights(True) if self.cfg['use_hierarchical_sampling'] else None
+        outs = {}
+        for s in range(0, coords.shape[1], self.cfg['ray_batch_num']):
+            que = {'coords': coords[:, s:s + self.cfg['ray_batch_num']].contiguous(), 'poses': que_imgs_info['poses'],
+                   'Ks': que_imgs_info['Ks'], 'depth_range': que_imgs_info['depth_range']}
+            rn = que['coords'].shape[1]
+            if hw_f is not None:
+                # sample_fine_depth uses torch.rand in training (render_ops.py:205), stratified midpoints in eval
+                u = torch.rand(1, rn, fdn, device=coords.device) if is_train else None
+                res = ops.render_rays(scene, hw_c, hw_f, que, dn, fdn, u)
+            else:
+                res = ops.render_by_depth(scene, hw_c, que, ops.k3_coarse_depths(que['depth_range'], rn, dn))
+            res['s'] = torch.full((1, 1), hw_c.variance, device=coords.device)
+            if hw_f is not None:
+                res['s_fine'] = torch.full((1, 1), hw_f.variance, device=coords.device)
+            if 'imgs' in que_imgs_info:                     # renderer.py:125-127 (align_corners=True lookup of the GT colours)
+                gt = _bilinear_gt(que_imgs_info['imgs'], que['coords'])
+                res['pixel_colors_gt'] = gt
+                if hw_f is not None:
+                    res['pixel_colors_gt_fine'] = gt
+            for k, v in res.items():
+                if k in ('depth', 'depth_fine', 'fine_inds', 'sdf_grad', 'sdf_grad_fine'):
+                    continue
+                outs.setdefault(k, []).append(v)
+        return {k: torch.cat(v, 1) for k, v in outs.items()}
+
+    # ------------------------------------------------------------------------------------------------ torch-side heads
+    def predict_mean_for_depth_loss(self, ref_imgs_info):
+        """renderer.py:222-266: depth_loss_coords_num random pixels x V -> mean_decoder (+fine).  Small; stays in torch."""
+        ray_feats, imgs = ref_imgs_info['ray_feats'], ref_imgs_info['imgs']
+        rfn, _, h, w = imgs.shape
+        num = self.cfg['depth_loss_coords_num']
+        idx = torch.randperm(h * w)[:num].to(imgs.device)
+        coords = torch.stack([idx // w, idx % w], -1)        # the reference stacks (row, col) of meshgrid(arange(h), arange(w))
+        coords = coords.unsqueeze(0).repeat(rfn, 1, 1)
+        cf = coords.float()
+        grid = torch.stack([cf[..., 0] / (w - 1) * 2 - 1, cf[..., 1] / (h - 1) * 2 - 1], -1).unsqueeze(1)   # ops.py:29-31
+        feats = torch.nn.functional.grid_sample(ray_feats, grid, mode='bilinear', padding_mode='border',
+                                                align_corners=(ray_feats.shape[-2:] == imgs.shape[-2:])).squeeze(2).permute(0, 2, 1)
+        m = self.dist_decoder.predict_mean(feats)
+        out = {'depth_mean': m[..., 0], 'depth_coords': coords, 'depth_mean_2': m[..., 1]}
+        if self.cfg['use_hierarchical_sampling']:
+            mf = self.fine_dist_decoder.predict_mean(feats)
+            out['depth_mean_fine'], out['depth_mean_fine_2'] = mf[..., 0], mf[..., 1]
+        return out
+
+    def forward(self, data):
+        """renderer.py:268-291."""
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError('graspnerf_b200 round 1 is forward-only: call under torch.no_grad() '
+                                      '(backward kernels / training are not implemented yet)')
+        ref = data['ref_imgs_info'].copy()
+        que = data['que_imgs_info'].copy()
+        is_train = 'eval' not in data
+        src = data['src_imgs_info'].copy() if 'src_imgs_info' in data else None
+        ref['img_feats'] = self.image_encoder(ref['imgs'])
+        ref['ray_feats'] = self.init_net(ref, src, is_train)
+        ref['ray_feats'] = self.vis_encoder(ref['ray_feats'], ref['img_feats'])
+        out = {}
+        if self.cfg['render_rgb']:
+            out = self.render(que, ref, is_train)
+        if self.cfg['sample_volume']:
+            out['volume'] = self.sample_volume(ref)
+        if (self.cfg['use_depth_loss'] and 'true_depth' in ref) or (not is_train):
+            out.update(self.predict_mean_for_depth_loss(ref))
+        return out
+
+
+def _bilinear_gt(imgs, coords):
+    """interpolate_feats(imgs, coords, align_corners=True) with the default zero padding (ops.py:14-34, renderer.py:126)."""
+    _, _, h, w = imgs.shape
+    grid = torch.stack([coords[..., 0] / (w - 1) * 2 - 1, coords[..., 1] / (h - 1) * 2 - 1], -1).unsqueeze(1)
+    return torch.nn.functional.grid_sample(imgs, grid, mode='bilinear', padding_mode='zeros', align_corners=True).squeeze(2).permute(0, 2, 1)
+
+
+class GraspNeRF(nn.Module):
+    default_cfg_vgn = {'nr_initial_training_steps': 0, 'freeze_nr_after_init': False}   # renderer.py:294-297
+
+    def __init__(self, cfg):
+        super().__init__()
+        self.cfg = {**self.default_cfg_vgn, **cfg}
+        self.nr_net = NeuralRayRenderer(self.cfg)
+        self.vgn_net = VgnConvNet()
+
+    def select(self, out, index):                                                         # renderer.py:305-311
+        qual, rot, width = out
+        bi = torch.arange(qual.shape[0])
+        return (qual[bi, :, index[:, 0], index[:, 1], index[:, 2]].squeeze(), rot[bi, :, index[:, 0], index[:, 1], index[:, 2]],
+                width[bi, :, index[:, 0], index[:, 1], index[:, 2]].squeeze())
+
+    def forward(self, data):                                                              # renderer.py:313-331
+        out = self.nr_net(data)
+        vgn_pred = self.vgn_net(out['volume'])
+        out['vgn_pred'] = vgn_pred if 'full_vol' in data else self.select(vgn_pred, data['grasp_info'][0])
+        return out
+
+
+name2network = {'grasp_nerf': GraspNeRF}

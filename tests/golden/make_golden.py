@@ -111,3 +111,31 @@ def main():
 
 if __name__ == '__main__':
     main()
+
+
+def make_model_golden():
+    """state_dict key/shape/checksum table of the reference model under torch.manual_seed(0) and one full
+    GraspNeRF.forward (eval, render_rgb off as main.py:150 does) on a small scene."""
+    import json
+    cfg, net = build_reference_net(0)
+    table = {k: [list(v.shape), float(v.double().sum()), float(v.double().abs().sum())] for k, v in net.state_dict().items()}
+    with open(os.path.join(HERE, 'state_dict_keys.json'), 'w') as f:
+        json.dump(table, f, indent=0)
+    kw = dict(seed=3, num_views=4, h=96, w=160, radius=0.45)
+    scene = make_scene(**kw)
+    ref = to_torch({k: v for k, v in scene.items() if k not in ('img_feats', 'ray_feats')})
+    q = to_torch(make_query(scene, 16, 7))
+    net.nr_net.cfg['render_rgb'] = False
+    data = {'step': 0, 'eval': True, 'full_vol': True, 'ref_imgs_info': ref, 'que_imgs_info': q,
+            'src_imgs_info': ref}
+    torch.manual_seed(123)
+    with torch.no_grad():
+        out = net(data)
+    np.savez_compressed(os.path.join(HERE, 'forward_small_v4.npz'), volume=out['volume'][0, 0].numpy(),
+                        qual=out['vgn_pred'][0][0, 0].numpy(), depth_mean=out['depth_mean'].numpy(),
+                        depth_coords=out['depth_coords'].numpy())
+    print('model golden: keys', len(table), 'volume std', out['volume'].std().item(), sorted(out.keys()))
+
+
+if __name__ == '__main__' and '--model' in sys.argv:
+    make_model_golden()
