@@ -203,12 +203,15 @@ __device__ __noinline__ void tc_pool_rows(float* scr, int g, int v, int gb, int 
     float* sums = scr + (32 + g) * TC_POOL_STRIDE;
     const float* base = scr + gb * TC_POOL_STRIDE;
 #pragma unroll 1
-    for (int c = v; c < 36; c += V) {
-        float s = 0.f;
-        const float* q = base + c;
+    for (int ch = v; ch < 9; ch += V) {                 // lane (g,v) sums the float4 chunks v, v+V, ... of its point's V rows
+        const float* q = base + 4 * ch;
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 2
-        for (int jv = 0; jv < V; ++jv) s += q[jv * TC_POOL_STRIDE];
-        if (lane_active) sums[c] = s;
+        for (int jv = 0; jv < V; ++jv) {
+            const float4 t = *reinterpret_cast<const float4*>(q + jv * TC_POOL_STRIDE);
+            s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+        }
+        if (lane_active) st4(sums + 4 * ch, s);
     }
     __syncwarp();
 }
@@ -449,6 +452,7 @@ gn_k2a_tc_kernel(const __grid_constant__ GnK2aParams p, int num_tiles, int G)
             vis = ((1.f - c00) * aw + (1.f - c01) * mix1) * mask;
             hit = ((c10 - c00) * aw + (c11 - c01) * mix1) * mask;
         }
+        asm volatile("prefetch.global.L1 [%0];" :: "l"(row + GN_REC_IMGF));      // needed at S7: pull it into L1 under S3..S6
         // ================= S3: prob_embed.0 on [ray | 2hit-1 | 2vis-1]  (K = 34 -> 48) ====================
         {
             float hv[16];
@@ -530,6 +534,14 @@ gn_k2a_tc_kernel(const __grid_constant__ GnK2aParams p, int num_tiles, int G)
             tm_store_a<16>(cx.lane_addr, 128, tl);
         }
         TC_GEMM_BEGIN(cx) tc_issue<L_BF0B>(cx, 0, 0, true); TC_GEMM_END(cx)
+        {   // next tile's first record line (ray_feats) and per-point word: hide their latency under S8..S11
+            const long long npidx = ((long long)(tile + gridDim.x * TC_SLOTS) * 4 + (warp & 3)) * G + g;
+            if (npidx < total_pts) {
+                asm volatile("prefetch.global.L1 [%0];" :: "l"(p.rec + ((size_t)npidx * V + v) * GN_REC_STRIDE));
+                asm volatile("prefetch.global.L1 [%0];" :: "l"(p.rec + ((size_t)npidx * V + v) * GN_REC_STRIDE + GN_REC_RGB));
+                asm volatile("prefetch.global.L1 [%0];" :: "l"(p.pt + (size_t)npidx * GN_PT_STRIDE));
+            }
+        }
         // ================= S8: base_fc.2 ====================================================================
         tc_epilogue<1>(cx.lane_addr, 0, 4, sw + TS(BF_B0), 0);
         TC_GEMM_BEGIN(cx) tc_issue<L_BF2>(cx, 0, 0, false); TC_GEMM_END(cx)
