@@ -65,7 +65,7 @@ constexpr int TC_CONST_BYTES = TC_IMG_HALVES * 2 + TC_SMALL_FLOATS * 4;      // 
 static_assert(TC_CONST_BYTES % 16 == 0, "tc_const must be copyable with 16-byte loads");
 #define TC_POOL_STRIDE 44                                                     // floats per row of the pooling scratch
 __host__ __device__ constexpr size_t tc_smem_bytes(int G) {
-    return (size_t)TC_CONST_BYTES + (size_t)(TC_THREADS / 32) * (32 + G) * TC_POOL_STRIDE * 4 + 64;
+    return (size_t)TC_CONST_BYTES + (size_t)(TC_THREADS / 32) * (32 + G) * TC_POOL_STRIDE * 4 + 64;   // + barriers, tmem ptr
 }
 static_assert(tc_smem_bytes(5) <= 227 * 1024, "K2a-TC shared memory budget at V = 6");
 
@@ -342,11 +342,18 @@ gn_k2a_tc_kernel(const __grid_constant__ GnK2aParams p, int num_tiles, int G)
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);          // warp-uniform by construction
     const int slot = warp >> 2;
-    // ---- one-time setup: constants copy, TMEM, mbarriers
-    {
-        const uint4* src = reinterpret_cast<const uint4*>(p.tc_const);
-        uint4* dst = reinterpret_cast<uint4*>(smem_raw);
-        for (int i = tid; i < TC_CONST_BYTES / 16; i += TC_THREADS) dst[i] = __ldg(src + i);
+    // ---- one-time setup: constants (TMA bulk copy global -> shared, completion on an mbarrier), TMEM, mbarriers
+    uint64_t* s_cbar = reinterpret_cast<uint64_t*>(s_tmem + 2);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(s_cbar)), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(s_cbar)), "r"((uint32_t)TC_CONST_BYTES) : "memory");
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(p.tc_const);
+        for (uint32_t off = 0; off < (uint32_t)TC_CONST_BYTES; off += 32768u) {
+            const uint32_t n = min(32768u, (uint32_t)TC_CONST_BYTES - off);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         :: "r"(smem_u32(smem_raw + off)), "l"(src + off), "r"(n), "r"(smem_u32(s_cbar)) : "memory");
+        }
     }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(s_tmem)), "r"(512));
@@ -357,10 +364,10 @@ gn_k2a_tc_kernel(const __grid_constant__ GnK2aParams p, int num_tiles, int G)
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(&s_bar[1])), "r"(1));
         asm volatile("fence.mbarrier_init.release.cluster;");
     }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy smem writes -> visible to tcgen05.mma
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    mbar_wait(smem_u32(s_cbar), 0u);                                  // operand images + constants have landed (async proxy)
 
     TcCtx cx;
     cx.tmem_slot = *s_tmem + slot * TM_SLOT;
