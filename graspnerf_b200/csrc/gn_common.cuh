@@ -56,3 +56,23 @@ __device__ __forceinline__ GnTap1D gn_tap1d(float u, int size_img, int size_map,
     t.i1 = min(t.i0 + 1, size_map - 1);
     return t;
 }
+
+// Opt a kernel in to `bytes` of dynamic shared memory once per device (cached: later launches - including launches made
+// while a stream is being captured into a CUDA graph - do not call into the runtime again).
+template <typename K>
+static inline cudaError_t gn_ensure_smem(K kernel, size_t bytes, size_t (&cache)[16]) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 15;
+    if (bytes <= cache[dev]) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) cache[dev] = bytes;
+    return e;
+}
+static inline int gn_sm_count() {
+    static int cache[16] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!cache[dev & 15]) cudaDeviceGetAttribute(&cache[dev & 15], cudaDevAttrMultiProcessorCount, dev);
+    return cache[dev & 15];
+}

@@ -217,7 +217,8 @@ extern "C" int gn_k1_forward(const GnK1Params* hp, void* stream)
     const int npair = K1_TILE_P * p.V;
     const size_t smem = (size_t)npair * (sizeof(K1PairInfo) + K1_MISC * sizeof(float));
     if (smem > 227 * 1024) return -5;
-    cudaError_t e = cudaFuncSetAttribute(gn_k1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static size_t smem_cache_gn_k1_kernel[16] = {0};
+    cudaError_t e = gn_ensure_smem(gn_k1_kernel, smem, smem_cache_gn_k1_kernel);
     if (e != cudaSuccess) return (int)e;
     const long long grid = (long long)p.B * p.tiles_per_scene;
     if (grid > 0x7fffffffLL) return -6;

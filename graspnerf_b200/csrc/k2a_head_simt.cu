@@ -357,11 +357,10 @@ extern "C" int gn_k2a_forward(const GnK2aParams* hp, void* stream)
     if (tiles > 0x7fffffffLL) return -6;
     const size_t smem = ((size_t)GN_W_K2A_FLOATS + (size_t)K2A_WARPS * G * 64) * sizeof(float);
     if (smem > 227 * 1024) return -5;
-    cudaError_t e = cudaFuncSetAttribute(gn_k2a_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static size_t smem_cache_gn_k2a_simt_kernel[16] = {0};
+    cudaError_t e = gn_ensure_smem(gn_k2a_simt_kernel, smem, smem_cache_gn_k2a_simt_kernel);
     if (e != cudaSuccess) return (int)e;
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int sms = gn_sm_count();
     const int grid = (int)(tiles < sms ? tiles : sms);
     gn_k2a_simt_kernel<<<grid, K2A_THREADS, smem, (cudaStream_t)stream>>>(p, (int)tiles, G);
     return (int)cudaGetLastError();

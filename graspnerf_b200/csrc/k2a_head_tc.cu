@@ -738,11 +738,10 @@ extern "C" int gn_k2a_forward_tc(const GnK2aParams* hp, void* stream)
     if (tiles > 0x7fffffffLL) return -6;
     const size_t smem = tc_smem_bytes(G);
     if (smem > 227 * 1024) return -5;
-    cudaError_t e = cudaFuncSetAttribute(gn_k2a_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static size_t smem_cache_gn_k2a_tc_kernel[16] = {0};
+    cudaError_t e = gn_ensure_smem(gn_k2a_tc_kernel, smem, smem_cache_gn_k2a_tc_kernel);
     if (e != cudaSuccess) return (int)e;
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int sms = gn_sm_count();
     const long long want = (tiles + TC_SLOTS - 1) / TC_SLOTS;
     const int grid = (int)(want < sms ? want : sms);
     gn_k2a_tc_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(p, (int)tiles, G);

@@ -506,11 +506,13 @@ extern "C" int gn_k2b_forward(const GnK2bParams* hp, void* stream)
     if (wg) smem += (size_t)K2B_THREADS * (16 + 16 + 12 + 65) * sizeof(float);
     cudaError_t e;
     if (wg) {
-        e = cudaFuncSetAttribute(gn_k2b_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        static size_t cache_t[16] = {0};
+        e = gn_ensure_smem(gn_k2b_kernel<true>, smem, cache_t);
         if (e != cudaSuccess) return (int)e;
         gn_k2b_kernel<true><<<(unsigned)grid, K2B_THREADS, smem, (cudaStream_t)stream>>>(p, rpb);
     } else {
-        e = cudaFuncSetAttribute(gn_k2b_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        static size_t cache_f[16] = {0};
+        e = gn_ensure_smem(gn_k2b_kernel<false>, smem, cache_f);
         if (e != cudaSuccess) return (int)e;
         gn_k2b_kernel<false><<<(unsigned)grid, K2B_THREADS, smem, (cudaStream_t)stream>>>(p, rpb);
     }

@@ -141,7 +141,8 @@ extern "C" int gn_k3_fine_depths(const float* depth, const float* hit_prob, cons
     if (B < 1 || rn < 1 || dn < 2 || fdn < 1) return -1;
     const size_t smem = (size_t)K3F_THREADS * (2 * (dn + 1) + fdn) * sizeof(float);
     if (smem > 227 * 1024) return -5;
-    cudaError_t e = cudaFuncSetAttribute(gn_k3_fine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static size_t smem_cache_gn_k3_fine_kernel[16] = {0};
+    cudaError_t e = gn_ensure_smem(gn_k3_fine_kernel, smem, smem_cache_gn_k3_fine_kernel);
     if (e != cudaSuccess) return (int)e;
     const long long rays = (long long)B * rn;
     gn_k3_fine_kernel<<<(unsigned)((rays + K3F_THREADS - 1) / K3F_THREADS), K3F_THREADS, smem, (cudaStream_t)stream>>>(

@@ -35,6 +35,7 @@ class _Slot:
         self.poses, self.Ks, self.depth_range = dev(hs.poses)[None], dev(hs.Ks)[None], dev(hs.depth_range)[None]
         self.bbox_min = dev(hs.bbox_min).reshape(1, 3)
         self.out_host = torch.empty((1, 1, resolution, resolution, resolution), dtype=torch.float32).pin_memory()
+        self.graph = None
         self.ev_in = torch.cuda.Event()
         self.ev_done = torch.cuda.Event()
         self.busy = False
@@ -67,8 +68,11 @@ class VolumeEngine:
             s.ev_in.record(self.copy_stream)
         with torch.cuda.stream(self.compute_stream):
             self.compute_stream.wait_event(s.ev_in)
-            scene = ops.Scene(s.imgs, s.img_feats, s.ray_feats, s.poses, s.Ks, s.depth_range, feats_channels_last=True)
-            vol = ops.sample_volume(scene, self.hw, s.bbox_min, self.R, self.vs)
+            if s.graph is None:                   # first use of the slot: capture (layout prep + K1 + K2a + K2b) once
+                def prologue(s=s):
+                    return ops.Scene(s.imgs, s.img_feats, s.ray_feats, s.poses, s.Ks, s.depth_range, feats_channels_last=True)
+                s.graph = ops.VolumeGraph(None, self.hw, s.bbox_min, self.R, self.vs, prologue=prologue)
+            vol = s.graph.replay()
             s.out_host.copy_(vol, non_blocking=True)
             s.ev_done.record(self.compute_stream)
         s.busy, s.tag = True, tag
