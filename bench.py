@@ -178,19 +178,13 @@ def main():
         torch.cuda.synchronize()
 
     def step(i, evs=None):
+        """the three launches, eagerly; evs = 6 events recorded immediately around each launch"""
         s, bb = scenes[i % POOL], bboxes[i % POOL]
-        if evs is not None:
-            evs[0].record()
-        rec, pt = ops.k1_forward(s, hw, resolution=R, bbox_min=bb)
-        if evs is not None:
-            evs[1].record()
+        e = (lambda j: (evs[2 * j], evs[2 * j + 1])) if evs is not None else (lambda j: None)
+        rec, pt = ops.k1_forward(s, hw, resolution=R, bbox_min=bb, ev=e(0))
         _, _, _, tok = ops.k2a_forward(rec, pt, hw, s.depth_range, impl='tc', want_pooled=False, want_tok=True,
-                                       resolution=R, bbox_min=bb)
-        if evs is not None:
-            evs[2].record()
-        vol, _ = ops.k2b_forward(None, hw, dn=R, resolution=R, bbox_min=bb, tok=tok)
-        if evs is not None:
-            evs[3].record()
+                                       resolution=R, bbox_min=bb, ev=e(1))
+        vol, _ = ops.k2b_forward(None, hw, dn=R, resolution=R, bbox_min=bb, tok=tok, ev=e(2))
         return vol
 
     # ---------------- device-resident timing ----------------
@@ -209,13 +203,18 @@ def main():
     barrier()
     sampler.stop_flag = True
     total_ms = ev0.elapsed_time(ev1)
-    # per-kernel durations: the same launches issued eagerly on the same stream with CUDA events around each kernel
-    KI = min(K, 48)
-    kev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(KI)]
+    # per-kernel durations: the same launches issued eagerly on the same stream, CUDA events recorded immediately around each
+    # launch.  A 1 GiB fill is queued first so that (a) the launches are already queued when the GPU reaches them (no host
+    # gap inside an event pair) and (b) every kernel starts from a flushed L2.
+    KI = min(K, 32)
+    filler = torch.empty(1 << 28, device=dev, dtype=torch.float32)
+    kev = [[torch.cuda.Event(enable_timing=True) for _ in range(6)] for _ in range(KI)]
     for i in range(KI):
+        filler.fill_(float(i))
         step(W_ + i, kev[i])
     torch.cuda.synchronize()
-    kt = np.array([[e[j].elapsed_time(e[j + 1]) for j in range(3)] for e in kev]).mean(0)     # ms per launch: K1, K2a, K2b
+    del filler
+    kt = np.array([[e[2 * j].elapsed_time(e[2 * j + 1]) for j in range(3)] for e in kev]).mean(0)     # ms per launch: K1, K2a, K2b
 
     # ---------------- end-to-end timing (pinned host in, pinned host out) ----------------
     eng = VolumeEngine(hw, hosts[0], R, slots=3, device=dev)

@@ -115,7 +115,7 @@ class Scene:
 
 
 def k1_forward(scene, hw, *, resolution=None, bbox_min=None, volume_size=0.3, pts=None, que_dir=None, dn=None,
-               debug_idx=False):
+               debug_idx=False, ev=None):
     """K1 launch.  Volume mode: resolution + bbox_min [B,3].  Ray mode: pts [B,N,3], que_dir [B,N/dn,3], dn."""
     lib = _lib.load()
     dev = scene.device
@@ -140,7 +140,12 @@ def k1_forward(scene, hw, *, resolution=None, bbox_min=None, volume_size=0.3, pt
     p.rec, p.pt, p.dbg_feat_idx = _ptr(rec).value, _ptr(pt).value, _ptr(dbg).value
     p.B, p.V, p.H, p.W, p.fh, p.fw = scene.B, scene.V, scene.H, scene.W, scene.fh, scene.fw
     p.N, p.dn, p.volume_mode = N, dn_, 1 if vol else 0
-    _lib.check(lib.gn_k1_forward(C.byref(p), _stream()), 'gn_k1_forward')
+    if ev is not None:
+        ev[0].record()
+    rc = lib.gn_k1_forward(C.byref(p), _stream())
+    if ev is not None:
+        ev[1].record()
+    _lib.check(rc, 'gn_k1_forward')
     return (rec, pt, dbg) if debug_idx else (rec, pt)
 
 
@@ -148,7 +153,7 @@ K2A_IMPL = 'tc'      # 'tc' (tcgen05, default) or 'simt' (fp32 CUDA-core impleme
 
 
 def k2a_forward(rec, pt, hw, depth_range, *, que_dists=None, dn=1, want_colors=False, debug=False, impl=None,
-                want_pooled=True, want_tok=False, resolution=None, bbox_min=None, volume_size=0.3, pts=None):
+                want_pooled=True, want_tok=False, resolution=None, bbox_min=None, volume_size=0.3, pts=None, ev=None):
     """K2a launch.  impl 'tc' (tcgen05) or 'simt'.  want_tok (tc only): also run geometry_fc and emit per-point tokens
     [B,N,20] for the attention-only K2b; needs the points: (resolution, bbox_min) in volume mode or pts [B,N,3]."""
     lib = _lib.load()
@@ -181,13 +186,18 @@ def k2a_forward(rec, pt, hw, depth_range, *, que_dists=None, dn=1, want_colors=F
     elif want_tok or not want_pooled:
         raise ValueError("tokens are produced by the tensor-core K2a only")
     fn = lib.gn_k2a_forward_tc if impl == 'tc' else lib.gn_k2a_forward
-    _lib.check(fn(C.byref(p), _stream()), f'gn_k2a_forward[{impl}]')
+    if ev is not None:
+        ev[0].record()
+    rc = fn(C.byref(p), _stream())
+    if ev is not None:
+        ev[1].record()
+    _lib.check(rc, f'gn_k2a_forward[{impl}]')
     if want_tok:
         return pooled, colors, dbg, tok
     return pooled, colors, dbg
 
 
-def k2b_forward(pooled, hw, *, dn, resolution=None, bbox_min=None, volume_size=0.3, pts=None, want_grad=False, tok=None):
+def k2b_forward(pooled, hw, *, dn, resolution=None, bbox_min=None, volume_size=0.3, pts=None, want_grad=False, tok=None, ev=None):
     """K2b launch.  pooled [B,N,68] -> full head (embed, geometry_fc, attention; grad optional);
     tok [B,N,20] (pooled=None) -> attention-only kernel on K2a-TC's tokens."""
     lib = _lib.load()
@@ -211,7 +221,12 @@ def k2b_forward(pooled, hw, *, dn, resolution=None, bbox_min=None, volume_size=0
     pos = hw.pos_table(int(dn))
     p.pooled, p.tok, p.weights, p.pos_table, p.sdf, p.grad = _ptr(pooled).value, _ptr(tok).value, _ptr(hw.blob).value, _ptr(pos).value, _ptr(out).value, _ptr(grad).value
     p.B, p.N, p.dn, p.volume_mode = B, N, int(dn), 1 if vol else 0
-    _lib.check(lib.gn_k2b_forward(C.byref(p), _stream()), 'gn_k2b_forward')
+    if ev is not None:
+        ev[0].record()
+    rc = lib.gn_k2b_forward(C.byref(p), _stream())
+    if ev is not None:
+        ev[1].record()
+    _lib.check(rc, 'gn_k2b_forward')
     return out, grad
 
 
