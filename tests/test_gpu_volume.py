@@ -144,3 +144,25 @@ def test_graph_replay_and_engine_match_eager():
         got[tag] = out.clone()
     for i in range(4):
         assert torch.equal(got[i], eager[i].cpu()), f'engine volume {i} differs from eager'
+
+
+def test_configs4_shape_v12_r80():
+    """BASELINE configs[4] shape family (12 views, 80^3 grid; small images here): the kernels are not tied to V=6 / R=40.
+    The reference hard-codes 40 (field_utils.py:12-15, ibrnet.py:425), so the comparator is the parameterised oracle
+    (SURVEY.md section 7 'hard-coded 40s')."""
+    from graspnerf_b200 import ops
+    from oracle import nr_oracle as O
+    sd = golden_weights()
+    kw = dict(seed=9, num_views=12, h=144, w=256, radius=0.55)
+    sc = _scene_t(kw)
+    dev = torch.device('cuda:0')
+    hw = ops.HeadWeights(sd, 'agg_net.', 'dist_decoder.', dev)
+    scene = ops.Scene(*[sc[k].to(dev) for k in ('imgs', 'img_feats', 'ray_feats', 'poses', 'Ks', 'depth_range')])
+    bbox = torch.tensor([sc['bbox3d'][0]], device=dev)
+    vol = ops.sample_volume(scene, hw, bbox, 80)
+    vol_simt = ops.sample_volume(scene, hw, bbox, 80, impl='simt')
+    torch.cuda.synchronize()
+    ovol = O.sample_volume(sd, sc, resolution=80)
+    assert vol.shape == (1, 1, 80, 80, 80)
+    assert_close(vol.cpu(), ovol, what='80^3 / 12-view volume (tensor-core path) vs oracle')
+    assert_close(vol_simt.cpu(), ovol, what='80^3 / 12-view volume (SIMT path) vs oracle')
