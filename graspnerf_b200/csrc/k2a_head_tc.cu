@@ -14,159 +14,16 @@
 //   * optionally (tok != NULL) geometry_fc (ibrnet.py:487-489: 86 -> 64 -> 16 on [mean, var, mean_v(w), embed(pts)]) runs
 //     as two more GEMMs on the pooled rows, so the per-ray kernel K2b only does attention + LayerNorm + output MLP.
 // Operand layouts were validated on B200 with tools/tc_probe.cu (profiles/tc_probe_r01.txt).
-#include "gn_common.cuh"
-#include "gn_weights.cuh"
-#include "../../include/graspnerf_b200.h"
-#include <cuda_fp16.h>
+#include "k2a_tc_common.cuh"
 
 #define TC_THREADS 256
 #define TC_SLOTS 2
 
-// ---- TMEM column map per slot (256 columns each) -------------------------------------------------------------
-#define TM_D 0            // accumulator, up to 96 columns
-#define TM_AHI 96         // A operand hi halves, 72 columns (K <= 144)
-#define TM_ALO 168        // A operand lo halves
-#define TM_SLOT 256
-
-// ---- shared-memory B images (fp16, element (n,k) at (k/8)*(N*8) + n*8 + k%8) ------------------------------------
-struct TcLayer { int N, K; };
-enum { L_DD1, L_DD2M, L_DD2V, L_DD2A, L_PE0, L_PE2, L_NF0, L_RD0, L_RD1, L_BF0A, L_BF0B, L_BF2, L_VF0, L_VF2, L_V20, L_GF0, L_GF2, L_COUNT };
-__host__ __device__ constexpr TcLayer tc_layer(int i) {
-    return i == L_DD1 ? TcLayer{96, 32} : i == L_DD2M ? TcLayer{32, 32} : i == L_DD2V ? TcLayer{32, 32} : i == L_DD2A ? TcLayer{32, 32}
-         : i == L_PE0 ? TcLayer{32, 48} : i == L_PE2 ? TcLayer{32, 32} : i == L_NF0 ? TcLayer{16, 32} : i == L_RD0 ? TcLayer{16, 16}
-         : i == L_RD1 ? TcLayer{48, 16} : i == L_BF0A ? TcLayer{64, 80} : i == L_BF0B ? TcLayer{64, 144} : i == L_BF2 ? TcLayer{32, 64}
-         : i == L_VF0 ? TcLayer{32, 32} : i == L_VF2 ? TcLayer{48, 32} : i == L_V20 ? TcLayer{32, 32}
-         : i == L_GF0 ? TcLayer{64, 96} : TcLayer{16, 64};
-}
-__host__ __device__ constexpr int tc_img_off(int i) {          // offset in halves of the HI image; LO follows at +N*K
-    int o = 0;
-    for (int j = 0; j < i; ++j) o += 2 * tc_layer(j).N * tc_layer(j).K;
-    return o;
-}
-constexpr int TC_IMG_HALVES = tc_img_off(L_COUNT);
-
-// ---- small fp32 constants (biases + the CUDA-core layers), stored right after the images --------------------------
-constexpr int kTcSmall[] = {
-    GN_W_DD_MEAN_B0, GN_W_DD_VAR_B0, GN_W_DD_AW_B0, GN_W_DD_MEAN_B2, GN_W_DD_VAR_B2, GN_W_DD_AW_B2,
-    GN_W_DD_MEAN_W4, GN_W_DD_VAR_W4, GN_W_DD_AW_W4, GN_W_DD_MEAN_B4, GN_W_DD_VAR_B4, GN_W_DD_AW_B4,
-    GN_W_PE_B0, GN_W_PE_B2, GN_W_NF_B0, GN_W_NF_W2, GN_W_NF_B2, GN_W_RD_B0, GN_W_RD_B1, GN_W_BF_B0, GN_W_BF_B2,
-    GN_W_VF_B0, GN_W_VF_B2, GN_W_V2_B0, GN_W_V2_W2, GN_W_V2_B2,
-    GN_W_RF_W0, GN_W_RF_B0, GN_W_RF_W2, GN_W_RF_B2, GN_W_RF_W4, GN_W_RF_B4, GN_W_GF_B0, GN_W_GF_B2 };
-constexpr int kTcSmallCount = sizeof(kTcSmall) / sizeof(int);
-constexpr int ts_off_idx(int j) { int o = 0; for (int i = 0; i < j; ++i) o += gn_w_size(kTcSmall[i]); return o; }
-constexpr int ts_find(int id) { for (int i = 0; i < kTcSmallCount; ++i) if (kTcSmall[i] == id) return i; return -1; }
-template <int ID> struct TsOffT {
-    static_assert(ts_find(ID) >= 0, "entry is not in the small-constant list");
-    static constexpr int value = ts_off_idx(ts_find(ID));
-};
-constexpr int TC_SMALL_FLOATS = ts_off_idx(kTcSmallCount);
-#define TS(id) (TsOffT<GN_W_##id>::value)
-constexpr int TC_CONST_BYTES = TC_IMG_HALVES * 2 + TC_SMALL_FLOATS * 4;      // global "tc_const" buffer == its smem image
-static_assert(TC_CONST_BYTES % 16 == 0, "tc_const must be copyable with 16-byte loads");
 #define TC_POOL_STRIDE 44                                                     // floats per row of the pooling scratch
 __host__ __device__ constexpr size_t tc_smem_bytes(int G) {
     return (size_t)TC_CONST_BYTES + (size_t)(TC_THREADS / 32) * (32 + G) * TC_POOL_STRIDE * 4 + 64;   // + barriers, tmem ptr
 }
 static_assert(tc_smem_bytes(5) <= 227 * 1024, "K2a-TC shared memory budget at V = 6");
-
-// ---- PTX wrappers ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ uint64_t tc_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
-    // tcgen05 shared-memory matrix descriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), SWIZZLE_NONE
-    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46);
-}
-__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint32_t a_tmem, uint32_t bdesc_lo, uint32_t idesc, uint32_t acc, uint32_t elected) {
-    // executed by the whole issuing warp with warp-uniform operands; only the elected lane issues (CUTLASS idiom), so the
-    // operands live in uniform registers.  High descriptor word is constant: SBO = 128 B (>>4 = 8), version 1 (bit 46).
-    asm volatile("{\n\t.reg .pred p, q;\n\t.reg .b64 bd;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"
-                 "mov.b64 bd, {%2, %6};\n\t"
-                 "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], bd, %3, p;\n\t}"
-                 :: "r"(d_tmem), "r"(a_tmem), "r"(bdesc_lo), "r"(idesc), "r"(acc), "r"(elected), "n"(0x4008) : "memory");
-}
-__device__ __forceinline__ void tc_commit(uint32_t bar, uint32_t elected) {
-    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
-                 "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" :: "r"(bar), "r"(elected) : "memory");
-}
-__device__ __forceinline__ uint32_t elect_one() {
-    uint32_t pred;
-    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
-    return pred;
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    // try_wait suspends the thread for a HW-bounded time per attempt; the attempt counter turns a lost arrival
-    // (a bug) into a trap instead of a hung GPU.
-    uint32_t done = 0;
-    for (uint32_t it = 0; !done; ++it) {
-        asm volatile("{\n\t.reg .pred p;\n\t"
-                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-                     "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-        if (it > (1u << 24)) __trap();
-    }
-}
-__device__ __forceinline__ void tm_ld16_issue(uint32_t taddr, uint32_t* r) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-                   "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]) : "r"(taddr));
-}
-__device__ __forceinline__ void tm_ld16_fence(uint32_t* r) {
-    // ties the loaded registers to a point AFTER tcgen05.wait::ld so no use can be scheduled above the wait
-    asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
-                      "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]) :: "memory");
-}
-// N accumulator columns -> registers: all loads in flight, ONE wait
-template <int N> __device__ __forceinline__ void tm_ld(uint32_t taddr, float* y) {
-    uint32_t r[N];
-#pragma unroll
-    for (int c = 0; c < N; c += 16) tm_ld16_issue(taddr + c, r + c);
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int c = 0; c < N; c += 16) tm_ld16_fence(r + c);
-#pragma unroll
-    for (int i = 0; i < N; ++i) y[i] = __uint_as_float(r[i]);
-}
-__device__ __forceinline__ void tm_st8(uint32_t taddr, const uint32_t* r) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
-                 :: "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
-}
-// split K fp32 values into fp16 hi/lo pairs and store them as the A operand (k0 = first k index, multiple of 16)
-template <int K> __device__ __forceinline__ void tm_store_a(uint32_t slot_lane_addr, int k0, const float* a) {
-#pragma unroll
-    for (int c = 0; c < K / 2; c += 8) {
-        uint32_t hi[8], lo[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const float a0 = a[2 * (c + i)], a1 = a[2 * (c + i) + 1];
-            const __half2 h = __floats2half2_rn(a0, a1);                 // .x (low 16 bits) = even k  (tc_probe variant 0)
-            const float2 hf = __half22float2(h);
-            const __half2 l = __floats2half2_rn(a0 - hf.x, a1 - hf.y);
-            hi[i] = *reinterpret_cast<const uint32_t*>(&h);
-            lo[i] = *reinterpret_cast<const uint32_t*>(&l);
-        }
-        tm_st8(slot_lane_addr + TM_AHI + k0 / 2 + c, hi);
-        tm_st8(slot_lane_addr + TM_ALO + k0 / 2 + c, lo);
-    }
-}
-// ELU with one MUFU: ex2.approx.ftz (rel. err 2^-22)
-__device__ __forceinline__ float tc_elu(float x) {
-    float e;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 1.4426950408889634f));
-    return x > 0.f ? x : e - 1.f;
-}
-// y = elu(y + b)
-template <int N> __device__ __forceinline__ void bias_elu(const float* __restrict__ b, float* y) {
-#pragma unroll
-    for (int n = 0; n < N; n += 4) {
-        const float4 w = *reinterpret_cast<const float4*>(b + n);
-        y[n] = tc_elu(y[n] + w.x); y[n + 1] = tc_elu(y[n + 1] + w.y); y[n + 2] = tc_elu(y[n + 2] + w.z); y[n + 3] = tc_elu(y[n + 3] + w.w);
-    }
-}
-template <int N> __device__ __forceinline__ void add_bias(const float* __restrict__ b, float* y) {
-#pragma unroll
-    for (int n = 0; n < N; n += 4) {
-        const float4 w = *reinterpret_cast<const float4*>(b + n);
-        y[n] += w.x; y[n + 1] += w.y; y[n + 2] += w.z; y[n + 3] += w.w;
-    }
-}
 
 // Generic layer epilogue, shared by every "plain" layer (NOT inlined: one copy of the code serves ~60 % of all
 // activations, which keeps the kernel's instruction footprint cache-friendly):
@@ -255,10 +112,12 @@ __device__ __forceinline__ void tc_issue(const TcCtx& cx, int d_col, int a_k0, b
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");                 \
     asm volatile("bar.sync %0, 128;" :: "r"((cx).bar_id) : "memory");                \
     if ((cx).issuer) { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#define TC_GEMM_END(cx)                                                              \
-        tc_commit((cx).bar, (cx).elected); __syncwarp(); }                                                     \
+#define TC_GEMM_COMMIT(cx)                                                           \
+        tc_commit((cx).bar, (cx).elected); __syncwarp(); }
+#define TC_GEMM_WAIT(cx)                                                             \
     mbar_wait((cx).bar, (cx).parity); (cx).parity ^= 1u;                             \
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#define TC_GEMM_END(cx) TC_GEMM_COMMIT(cx) TC_GEMM_WAIT(cx)
 
 // Cross-view sum of 36 per-row values through the warp's scratch: out[c] = sum over the V rows of my point of vals[c].
 __device__ __forceinline__ void pool36(float* scr, int lane, int g, int v, int gb, int V, bool lane_active, const float* vals, float* out)
@@ -274,59 +133,6 @@ __device__ __forceinline__ void pool36(float* scr, int lane, int g, int v, int g
         out[c] = t.x; out[c + 1] = t.y; out[c + 2] = t.z; out[c + 3] = t.w;
     }
     __syncwarp();
-}
-
-// ---- prepare: fp32 blob -> [fp16 hi/lo images | small fp32 constants] in global memory ---------------------------------
-__device__ void tc_fill(__half* img, int N, int K, const float* __restrict__ src, int ksrc, int nsrc, int cp, int k_dst, int n_dst) {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ksrc * nsrc; i += gridDim.x * blockDim.x) {
-        const int k = i / nsrc, n = i - k * nsrc;
-        const float w = __ldg(src + k * cp + n);
-        const __half hi = __float2half_rn(w);
-        const __half lo = __float2half_rn(w - __half2float(hi));
-        const int kk = k + k_dst, nn = n + n_dst;
-        const int off = (kk >> 3) * (N * 8) + nn * 8 + (kk & 7);
-        img[off] = hi;
-        img[N * K + off] = lo;
-    }
-}
-struct TcSmallPlan { int src[kTcSmallCount], n[kTcSmallCount], dst[kTcSmallCount]; };
-__global__ void gn_k2a_tc_prepare_kernel(const float* __restrict__ W, unsigned char* __restrict__ out, const TcSmallPlan plan)
-{
-    __half* s_img = reinterpret_cast<__half*>(out);               // caller zero-fills `out` first
-#define IMG(L) (s_img + tc_img_off(L))
-    tc_fill(IMG(L_DD1), 96, 32, W + GN_OFF(DD_MEAN_W0), 32, 32, 32, 0, 0);
-    tc_fill(IMG(L_DD1), 96, 32, W + GN_OFF(DD_VAR_W0), 32, 32, 32, 0, 32);
-    tc_fill(IMG(L_DD1), 96, 32, W + GN_OFF(DD_AW_W0), 32, 32, 32, 0, 64);
-    tc_fill(IMG(L_DD2M), 32, 32, W + GN_OFF(DD_MEAN_W2), 32, 32, 32, 0, 0);
-    tc_fill(IMG(L_DD2V), 32, 32, W + GN_OFF(DD_VAR_W2), 32, 32, 32, 0, 0);
-    tc_fill(IMG(L_DD2A), 32, 32, W + GN_OFF(DD_AW_W2), 32, 32, 32, 0, 0);
-    tc_fill(IMG(L_PE0), 32, 48, W + GN_OFF(PE_W0), 34, 32, 32, 0, 0);
-    tc_fill(IMG(L_PE2), 32, 32, W + GN_OFF(PE_W2), 32, 32, 32, 0, 0);
-    tc_fill(IMG(L_NF0), 16, 32, W + GN_OFF(NF_W0), 32, 8, 8, 0, 0);
-    tc_fill(IMG(L_RD0), 16, 16, W + GN_OFF(RD_W0), 4, 16, 16, 0, 0);
-    tc_fill(IMG(L_RD1), 48, 16, W + GN_OFF(RD_W1), 16, 36, 36, 0, 0);
-    tc_fill(IMG(L_BF0A), 64, 80, W + GN_OFF(BF_WF), 36, 64, 64, 0, 0);
-    tc_fill(IMG(L_BF0A), 64, 80, W + GN_OFF(BF_WP), 32, 64, 64, 48, 0);
-    // bf.wg rows are [mean0 36 | var0 36 | mean1 36 | var1 36]; image k order: m0[0..31] m1[0..31] v0[0..31] v1[0..31] tails
-    tc_fill(IMG(L_BF0B), 64, 144, W + GN_OFF(BF_WG) + 0 * 64, 32, 64, 64, 0, 0);
-    tc_fill(IMG(L_BF0B), 64, 144, W + GN_OFF(BF_WG) + 72 * 64, 32, 64, 64, 32, 0);
-    tc_fill(IMG(L_BF0B), 64, 144, W + GN_OFF(BF_WG) + 36 * 64, 32, 64, 64, 64, 0);
-    tc_fill(IMG(L_BF0B), 64, 144, W + GN_OFF(BF_WG) + 108 * 64, 32, 64, 64, 96, 0);
-    tc_fill(IMG(L_BF0B), 64, 144, W + GN_OFF(BF_WG) + 32 * 64, 3, 64, 64, 128, 0);
-    tc_fill(IMG(L_BF0B), 64, 144, W + GN_OFF(BF_WG) + 104 * 64, 3, 64, 64, 131, 0);
-    tc_fill(IMG(L_BF0B), 64, 144, W + GN_OFF(BF_WG) + 68 * 64, 3, 64, 64, 134, 0);
-    tc_fill(IMG(L_BF0B), 64, 144, W + GN_OFF(BF_WG) + 140 * 64, 3, 64, 64, 137, 0);
-    tc_fill(IMG(L_BF2), 32, 64, W + GN_OFF(BF_W2), 64, 32, 32, 0, 0);
-    tc_fill(IMG(L_VF0), 32, 32, W + GN_OFF(VF_W0), 32, 32, 32, 0, 0);
-    tc_fill(IMG(L_VF2), 48, 32, W + GN_OFF(VF_W2), 32, 36, 36, 0, 0);
-    tc_fill(IMG(L_V20), 32, 32, W + GN_OFF(V2_W0), 32, 32, 32, 0, 0);
-    tc_fill(IMG(L_GF0), 64, 96, W + GN_OFF(GF_W0), 86, 64, 64, 0, 0);
-    tc_fill(IMG(L_GF2), 16, 64, W + GN_OFF(GF_W2), 64, 16, 16, 0, 0);
-#undef IMG
-    float* small = reinterpret_cast<float*>(out + (size_t)TC_IMG_HALVES * 2);
-    for (int e = 0; e < kTcSmallCount; ++e)
-        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < plan.n[e]; i += gridDim.x * blockDim.x)
-            small[plan.dst[e] + i] = __ldg(W + plan.src[e] + i);
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -513,14 +319,15 @@ gn_k2a_tc_kernel(const __grid_constant__ GnK2aParams p, int num_tiles, int G)
 #pragma unroll
             for (int c = 35; c < 48; ++c) f[c] = 0.f;
             tm_store_a<48>(cx.lane_addr, 0, f);                 // A[k 0..47] = f (ray_feats no longer needed)
-            // ibrnet.py:470-471 means
+            TC_GEMM_BEGIN(cx) tc_issue<L_BF0A>(cx, 0, 0, false); TC_GEMM_COMMIT(cx)      // S7a runs under the mean poolings
+            // ibrnet.py:470-471 means (shared-memory scratch only: no TMEM access while the MMAs are in flight)
 #pragma unroll
             for (int c = 0; c < 36; ++c) tmp[c] = w0 * f[c];
             pool36(scr, lane, g, v, gb, V, lane_active, tmp, g0);
 #pragma unroll
             for (int c = 0; c < 36; ++c) tmp[c] = wgt * f[c];
             pool36(scr, lane, g, v, gb, V, lane_active, tmp, g1);
-            TC_GEMM_BEGIN(cx) tc_issue<L_BF0A>(cx, 0, 0, false); TC_GEMM_END(cx)
+            TC_GEMM_WAIT(cx)
             // S7b operand, k layout: mean0[0..31] | mean1[0..31] | var0[0..31] | var1[0..31] | tails (channels 32..34 of the four)
             tm_store_a<32>(cx.lane_addr, 0, g0);
             tm_store_a<32>(cx.lane_addr, 32, g1);
@@ -707,18 +514,6 @@ gn_k2a_tc_kernel(const __grid_constant__ GnK2aParams p, int num_tiles, int G)
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(*s_tmem), "r"(512));
-}
-
-extern "C" int gn_k2a_tc_const_bytes(void) { return TC_CONST_BYTES; }
-
-extern "C" int gn_k2a_tc_prepare(const float* weights, void* tc_const, void* stream)
-{
-    cudaError_t e = cudaMemsetAsync(tc_const, 0, TC_CONST_BYTES, (cudaStream_t)stream);
-    if (e != cudaSuccess) return (int)e;
-    TcSmallPlan plan;
-    for (int i = 0; i < kTcSmallCount; ++i) { plan.src[i] = gn_w_off(kTcSmall[i]); plan.n[i] = gn_w_size(kTcSmall[i]); plan.dst[i] = ts_off_idx(i); }
-    gn_k2a_tc_prepare_kernel<<<32, 256, 0, (cudaStream_t)stream>>>(weights, reinterpret_cast<unsigned char*>(tc_const), plan);
-    return (int)cudaGetLastError();
 }
 
 extern "C" int gn_k2a_forward_tc(const GnK2aParams* hp, void* stream)

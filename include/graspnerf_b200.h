@@ -9,7 +9,8 @@
  *   - every pointer is a DEVICE pointer to fp32 unless stated; the caller owns all buffers (kernels never allocate);
  *   - all launches go to the caller's `stream` (a cudaStream_t passed as void*), no host synchronisation;
  *   - return value: 0 = ok, <0 = argument error, >0 = cudaError_t of the launch; no exceptions cross the ABI;
- *   - re-entrant, no global state; one process per GPU under data parallelism.
+ *   - re-entrant; the only process-global state is an idempotent per-device cache of kernel attributes; one process
+ *     per GPU under data parallelism.
  *
  * Data layout in HBM:
  *   feature maps  : channels-last  [B, V, fh, fw, 32]
@@ -86,6 +87,7 @@ typedef struct GnK2aParams {
 } GnK2aParams;
 int gn_k2a_forward(const GnK2aParams* params, void* stream);      /* fp32 SIMT implementation (reference for the TC path) */
 int gn_k2a_forward_tc(const GnK2aParams* params, void* stream);   /* tcgen05 / TMEM implementation (fp16 hi/lo split, 3 MMAs per product) */
+int gn_k2a_forward_tc2(const GnK2aParams* params, void* stream);  /* same, 8 warps per 128-row tile (two threads per row): default */
 int gn_k2a_tc_const_bytes(void);
 int gn_k2a_tc_prepare(const float* weights, void* tc_const, void* stream);   /* fp32 blob -> fp16 hi/lo operand images + small constants */
 
