@@ -39,7 +39,10 @@ struct GnWEntry { const char* name; int rows; int cols; int cols_pad; };
     X(AT_WQ, "at.wq", 16, 16, 16) X(AT_WK, "at.wk", 16, 16, 16) X(AT_WV, "at.wv", 16, 16, 16) X(AT_FC, "at.fc", 16, 16, 16) \
     X(AT_LNW, "at.ln_w", 1, 16, 16) X(AT_LNB, "at.ln_b", 1, 16, 16) \
     /* out_geometry_fc (ibrnet.py:410-412) */ \
-    X(OG_W0, "og.w0", 16, 16, 16) X(OG_B0, "og.b0", 1, 16, 16) X(OG_W1, "og.w1", 1, 16, 16) X(OG_B1, "og.b1", 1, 1, 4)
+    X(OG_W0, "og.w0", 16, 16, 16) X(OG_B0, "og.b0", 1, 16, 16) X(OG_W1, "og.w1", 1, 16, 16) X(OG_B1, "og.b1", 1, 1, 4) \
+    /* host-side algebraic fusions used by the tensor-core K2a: prob_embed.2 has no activation, so its consumers take the  \
+       ReLU'd hidden e1 directly: neuray_fc.0 o prob_embed.2 (32 -> 8) and the prob_embed block of base_fc.0 o prob_embed.2 */ \
+    X(NFC_W0, "nfc.w0", 32, 8, 8) X(NFC_B0, "nfc.b0", 1, 8, 8) X(BF_WPC, "bf.wpc", 32, 64, 64) X(BF_B0C, "bf.b0c", 1, 64, 64)
 
 enum GnWIdx {
 #define X(id, name, r, c, cp) GN_W_##id,
@@ -64,6 +67,6 @@ constexpr int GN_W_TOTAL = gn_w_off(GN_W_COUNT);
 // K2a uses entries [DD_MEAN_W0, GF_W0); K2b uses [GF_W0, COUNT)
 constexpr int GN_W_K2A_FLOATS = gn_w_off(GN_W_GF_W0);
 constexpr int GN_W_K2B_OFF = gn_w_off(GN_W_GF_W0);
-constexpr int GN_W_K2B_FLOATS = GN_W_TOTAL - GN_W_K2B_OFF;
+constexpr int GN_W_K2B_FLOATS = gn_w_off(GN_W_NFC_W0) - GN_W_K2B_OFF;       // geometry_fc .. out_geometry_fc
 template <int I> struct GnOffT { static constexpr int value = gn_w_off(I); };
 #define GN_OFF(id) (GnOffT<GN_W_##id>::value)

@@ -209,7 +209,7 @@ gn_k2a_tc_kernel(const __grid_constant__ GnK2aParams p, int num_tiles, int G)
         const float nvalid = ptv.x;
         const float wgt = __fdiv_rn(mask, nvalid + 1e-8f);      // ibrnet.py:466
 
-        // ================= S1: dist-decoder first layers (3 x 32 -> 32 as one N=96 GEMM) =================
+        // ================= S1: dist-decoder first layers (N = 96) + ray_dir_fc.0 on dir_diff (N = 16) ====================
         {
             float ray[32];
 #pragma unroll
@@ -218,11 +218,16 @@ gn_k2a_tc_kernel(const __grid_constant__ GnK2aParams p, int num_tiles, int G)
                 ray[c] = t.x; ray[c + 1] = t.y; ray[c + 2] = t.z; ray[c + 3] = t.w;
             }
             tm_store_a<32>(cx.lane_addr, 0, ray);               // A[k 0..31] = ray_feats (kept for S3)
+            float dd[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) dd[c] = 0.f;
+            dd[0] = ddv.x; dd[1] = ddv.y; dd[2] = ddv.z; dd[3] = ddv.w;
+            tm_store_a<16>(cx.lane_addr, 112, dd);
         }
-        TC_GEMM_BEGIN(cx) tc_issue<L_DD1>(cx, 0, 0, false); TC_GEMM_END(cx)
-        // ================= S2: second layers (block diagonal: three N=32,K=32 GEMMs) =====================
+        TC_GEMM_BEGIN(cx) tc_issue<L_DD1>(cx, 0, 0, false); tc_issue<L_RD0>(cx, 96, 112, false); TC_GEMM_END(cx)
+        // ================= S2: dist-decoder second layers (block diagonal: three N=32,K=32 GEMMs) ========================
         static_assert(TS(DD_VAR_B0) == TS(DD_MEAN_B0) + 32 && TS(DD_AW_B0) == TS(DD_MEAN_B0) + 64, "dist-decoder biases must be contiguous");
-        tc_epilogue<1>(cx.lane_addr, 0, 6, sw + TS(DD_MEAN_B0), 48);      // D[0..95] -> ELU -> A[k 48..143]
+        tc_epilogue<1>(cx.lane_addr, 0, 6, sw + TS(DD_MEAN_B0), 48);      // D[0..95] -> ELU -> A[k 48..143]  (dir_diff no longer needed)
         TC_GEMM_BEGIN(cx)
             tc_issue<L_DD2M>(cx, 0, 48, false); tc_issue<L_DD2V>(cx, 32, 80, false); tc_issue<L_DD2A>(cx, 64, 112, false);
         TC_GEMM_END(cx)
@@ -265,8 +270,8 @@ gn_k2a_tc_kernel(const __grid_constant__ GnK2aParams p, int num_tiles, int G)
             vis = ((1.f - c00) * aw + (1.f - c01) * mix1) * mask;
             hit = ((c10 - c00) * aw + (c11 - c01) * mix1) * mask;
         }
-        asm volatile("prefetch.global.L1 [%0];" :: "l"(row + GN_REC_IMGF));      // needed at S7: pull it into L1 under S3..S6
-        // ================= S3: prob_embed.0 on [ray | 2hit-1 | 2vis-1]  (K = 34 -> 48) ====================
+        asm volatile("prefetch.global.L1 [%0];" :: "l"(row + GN_REC_IMGF));      // needed after S3
+        // ================= S3: prob_embed.0 on [ray | 2hit-1 | 2vis-1] (K = 34 -> 48)  +  ray_dir_fc.2 (16 -> 35) ==========
         {
             float hv[16];
 #pragma unroll
@@ -274,42 +279,16 @@ gn_k2a_tc_kernel(const __grid_constant__ GnK2aParams p, int num_tiles, int G)
             hv[0] = (hit - 0.5f) * 2.f; hv[1] = (vis - 0.5f) * 2.f;
             tm_store_a<16>(cx.lane_addr, 32, hv);
         }
-        TC_GEMM_BEGIN(cx) tc_issue<L_PE0>(cx, 0, 0, false); TC_GEMM_END(cx)
-        // ================= S4: prob_embed.2 ===============================================================
-        tc_epilogue<2>(cx.lane_addr, 0, 2, sw + TS(PE_B0), 80);           // ReLU (aggregate_net.py:31)
-        TC_GEMM_BEGIN(cx) tc_issue<L_PE2>(cx, 0, 80, false); TC_GEMM_END(cx)
-        // ================= S5: neuray_fc.0 on prob_emb, ray_dir_fc.0 on dir_diff ==========================
-        float pe01[2] = { 0.f, 0.f };
-        if (p.dbg_rows) {                                        // debug only: first two prob_embed outputs
-            float t16[16];
-            tm_ld<16>(cx.lane_addr + TM_D, t16);
-            pe01[0] = t16[0] + sw[TS(PE_B2)]; pe01[1] = t16[1] + sw[TS(PE_B2) + 1];
-        }
-        tc_epilogue<0>(cx.lane_addr, 0, 2, sw + TS(PE_B2), 48);           // prob_embed stays at k 48..79 for base_fc (S7a)
-        {
-            float dd[16];
-#pragma unroll
-            for (int c = 0; c < 16; ++c) dd[c] = 0.f;
-            dd[0] = ddv.x; dd[1] = ddv.y; dd[2] = ddv.z; dd[3] = ddv.w;
-            tm_store_a<16>(cx.lane_addr, 112, dd);
-        }
-        TC_GEMM_BEGIN(cx) tc_issue<L_NF0>(cx, 0, 48, false); tc_issue<L_RD0>(cx, 16, 112, false); TC_GEMM_END(cx)
-        // ================= S6: ray_dir_fc.2 ; weight0 =======================================================
+        tc_epilogue<1>(cx.lane_addr, 96, 1, sw + TS(RD_B0), 128);        // ray_dir_fc hidden: D[96..111] -> ELU -> A[k 128..143]
+        TC_GEMM_BEGIN(cx) tc_issue<L_PE0>(cx, 0, 0, false); tc_issue<L_RD1>(cx, 32, 128, false); TC_GEMM_END(cx)
+        // ================= S4: {neuray_fc.0 o prob_embed.2} and base_fc.0's per-view part, both on [f | e1] ===================
+        // prob_embed.2 has no activation, so its two consumers are pre-multiplied on the host (weights.py) and read the
+        // ReLU'd hidden e1 directly: prob_embed itself is never materialised.
+        tc_epilogue<2>(cx.lane_addr, 0, 2, sw + TS(PE_B0), 48);           // e1 = ReLU(.) -> A[k 48..79]
         float w0;
         {
-            float t[16];
-            tm_ld<16>(cx.lane_addr + TM_D, t);
-            float s = sw[TS(NF_B2)];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) s = fmaf(tc_elu(t[k] + sw[TS(NF_B0) + k]), sw[TS(NF_W2) + k], s);
-            w0 = gn_sigmoid(s) * wgt;                           // ibrnet.py:469
-        }
-        tc_epilogue<1>(cx.lane_addr, 16, 1, sw + TS(RD_B0), 128);       // ray_dir_fc hidden: D[16..31] -> ELU -> A[k 128..143]
-        TC_GEMM_BEGIN(cx) tc_issue<L_RD1>(cx, 0, 128, false); TC_GEMM_END(cx)
-        // ================= f = feats + direction feature; mean/var poolings; S7a, S7b =======================
-        {
             float f[48], g0[36], g1[36], tmp[36];
-            tm_ld<48>(cx.lane_addr + TM_D, f); bias_elu<36>(sw + TS(RD_B1), f);
+            tm_ld<48>(cx.lane_addr + TM_D + 32, f); bias_elu<36>(sw + TS(RD_B1), f);
 #pragma unroll
             for (int c = 0; c < 32; c += 4) {
                 const float4 t = ldg4(row + GN_REC_IMGF + c);
@@ -319,15 +298,23 @@ gn_k2a_tc_kernel(const __grid_constant__ GnK2aParams p, int num_tiles, int G)
 #pragma unroll
             for (int c = 35; c < 48; ++c) f[c] = 0.f;
             tm_store_a<48>(cx.lane_addr, 0, f);                 // A[k 0..47] = f (ray_feats no longer needed)
-            TC_GEMM_BEGIN(cx) tc_issue<L_BF0A>(cx, 0, 0, false); TC_GEMM_COMMIT(cx)      // S7a runs under the mean poolings
-            // ibrnet.py:470-471 means (shared-memory scratch only: no TMEM access while the MMAs are in flight)
-#pragma unroll
-            for (int c = 0; c < 36; ++c) tmp[c] = w0 * f[c];
-            pool36(scr, lane, g, v, gb, V, lane_active, tmp, g0);
+            TC_GEMM_BEGIN(cx) tc_issue<L_NFC>(cx, 96, 48, false); tc_issue<L_BF0C>(cx, 0, 0, false); TC_GEMM_COMMIT(cx)
+            // mean1 (weights w = mask / sum mask) does not need weight0: pooled while the MMAs run (shared memory only)
 #pragma unroll
             for (int c = 0; c < 36; ++c) tmp[c] = wgt * f[c];
             pool36(scr, lane, g, v, gb, V, lane_active, tmp, g1);
             TC_GEMM_WAIT(cx)
+            {
+                float t[16];
+                tm_ld<16>(cx.lane_addr + TM_D + 96, t);
+                float s = sw[TS(NF_B2)];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) s = fmaf(tc_elu(t[k] + sw[TS(NFC_B0) + k]), sw[TS(NF_W2) + k], s);
+                w0 = gn_sigmoid(s) * wgt;                       // ibrnet.py:469
+            }
+#pragma unroll
+            for (int c = 0; c < 36; ++c) tmp[c] = w0 * f[c];
+            pool36(scr, lane, g, v, gb, V, lane_active, tmp, g0);
             // S7b operand, k layout: mean0[0..31] | mean1[0..31] | var0[0..31] | var1[0..31] | tails (channels 32..34 of the four)
             tm_store_a<32>(cx.lane_addr, 0, g0);
             tm_store_a<32>(cx.lane_addr, 32, g1);
@@ -357,7 +344,7 @@ gn_k2a_tc_kernel(const __grid_constant__ GnK2aParams p, int num_tiles, int G)
             }
         }
         // ================= S8: base_fc.2 ====================================================================
-        tc_epilogue<1>(cx.lane_addr, 0, 4, sw + TS(BF_B0), 0);
+        tc_epilogue<1>(cx.lane_addr, 0, 4, sw + TS(BF_B0C), 0);          // bias includes the folded prob_embed.2 bias
         TC_GEMM_BEGIN(cx) tc_issue<L_BF2>(cx, 0, 0, false); TC_GEMM_END(cx)
         // ================= S9/S10: vis_fc ====================================================================
         float x[36];
@@ -424,7 +411,7 @@ gn_k2a_tc_kernel(const __grid_constant__ GnK2aParams p, int num_tiles, int G)
         if (p.dbg_rows && valid) {
             float* dr = p.dbg_rows + ((size_t)pidx * V + v) * 8;
             st4(dr, make_float4(hit, vis, w0, vis2));
-            st4(dr + 4, make_float4(x[0], x[1], pe01[0], pe01[1]));
+            st4(dr + 4, make_float4(x[0], x[1], 0.f, 0.f));      // prob_embed is fused away in this kernel (not materialised)
         }
         // ================= geometry_fc on the pooled rows (ibrnet.py:487-489) -> per-point token =================
         if (p.tok) {            // uniform branch

@@ -1,4 +1,4 @@
-// Shared pieces of the tensor-core K2a kernels (k2a_head_tc.cu: 4 warps per tile; k2a_head_tc2.cu: 8 warps per tile):
+// Shared pieces of the tensor-core K2a kernel (k2a_head_tc.cu) and its prepare step (k2a_tc_prepare.cu):
 // TMEM column map, fp16 operand-image table, small-constant table, tcgen05 / mbarrier PTX wrappers, the prepare kernel.
 #pragma once
 #include "gn_common.cuh"
@@ -7,21 +7,20 @@
 #include <cuda_fp16.h>
 
 // ---- TMEM column map per slot (256 columns each) -------------------------------------------------------------
-#define TM_D 0            // accumulator, up to 96 columns
-#define TM_AHI 96         // A operand hi halves, 72 columns (K <= 144)
-#define TM_ALO 168        // A operand lo halves
+#define TM_D 0            // accumulator, up to 112 columns
+#define TM_AHI 112        // A operand hi halves, 72 columns (K <= 144)
+#define TM_ALO 184        // A operand lo halves
 #define TM_SLOT 256
 
 // ---- shared-memory B images (fp16, element (n,k) at (k/8)*(N*8) + n*8 + k%8) ------------------------------------
 struct TcLayer { int N, K; };
-enum { L_DD1, L_DD2M, L_DD2V, L_DD2A, L_PE0, L_PE2, L_NF0, L_RD0, L_RD1, L_BF0A, L_BF0B, L_BF2, L_VF0, L_VF2, L_V20, L_GF0, L_GF2, L_DD3, L_V22, L_RF0, L_COUNT };
+enum { L_DD1, L_DD2M, L_DD2V, L_DD2A, L_PE0, L_NFC, L_RD0, L_RD1, L_BF0C, L_BF0B, L_BF2, L_VF0, L_VF2, L_V20, L_GF0, L_GF2, L_COUNT };
 __host__ __device__ constexpr TcLayer tc_layer(int i) {
     return i == L_DD1 ? TcLayer{96, 32} : i == L_DD2M ? TcLayer{32, 32} : i == L_DD2V ? TcLayer{32, 32} : i == L_DD2A ? TcLayer{32, 32}
-         : i == L_PE0 ? TcLayer{32, 48} : i == L_PE2 ? TcLayer{32, 32} : i == L_NF0 ? TcLayer{16, 32} : i == L_RD0 ? TcLayer{16, 16}
-         : i == L_RD1 ? TcLayer{48, 16} : i == L_BF0A ? TcLayer{64, 80} : i == L_BF0B ? TcLayer{64, 144} : i == L_BF2 ? TcLayer{32, 64}
+         : i == L_PE0 ? TcLayer{32, 48} : i == L_NFC ? TcLayer{16, 32} : i == L_RD0 ? TcLayer{16, 16} : i == L_RD1 ? TcLayer{48, 16}
+         : i == L_BF0C ? TcLayer{64, 80} : i == L_BF0B ? TcLayer{64, 144} : i == L_BF2 ? TcLayer{32, 64}
          : i == L_VF0 ? TcLayer{32, 32} : i == L_VF2 ? TcLayer{48, 32} : i == L_V20 ? TcLayer{32, 32}
-         : i == L_GF0 ? TcLayer{64, 96} : i == L_GF2 ? TcLayer{16, 64}
-         : i == L_DD3 ? TcLayer{16, 96} : i == L_V22 ? TcLayer{16, 32} : TcLayer{16, 48};
+         : i == L_GF0 ? TcLayer{64, 96} : TcLayer{16, 64};
 }
 __host__ __device__ constexpr int tc_img_off(int i) {          // offset in halves of the HI image; LO follows at +N*K
     int o = 0;
@@ -34,9 +33,10 @@ constexpr int TC_IMG_HALVES = tc_img_off(L_COUNT);
 constexpr int kTcSmall[] = {
     GN_W_DD_MEAN_B0, GN_W_DD_VAR_B0, GN_W_DD_AW_B0, GN_W_DD_MEAN_B2, GN_W_DD_VAR_B2, GN_W_DD_AW_B2,
     GN_W_DD_MEAN_W4, GN_W_DD_VAR_W4, GN_W_DD_AW_W4, GN_W_DD_MEAN_B4, GN_W_DD_VAR_B4, GN_W_DD_AW_B4,
-    GN_W_PE_B0, GN_W_PE_B2, GN_W_NF_B0, GN_W_NF_W2, GN_W_NF_B2, GN_W_RD_B0, GN_W_RD_B1, GN_W_BF_B0, GN_W_BF_B2,
+    GN_W_PE_B0, GN_W_NF_W2, GN_W_NF_B2, GN_W_RD_B0, GN_W_RD_B1, GN_W_BF_B2,
     GN_W_VF_B0, GN_W_VF_B2, GN_W_V2_B0, GN_W_V2_W2, GN_W_V2_B2,
-    GN_W_RF_W0, GN_W_RF_B0, GN_W_RF_W2, GN_W_RF_B2, GN_W_RF_W4, GN_W_RF_B4, GN_W_GF_B0, GN_W_GF_B2 };
+    GN_W_RF_W0, GN_W_RF_B0, GN_W_RF_W2, GN_W_RF_B2, GN_W_RF_W4, GN_W_RF_B4, GN_W_GF_B0, GN_W_GF_B2,
+    GN_W_NFC_B0, GN_W_BF_B0C };
 constexpr int kTcSmallCount = sizeof(kTcSmall) / sizeof(int);
 constexpr int ts_off_idx(int j) { int o = 0; for (int i = 0; i < j; ++i) o += gn_w_size(kTcSmall[i]); return o; }
 constexpr int ts_find(int id) { for (int i = 0; i < kTcSmallCount; ++i) if (kTcSmall[i] == id) return i; return -1; }

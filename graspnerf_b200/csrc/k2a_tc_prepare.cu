@@ -27,12 +27,8 @@ __global__ void gn_k2a_tc_prepare_kernel(const float* __restrict__ W, unsigned c
     tc_fill(IMG(L_DD2V), 32, 32, W + GN_OFF(DD_VAR_W2), 32, 32, 32, 0, 0);
     tc_fill(IMG(L_DD2A), 32, 32, W + GN_OFF(DD_AW_W2), 32, 32, 32, 0, 0);
     tc_fill(IMG(L_PE0), 32, 48, W + GN_OFF(PE_W0), 34, 32, 32, 0, 0);
-    tc_fill(IMG(L_PE2), 32, 32, W + GN_OFF(PE_W2), 32, 32, 32, 0, 0);
-    tc_fill(IMG(L_NF0), 16, 32, W + GN_OFF(NF_W0), 32, 8, 8, 0, 0);
     tc_fill(IMG(L_RD0), 16, 16, W + GN_OFF(RD_W0), 4, 16, 16, 0, 0);
     tc_fill(IMG(L_RD1), 48, 16, W + GN_OFF(RD_W1), 16, 36, 36, 0, 0);
-    tc_fill(IMG(L_BF0A), 64, 80, W + GN_OFF(BF_WF), 36, 64, 64, 0, 0);
-    tc_fill(IMG(L_BF0A), 64, 80, W + GN_OFF(BF_WP), 32, 64, 64, 48, 0);
     // bf.wg rows are [mean0 36 | var0 36 | mean1 36 | var1 36]; image k order: m0[0..31] m1[0..31] v0[0..31] v1[0..31] tails
     tc_fill(IMG(L_BF0B), 64, 144, W + GN_OFF(BF_WG) + 0 * 64, 32, 64, 64, 0, 0);
     tc_fill(IMG(L_BF0B), 64, 144, W + GN_OFF(BF_WG) + 72 * 64, 32, 64, 64, 32, 0);
@@ -48,12 +44,9 @@ __global__ void gn_k2a_tc_prepare_kernel(const float* __restrict__ W, unsigned c
     tc_fill(IMG(L_V20), 32, 32, W + GN_OFF(V2_W0), 32, 32, 32, 0, 0);
     tc_fill(IMG(L_GF0), 64, 96, W + GN_OFF(GF_W0), 86, 64, 64, 0, 0);
     tc_fill(IMG(L_GF2), 16, 64, W + GN_OFF(GF_W2), 64, 16, 16, 0, 0);
-    // third dist-decoder layers as one block GEMM: n 0,1 <- mean (k 0..31), n 2,3 <- var (k 32..63), n 4 <- aw (k 64..95)
-    tc_fill(IMG(L_DD3), 16, 96, W + GN_OFF(DD_MEAN_W4), 32, 2, 4, 0, 0);
-    tc_fill(IMG(L_DD3), 16, 96, W + GN_OFF(DD_VAR_W4), 32, 2, 4, 32, 2);
-    tc_fill(IMG(L_DD3), 16, 96, W + GN_OFF(DD_AW_W4), 32, 1, 4, 64, 4);
-    tc_fill(IMG(L_V22), 16, 32, W + GN_OFF(V2_W2), 32, 1, 1, 0, 0);          // vis_fc2.2 row vector as column n = 0
-    tc_fill(IMG(L_RF0), 16, 48, W + GN_OFF(RF_W0), 37, 16, 16, 0, 0);       // rgb_fc.0: rows [x 32 | vis | dir_diff 4]
+    tc_fill(IMG(L_NFC), 16, 32, W + GN_OFF(NFC_W0), 32, 8, 8, 0, 0);         // neuray_fc.0 o prob_embed.2 on the ReLU'd hidden
+    tc_fill(IMG(L_BF0C), 64, 80, W + GN_OFF(BF_WF), 36, 64, 64, 0, 0);       // base_fc.0: f block (k 0..47) ...
+    tc_fill(IMG(L_BF0C), 64, 80, W + GN_OFF(BF_WPC), 32, 64, 64, 48, 0);     // ... | (prob_embed block o prob_embed.2) (k 48..79)
 #undef IMG
     float* small = reinterpret_cast<float*>(out + (size_t)TC_IMG_HALVES * 2);
     for (int e = 0; e < kTcSmallCount; ++e)

@@ -63,6 +63,12 @@ def _entries(sd, agg_prefix, dd_prefix):
     e['at.ln_b'] = _np(sd[A + 'ray_attention.layer_norm.bias'])[None, :]
     lin('og.w0', 'og.b0', A + 'out_geometry_fc.0')
     lin('og.w1', 'og.b1', A + 'out_geometry_fc.1', vector=True)
+    # fusions through the activation-free prob_embed.2 (fp64 products, rounded once to fp32)
+    w2k, b2 = e['pe.w2'].astype(np.float64), e['pe.b2'].astype(np.float64)              # [32 in][32 out], [1,32]
+    e['nfc.w0'] = (w2k @ e['nf.w0'].astype(np.float64)).astype(np.float32)
+    e['nfc.b0'] = (b2 @ e['nf.w0'].astype(np.float64) + e['nf.b0']).astype(np.float32)
+    e['bf.wpc'] = (w2k @ e['bf.wp'].astype(np.float64)).astype(np.float32)
+    e['bf.b0c'] = (b2 @ e['bf.wp'].astype(np.float64) + e['bf.b0']).astype(np.float32)
     return e
 
 

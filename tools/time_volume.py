@@ -11,7 +11,7 @@ from tests.helpers import golden_weights
 def main():
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 1
     iters = int(sys.argv[2]) if len(sys.argv) > 2 else 20
-    ops.K2A_IMPL = sys.argv[3] if len(sys.argv) > 3 else 'tc2'
+    ops.K2A_IMPL = sys.argv[3] if len(sys.argv) > 3 else 'tc'
     dev = torch.device('cuda:0')
     sd = golden_weights()
     hw = ops.HeadWeights(sd, 'agg_net.', 'dist_decoder.', dev)
@@ -28,7 +28,7 @@ def main():
         ev[0].record()
         rec, pt = ops.k1_forward(scene, hw, resolution=40, bbox_min=bbox)
         ev[1].record()
-        if ops.K2A_IMPL in ('tc', 'tc2'):
+        if ops.K2A_IMPL == 'tc':
             _, _, _, tok = ops.k2a_forward(rec, pt, hw, scene.depth_range, want_pooled=False, want_tok=True, resolution=40, bbox_min=bbox)
             ev[2].record()
             vol, _ = ops.k2b_forward(None, hw, dn=40, resolution=40, bbox_min=bbox, tok=tok)
