@@ -18,6 +18,7 @@
 //            as coalesced float4 streaming stores.
 #include "gn_common.cuh"
 #include "../../include/graspnerf_b200.h"
+#include <cstdlib>
 
 #define K1_THREADS 256
 #define K1_TILE_P 32
@@ -32,7 +33,8 @@ struct K1PairInfo {           // written in phase A, read (broadcast within an 8
 };
 #define K1_MISC 12            // floats per pair in s_misc: dd0..3, mask, depth, pad
 
-__global__ void __launch_bounds__(K1_THREADS, 4)
+template <int MINB>
+__global__ void __launch_bounds__(K1_THREADS, MINB)
 gn_k1_kernel(const __grid_constant__ GnK1Params p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -217,11 +219,23 @@ extern "C" int gn_k1_forward(const GnK1Params* hp, void* stream)
     const int npair = K1_TILE_P * p.V;
     const size_t smem = (size_t)npair * (sizeof(K1PairInfo) + K1_MISC * sizeof(float));
     if (smem > 227 * 1024) return -5;
-    static size_t smem_cache_gn_k1_kernel[16] = {0};
-    cudaError_t e = gn_ensure_smem(gn_k1_kernel, smem, smem_cache_gn_k1_kernel);
-    if (e != cudaSuccess) return (int)e;
+    // resident CTAs per SM the kernel is compiled for (register budget): 4 by default; GN_K1_MINB=4|5|6 selects another
+    // instantiation (tuning aid)
+    static int minb = 0;
+    if (!minb) { const char* e = getenv("GN_K1_MINB"); minb = e ? atoi(e) : 4; if (minb < 4 || minb > 6) minb = 4; }
     const long long grid = (long long)p.B * p.tiles_per_scene;
     if (grid > 0x7fffffffLL) return -6;
-    gn_k1_kernel<<<(unsigned)grid, K1_THREADS, smem, (cudaStream_t)stream>>>(p);
+    cudaError_t e;
+    static size_t c4[16] = {0}, c5[16] = {0}, c6[16] = {0};
+    if (minb == 5) {
+        e = gn_ensure_smem(gn_k1_kernel<5>, smem, c5); if (e != cudaSuccess) return (int)e;
+        gn_k1_kernel<5><<<(unsigned)grid, K1_THREADS, smem, (cudaStream_t)stream>>>(p);
+    } else if (minb == 6) {
+        e = gn_ensure_smem(gn_k1_kernel<6>, smem, c6); if (e != cudaSuccess) return (int)e;
+        gn_k1_kernel<6><<<(unsigned)grid, K1_THREADS, smem, (cudaStream_t)stream>>>(p);
+    } else {
+        e = gn_ensure_smem(gn_k1_kernel<4>, smem, c4); if (e != cudaSuccess) return (int)e;
+        gn_k1_kernel<4><<<(unsigned)grid, K1_THREADS, smem, (cudaStream_t)stream>>>(p);
+    }
     return (int)cudaGetLastError();
 }
