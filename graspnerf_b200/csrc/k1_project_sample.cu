@@ -35,7 +35,7 @@ struct K1PairInfo {           // written in phase A, read (broadcast within an 8
 
 template <int MINB>
 __global__ void __launch_bounds__(K1_THREADS, MINB)
-gn_k1_kernel(const __grid_constant__ GnK1Params p)
+gn_k1_kernel(const __grid_constant__ GnK1Params p, const int nsub)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int V = p.V;
@@ -43,21 +43,31 @@ gn_k1_kernel(const __grid_constant__ GnK1Params p)
     K1PairInfo* s_info = reinterpret_cast<K1PairInfo*>(smem_raw);                    // [npair]
     float* s_misc  = reinterpret_cast<float*>(s_info + npair);                       // [npair][12]: dd0..3, mask, depth, pad
 
-    const int tiles_per_scene = p.tiles_per_scene;
+    const int tiles_per_scene = p.tiles_per_scene;          // CTAs per scene
     const int b = blockIdx.x / tiles_per_scene;
-    const int tile = blockIdx.x - b * tiles_per_scene;
+    const int cta_tile = blockIdx.x - b * tiles_per_scene;
     const int tid = threadIdx.x;
+    const int R = p.R;
 
     // ---- tile -> point mapping -------------------------------------------------------------------
     // volume mode: tile = 2x2x8 block of voxels (i,j,k); record index n = (i*R+j)*R + (R-1-k)
-    //              (renderer.py:169-170: reshape (1,R*R,R,3) then flip the sample axis)
+    //              (renderer.py:169-170: reshape (1,R*R,R,3) then flip the sample axis).  With nsub = 4 a CTA walks the
+    //              four x/y-adjacent tiles of a 4x4x8 block one after the other, so their shared taps hit in L1.
     // ray mode   : tile = 32 consecutive points n of the explicit pts array
-    const int R = p.R;
+    for (int sub = 0; sub < nsub; ++sub) {
+    int tile = cta_tile;
     int tk = 0, tj = 0, ti = 0;
     if (p.volume_mode) {
-        const int nz = R >> 3, ny = R >> 1;
-        tk = tile % nz; tj = (tile / nz) % ny; ti = tile / (nz * ny);
+        const int nz = R >> 3;
+        if (nsub == 4) {
+            const int ny2 = R >> 2;
+            tk = cta_tile % nz; tj = ((cta_tile / nz) % ny2) * 2 + (sub & 1); ti = (cta_tile / (nz * ny2)) * 2 + (sub >> 1);
+        } else {
+            const int ny = R >> 1;
+            tk = tile % nz; tj = (tile / nz) % ny; ti = tile / (nz * ny);
+        }
     }
+    if (sub) __syncthreads();                                // shared-memory records of the previous sub-tile are done
 
     // =============================== phase A ======================================================
     for (int pair = tid; pair < npair; pair += K1_THREADS) {
@@ -203,6 +213,7 @@ gn_k1_kernel(const __grid_constant__ GnK1Params p)
         float2 o; o.x = nvalid; o.y = __uint_as_float(bits);
         *reinterpret_cast<float2*>(p.pt + ((size_t)b * p.N + n) * GN_PT_STRIDE) = o;
     }
+    }   // sub-tile loop
 }
 
 extern "C" int gn_k1_forward(const GnK1Params* hp, void* stream)
@@ -221,6 +232,10 @@ extern "C" int gn_k1_forward(const GnK1Params* hp, void* stream)
     if (smem > 227 * 1024) return -5;
     // resident CTAs per SM the kernel is compiled for (register budget): 4 by default; GN_K1_MINB=4|5|6 selects another
     // instantiation (tuning aid)
+    static int nsub_env = -1;
+    if (nsub_env < 0) { const char* e = getenv("GN_K1_SUPER"); nsub_env = (e && atoi(e) == 1) ? 4 : 1; }
+    int nsub = 1;
+    if (p.volume_mode && nsub_env == 4 && (p.R % 4) == 0) { nsub = 4; p.tiles_per_scene /= 4; }
     static int minb = 0;
     if (!minb) { const char* e = getenv("GN_K1_MINB"); minb = e ? atoi(e) : 4; if (minb < 4 || minb > 6) minb = 4; }
     const long long grid = (long long)p.B * p.tiles_per_scene;
@@ -229,13 +244,13 @@ extern "C" int gn_k1_forward(const GnK1Params* hp, void* stream)
     static size_t c4[16] = {0}, c5[16] = {0}, c6[16] = {0};
     if (minb == 5) {
         e = gn_ensure_smem(gn_k1_kernel<5>, smem, c5); if (e != cudaSuccess) return (int)e;
-        gn_k1_kernel<5><<<(unsigned)grid, K1_THREADS, smem, (cudaStream_t)stream>>>(p);
+        gn_k1_kernel<5><<<(unsigned)grid, K1_THREADS, smem, (cudaStream_t)stream>>>(p, nsub);
     } else if (minb == 6) {
         e = gn_ensure_smem(gn_k1_kernel<6>, smem, c6); if (e != cudaSuccess) return (int)e;
-        gn_k1_kernel<6><<<(unsigned)grid, K1_THREADS, smem, (cudaStream_t)stream>>>(p);
+        gn_k1_kernel<6><<<(unsigned)grid, K1_THREADS, smem, (cudaStream_t)stream>>>(p, nsub);
     } else {
         e = gn_ensure_smem(gn_k1_kernel<4>, smem, c4); if (e != cudaSuccess) return (int)e;
-        gn_k1_kernel<4><<<(unsigned)grid, K1_THREADS, smem, (cudaStream_t)stream>>>(p);
+        gn_k1_kernel<4><<<(unsigned)grid, K1_THREADS, smem, (cudaStream_t)stream>>>(p, nsub);
     }
     return (int)cudaGetLastError();
 }

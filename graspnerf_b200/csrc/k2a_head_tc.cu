@@ -42,12 +42,15 @@ __device__ __noinline__ void tc_epilogue(uint32_t lane_addr, int d_col, int nchu
 #pragma unroll
         for (int i = 0; i < 16; i += 4) {
             const float4 w = *reinterpret_cast<const float4*>(bias + c * 16 + i);
-            y[i] = __uint_as_float(r[i]) + w.x; y[i + 1] = __uint_as_float(r[i + 1]) + w.y;
-            y[i + 2] = __uint_as_float(r[i + 2]) + w.z; y[i + 3] = __uint_as_float(r[i + 3]) + w.w;
+            upk2(add2(pk2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), pk2(w.x, w.y)), y[i], y[i + 1]);
+            upk2(add2(pk2(__uint_as_float(r[i + 2]), __uint_as_float(r[i + 3])), pk2(w.z, w.w)), y[i + 2], y[i + 3]);
         }
         if (c + 1 < nchunk) tm_ld16_issue(lane_addr + TM_D + d_col + (c + 1) * 16, r);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) y[i] = ACT == 1 ? tc_elu(y[i]) : (ACT == 2 ? fmaxf(y[i], 0.f) : y[i]);
+        for (int i = 0; i < 16; i += 2) {
+            if (ACT == 1) tc_elu2(y[i], y[i + 1]);
+            else if (ACT == 2) { y[i] = fmaxf(y[i], 0.f); y[i + 1] = fmaxf(y[i + 1], 0.f); }
+        }
         tm_store_a<16>(lane_addr, k0 + c * 16, y);
     }
 }

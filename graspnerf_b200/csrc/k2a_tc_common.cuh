@@ -107,6 +107,20 @@ __device__ __forceinline__ void tm_st8(uint32_t taddr, const uint32_t* r) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
                  :: "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
 }
+// ---- packed fp32x2 arithmetic (Blackwell FADD2 / FMUL2 / FFMA2: two fp32 lanes per instruction) -------------------------
+__device__ __forceinline__ unsigned long long pk2(float lo, float hi) {
+    unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r;
+}
+__device__ __forceinline__ void upk2(unsigned long long v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) {
+    unsigned long long r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r;
+}
+__device__ __forceinline__ unsigned long long sub2(unsigned long long a, unsigned long long b) {
+    unsigned long long r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r;
+}
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) {
+    unsigned long long r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r;
+}
 // split K fp32 values into fp16 hi/lo pairs and store them as the A operand (k0 = first k index, multiple of 16)
 template <int K> __device__ __forceinline__ void tm_store_a(uint32_t slot_lane_addr, int k0, const float* a) {
 #pragma unroll
@@ -117,7 +131,9 @@ template <int K> __device__ __forceinline__ void tm_store_a(uint32_t slot_lane_a
             const float a0 = a[2 * (c + i)], a1 = a[2 * (c + i) + 1];
             const __half2 h = __floats2half2_rn(a0, a1);                 // .x (low 16 bits) = even k  (tc_probe variant 0)
             const float2 hf = __half22float2(h);
-            const __half2 l = __floats2half2_rn(a0 - hf.x, a1 - hf.y);
+            float d0, d1;
+            upk2(sub2(pk2(a0, a1), pk2(hf.x, hf.y)), d0, d1);            // one FADD2 for both residuals
+            const __half2 l = __floats2half2_rn(d0, d1);
             hi[i] = *reinterpret_cast<const uint32_t*>(&h);
             lo[i] = *reinterpret_cast<const uint32_t*>(&l);
         }
@@ -131,12 +147,24 @@ __device__ __forceinline__ float tc_elu(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 1.4426950408889634f));
     return x > 0.f ? x : e - 1.f;
 }
+// two ELUs: the scale and the "-1" are packed (FMUL2 / FADD2), the exponentials stay scalar MUFUs
+__device__ __forceinline__ void tc_elu2(float& x0, float& x1) {
+    float m0, m1, e0, e1, r0, r1;
+    upk2(mul2(pk2(x0, x1), pk2(1.4426950408889634f, 1.4426950408889634f)), m0, m1);
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(m0));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(m1));
+    upk2(add2(pk2(e0, e1), pk2(-1.f, -1.f)), r0, r1);
+    x0 = x0 > 0.f ? x0 : r0;
+    x1 = x1 > 0.f ? x1 : r1;
+}
 // y = elu(y + b)
 template <int N> __device__ __forceinline__ void bias_elu(const float* __restrict__ b, float* y) {
 #pragma unroll
     for (int n = 0; n < N; n += 4) {
         const float4 w = *reinterpret_cast<const float4*>(b + n);
-        y[n] = tc_elu(y[n] + w.x); y[n + 1] = tc_elu(y[n + 1] + w.y); y[n + 2] = tc_elu(y[n + 2] + w.z); y[n + 3] = tc_elu(y[n + 3] + w.w);
+        upk2(add2(pk2(y[n], y[n + 1]), pk2(w.x, w.y)), y[n], y[n + 1]);
+        upk2(add2(pk2(y[n + 2], y[n + 3]), pk2(w.z, w.w)), y[n + 2], y[n + 3]);
+        tc_elu2(y[n], y[n + 1]); tc_elu2(y[n + 2], y[n + 3]);
     }
 }
 template <int N> __device__ __forceinline__ void add_bias(const float* __restrict__ b, float* y) {
