@@ -42,6 +42,13 @@ def load_peaks():
     return {'hbm_gbs': 6650.0, 'tf_burst': 1590.0, 'tf_sustained': 1400.0, 'source': 'fallback'}
 
 
+def load_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed `ncu --set full` captures
+    (profiles/traffic.json, written by tools/ncu_summary.py); {} when no capture has been summarised yet."""
+    p = os.path.join(ROOT, 'profiles', 'traffic.json')
+    return json.load(open(p)) if os.path.exists(p) else {}
+
+
 class ClockSampler(threading.Thread):
     """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
     Q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
@@ -136,6 +143,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--cpu-volumes', type=int, default=12, help='size of the bounded CPU-baseline sample')
+    ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg (profiling runs under ncu only)')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
@@ -237,18 +245,19 @@ def main():
     sampler.join(timeout=2)
     if rank == 0:
         peaks = load_peaks()
+        traffic = load_traffic()
         value = world * K / (total_ms / 1e3)
         k1_gbs = K1_BYTES / (kt[0] * 1e-3) / 1e9
         k2_tfs = K2_FLOPS / ((kt[1] + kt[2]) * 1e-3) / 1e12
         dominant_k2 = (kt[1] + kt[2]) >= kt[0]
         roof_k1 = {'kernel': 'gn_k1_kernel', 'bound': 'hbm', 'achieved': k1_gbs, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
-                   'frac': k1_gbs / peaks['hbm_gbs'], 'traffic': None, 'us_per_launch': kt[0] * 1e3, 'peak_source': peaks['source'],
+                   'frac': k1_gbs / peaks['hbm_gbs'], 'traffic': traffic.get('gn_k1_kernel'), 'us_per_launch': kt[0] * 1e3, 'peak_source': peaks['source'],
                    'algorithmic_bytes': K1_BYTES,
                    'achieved_survey_bytes': K1_BYTES_SURVEY / (kt[0] * 1e-3) / 1e9,
                    'note': 'achieved uses the bytes K1 itself must move (inputs once + 72-float record + 2 floats/point); '
                            'achieved_survey_bytes uses SURVEY 8d figure (153,284,608 B, counts mean/var that now live in K2a)'}
         roof_k2 = {'kernel': 'gn_k2a_tc_kernel+gn_k2b_attn_kernel', 'bound': 'tensor', 'achieved': k2_tfs, 'peak': peaks['tf_sustained'],
-                   'unit': 'TFLOP/s', 'frac': k2_tfs / peaks['tf_sustained'], 'traffic': None,
+                   'unit': 'TFLOP/s', 'frac': k2_tfs / peaks['tf_sustained'], 'traffic': traffic.get('gn_k2a_tc_kernel'),
                    'us_per_launch': (kt[1] + kt[2]) * 1e3, 'peak_source': peaks['source'],
                    'note': 'algorithmic fp32 FLOPs of the reference semantics (SURVEY 8d: 23.2 GFLOP/volume) over the K2a+K2b time; '
                            'the kernel issues 3 fp16 MMAs per product (hi/lo split), so tensor-pipe activity is ~3x this fraction'}
@@ -268,7 +277,7 @@ def main():
             'clocks': sampler.summary(),
             'checksum': checksum,
         }
-        if world == 1:
+        if world == 1 and not args.no_cpu:
             vps, dt, nvol, nthr = cpu_reference_volumes(args.cpu_volumes, 1, budget_s=25.0)
             line['cpu_baseline'] = {'value': vps, 'unit': 'volumes/s', 'cores': nthr, 'kind': 'port', 'host_cpus': os.cpu_count(),
                                     'sample': f'{nvol} volumes of the same workload in {dt:.1f} s (oracle/nr_oracle.sample_volume, '
