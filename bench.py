@@ -139,7 +139,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--steps', type=int, default=1000)
     ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--cpu-volumes', type=int, default=12, help='size of the bounded CPU-baseline sample')
@@ -209,7 +209,6 @@ def main():
         graphs[(W_ + i) % POOL].replay()
     ev1.record()
     barrier()
-    sampler.stop_flag = True
     total_ms = ev0.elapsed_time(ev1)
     # per-kernel durations: the same launches issued eagerly on the same stream, CUDA events recorded immediately around each
     # launch.  A 1 GiB fill is queued first so that (a) the launches are already queued when the GPU reaches them (no host
@@ -240,6 +239,7 @@ def main():
         checksum += float(out[0, 0, 0, 0, 0])
     torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - t0) * 1e3
+    sampler.stop_flag = True              # sampled across both timed regions (device-resident and end-to-end)
 
     total_ms, e2e_ms = max_over_ranks([total_ms, e2e_ms], dist, dev)
     sampler.join(timeout=2)

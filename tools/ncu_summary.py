@@ -30,7 +30,7 @@ def main():
         rows = list(csv.reader(io.StringIO(raw)))
         hdr, units, vals = rows[0], rows[1], rows[2]
         d = {h: (v, u) for h, u, v in zip(hdr, units, vals)}
-        kname = d['Kernel Name'][0].split('(')[0].split('<')[0]
+        kname = d['Kernel Name'][0].split('(')[0].split('<')[0].replace('void ', '').strip()
         lines = [f'# {os.path.basename(rep)}  kernel {d["Kernel Name"][0][:100]}', f'# ncu --set full --clock-control none --import-source on (one launch; cold-ish caches)']
         for k in KEYS:
             if k in d:
