@@ -273,7 +273,7 @@ def aggregate(sd, agg_prefix, rec, que_pts, rn, dn, que_dir=None, want_grad=Fals
     # ---- per-ray geometry head, ibrnet.py:485-504
     pos = positional_table(dn).to(dt)
     pts = que_pts.reshape(rn, dn, 3).to(dt).detach().clone().requires_grad_(want_grad)
-    with torch.set_grad_enabled(want_grad):
+    with torch.set_grad_enabled(want_grad or torch.is_grad_enabled()):      # outer grad mode = training-style autograd
         g = torch.cat([pooled.reshape(rn, dn, 65), embed_points(pts)], -1)
         g = F.elu(_lin(sd, A + 'geometry_fc.2', F.elu(_lin(sd, A + 'geometry_fc.0', g))))
         g = g + pos[None]
@@ -283,7 +283,7 @@ def aggregate(sd, agg_prefix, rec, que_pts, rn, dn, que_dir=None, want_grad=Fals
         grad = None
         if want_grad:
             grad = torch.autograd.grad(sdf, pts, torch.ones_like(sdf))[0]
-    out = {'sdf': sdf.detach(), 'grad': grad, 'prob_emb': prob_emb, 'dir_diff': dir_diff, 'f': f,
+    out = {'sdf': sdf if torch.is_grad_enabled() else sdf.detach(), 'grad': grad, 'prob_emb': prob_emb, 'dir_diff': dir_diff, 'f': f,
            'mean1': mean1[:, 0], 'var1': var1[:, 0], 'mean0': mean0[:, 0], 'var0': var0[:, 0],
            'x': x, 'vis2': vis2[..., 0], 'pooled': pooled, 'nvalid': nvalid, 'w0': w0[..., 0]}
     if want_rgb:

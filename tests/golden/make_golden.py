@@ -109,7 +109,7 @@ def main():
         print(name, {k: v.shape for k, v in out.items()})
 
 
-if __name__ == '__main__':
+if __name__ == '__main__' and len(sys.argv) == 1:
     main()
 
 
@@ -139,3 +139,32 @@ def make_model_golden():
 
 if __name__ == '__main__' and '--model' in sys.argv:
     make_model_golden()
+
+
+def make_grad_golden():
+    """First-order gradients of the volume path from the UNMODIFIED reference (CPU autograd):
+    loss = sum(volume * G), G ~ N(0,1) seeded; d loss / d {img_feats, ray_feats, every agg_net.* / dist_decoder.* parameter}.
+    Stored for the small_v4 case (tests/golden/volume_grad_small_v4.npz)."""
+    cfg, net = build_reference_net(0)
+    nr = net.nr_net
+    kw = VOLUME_CASES['small_v4']
+    ref = to_torch(make_scene(**kw))
+    ref['img_feats'].requires_grad_(True)
+    ref['ray_feats'].requires_grad_(True)
+    G = torch.from_numpy(np.random.default_rng(99).standard_normal((1, 1, 40, 40, 40)).astype(np.float32))
+    vol = nr.sample_volume(ref)
+    loss = (vol * G).sum()
+    loss.backward()
+    out = {'G': G.numpy(), 'loss': np.float64(loss.item()), 'd_img_feats': ref['img_feats'].grad.numpy(),
+           'd_ray_feats': ref['ray_feats'].grad.numpy()}
+    n = 0
+    for k, v in nr.named_parameters():
+        if k.startswith(('agg_net.', 'dist_decoder.')) and v.grad is not None:
+            out['dw/' + k] = v.grad.numpy(); n += 1
+    np.savez_compressed(os.path.join(HERE, 'volume_grad_small_v4.npz'), **out)
+    print('grad golden:', n, 'parameter grads; |d_img_feats|', float(ref['img_feats'].grad.abs().sum()),
+          '|d_ray_feats|', float(ref['ray_feats'].grad.abs().sum()))
+
+
+if __name__ == '__main__' and '--grads' in sys.argv:
+    make_grad_golden()

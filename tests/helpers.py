@@ -29,3 +29,19 @@ def assert_close(actual, expected, rtol=1e-4, atol_scale=1e-4, what=''):
     assert not bad.any(), (f'{what}: {bad.sum()}/{bad.size} outside tolerance; max abs err {err.max():.3e} '
                            f'(scale {scale:.3e}), rel-L2 {rel_l2:.3e}')
     return rel_l2
+
+
+def oracle_volume_grads(sd, scene_t, G):
+    """d sum(volume*G) / d {img_feats, ray_feats, every weight} by torch autograd through the oracle (CPU).
+    Returns (loss, d_img_feats, d_ray_feats, {key: grad})."""
+    import torch
+    from oracle import nr_oracle as O
+    sd = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items()}
+    sc = dict(scene_t)
+    sc['img_feats'] = sc['img_feats'].detach().clone().requires_grad_(True)
+    sc['ray_feats'] = sc['ray_feats'].detach().clone().requires_grad_(True)
+    with torch.enable_grad():
+        vol = O.sample_volume(sd, sc)
+        loss = (vol * torch.as_tensor(G)).sum()
+        loss.backward()
+    return float(loss), sc['img_feats'].grad, sc['ray_feats'].grad, {k: v.grad for k, v in sd.items() if v.grad is not None}
