@@ -35,6 +35,21 @@ class GnK3Params(C.Structure):
                [(n, C.c_int) for n in ('B', 'rn', 'dn')]
 
 
+class GnK2bBwdParams(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ('pooled', 'weights', 'axis', 'bbox_min', 'pts', 'pos_table', 'd_sdf', 'd_pooled', 'd_weights')] + \
+               [(n, C.c_int) for n in ('B', 'N', 'dn', 'R', 'volume_mode')]
+
+
+class GnK2aBwdParams(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ('rec', 'pt', 'weights', 'depth_range', 'que_dists', 'd_pooled', 'd_rec', 'd_weights')] + \
+               [(n, C.c_int) for n in ('B', 'N', 'V', 'dn')]
+
+
+class GnK1BwdParams(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ('KRt', 'axis', 'bbox_min', 'pts', 'd_rec', 'd_img_feats', 'd_ray_feats')] + \
+               [(n, C.c_int) for n in ('B', 'V', 'H', 'W', 'fh', 'fw', 'R', 'N', 'volume_mode')]
+
+
 _lib = None
 
 
@@ -50,7 +65,8 @@ def load():
     lib = C.CDLL(LIBPATH)
     lib.gn_version.restype = C.c_char_p
     for name, st in (('gn_k1_forward', GnK1Params), ('gn_k2a_forward', GnK2aParams), ('gn_k2a_forward_tc', GnK2aParams), ('gn_k2b_forward', GnK2bParams),
-                     ('gn_k3_composite', GnK3Params)):
+                     ('gn_k3_composite', GnK3Params), ('gn_k2b_backward', GnK2bBwdParams), ('gn_k2a_backward', GnK2aBwdParams),
+                     ('gn_k1_backward', GnK1BwdParams)):
         fn = getattr(lib, name)
         fn.restype = C.c_int
         fn.argtypes = [C.POINTER(st), C.c_void_p]
@@ -63,7 +79,9 @@ def load():
     lib.gn_weight_entry.restype = C.c_int
     lib.gn_weight_entry.argtypes = [C.c_int, C.POINTER(C.c_char_p)] + [C.POINTER(C.c_int)] * 4
     for name, st in (('gn_sizeof_k1_params', GnK1Params), ('gn_sizeof_k2a_params', GnK2aParams),
-                     ('gn_sizeof_k2b_params', GnK2bParams), ('gn_sizeof_k3_params', GnK3Params)):
+                     ('gn_sizeof_k2b_params', GnK2bParams), ('gn_sizeof_k3_params', GnK3Params),
+                     ('gn_sizeof_k2b_bwd_params', GnK2bBwdParams), ('gn_sizeof_k2a_bwd_params', GnK2aBwdParams),
+                     ('gn_sizeof_k1_bwd_params', GnK1BwdParams)):
         got = getattr(lib, name)()
         if got != C.sizeof(st):
             raise RuntimeError(f'{name}: library says {got} bytes, ctypes mirror has {C.sizeof(st)}')

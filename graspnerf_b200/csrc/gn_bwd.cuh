@@ -1,0 +1,67 @@
+// Helpers shared by the backward (training) kernels: ELU derivative, transposed mat-vec, and the CTA-wide
+// weight-gradient accumulation  dW[k][n] += sum_rows x[row][k] * dz[row][n]  staged through shared memory.
+#pragma once
+#include "gn_common.cuh"
+
+#define GN_BWD_LDX 33          // floats per row of the X staging tile (<= 32 inputs per chunk, +1 against bank conflicts)
+#define GN_BWD_LDZ 65          // floats per row of the dZ staging tile (<= 64 outputs)
+
+// derivative of ELU expressed with its OUTPUT y = elu(u):  u > 0 ? 1 : exp(u) = y + 1
+__device__ __forceinline__ float gn_delu(float y) { return y > 0.f ? 1.f : y + 1.f; }
+
+// dx[k] (+)= sum_{n<N} W[k*NP + n] * dz[n]      (W k-major in shared memory; the transpose of mv_acc)
+template <int K, int N, int NP, bool ACC>
+__device__ __forceinline__ void mv_bwd(const float* __restrict__ W, const float* dz, float* dx)
+{
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        float a = ACC ? dx[k] : 0.f;
+#pragma unroll
+        for (int n = 0; n < N; ++n) a = fmaf(W[k * NP + n], dz[n], a);
+        dx[k] = a;
+    }
+}
+
+// gW[k*NP + n] += sum_{r<nrows} sX[r][k] * sZ[r][n]   for k < KC, n < N; one (k,n) per thread and pass, coalesced atomics
+static __device__ __noinline__ void gn_dw_flush(float* __restrict__ gW, int NP, int KC, int N, const float* __restrict__ sX,
+                                         const float* __restrict__ sZ, int nrows, int nthreads)
+{
+    for (int idx = threadIdx.x; idx < KC * N; idx += nthreads) {
+        const int k = idx / N, n = idx - k * N;
+        float a0 = 0.f, a1 = 0.f;
+        for (int r = 0; r < nrows; r += 2) {
+            a0 = fmaf(sX[r * GN_BWD_LDX + k], sZ[r * GN_BWD_LDZ + n], a0);
+            a1 = fmaf(sX[(r + 1) * GN_BWD_LDX + k], sZ[(r + 1) * GN_BWD_LDZ + n], a1);
+        }
+        atomicAdd(gW + k * NP + n, a0 + a1);
+    }
+}
+static __device__ __noinline__ void gn_db_flush(float* __restrict__ gB, int N, const float* __restrict__ sZ, int nrows, int nthreads)
+{
+    for (int n = threadIdx.x; n < N; n += nthreads) {
+        float a = 0.f;
+        for (int r = 0; r < nrows; ++r) a += sZ[r * GN_BWD_LDZ + n];
+        atomicAdd(gB + n, a);
+    }
+}
+// Every thread of the CTA contributes its row (x[K], dz[N]); nthreads (even) rows are reduced.  gB may be NULL.
+// Contains __syncthreads(): must be reached by all threads of the CTA.
+template <int K, int N, int NP>
+__device__ __forceinline__ void dw_layer(float* gW, float* gB, const float* x, const float* dz, float* sX, float* sZ, int nthreads)
+{
+    static_assert(N <= 64, "dZ staging tile holds 64 outputs");
+    const int t = threadIdx.x;
+#pragma unroll
+    for (int n = 0; n < N; ++n) sZ[t * GN_BWD_LDZ + n] = dz[n];
+#pragma unroll
+    for (int kc = 0; kc < K; kc += 32) {
+        const int kn = (K - kc) < 32 ? (K - kc) : 32;
+#pragma unroll
+        for (int k = 0; k < 32; ++k)
+            if (kc + k < K) sX[t * GN_BWD_LDX + k] = x[kc + k];
+        __syncthreads();
+        gn_dw_flush(gW + kc * NP, NP, kn, N, sX, sZ, nthreads, nthreads);
+        if (kc == 0 && gB) gn_db_flush(gB, N, sZ, nthreads, nthreads);
+        __syncthreads();
+    }
+}

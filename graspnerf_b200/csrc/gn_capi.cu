@@ -19,3 +19,6 @@ extern "C" int gn_sizeof_k1_params(void) { return (int)sizeof(GnK1Params); }
 extern "C" int gn_sizeof_k2a_params(void) { return (int)sizeof(GnK2aParams); }
 extern "C" int gn_sizeof_k2b_params(void) { return (int)sizeof(GnK2bParams); }
 extern "C" int gn_sizeof_k3_params(void) { return (int)sizeof(GnK3Params); }
+extern "C" int gn_sizeof_k2b_bwd_params(void) { return (int)sizeof(GnK2bBwdParams); }
+extern "C" int gn_sizeof_k2a_bwd_params(void) { return (int)sizeof(GnK2aBwdParams); }
+extern "C" int gn_sizeof_k1_bwd_params(void) { return (int)sizeof(GnK1BwdParams); }

@@ -5,8 +5,9 @@
 What runs where:
   * 2-D encoders, depth-mean head, VGN 3-D conv: PyTorch/cuDNN (out of the CUDA hot path, SURVEY.md section 8f);
   * sample_volume and the RGB head (render): the sm_100a kernels through graspnerf_b200.ops - no torch fallback.
-Round-1 limitation: the CUDA hot path is forward-only (no autograd), so training through this class is not possible yet;
-`forward` raises if gradients are required of it."""
+Training: sample_volume has a hand-written first-order backward (gn_k2b_backward -> gn_k2a_backward -> gn_k1_backward,
+ops.sample_volume_autograd), so forward() under autograd works with render_rgb off (losses on volume / vgn_pred /
+depth_mean).  The RGB head (render) has no backward yet: forward raises when gradients are required with render_rgb on."""
 import numpy as np
 import torch
 import torch.nn as nn
@@ -68,10 +69,16 @@ class NeuralRayRenderer(nn.Module):
         """renderer.py:164-199 (volume_type ['sdf']): K1 -> K2a -> K2b; returns [1,1,R,R,R]."""
         if any(m != 'sdf' for m in self.cfg['volume_type']):
             raise NotImplementedError("volume_type other than ['sdf'] is not implemented")
-        scene = self._scene(ref_imgs_info)
+        dev = ref_imgs_info['imgs'].device
         # bbox3d is a python list in training (train_dataset.py) and an fp32 tensor [2,3] in inference (main.py:231)
-        bbox_min = torch.as_tensor(ref_imgs_info['bbox3d'][0], dtype=torch.float32).to(scene.device).reshape(1, 3)
-        return ops.sample_volume(scene, self._head_weights(False), bbox_min, self.cfg['volume_resolution'])
+        bbox_min = torch.as_tensor(ref_imgs_info['bbox3d'][0], dtype=torch.float32).to(dev).reshape(1, 3)
+        if torch.is_grad_enabled() and (ref_imgs_info['img_feats'].requires_grad or ref_imgs_info['ray_feats'].requires_grad
+                                        or any(p.requires_grad for p in self.agg_net.parameters())):
+            named = {k: v for k, v in self.named_parameters() if k.startswith(('agg_net.', 'dist_decoder.'))}
+            return ops.sample_volume_autograd(ref_imgs_info['imgs'], ref_imgs_info['img_feats'], ref_imgs_info['ray_feats'],
+                                              ref_imgs_info['poses'], ref_imgs_info['Ks'], ref_imgs_info['depth_range'],
+                                              bbox_min, named, self.cfg['volume_resolution'])
+        return ops.sample_volume(self._scene(ref_imgs_info), self._head_weights(False), bbox_min, self.cfg['volume_resolution'])
 
     def render(self, que_imgs_info, ref_imgs_info, is_train):
         """renderer.py:201-220: chunk the query rays by ray_batch_num, coarse + fine pass per chunk (render_impl 152-162)."""
@@ -127,9 +134,9 @@ class NeuralRayRenderer(nn.Module):
 
     def forward(self, data):
         """renderer.py:268-291."""
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError('graspnerf_b200 round 1 is forward-only: call under torch.no_grad() '
-                                      '(backward kernels / training are not implemented yet)')
+        if self.cfg['render_rgb'] and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError('the RGB head (render) has no backward kernels yet: train with render_rgb off, or call '
+                                      'under torch.no_grad(); the volume path (sample_volume) is differentiable')
         ref = data['ref_imgs_info'].copy()
         que = data['que_imgs_info'].copy()
         is_train = 'eval' not in data

@@ -372,3 +372,126 @@ def render_rays(scene, hw_coarse, hw_fine, que, dn=40, fdn=40, u=None):
         out[k + '_fine'] = v
     out['depth_fine'], out['fine_inds'] = fdepth, inds
     return out
+
+
+# ------------------------------------------------------------------------------------------------ training (volume path)
+def k2b_backward(pooled, hw, d_sdf, d_weights, *, dn, resolution=None, bbox_min=None, volume_size=0.3, pts=None):
+    """Reverse of k2b_forward (full head).  d_sdf: same layout as the forward output.  Accumulates into d_weights
+    (blob layout); returns d_pooled [B,N,68]."""
+    lib = _lib.load()
+    B, N, _ = pooled.shape
+    dev = pooled.device
+    p = _lib.GnK2bBwdParams()
+    vol = resolution is not None
+    if vol:
+        R = int(resolution)
+        bbox_min = _f32c(bbox_min, dev).reshape(B, 3)
+        axis = hw.axis(R, volume_size)
+        p.axis, p.bbox_min, p.R = _ptr(axis).value, _ptr(bbox_min).value, R
+    else:
+        pts = _f32c(pts, dev)
+        p.pts, p.R = _ptr(pts).value, 0
+    d_sdf = _f32c(d_sdf, dev)
+    d_pooled = torch.zeros((B, N, POOL_STRIDE), device=dev, dtype=torch.float32)
+    pos = hw.pos_table(int(dn))
+    p.pooled, p.weights, p.pos_table, p.d_sdf = _ptr(pooled).value, _ptr(hw.blob).value, _ptr(pos).value, _ptr(d_sdf).value
+    p.d_pooled, p.d_weights = _ptr(d_pooled).value, _ptr(d_weights).value
+    p.B, p.N, p.dn, p.volume_mode = B, N, int(dn), 1 if vol else 0
+    _lib.check(lib.gn_k2b_backward(C.byref(p), _stream()), 'gn_k2b_backward')
+    return d_pooled
+
+
+def k2a_backward(rec, pt, hw, depth_range, d_pooled, d_weights, *, que_dists=None, dn=1):
+    """Reverse of k2a_forward (volume-path part: no rgb_fc).  Accumulates into d_weights; returns d_rec [B,N,V,64]
+    (gradient of the record's ray_feats | img_feats entries)."""
+    lib = _lib.load()
+    B, N, V, _ = rec.shape
+    dev = rec.device
+    d_rec = torch.zeros((B, N, V, 64), device=dev, dtype=torch.float32)
+    p = _lib.GnK2aBwdParams()
+    if que_dists is not None:
+        que_dists = _f32c(que_dists, dev)
+    p.rec, p.pt, p.weights, p.depth_range = _ptr(rec).value, _ptr(pt).value, _ptr(hw.blob).value, _ptr(depth_range).value
+    p.que_dists, p.d_pooled, p.d_rec, p.d_weights = _ptr(que_dists).value, _ptr(d_pooled).value, _ptr(d_rec).value, _ptr(d_weights).value
+    p.B, p.N, p.V, p.dn = B, N, V, int(dn)
+    _lib.check(lib.gn_k2a_backward(C.byref(p), _stream()), 'gn_k2a_backward')
+    return d_rec
+
+
+def k1_backward(scene, hw, d_rec, *, resolution=None, bbox_min=None, volume_size=0.3, pts=None):
+    """Reverse of the two feature gathers of k1_forward: d_rec [B,N,V,64] -> (d_img_feats, d_ray_feats), both
+    channels-last [B,V,fh,fw,32]."""
+    lib = _lib.load()
+    dev = scene.device
+    B, N, V, _ = d_rec.shape
+    p = _lib.GnK1BwdParams()
+    vol = pts is None
+    if vol:
+        R = int(resolution)
+        bbox_min = _f32c(bbox_min, dev).reshape(B, 3)
+        axis = hw.axis(R, volume_size)
+        p.axis, p.bbox_min, p.R = _ptr(axis).value, _ptr(bbox_min).value, R
+    else:
+        pts = _f32c(pts, dev)
+        p.pts, p.R = _ptr(pts).value, 0
+    d_img = torch.zeros_like(scene.img_feats)
+    d_ray = torch.zeros_like(scene.ray_feats)
+    p.KRt, p.d_rec, p.d_img_feats, p.d_ray_feats = _ptr(scene.KRt).value, _ptr(d_rec).value, _ptr(d_img).value, _ptr(d_ray).value
+    p.B, p.V, p.H, p.W, p.fh, p.fw, p.N, p.volume_mode = B, V, scene.H, scene.W, scene.fh, scene.fw, N, 1 if vol else 0
+    _lib.check(lib.gn_k1_backward(C.byref(p), _stream()), 'gn_k1_backward')
+    return d_img, d_ray
+
+
+def sample_volume_backward(scene, hw, bbox_min, rec, pt, pooled, d_vol, resolution=40, volume_size=0.3):
+    """d volume [B,1,R,R,R] -> (d_img_feats, d_ray_feats) channels-last [B,V,fh,fw,32] and the weight gradient in blob
+    layout, through gn_k2b_backward -> gn_k2a_backward -> gn_k1_backward (fp32, forward recomputed per kernel)."""
+    d_w = torch.zeros_like(hw.blob)
+    d_pooled = k2b_backward(pooled, hw, d_vol, d_w, dn=resolution, resolution=resolution, bbox_min=bbox_min, volume_size=volume_size)
+    d_rec = k2a_backward(rec, pt, hw, scene.depth_range, d_pooled, d_w)
+    d_img, d_ray = k1_backward(scene, hw, d_rec, resolution=resolution, bbox_min=bbox_min, volume_size=volume_size)
+    return d_img, d_ray, d_w
+
+
+class _SampleVolumeFn(torch.autograd.Function):
+    """sample_volume with a hand-written backward: the autograd node the mirror's forward uses in training.
+    Forward = K1 -> K2a (fp32 SIMT) -> K2b (full head); the record, the per-point mask and the pooled features are kept
+    for the reverse kernels.  Inputs that can carry a gradient: img_feats, ray_feats ([V,32,fh,fw] or [B,V,32,fh,fw])
+    and the head parameters (passed as *params in the order of `keys`)."""
+
+    @staticmethod
+    def forward(ctx, img_feats, ray_feats, static, keys, *params):
+        from .weights import unpack_blob_grad  # noqa: F401  (import check before any launch)
+        imgs, poses, Ks, depth_range, bbox_min, R, vs, agg_prefix, dd_prefix = static
+        sd = {k: p.detach() for k, p in zip(keys, params)}
+        hw = HeadWeights(sd, agg_prefix, dd_prefix, img_feats.device)
+        scene = Scene(imgs, img_feats.detach(), ray_feats.detach(), poses, Ks, depth_range)
+        rec, pt = k1_forward(scene, hw, resolution=R, bbox_min=bbox_min, volume_size=vs)
+        pooled, _, _ = k2a_forward(rec, pt, hw, scene.depth_range, impl='simt')
+        vol, _ = k2b_forward(pooled, hw, dn=R, resolution=R, bbox_min=bbox_min, volume_size=vs)
+        ctx.scene, ctx.hw, ctx.saved = scene, hw, (rec, pt, pooled)
+        ctx.meta = (bbox_min, R, vs, agg_prefix, dd_prefix, keys, img_feats.dim() == 4, [p.shape for p in params])
+        return vol
+
+    @staticmethod
+    def backward(ctx, d_vol):
+        from .weights import unpack_blob_grad
+        bbox_min, R, vs, agg_prefix, dd_prefix, keys, single, shapes = ctx.meta
+        rec, pt, pooled = ctx.saved
+        d_img, d_ray, d_w = sample_volume_backward(ctx.scene, ctx.hw, bbox_min, rec, pt, pooled, d_vol.contiguous(), R, vs)
+        d_img = d_img.permute(0, 1, 4, 2, 3)                       # channels-last -> logical [B,V,32,fh,fw]
+        d_ray = d_ray.permute(0, 1, 4, 2, 3)
+        if single:
+            d_img, d_ray = d_img[0], d_ray[0]
+        g = unpack_blob_grad(d_w, agg_prefix, dd_prefix)
+        pg = tuple(g[k].reshape(s) if k in g else None for k, s in zip(keys, shapes))
+        ctx.scene = ctx.hw = ctx.saved = None
+        return (d_img, d_ray, None, None) + pg
+
+
+def sample_volume_autograd(imgs, img_feats, ray_feats, poses, Ks, depth_range, bbox_min, named_params, resolution=40,
+                           volume_size=0.3, agg_prefix='agg_net.', dd_prefix='dist_decoder.'):
+    """Differentiable sample_volume (first order): named_params = {reference key: nn.Parameter} of the agg_net.* /
+    dist_decoder.* tensors.  Returns volume [B,1,R,R,R] attached to the autograd graph of img_feats, ray_feats and params."""
+    keys = tuple(k for k in named_params if k.startswith(agg_prefix) or k.startswith(dd_prefix))
+    static = (imgs, poses, Ks, depth_range, bbox_min, int(resolution), volume_size, agg_prefix, dd_prefix)
+    return _SampleVolumeFn.apply(img_feats, ray_feats, static, keys, *[named_params[k] for k in keys])

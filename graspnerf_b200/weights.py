@@ -92,6 +92,61 @@ def pack_blob(sd, agg_prefix='agg_net.', dd_prefix='dist_decoder.'):
     return blob
 
 
+def unpack_blob_grad(dblob, agg_prefix='agg_net.', dd_prefix='dist_decoder.'):
+    """Adjoint of `pack_blob` over the raw (unfused) entries: a gradient in blob layout (torch tensor, any device)
+    -> {reference state_dict key: gradient tensor of that parameter's shape}.  The packing is a linear map (transposes,
+    the [rgb|img] <-> [img|rgb] permutation, the split of base_fc.0 into three blocks), so this is its transpose;
+    tests/test_cabi.py checks <pack(w), g> == <w, unpack(g)>.  rgb_fc (not on the volume path) is left out."""
+    table = {name: (off, rows, cols, cp) for name, off, rows, cols, cp in _lib.weight_table()}
+    A = agg_prefix + 'agg_impl.'
+    perm = torch.as_tensor(PERM35, device=dblob.device)
+
+    def ent(name):
+        off, rows, cols, cp = table[name]
+        return dblob[off:off + rows * cp].reshape(rows, cp)[:, :cols]
+    out = {}
+
+    def lin(dst_w, dst_b, key, vector=False):
+        g = ent(dst_w)
+        out[key + '.weight'] = g.clone() if vector else g.t().clone()
+        if dst_b is not None:
+            out[key + '.bias'] = ent(dst_b)[0].clone()
+    lin('rd.w0', 'rd.b0', A + 'ray_dir_fc.0')
+    g = ent('rd.w1')                                             # [16,35] columns in record order
+    w = g.new_zeros(35, 16); w[perm] = g.t(); out[A + 'ray_dir_fc.2.weight'] = w
+    b = g.new_zeros(35); b[perm] = ent('rd.b1')[0]; out[A + 'ray_dir_fc.2.bias'] = b
+    for short, name in (('mean', 'mean_decoder'), ('var', 'var_decoder'), ('aw', 'aw_decoder')):
+        lin(f'dd.{short}.w0', f'dd.{short}.b0', f'{dd_prefix}{name}.0')
+        lin(f'dd.{short}.w2', f'dd.{short}.b2', f'{dd_prefix}{name}.2')
+        lin(f'dd.{short}.w4', f'dd.{short}.b4', f'{dd_prefix}{name}.4')
+    lin('pe.w0', 'pe.b0', agg_prefix + 'prob_embed.0')
+    lin('pe.w2', 'pe.b2', agg_prefix + 'prob_embed.2')
+    lin('nf.w0', 'nf.b0', A + 'neuray_fc.0')
+    lin('nf.w2', 'nf.b2', A + 'neuray_fc.2', vector=True)
+    w = dblob.new_zeros(64, 207)
+    wg, wf = ent('bf.wg'), ent('bf.wf')
+    for q in range(4):
+        w[:, q * 35 + perm] = wg[q * 36:q * 36 + 35].t()
+    w[:, 140 + perm] = wf[:35].t()
+    w[:, 175:207] = ent('bf.wp').t()
+    out[A + 'base_fc.0.weight'] = w
+    out[A + 'base_fc.0.bias'] = ent('bf.b0')[0].clone()
+    lin('bf.w2', 'bf.b2', A + 'base_fc.2')
+    lin('vf.w0', 'vf.b0', A + 'vis_fc.0')
+    lin('vf.w2', 'vf.b2', A + 'vis_fc.2')
+    lin('v2.w0', 'v2.b0', A + 'vis_fc2.0')
+    lin('v2.w2', 'v2.b2', A + 'vis_fc2.2', vector=True)
+    lin('gf.w0', 'gf.b0', A + 'geometry_fc.0')
+    lin('gf.w2', 'gf.b2', A + 'geometry_fc.2')
+    for dst, src in (('at.wq', 'w_qs'), ('at.wk', 'w_ks'), ('at.wv', 'w_vs'), ('at.fc', 'fc')):
+        out[f'{A}ray_attention.{src}.weight'] = ent(dst).t().clone()
+    out[A + 'ray_attention.layer_norm.weight'] = ent('at.ln_w')[0].clone()
+    out[A + 'ray_attention.layer_norm.bias'] = ent('at.ln_b')[0].clone()
+    lin('og.w0', 'og.b0', A + 'out_geometry_fc.0')
+    lin('og.w1', 'og.b1', A + 'out_geometry_fc.1', vector=True)
+    return out
+
+
 def positional_table(n_samples, d_hid=16):
     """Sinusoid table of IBRNetWithNeuRayNeus.posenc (ibrnet.py:437-445), [n_samples, 16] fp32; the reference builds it
     in float64 numpy and casts, so it is host-side constant data rather than kernel arithmetic."""

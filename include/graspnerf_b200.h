@@ -136,11 +136,59 @@ int gn_k3_fine_depths(const float* depth /*[B,rn,dn]*/, const float* hit_prob /*
                       const float* u /*[B,rn,fdn]*/, float* fine_depth /*[B,rn,fdn] sorted*/, int64_t* inds /*[B,rn,fdn] or NULL*/,
                       int B, int rn, int dn, int fdn, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------------
+ * Backward (training) entry points of the volume path: d volume -> d weights, d feature maps.  First order only.
+ * The reference gets these from torch autograd through renderer.py:164-199; here each forward kernel has a hand-derived
+ * reverse kernel that RECOMPUTES its forward from the saved inputs (rec / pt from K1, pooled from K2a) and accumulates
+ * with atomics (outputs must be zero-initialised by the caller).  Weight gradients are produced in the blob layout
+ * (same offsets as `weights`; fused composites nfc.* / bf.wpc / bf.b0c are not touched). */
+typedef struct GnK2bBwdParams {
+    const float* pooled;       /* [B,N,68] saved K2a (SIMT) output */
+    const float* weights;      /* blob */
+    const float* axis;         /* [R] (volume mode) */
+    const float* bbox_min;     /* [B,3] (volume mode) */
+    const float* pts;          /* [B,N,3] (ray mode) */
+    const float* pos_table;    /* [dn,16] */
+    const float* d_sdf;        /* upstream gradient, SAME layout as the forward output: volume [B,R,R,R] or sdf [B,N] */
+    float* d_pooled;           /* out [B,N,68]: gradient of mean32 | var32 | wmean (entries 65..67 written as 0) */
+    float* d_weights;          /* accumulated (atomicAdd) [gn_weight_blob_floats()] */
+    int B, N, dn, R, volume_mode;
+} GnK2bBwdParams;
+int gn_k2b_backward(const GnK2bBwdParams* params, void* stream);
+
+typedef struct GnK2aBwdParams {
+    const float* rec;          /* [B,N,V,72] saved K1 output */
+    const float* pt;           /* [B,N,2] */
+    const float* weights;      /* blob */
+    const float* depth_range;  /* [B,V,2] */
+    const float* que_dists;    /* [B,N] or NULL (volume mode) */
+    const float* d_pooled;     /* [B,N,68] from gn_k2b_backward */
+    float* d_rec;              /* out [B,N,V,64]: gradient of the record's ray_feats (32) | img_feats (32) entries */
+    float* d_weights;          /* accumulated (atomicAdd) [gn_weight_blob_floats()] */
+    int B, N, V, dn;
+} GnK2aBwdParams;
+int gn_k2a_backward(const GnK2aBwdParams* params, void* stream);
+
+typedef struct GnK1BwdParams {
+    const float* KRt;          /* [B,V,3,4] */
+    const float* axis;         /* [R] (volume mode) */
+    const float* bbox_min;     /* [B,3] (volume mode) */
+    const float* pts;          /* [B,N,3] (ray mode) */
+    const float* d_rec;        /* [B,N,V,64] from gn_k2a_backward */
+    float* d_img_feats;        /* accumulated [B,V,fh,fw,32] channels-last */
+    float* d_ray_feats;        /* accumulated [B,V,fh,fw,32] channels-last */
+    int B, V, H, W, fh, fw, R, N, volume_mode;
+} GnK1BwdParams;
+int gn_k1_backward(const GnK1BwdParams* params, void* stream);
+
 const char* gn_version(void);
 int gn_sizeof_k1_params(void);
 int gn_sizeof_k2a_params(void);
 int gn_sizeof_k2b_params(void);
 int gn_sizeof_k3_params(void);
+int gn_sizeof_k2b_bwd_params(void);
+int gn_sizeof_k2a_bwd_params(void);
+int gn_sizeof_k1_bwd_params(void);
 
 #ifdef __cplusplus
 }

@@ -283,7 +283,7 @@ def aggregate(sd, agg_prefix, rec, que_pts, rn, dn, que_dir=None, want_grad=Fals
         grad = None
         if want_grad:
             grad = torch.autograd.grad(sdf, pts, torch.ones_like(sdf))[0]
-    out = {'sdf': sdf if torch.is_grad_enabled() else sdf.detach(), 'grad': grad, 'prob_emb': prob_emb, 'dir_diff': dir_diff, 'f': f,
+    out = {'sdf': sdf if (torch.is_grad_enabled() and not want_grad) else sdf.detach(), 'grad': grad, 'prob_emb': prob_emb, 'dir_diff': dir_diff, 'f': f,
            'mean1': mean1[:, 0], 'var1': var1[:, 0], 'mean0': mean0[:, 0], 'var0': var0[:, 0],
            'x': x, 'vis2': vis2[..., 0], 'pooled': pooled, 'nvalid': nvalid, 'w0': w0[..., 0]}
     if want_rgb:

@@ -75,3 +75,25 @@ def test_product_path_refuses_cpu():
     t = torch.zeros(2, 3, 8, 8)
     with pytest.raises(RuntimeError):
         ops.Scene(t, torch.zeros(2, 32, 2, 2), torch.zeros(2, 32, 2, 2), torch.zeros(2, 3, 4), torch.zeros(2, 3, 3), torch.zeros(2, 2))
+
+
+def test_unpack_blob_grad_is_the_adjoint_of_pack_blob(lib):
+    """<pack(w), g> == <w, unpack(g)> for random w, g: the weight gradients the backward kernels produce in blob layout map
+    back onto the reference's parameters by the exact transpose of the packing (permutations, transposes, block split)."""
+    import torch
+    from graspnerf_b200 import _lib
+    from graspnerf_b200.weights import pack_blob, unpack_blob_grad
+    from tests.helpers import golden_weights
+    rng = np.random.default_rng(0)
+    w = {k: torch.from_numpy(rng.standard_normal(v.shape).astype(np.float32)) for k, v in golden_weights().items()
+         if k.startswith(('agg_net.', 'dist_decoder.'))}
+    blob = pack_blob(w)
+    g = rng.standard_normal(blob.shape).astype(np.float32)
+    for name, off, rows, cols, cp in _lib.weight_table():          # entries the backward kernels never write
+        if name.startswith(('nfc.', 'rf.')) or name in ('bf.wpc', 'bf.b0c'):
+            g[off:off + rows * cp] = 0
+    ug = unpack_blob_grad(torch.from_numpy(g))
+    lhs = float(np.dot(blob.astype(np.float64), g.astype(np.float64)))
+    rhs = sum(float((w[k].double() * ug[k].double()).sum()) for k in ug)
+    assert abs(lhs - rhs) <= 1e-9 * max(1.0, abs(lhs))
+    assert all(ug[k].shape == w[k].shape for k in ug) and len(ug) == 56
