@@ -23,7 +23,7 @@ __device__ __forceinline__ void mv_bwd(const float* __restrict__ W, const float*
 }
 
 // gW[k*NP + n] += sum_{r<nrows} sX[r][k] * sZ[r][n]   for k < KC, n < N; one (k,n) per thread and pass, coalesced atomics
-static __device__ __noinline__ void gn_dw_flush(float* __restrict__ gW, int NP, int KC, int N, const float* __restrict__ sX,
+static __device__ __noinline__ void gn_dw_flush(double* __restrict__ gW, int NP, int KC, int N, const float* __restrict__ sX,
                                          const float* __restrict__ sZ, int nrows, int nthreads)
 {
     for (int idx = threadIdx.x; idx < KC * N; idx += nthreads) {
@@ -33,21 +33,21 @@ static __device__ __noinline__ void gn_dw_flush(float* __restrict__ gW, int NP, 
             a0 = fmaf(sX[r * GN_BWD_LDX + k], sZ[r * GN_BWD_LDZ + n], a0);
             a1 = fmaf(sX[(r + 1) * GN_BWD_LDX + k], sZ[(r + 1) * GN_BWD_LDZ + n], a1);
         }
-        atomicAdd(gW + k * NP + n, a0 + a1);
+        atomicAdd(gW + k * NP + n, (double)a0 + (double)a1);
     }
 }
-static __device__ __noinline__ void gn_db_flush(float* __restrict__ gB, int N, const float* __restrict__ sZ, int nrows, int nthreads)
+static __device__ __noinline__ void gn_db_flush(double* __restrict__ gB, int N, const float* __restrict__ sZ, int nrows, int nthreads)
 {
     for (int n = threadIdx.x; n < N; n += nthreads) {
         float a = 0.f;
         for (int r = 0; r < nrows; ++r) a += sZ[r * GN_BWD_LDZ + n];
-        atomicAdd(gB + n, a);
+        atomicAdd(gB + n, (double)a);
     }
 }
 // Every thread of the CTA contributes its row (x[K], dz[N]); nthreads (even) rows are reduced.  gB may be NULL.
 // Contains __syncthreads(): must be reached by all threads of the CTA.
 template <int K, int N, int NP>
-__device__ __forceinline__ void dw_layer(float* gW, float* gB, const float* x, const float* dz, float* sX, float* sZ, int nthreads)
+__device__ __forceinline__ void dw_layer(double* gW, double* gB, const float* x, const float* dz, float* sX, float* sZ, int nthreads)
 {
     static_assert(N <= 64, "dZ staging tile holds 64 outputs");
     const int t = threadIdx.x;

@@ -65,7 +65,7 @@ __device__ __forceinline__ void dd_fwd(const float* __restrict__ sw, const float
     load_bias<4>(sw + B4, o); mv_acc<32, 4>(sw + W4, h2, o);
 }
 template <int W0, int B0, int W2, int B2, int W4, int B4>
-__device__ __forceinline__ void dd_bwd(const float* __restrict__ sw, float* gw, const float* ray, const float* h1, const float* h2,
+__device__ __forceinline__ void dd_bwd(const float* __restrict__ sw, double* gw, const float* ray, const float* h1, const float* h2,
                                        const float* d_o, float* d_ray, float* sX, float* sZ)
 {
     dw_layer<32, 4, 4>(gw + W4, gw + B4, h2, d_o, sX, sZ, KB_THREADS);
@@ -116,7 +116,7 @@ gn_k2a_backward_kernel(const __grid_constant__ GnK2aBwdParams p, int num_tiles, 
     for (int i = threadIdx.x * 4; i < GN_W_K2A_FLOATS; i += KB_THREADS * 4)
         *reinterpret_cast<float4*>(sw + i) = ldg4(p.weights + i);
     __syncthreads();
-    float* gw = p.d_weights;
+    double* gw = p.d_weights;
 
     const int V = p.V;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

@@ -30,7 +30,7 @@ gn_k2b_backward_kernel(const __grid_constant__ GnK2bBwdParams p, int rpb)
 
     for (int i = threadIdx.x * 4; i < GN_W_K2B_FLOATS; i += K2B_THREADS * 4)
         *reinterpret_cast<float4*>(sw + i) = ldg4(p.weights + GN_W_K2B_OFF + i);
-    float* gw = p.d_weights + GN_W_K2B_OFF;             // gradient blob, same offsets as sw
+    double* gw = p.d_weights + GN_W_K2B_OFF;             // gradient blob, same offsets as sw
 
     const int t = threadIdx.x;
     const int dn = p.dn;

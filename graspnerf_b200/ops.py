@@ -377,7 +377,8 @@ def render_rays(scene, hw_coarse, hw_fine, que, dn=40, fdn=40, u=None):
 # ------------------------------------------------------------------------------------------------ training (volume path)
 def k2b_backward(pooled, hw, d_sdf, d_weights, *, dn, resolution=None, bbox_min=None, volume_size=0.3, pts=None):
     """Reverse of k2b_forward (full head).  d_sdf: same layout as the forward output.  Accumulates into d_weights
-    (blob layout); returns d_pooled [B,N,68]."""
+    (blob layout, float64); returns d_pooled [B,N,68]."""
+    assert d_weights.dtype == torch.float64
     lib = _lib.load()
     B, N, _ = pooled.shape
     dev = pooled.device
@@ -402,8 +403,9 @@ def k2b_backward(pooled, hw, d_sdf, d_weights, *, dn, resolution=None, bbox_min=
 
 
 def k2a_backward(rec, pt, hw, depth_range, d_pooled, d_weights, *, que_dists=None, dn=1):
-    """Reverse of k2a_forward (volume-path part: no rgb_fc).  Accumulates into d_weights; returns d_rec [B,N,V,64]
-    (gradient of the record's ray_feats | img_feats entries)."""
+    """Reverse of k2a_forward (volume-path part: no rgb_fc).  Accumulates into d_weights (float64); returns d_rec
+    [B,N,V,64] (gradient of the record's ray_feats | img_feats entries)."""
+    assert d_weights.dtype == torch.float64
     lib = _lib.load()
     B, N, V, _ = rec.shape
     dev = rec.device
@@ -445,11 +447,11 @@ def k1_backward(scene, hw, d_rec, *, resolution=None, bbox_min=None, volume_size
 def sample_volume_backward(scene, hw, bbox_min, rec, pt, pooled, d_vol, resolution=40, volume_size=0.3):
     """d volume [B,1,R,R,R] -> (d_img_feats, d_ray_feats) channels-last [B,V,fh,fw,32] and the weight gradient in blob
     layout, through gn_k2b_backward -> gn_k2a_backward -> gn_k1_backward (fp32, forward recomputed per kernel)."""
-    d_w = torch.zeros_like(hw.blob)
+    d_w = torch.zeros(hw.blob.shape, dtype=torch.float64, device=hw.blob.device)     # fp64 accumulators
     d_pooled = k2b_backward(pooled, hw, d_vol, d_w, dn=resolution, resolution=resolution, bbox_min=bbox_min, volume_size=volume_size)
     d_rec = k2a_backward(rec, pt, hw, scene.depth_range, d_pooled, d_w)
     d_img, d_ray = k1_backward(scene, hw, d_rec, resolution=resolution, bbox_min=bbox_min, volume_size=volume_size)
-    return d_img, d_ray, d_w
+    return d_img, d_ray, d_w.float()
 
 
 class _SampleVolumeFn(torch.autograd.Function):

@@ -140,8 +140,8 @@ int gn_k3_fine_depths(const float* depth /*[B,rn,dn]*/, const float* hit_prob /*
  * Backward (training) entry points of the volume path: d volume -> d weights, d feature maps.  First order only.
  * The reference gets these from torch autograd through renderer.py:164-199; here each forward kernel has a hand-derived
  * reverse kernel that RECOMPUTES its forward from the saved inputs (rec / pt from K1, pooled from K2a) and accumulates
- * with atomics (outputs must be zero-initialised by the caller).  Weight gradients are produced in the blob layout
- * (same offsets as `weights`; fused composites nfc.* / bf.wpc / bf.b0c are not touched). */
+ * with atomics (outputs must be zero-initialised by the caller).  Weight gradients are produced in the blob layout, in
+ * DOUBLE precision (same element offsets as `weights`; fused composites nfc.* / bf.wpc / bf.b0c are not touched). */
 typedef struct GnK2bBwdParams {
     const float* pooled;       /* [B,N,68] saved K2a (SIMT) output */
     const float* weights;      /* blob */
@@ -151,7 +151,7 @@ typedef struct GnK2bBwdParams {
     const float* pos_table;    /* [dn,16] */
     const float* d_sdf;        /* upstream gradient, SAME layout as the forward output: volume [B,R,R,R] or sdf [B,N] */
     float* d_pooled;           /* out [B,N,68]: gradient of mean32 | var32 | wmean (entries 65..67 written as 0) */
-    float* d_weights;          /* accumulated (atomicAdd) [gn_weight_blob_floats()] */
+    double* d_weights;         /* accumulated (atomicAdd, fp64: the sum over ~10^5 rows loses no bits) [gn_weight_blob_floats()] */
     int B, N, dn, R, volume_mode;
 } GnK2bBwdParams;
 int gn_k2b_backward(const GnK2bBwdParams* params, void* stream);
@@ -164,7 +164,7 @@ typedef struct GnK2aBwdParams {
     const float* que_dists;    /* [B,N] or NULL (volume mode) */
     const float* d_pooled;     /* [B,N,68] from gn_k2b_backward */
     float* d_rec;              /* out [B,N,V,64]: gradient of the record's ray_feats (32) | img_feats (32) entries */
-    float* d_weights;          /* accumulated (atomicAdd) [gn_weight_blob_floats()] */
+    double* d_weights;         /* accumulated (atomicAdd, fp64: the sum over ~10^5 rows loses no bits) [gn_weight_blob_floats()] */
     int B, N, V, dn;
 } GnK2aBwdParams;
 int gn_k2a_backward(const GnK2aBwdParams* params, void* stream);

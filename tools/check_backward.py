@@ -54,6 +54,8 @@ def main():
         worst = max(worst, r[0])
         print('%-60s max %.2e l2 %.2e | vs fp64: ours %.2e ref32 %.2e' % (k, r[0], r[1], rel(params[k].grad.cpu(), g64[gk])[0], rel(g[gk], g64[gk])[0]))
     print('worst parameter-gradient max-rel error: %.2e' % worst)
+    os.makedirs('gpurun_out', exist_ok=True)
+    np.savez_compressed('gpurun_out/ours_grads.npz', d_img=imgf.grad.cpu().numpy(), d_ray=rayf.grad.cpu().numpy(), **{k: v.grad.cpu().numpy() for k, v in params.items() if v.grad is not None})
 
     # ---------------- stage: K2b backward alone (torch head from pooled on the CPU)
     with torch.no_grad():
@@ -62,7 +64,7 @@ def main():
                           sct['Ks'].to(dev), sct['depth_range'].to(dev))
         rec, pt = ops.k1_forward(scene, hw, resolution=R, bbox_min=bbox)
         pooled, _, _ = ops.k2a_forward(rec, pt, hw, scene.depth_range, impl='simt')
-        d_w = torch.zeros_like(hw.blob)
+        d_w = torch.zeros(hw.blob.shape, dtype=torch.float64, device=dev)
         d_pooled = ops.k2b_backward(pooled, hw, G, d_w, dn=R, resolution=R, bbox_min=bbox)
         torch.cuda.synchronize()
     A = 'agg_net.agg_impl.'
@@ -80,7 +82,7 @@ def main():
     volc = sdf.reshape(1, 1, R, R, R).flip(-1)
     (volc * torch.from_numpy(g['G'])).sum().backward()
     print('[K2b] d_pooled', rel(d_pooled[0, :, :65].cpu(), pin.grad))
-    gk = unpack_blob_grad(d_w.cpu())
+    gk = unpack_blob_grad(d_w.float().cpu())
     for k in sorted(sdc):
         print('[K2b] %-55s' % k, rel(gk[k], sdc[k].grad))
 
