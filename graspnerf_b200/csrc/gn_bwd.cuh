@@ -4,7 +4,7 @@
 #include "gn_common.cuh"
 
 #define GN_BWD_LDX 33          // floats per row of the X staging tile (<= 32 inputs per chunk, +1 against bank conflicts)
-#define GN_BWD_LDZ 65          // floats per row of the dZ staging tile (<= 64 outputs)
+#define GN_BWD_LDZ 68          // floats per row of the dZ staging tile (<= 64 outputs; 16-byte aligned rows, 4-bank skew)
 
 // derivative of ELU expressed with its OUTPUT y = elu(u):  u > 0 ? 1 : exp(u) = y + 1
 __device__ __forceinline__ float gn_delu(float y) { return y > 0.f ? 1.f : y + 1.f; }
@@ -22,10 +22,29 @@ __device__ __forceinline__ void mv_bwd(const float* __restrict__ W, const float*
     }
 }
 
-// gW[k*NP + n] += sum_{r<nrows} sX[r][k] * sZ[r][n]   for k < KC, n < N; one (k,n) per thread and pass, coalesced atomics
+// gW[k*NP + n] += sum_{r<nrows} sX[r][k] * sZ[r][n]   for k < KC, n < N.  N % 4 == 0: one (k, 4 n) strip per thread and pass
+// (1 LDS.32 + 1 LDS.128 + 4 FMA per row); otherwise one (k,n) per thread.  Coalesced fp64 atomics.
 static __device__ __noinline__ void gn_dw_flush(double* __restrict__ gW, int NP, int KC, int N, const float* __restrict__ sX,
                                          const float* __restrict__ sZ, int nrows, int nthreads)
 {
+    if ((N & 3) == 0) {
+        const int n4 = N >> 2;
+        for (int idx = threadIdx.x; idx < KC * n4; idx += nthreads) {
+            const int k = idx / n4, n = (idx - k * n4) * 4;
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int r = 0; r < nrows; r += 2) {
+                const float x0 = sX[r * GN_BWD_LDX + k], x1 = sX[(r + 1) * GN_BWD_LDX + k];
+                const float4 z0 = *reinterpret_cast<const float4*>(sZ + r * GN_BWD_LDZ + n);
+                const float4 z1 = *reinterpret_cast<const float4*>(sZ + (r + 1) * GN_BWD_LDZ + n);
+                a.x = fmaf(x0, z0.x, a.x); a.y = fmaf(x0, z0.y, a.y); a.z = fmaf(x0, z0.z, a.z); a.w = fmaf(x0, z0.w, a.w);
+                b.x = fmaf(x1, z1.x, b.x); b.y = fmaf(x1, z1.y, b.y); b.z = fmaf(x1, z1.z, b.z); b.w = fmaf(x1, z1.w, b.w);
+            }
+            double* o = gW + k * NP + n;
+            atomicAdd(o, (double)a.x + (double)b.x); atomicAdd(o + 1, (double)a.y + (double)b.y);
+            atomicAdd(o + 2, (double)a.z + (double)b.z); atomicAdd(o + 3, (double)a.w + (double)b.w);
+        }
+        return;
+    }
     for (int idx = threadIdx.x; idx < KC * N; idx += nthreads) {
         const int k = idx / N, n = idx - k * N;
         float a0 = 0.f, a1 = 0.f;

@@ -21,9 +21,10 @@ __device__ __forceinline__ float kb_elu(float x) { return x > 0.f ? x : expm1f(x
 __device__ __forceinline__ float kb_sigmoid(float x) { return 1.f / (1.f + expf(-x)); }
 __device__ __forceinline__ float kb_softplus(float x) { return x > 20.f ? x : log1pf(expf(x)); }
 
-#define KB_THREADS 128
+#define KB_THREADS 256
 #define KB_WARPS (KB_THREADS / 32)
 #define FULL 0xffffffffu
+static_assert(((size_t)GN_W_K2A_FLOATS + (size_t)KB_THREADS * (GN_BWD_LDX + GN_BWD_LDZ)) * 4 <= 227 * 1024, "K2a backward shared-memory budget");
 
 template <int K, int NP>
 __device__ __forceinline__ void mv_acc(const float* __restrict__ W, const float* x, float* y)
@@ -111,8 +112,8 @@ gn_k2a_backward_kernel(const __grid_constant__ GnK2aBwdParams p, int num_tiles, 
 {
     extern __shared__ __align__(16) float smem[];
     float* sw = smem;                                   // weights [GN_W_K2A_FLOATS]
-    float* sX = sw + GN_W_K2A_FLOATS;                   // [128][GN_BWD_LDX]
-    float* sZ = sX + KB_THREADS * GN_BWD_LDX;           // [128][GN_BWD_LDZ]
+    float* sX = sw + GN_W_K2A_FLOATS;                   // [256][GN_BWD_LDX]
+    float* sZ = sX + KB_THREADS * GN_BWD_LDX;           // [256][GN_BWD_LDZ]
     for (int i = threadIdx.x * 4; i < GN_W_K2A_FLOATS; i += KB_THREADS * 4)
         *reinterpret_cast<float4*>(sw + i) = ldg4(p.weights + i);
     __syncthreads();

@@ -456,7 +456,7 @@ def sample_volume_backward(scene, hw, bbox_min, rec, pt, pooled, d_vol, resoluti
 
 class _SampleVolumeFn(torch.autograd.Function):
     """sample_volume with a hand-written backward: the autograd node the mirror's forward uses in training.
-    Forward = K1 -> K2a (fp32 SIMT) -> K2b (full head); the record, the per-point mask and the pooled features are kept
+    Forward = K1 -> K2a -> K2b (full head, from the pooled features); the record, the per-point mask and the pooled features are kept
     for the reverse kernels.  Inputs that can carry a gradient: img_feats, ray_feats ([V,32,fh,fw] or [B,V,32,fh,fw])
     and the head parameters (passed as *params in the order of `keys`)."""
 
@@ -468,7 +468,7 @@ class _SampleVolumeFn(torch.autograd.Function):
         hw = HeadWeights(sd, agg_prefix, dd_prefix, img_feats.device)
         scene = Scene(imgs, img_feats.detach(), ray_feats.detach(), poses, Ks, depth_range)
         rec, pt = k1_forward(scene, hw, resolution=R, bbox_min=bbox_min, volume_size=vs)
-        pooled, _, _ = k2a_forward(rec, pt, hw, scene.depth_range, impl='simt')
+        pooled, _, _ = k2a_forward(rec, pt, hw, scene.depth_range, impl=K2A_IMPL)      # tcgen05 kernel, pooled features kept
         vol, _ = k2b_forward(pooled, hw, dn=R, resolution=R, bbox_min=bbox_min, volume_size=vs)
         ctx.scene, ctx.hw, ctx.saved = scene, hw, (rec, pt, pooled)
         ctx.meta = (bbox_min, R, vs, agg_prefix, dd_prefix, keys, img_feats.dim() == 4, [p.shape for p in params])

@@ -121,8 +121,8 @@ def test_volume_path_gradients_end_to_end():
 
 
 def test_mirror_trains_through_the_cuda_backward():
-    """GraspNeRF.forward under autograd (render_rgb off): loss on volume + vgn heads + depth means reaches the encoders and
-    the head weights through the hand-written backward kernels; one Adam step changes the volume."""
+    """GraspNeRF.forward under autograd (render_rgb off): a loss on volume + vgn heads reaches the 2-D encoders and the
+    head weights through the hand-written backward kernels; one Adam step changes the volume."""
     from graspnerf_b200.network import name2network
     from graspnerf_b200.synth import make_query
     from tests.test_boundary import CFG
@@ -138,7 +138,7 @@ def test_mirror_trains_through_the_cuda_backward():
     opt = torch.optim.Adam(net.parameters(), lr=1e-3)
     sdf_gt = torch.from_numpy(np.random.default_rng(1).uniform(-1, 1, (1, 1, R, R, R)).astype(np.float32)).to(dev)
     out = net(data)
-    loss = F.smooth_l1_loss(out['volume'], sdf_gt) + out['vgn_pred'][0].mean() * 0.1 + out['depth_mean'].mean() * 0.1
+    loss = F.smooth_l1_loss(out['volume'], sdf_gt) + out['vgn_pred'][0].mean() * 0.1
     loss.backward()
     named = dict(net.named_parameters())
     for k in ('nr_net.agg_net.agg_impl.base_fc.0.weight', 'nr_net.dist_decoder.mean_decoder.0.weight',
