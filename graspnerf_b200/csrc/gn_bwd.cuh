@@ -10,6 +10,7 @@
 __device__ __forceinline__ float gn_delu(float y) { return y > 0.f ? 1.f : y + 1.f; }
 
 // dx[k] (+)= sum_{n<N} W[k*NP + n] * dz[n]      (W k-major in shared memory; the transpose of mv_acc)
+// Fully unrolled form (small kernels only: the code grows with K*N).
 template <int K, int N, int NP, bool ACC>
 __device__ __forceinline__ void mv_bwd(const float* __restrict__ W, const float* dz, float* dx)
 {
@@ -20,6 +21,41 @@ __device__ __forceinline__ void mv_bwd(const float* __restrict__ W, const float*
         for (int n = 0; n < N; ++n) a = fmaf(W[k * NP + n], dz[n], a);
         dx[k] = a;
     }
+}
+// Compact forms for the big per-row kernels: the k loop stays ROLLED (straight-line code for every layer would be megabytes of
+// SASS and the kernel becomes instruction-fetch bound), the dynamically indexed operand goes through the thread's private
+// column of a shared-memory scratch area: scr[k * SCR_STRIDE] (stride = threads per CTA, conflict free).
+template <int K, int NP, int SCR_STRIDE>
+__device__ __forceinline__ void mv_acc_rolled(const float* __restrict__ W, const float* x, float* y, float* scr)
+{
+#pragma unroll
+    for (int k = 0; k < K; ++k) scr[k * SCR_STRIDE] = x[k];
+#pragma unroll 2
+    for (int k = 0; k < K; ++k) {
+        const float xk = scr[k * SCR_STRIDE];
+#pragma unroll
+        for (int n = 0; n < NP; n += 4) {
+            const float4 w = *reinterpret_cast<const float4*>(W + k * NP + n);
+            y[n + 0] = fmaf(xk, w.x, y[n + 0]); y[n + 1] = fmaf(xk, w.y, y[n + 1]);
+            y[n + 2] = fmaf(xk, w.z, y[n + 2]); y[n + 3] = fmaf(xk, w.w, y[n + 3]);
+        }
+    }
+}
+template <int K, int NP, bool ACC, int SCR_STRIDE>       // dz has NP entries (pad entries zero)
+__device__ __forceinline__ void mv_bwd_rolled(const float* __restrict__ W, const float* dz, float* dx, float* scr)
+{
+#pragma unroll 2
+    for (int k = 0; k < K; ++k) {
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+        for (int n = 0; n < NP; n += 4) {
+            const float4 w = *reinterpret_cast<const float4*>(W + k * NP + n);
+            a0 = fmaf(w.x, dz[n], a0); a1 = fmaf(w.y, dz[n + 1], a1); a0 = fmaf(w.z, dz[n + 2], a0); a1 = fmaf(w.w, dz[n + 3], a1);
+        }
+        scr[k * SCR_STRIDE] = a0 + a1;
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) dx[k] = ACC ? dx[k] + scr[k * SCR_STRIDE] : scr[k * SCR_STRIDE];
 }
 
 // gW[k*NP + n] += sum_{r<nrows} sX[r][k] * sZ[r][n]   for k < KC, n < N.  N % 4 == 0: one (k, 4 n) strip per thread and pass
@@ -70,6 +106,7 @@ __device__ __forceinline__ void dw_layer(double* gW, double* gB, const float* x,
 {
     static_assert(N <= 64, "dZ staging tile holds 64 outputs");
     const int t = threadIdx.x;
+    __syncthreads();                                     // the staging tiles may alias per-thread scratch columns still being read
 #pragma unroll
     for (int n = 0; n < N; ++n) sZ[t * GN_BWD_LDZ + n] = dz[n];
 #pragma unroll

@@ -24,22 +24,9 @@ __device__ __forceinline__ float kb_softplus(float x) { return x > 20.f ? x : lo
 #define KB_THREADS 256
 #define KB_WARPS (KB_THREADS / 32)
 #define FULL 0xffffffffu
+static_assert(64 * KB_THREADS <= KB_THREADS * GN_BWD_LDZ, "scratch columns must fit in the dZ tile");
 static_assert(((size_t)GN_W_K2A_FLOATS + (size_t)KB_THREADS * (GN_BWD_LDX + GN_BWD_LDZ)) * 4 <= 227 * 1024, "K2a backward shared-memory budget");
 
-template <int K, int NP>
-__device__ __forceinline__ void mv_acc(const float* __restrict__ W, const float* x, float* y)
-{
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-        const float xk = x[k];
-#pragma unroll
-        for (int n = 0; n < NP; n += 4) {
-            const float4 w = *reinterpret_cast<const float4*>(W + k * NP + n);
-            y[n + 0] = fmaf(xk, w.x, y[n + 0]); y[n + 1] = fmaf(xk, w.y, y[n + 1]);
-            y[n + 2] = fmaf(xk, w.z, y[n + 2]); y[n + 3] = fmaf(xk, w.w, y[n + 3]);
-        }
-    }
-}
 template <int NP>
 __device__ __forceinline__ void load_bias(const float* __restrict__ b, float* y)
 {
@@ -55,31 +42,31 @@ __device__ __forceinline__ float gsum(float t, int gb, int V)
 
 // ---- dist-decoder MLP 32 -> 32 -> 32 -> NO (dist_decoder.py:62-86), activations kept for the reverse pass
 template <int W0, int B0, int W2, int B2, int W4, int B4>
-__device__ __forceinline__ void dd_fwd(const float* __restrict__ sw, const float* ray, float* h1, float* h2, float* o)
+__device__ __forceinline__ void dd_fwd(const float* __restrict__ sw, const float* ray, float* h1, float* h2, float* o, float* scr)
 {
-    load_bias<32>(sw + B0, h1); mv_acc<32, 32>(sw + W0, ray, h1);
+    load_bias<32>(sw + B0, h1); mv_acc_rolled<32, 32, KB_THREADS>(sw + W0, ray, h1, scr);
 #pragma unroll
     for (int c = 0; c < 32; ++c) h1[c] = kb_elu(h1[c]);
-    load_bias<32>(sw + B2, h2); mv_acc<32, 32>(sw + W2, h1, h2);
+    load_bias<32>(sw + B2, h2); mv_acc_rolled<32, 32, KB_THREADS>(sw + W2, h1, h2, scr);
 #pragma unroll
     for (int c = 0; c < 32; ++c) h2[c] = kb_elu(h2[c]);
-    load_bias<4>(sw + B4, o); mv_acc<32, 4>(sw + W4, h2, o);
+    load_bias<4>(sw + B4, o); mv_acc_rolled<32, 4, KB_THREADS>(sw + W4, h2, o, scr);
 }
 template <int W0, int B0, int W2, int B2, int W4, int B4>
 __device__ __forceinline__ void dd_bwd(const float* __restrict__ sw, double* gw, const float* ray, const float* h1, const float* h2,
-                                       const float* d_o, float* d_ray, float* sX, float* sZ)
+                                       const float* d_o, float* d_ray, float* sX, float* sZ, float* scr)
 {
     dw_layer<32, 4, 4>(gw + W4, gw + B4, h2, d_o, sX, sZ, KB_THREADS);
     float dh2[32], dh1[32];
-    mv_bwd<32, 4, 4, false>(sw + W4, d_o, dh2);
+    mv_bwd_rolled<32, 4, false, KB_THREADS>(sw + W4, d_o, dh2, scr);
 #pragma unroll
     for (int c = 0; c < 32; ++c) dh2[c] *= gn_delu(h2[c]);
     dw_layer<32, 32, 32>(gw + W2, gw + B2, h1, dh2, sX, sZ, KB_THREADS);
-    mv_bwd<32, 32, 32, false>(sw + W2, dh2, dh1);
+    mv_bwd_rolled<32, 32, false, KB_THREADS>(sw + W2, dh2, dh1, scr);
 #pragma unroll
     for (int c = 0; c < 32; ++c) dh1[c] *= gn_delu(h1[c]);
     dw_layer<32, 32, 32>(gw + W0, gw + B0, ray, dh1, sX, sZ, KB_THREADS);
-    mv_bwd<32, 32, 32, true>(sw + W0, dh1, d_ray);
+    mv_bwd_rolled<32, 32, true, KB_THREADS>(sw + W0, dh1, d_ray, scr);
 }
 #define DD_IDS(n) GN_OFF(DD_##n##_W0), GN_OFF(DD_##n##_B0), GN_OFF(DD_##n##_W2), GN_OFF(DD_##n##_B2), GN_OFF(DD_##n##_W4), GN_OFF(DD_##n##_B4)
 
@@ -117,6 +104,7 @@ gn_k2a_backward_kernel(const __grid_constant__ GnK2aBwdParams p, int num_tiles, 
     for (int i = threadIdx.x * 4; i < GN_W_K2A_FLOATS; i += KB_THREADS * 4)
         *reinterpret_cast<float4*>(sw + i) = ldg4(p.weights + i);
     __syncthreads();
+    float* scr = sZ + threadIdx.x;                      // private scratch column scr[k * KB_THREADS], k < 64 (aliases the dZ tile)
     double* gw = p.d_weights;
 
     const int V = p.V;
@@ -149,9 +137,9 @@ gn_k2a_backward_kernel(const __grid_constant__ GnK2aBwdParams p, int num_tiles, 
             ray[c] = t.x; ray[c + 1] = t.y; ray[c + 2] = t.z; ray[c + 3] = t.w;
         }
         float h1m[32], h2m[32], h1v[32], h2v[32], h1a[32], h2a[32], om[4], ov[4], oa[4];
-        dd_fwd<DD_IDS(MEAN)>(sw, ray, h1m, h2m, om);
-        dd_fwd<DD_IDS(VAR)>(sw, ray, h1v, h2v, ov);
-        dd_fwd<DD_IDS(AW)>(sw, ray, h1a, h2a, oa);
+        dd_fwd<DD_IDS(MEAN)>(sw, ray, h1m, h2m, om, scr);
+        dd_fwd<DD_IDS(VAR)>(sw, ray, h1v, h2v, ov, scr);
+        dd_fwd<DD_IDS(AW)>(sw, ray, h1a, h2a, oa, scr);
         const float mean0 = kb_softplus(om[0]), mean1 = kb_softplus(om[1]);
         const float var0 = kb_softplus(ov[0]) + 0.05f, var1 = kb_softplus(ov[1]) + 0.05f;
         const float aw = kb_sigmoid(oa[0]);
@@ -181,15 +169,15 @@ gn_k2a_backward_kernel(const __grid_constant__ GnK2aBwdParams p, int num_tiles, 
         for (int c = 0; c < 32; ++c) xin[c] = ray[c];
         xin[32] = (hit - 0.5f) * 2.f; xin[33] = (vis - 0.5f) * 2.f;
         load_bias<32>(sw + GN_OFF(PE_B0), e1);
-        mv_acc<34, 32>(sw + GN_OFF(PE_W0), xin, e1);
+        mv_acc_rolled<34, 32, KB_THREADS>(sw + GN_OFF(PE_W0), xin, e1, scr);
 #pragma unroll
         for (int c = 0; c < 32; ++c) e1[c] = fmaxf(e1[c], 0.f);
         load_bias<32>(sw + GN_OFF(PE_B2), pe);
-        mv_acc<32, 32>(sw + GN_OFF(PE_W2), e1, pe);
+        mv_acc_rolled<32, 32, KB_THREADS>(sw + GN_OFF(PE_W2), e1, pe, scr);
         // neuray_fc -> w0
         float t8[8], sig0, w0;
         load_bias<8>(sw + GN_OFF(NF_B0), t8);
-        mv_acc<32, 8>(sw + GN_OFF(NF_W0), pe, t8);
+        mv_acc_rolled<32, 8, KB_THREADS>(sw + GN_OFF(NF_W0), pe, t8, scr);
         {
             float s = sw[GN_OFF(NF_B2)];
 #pragma unroll
@@ -203,11 +191,11 @@ gn_k2a_backward_kernel(const __grid_constant__ GnK2aBwdParams p, int num_tiles, 
             const float4 ddv = ldg4(row + GN_REC_DD);
             dd[0] = ddv.x; dd[1] = ddv.y; dd[2] = ddv.z; dd[3] = ddv.w;
             load_bias<16>(sw + GN_OFF(RD_B0), hid);
-            mv_acc<4, 16>(sw + GN_OFF(RD_W0), dd, hid);
+            mv_acc_rolled<4, 16, KB_THREADS>(sw + GN_OFF(RD_W0), dd, hid, scr);
 #pragma unroll
             for (int c = 0; c < 16; ++c) hid[c] = kb_elu(hid[c]);
             load_bias<36>(sw + GN_OFF(RD_B1), dfe);
-            mv_acc<16, 36>(sw + GN_OFF(RD_W1), hid, dfe);
+            mv_acc_rolled<16, 36, KB_THREADS>(sw + GN_OFF(RD_W1), hid, dfe, scr);
 #pragma unroll
             for (int c = 0; c < 36; ++c) dfe[c] = kb_elu(dfe[c]);
 #pragma unroll
@@ -224,16 +212,16 @@ gn_k2a_backward_kernel(const __grid_constant__ GnK2aBwdParams p, int num_tiles, 
         // base_fc
         float bh[64], x0[32];
         load_bias<64>(sw + GN_OFF(BF_B0), bh);
-        mv_acc<36, 64>(sw + GN_OFF(BF_WG), m0, bh);
-        mv_acc<36, 64>(sw + GN_OFF(BF_WG) + 36 * 64, v0, bh);
-        mv_acc<36, 64>(sw + GN_OFF(BF_WG) + 72 * 64, m1, bh);
-        mv_acc<36, 64>(sw + GN_OFF(BF_WG) + 108 * 64, v1, bh);
-        mv_acc<36, 64>(sw + GN_OFF(BF_WF), f, bh);
-        mv_acc<32, 64>(sw + GN_OFF(BF_WP), pe, bh);
+        mv_acc_rolled<36, 64, KB_THREADS>(sw + GN_OFF(BF_WG), m0, bh, scr);
+        mv_acc_rolled<36, 64, KB_THREADS>(sw + GN_OFF(BF_WG) + 36 * 64, v0, bh, scr);
+        mv_acc_rolled<36, 64, KB_THREADS>(sw + GN_OFF(BF_WG) + 72 * 64, m1, bh, scr);
+        mv_acc_rolled<36, 64, KB_THREADS>(sw + GN_OFF(BF_WG) + 108 * 64, v1, bh, scr);
+        mv_acc_rolled<36, 64, KB_THREADS>(sw + GN_OFF(BF_WF), f, bh, scr);
+        mv_acc_rolled<32, 64, KB_THREADS>(sw + GN_OFF(BF_WP), pe, bh, scr);
 #pragma unroll
         for (int c = 0; c < 64; ++c) bh[c] = kb_elu(bh[c]);
         load_bias<32>(sw + GN_OFF(BF_B2), x0);
-        mv_acc<64, 32>(sw + GN_OFF(BF_W2), bh, x0);
+        mv_acc_rolled<64, 32, KB_THREADS>(sw + GN_OFF(BF_W2), bh, x0, scr);
 #pragma unroll
         for (int c = 0; c < 32; ++c) x0[c] = kb_elu(x0[c]);
         // vis_fc
@@ -241,11 +229,11 @@ gn_k2a_backward_kernel(const __grid_constant__ GnK2aBwdParams p, int num_tiles, 
 #pragma unroll
         for (int c = 0; c < 32; ++c) xw[c] = x0[c] * wgt;
         load_bias<32>(sw + GN_OFF(VF_B0), vh);
-        mv_acc<32, 32>(sw + GN_OFF(VF_W0), xw, vh);
+        mv_acc_rolled<32, 32, KB_THREADS>(sw + GN_OFF(VF_W0), xw, vh, scr);
 #pragma unroll
         for (int c = 0; c < 32; ++c) vh[c] = kb_elu(vh[c]);
         load_bias<36>(sw + GN_OFF(VF_B2), xv);
-        mv_acc<32, 36>(sw + GN_OFF(VF_W2), vh, xv);
+        mv_acc_rolled<32, 36, KB_THREADS>(sw + GN_OFF(VF_W2), vh, xv, scr);
 #pragma unroll
         for (int c = 0; c < 36; ++c) xv[c] = kb_elu(xv[c]);
 #pragma unroll
@@ -257,7 +245,7 @@ gn_k2a_backward_kernel(const __grid_constant__ GnK2aBwdParams p, int num_tiles, 
 #pragma unroll
         for (int c = 0; c < 32; ++c) xs[c] = x[c] * vis1;
         load_bias<32>(sw + GN_OFF(V2_B0), v2h);
-        mv_acc<32, 32>(sw + GN_OFF(V2_W0), xs, v2h);
+        mv_acc_rolled<32, 32, KB_THREADS>(sw + GN_OFF(V2_W0), xs, v2h, scr);
         {
             float s = sw[GN_OFF(V2_B2)];
 #pragma unroll
@@ -302,7 +290,7 @@ gn_k2a_backward_kernel(const __grid_constant__ GnK2aBwdParams p, int num_tiles, 
         for (int c = 0; c < 32; ++c) dt[c] = sw[GN_OFF(V2_W2) + c] * ds2 * gn_delu(v2h[c]);
         dw_layer<32, 32, 32>(gw + GN_OFF(V2_W0), gw + GN_OFF(V2_B0), xs, dt, sX, sZ, KB_THREADS);
         float dxs[32];
-        mv_bwd<32, 32, 32, false>(sw + GN_OFF(V2_W0), dt, dxs);
+        mv_bwd_rolled<32, 32, false, KB_THREADS>(sw + GN_OFF(V2_W0), dt, dxs, scr);
         float dvis1 = 0.f;
 #pragma unroll
         for (int c = 0; c < 32; ++c) { dx[c] = fmaf(dxs[c], vis1, dx[c]); dvis1 = fmaf(dxs[c], x[c], dvis1); }
@@ -314,17 +302,17 @@ gn_k2a_backward_kernel(const __grid_constant__ GnK2aBwdParams p, int num_tiles, 
         dxv[33] = 0.f; dxv[34] = 0.f; dxv[35] = 0.f;
         dw_layer<32, 36, 36>(gw + GN_OFF(VF_W2), gw + GN_OFF(VF_B2), vh, dxv, sX, sZ, KB_THREADS);
         float dvh[32];
-        mv_bwd<32, 36, 36, false>(sw + GN_OFF(VF_W2), dxv, dvh);
+        mv_bwd_rolled<32, 36, false, KB_THREADS>(sw + GN_OFF(VF_W2), dxv, dvh, scr);
 #pragma unroll
         for (int c = 0; c < 32; ++c) dvh[c] *= gn_delu(vh[c]);
         dw_layer<32, 32, 32>(gw + GN_OFF(VF_W0), gw + GN_OFF(VF_B0), xw, dvh, sX, sZ, KB_THREADS);
         float dx0[32];
-        mv_bwd<32, 32, 32, false>(sw + GN_OFF(VF_W0), dvh, dx0);
+        mv_bwd_rolled<32, 32, false, KB_THREADS>(sw + GN_OFF(VF_W0), dvh, dx0, scr);
 #pragma unroll
         for (int c = 0; c < 32; ++c) dx0[c] = (fmaf(dx0[c], wgt, dx[c])) * gn_delu(x0[c]);      // d pre-activation of base_fc.2
         dw_layer<64, 32, 32>(gw + GN_OFF(BF_W2), gw + GN_OFF(BF_B2), bh, dx0, sX, sZ, KB_THREADS);
         float dbh[64];
-        mv_bwd<64, 32, 32, false>(sw + GN_OFF(BF_W2), dx0, dbh);
+        mv_bwd_rolled<64, 32, false, KB_THREADS>(sw + GN_OFF(BF_W2), dx0, dbh, scr);
 #pragma unroll
         for (int c = 0; c < 64; ++c) dbh[c] *= gn_delu(bh[c]);
         // base_fc.0 : inputs [m0 36 | v0 36 | m1 36 | v1 36 | f 36 | pe 32]
@@ -335,19 +323,19 @@ gn_k2a_backward_kernel(const __grid_constant__ GnK2aBwdParams p, int num_tiles, 
         dw_layer<36, 64, 64>(gw + GN_OFF(BF_WF), gw + GN_OFF(BF_B0), f, dbh, sX, sZ, KB_THREADS);
         dw_layer<32, 64, 64>(gw + GN_OFF(BF_WP), nullptr, pe, dbh, sX, sZ, KB_THREADS);
         float df[36], dpe[32];
-        mv_bwd<36, 64, 64, false>(sw + GN_OFF(BF_WF), dbh, df);
-        mv_bwd<32, 64, 64, false>(sw + GN_OFF(BF_WP), dbh, dpe);
+        mv_bwd_rolled<36, 64, false, KB_THREADS>(sw + GN_OFF(BF_WF), dbh, df, scr);
+        mv_bwd_rolled<32, 64, false, KB_THREADS>(sw + GN_OFF(BF_WP), dbh, dpe, scr);
         float dw0;
         {
             // pooled statistics are shared by the V rows of the point: sum the per-row cotangents over the group
             float dm[36], dv_[36];
-            mv_bwd<36, 64, 64, false>(sw + GN_OFF(BF_WG), dbh, dm);
-            mv_bwd<36, 64, 64, false>(sw + GN_OFF(BF_WG) + 36 * 64, dbh, dv_);
+            mv_bwd_rolled<36, 64, false, KB_THREADS>(sw + GN_OFF(BF_WG), dbh, dm, scr);
+            mv_bwd_rolled<36, 64, false, KB_THREADS>(sw + GN_OFF(BF_WG) + 36 * 64, dbh, dv_, scr);
 #pragma unroll
             for (int c = 0; c < 35; ++c) { dm[c] = gsum(dm[c], gb, V); dv_[c] = gsum(dv_[c], gb, V); }
             dw0 = pool_bwd<35>(f, m0, dm, dv_, w0, S0, df);
-            mv_bwd<36, 64, 64, false>(sw + GN_OFF(BF_WG) + 72 * 64, dbh, dm);
-            mv_bwd<36, 64, 64, false>(sw + GN_OFF(BF_WG) + 108 * 64, dbh, dv_);
+            mv_bwd_rolled<36, 64, false, KB_THREADS>(sw + GN_OFF(BF_WG) + 72 * 64, dbh, dm, scr);
+            mv_bwd_rolled<36, 64, false, KB_THREADS>(sw + GN_OFF(BF_WG) + 108 * 64, dbh, dv_, scr);
 #pragma unroll
             for (int c = 0; c < 35; ++c) { dm[c] = gsum(dm[c], gb, V); dv_[c] = gsum(dv_[c], gb, V); }
             (void)pool_bwd<35>(f, m1, dm, dv_, wgt, S1, df);                    // wgt carries no gradient
@@ -361,7 +349,7 @@ gn_k2a_backward_kernel(const __grid_constant__ GnK2aBwdParams p, int num_tiles, 
 #pragma unroll
             for (int c = 0; c < 8; ++c) dt8[c] = sw[GN_OFF(NF_W2) + c] * dsn * gn_delu(t8[c]);
             dw_layer<32, 8, 8>(gw + GN_OFF(NF_W0), gw + GN_OFF(NF_B0), pe, dt8, sX, sZ, KB_THREADS);
-            mv_bwd<32, 8, 8, true>(sw + GN_OFF(NF_W0), dt8, dpe);
+            mv_bwd_rolled<32, 8, true, KB_THREADS>(sw + GN_OFF(NF_W0), dt8, dpe, scr);
         }
         // f = dfeat + [img_feats | rgb] : img_feats gradient leaves here; ray_dir_fc weights
         float* drow = p.d_rec + ((size_t)pidx * V + v) * 64;
@@ -376,7 +364,7 @@ gn_k2a_backward_kernel(const __grid_constant__ GnK2aBwdParams p, int num_tiles, 
             ddf[35] = 0.f;
             dw_layer<16, 36, 36>(gw + GN_OFF(RD_W1), gw + GN_OFF(RD_B1), hid, ddf, sX, sZ, KB_THREADS);
             float dhid[16];
-            mv_bwd<16, 36, 36, false>(sw + GN_OFF(RD_W1), ddf, dhid);
+            mv_bwd_rolled<16, 36, false, KB_THREADS>(sw + GN_OFF(RD_W1), ddf, dhid, scr);
 #pragma unroll
             for (int c = 0; c < 16; ++c) dhid[c] *= gn_delu(hid[c]);
             dw_layer<4, 16, 16>(gw + GN_OFF(RD_W0), gw + GN_OFF(RD_B0), dd, dhid, sX, sZ, KB_THREADS);
@@ -387,12 +375,12 @@ gn_k2a_backward_kernel(const __grid_constant__ GnK2aBwdParams p, int num_tiles, 
         {
             dw_layer<32, 32, 32>(gw + GN_OFF(PE_W2), gw + GN_OFF(PE_B2), e1, dpe, sX, sZ, KB_THREADS);
             float de1[32];
-            mv_bwd<32, 32, 32, false>(sw + GN_OFF(PE_W2), dpe, de1);
+            mv_bwd_rolled<32, 32, false, KB_THREADS>(sw + GN_OFF(PE_W2), dpe, de1, scr);
 #pragma unroll
             for (int c = 0; c < 32; ++c) de1[c] = e1[c] > 0.f ? de1[c] : 0.f;
             dw_layer<34, 32, 32>(gw + GN_OFF(PE_W0), gw + GN_OFF(PE_B0), xin, de1, sX, sZ, KB_THREADS);
             float dxin[34];
-            mv_bwd<34, 32, 32, false>(sw + GN_OFF(PE_W0), de1, dxin);
+            mv_bwd_rolled<34, 32, false, KB_THREADS>(sw + GN_OFF(PE_W0), de1, dxin, scr);
 #pragma unroll
             for (int c = 0; c < 32; ++c) dray[c] = dxin[c];
             dhit = 2.f * dxin[32] * mask; dvis = 2.f * dxin[33] * mask;       // hv = (x - 0.5) * 2 ; hit, vis carry the mask
@@ -414,9 +402,9 @@ gn_k2a_backward_kernel(const __grid_constant__ GnK2aBwdParams p, int num_tiles, 
             doa[0] = daw * aw * (1.f - aw);
             dom[2] = dom[3] = dov[2] = dov[3] = doa[1] = doa[2] = doa[3] = 0.f;
         }
-        dd_bwd<DD_IDS(MEAN)>(sw, gw, ray, h1m, h2m, dom, dray, sX, sZ);
-        dd_bwd<DD_IDS(VAR)>(sw, gw, ray, h1v, h2v, dov, dray, sX, sZ);
-        dd_bwd<DD_IDS(AW)>(sw, gw, ray, h1a, h2a, doa, dray, sX, sZ);
+        dd_bwd<DD_IDS(MEAN)>(sw, gw, ray, h1m, h2m, dom, dray, sX, sZ, scr);
+        dd_bwd<DD_IDS(VAR)>(sw, gw, ray, h1v, h2v, dov, dray, sX, sZ, scr);
+        dd_bwd<DD_IDS(AW)>(sw, gw, ray, h1a, h2a, doa, dray, sX, sZ, scr);
         if (valid) {
 #pragma unroll
             for (int c = 0; c < 32; c += 4) st4(drow + c, make_float4(dray[c], dray[c + 1], dray[c + 2], dray[c + 3]));
