@@ -6,6 +6,12 @@
 #define GN_BWD_LDX 33          // floats per row of the X staging tile (<= 32 inputs per chunk, +1 against bank conflicts)
 #define GN_BWD_LDZ 68          // floats per row of the dZ staging tile (<= 64 outputs; 16-byte aligned rows, 4-bank skew)
 
+// ---- packed fp32x2 arithmetic (Blackwell FFMA2: two IEEE fp32 FMAs per issued instruction, bit-identical to scalar fmaf)
+typedef unsigned long long gn_f2;
+__device__ __forceinline__ gn_f2 gn_pk2(float lo, float hi) { gn_f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void gn_upk2(gn_f2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ gn_f2 gn_fma2(gn_f2 a, gn_f2 b, gn_f2 c) { gn_f2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+
 // derivative of ELU expressed with its OUTPUT y = elu(u):  u > 0 ? 1 : exp(u) = y + 1
 __device__ __forceinline__ float gn_delu(float y) { return y > 0.f ? 1.f : y + 1.f; }
 
@@ -30,29 +36,41 @@ __device__ __forceinline__ void mv_acc_rolled(const float* __restrict__ W, const
 {
 #pragma unroll
     for (int k = 0; k < K; ++k) scr[k * SCR_STRIDE] = x[k];
+    gn_f2 acc[NP / 2];
+#pragma unroll
+    for (int n = 0; n < NP; n += 2) acc[n / 2] = gn_pk2(y[n], y[n + 1]);
 #pragma unroll 2
     for (int k = 0; k < K; ++k) {
         const float xk = scr[k * SCR_STRIDE];
+        const gn_f2 xx = gn_pk2(xk, xk);
 #pragma unroll
         for (int n = 0; n < NP; n += 4) {
-            const float4 w = *reinterpret_cast<const float4*>(W + k * NP + n);
-            y[n + 0] = fmaf(xk, w.x, y[n + 0]); y[n + 1] = fmaf(xk, w.y, y[n + 1]);
-            y[n + 2] = fmaf(xk, w.z, y[n + 2]); y[n + 3] = fmaf(xk, w.w, y[n + 3]);
+            const ulonglong2 w = *reinterpret_cast<const ulonglong2*>(W + k * NP + n);      // (w[n],w[n+1]) , (w[n+2],w[n+3])
+            acc[n / 2] = gn_fma2(w.x, xx, acc[n / 2]);
+            acc[n / 2 + 1] = gn_fma2(w.y, xx, acc[n / 2 + 1]);
         }
     }
+#pragma unroll
+    for (int n = 0; n < NP; n += 2) gn_upk2(acc[n / 2], y[n], y[n + 1]);
 }
 template <int K, int NP, bool ACC, int SCR_STRIDE>       // dz has NP entries (pad entries zero)
 __device__ __forceinline__ void mv_bwd_rolled(const float* __restrict__ W, const float* dz, float* dx, float* scr)
 {
+    gn_f2 dzp[NP / 2];
+#pragma unroll
+    for (int n = 0; n < NP; n += 2) dzp[n / 2] = gn_pk2(dz[n], dz[n + 1]);
 #pragma unroll 2
     for (int k = 0; k < K; ++k) {
-        float a0 = 0.f, a1 = 0.f;
+        gn_f2 a = 0ull, b = 0ull;                        // +0.0f, +0.0f
 #pragma unroll
         for (int n = 0; n < NP; n += 4) {
-            const float4 w = *reinterpret_cast<const float4*>(W + k * NP + n);
-            a0 = fmaf(w.x, dz[n], a0); a1 = fmaf(w.y, dz[n + 1], a1); a0 = fmaf(w.z, dz[n + 2], a0); a1 = fmaf(w.w, dz[n + 3], a1);
+            const ulonglong2 w = *reinterpret_cast<const ulonglong2*>(W + k * NP + n);
+            a = gn_fma2(w.x, dzp[n / 2], a);
+            b = gn_fma2(w.y, dzp[n / 2 + 1], b);
         }
-        scr[k * SCR_STRIDE] = a0 + a1;
+        float a0, a1, b0, b1;
+        gn_upk2(a, a0, a1); gn_upk2(b, b0, b1);
+        scr[k * SCR_STRIDE] = (a0 + b0) + (a1 + b1);
     }
 #pragma unroll
     for (int k = 0; k < K; ++k) dx[k] = ACC ? dx[k] + scr[k * SCR_STRIDE] : scr[k * SCR_STRIDE];
@@ -67,14 +85,17 @@ static __device__ __noinline__ void gn_dw_flush(double* __restrict__ gW, int NP,
         const int n4 = N >> 2;
         for (int idx = threadIdx.x; idx < KC * n4; idx += nthreads) {
             const int k = idx / n4, n = (idx - k * n4) * 4;
-            float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = make_float4(0.f, 0.f, 0.f, 0.f);
+            gn_f2 alo = 0ull, ahi = 0ull, blo = 0ull, bhi = 0ull;
             for (int r = 0; r < nrows; r += 2) {
                 const float x0 = sX[r * GN_BWD_LDX + k], x1 = sX[(r + 1) * GN_BWD_LDX + k];
-                const float4 z0 = *reinterpret_cast<const float4*>(sZ + r * GN_BWD_LDZ + n);
-                const float4 z1 = *reinterpret_cast<const float4*>(sZ + (r + 1) * GN_BWD_LDZ + n);
-                a.x = fmaf(x0, z0.x, a.x); a.y = fmaf(x0, z0.y, a.y); a.z = fmaf(x0, z0.z, a.z); a.w = fmaf(x0, z0.w, a.w);
-                b.x = fmaf(x1, z1.x, b.x); b.y = fmaf(x1, z1.y, b.y); b.z = fmaf(x1, z1.z, b.z); b.w = fmaf(x1, z1.w, b.w);
+                const ulonglong2 z0 = *reinterpret_cast<const ulonglong2*>(sZ + r * GN_BWD_LDZ + n);
+                const ulonglong2 z1 = *reinterpret_cast<const ulonglong2*>(sZ + (r + 1) * GN_BWD_LDZ + n);
+                const gn_f2 xx0 = gn_pk2(x0, x0), xx1 = gn_pk2(x1, x1);
+                alo = gn_fma2(z0.x, xx0, alo); ahi = gn_fma2(z0.y, xx0, ahi);
+                blo = gn_fma2(z1.x, xx1, blo); bhi = gn_fma2(z1.y, xx1, bhi);
             }
+            float4 a, b;
+            gn_upk2(alo, a.x, a.y); gn_upk2(ahi, a.z, a.w); gn_upk2(blo, b.x, b.y); gn_upk2(bhi, b.z, b.w);
             double* o = gW + k * NP + n;
             atomicAdd(o, (double)a.x + (double)b.x); atomicAdd(o + 1, (double)a.y + (double)b.y);
             atomicAdd(o + 2, (double)a.z + (double)b.z); atomicAdd(o + 3, (double)a.w + (double)b.w);
