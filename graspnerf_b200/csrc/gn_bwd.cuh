@@ -81,12 +81,20 @@ __device__ __forceinline__ void mv_bwd_rolled(const float* __restrict__ W, const
 static __device__ __noinline__ void gn_dw_flush(double* __restrict__ gW, int NP, int KC, int N, const float* __restrict__ sX,
                                          const float* __restrict__ sZ, int nrows, int nthreads)
 {
-    if ((N & 3) == 0) {
+    // small layers: also split the rows, so that every thread of the CTA has a strip to reduce (a few more atomics)
+    const bool vec = (N & 3) == 0;
+    const int items = vec ? KC * (N >> 2) : KC * N;
+    int nsplit = 1;
+    if (items * 2 <= nthreads) { nsplit = nthreads / items; if (nsplit > (nrows >> 1)) nsplit = nrows >> 1; }
+    const int rpp = (((nrows + nsplit - 1) / nsplit) + 1) & ~1;              // rows per part, even
+    if (vec) {
         const int n4 = N >> 2;
-        for (int idx = threadIdx.x; idx < KC * n4; idx += nthreads) {
-            const int k = idx / n4, n = (idx - k * n4) * 4;
+        for (int idx = threadIdx.x; idx < items * nsplit; idx += nthreads) {
+            const int part = idx / items, rem = idx - part * items;
+            const int k = rem / n4, n = (rem - k * n4) * 4;
+            const int r0 = part * rpp, r1 = min(nrows, r0 + rpp);
             gn_f2 alo = 0ull, ahi = 0ull, blo = 0ull, bhi = 0ull;
-            for (int r = 0; r < nrows; r += 2) {
+            for (int r = r0; r < r1; r += 2) {
                 const float x0 = sX[r * GN_BWD_LDX + k], x1 = sX[(r + 1) * GN_BWD_LDX + k];
                 const ulonglong2 z0 = *reinterpret_cast<const ulonglong2*>(sZ + r * GN_BWD_LDZ + n);
                 const ulonglong2 z1 = *reinterpret_cast<const ulonglong2*>(sZ + (r + 1) * GN_BWD_LDZ + n);
@@ -102,10 +110,12 @@ static __device__ __noinline__ void gn_dw_flush(double* __restrict__ gW, int NP,
         }
         return;
     }
-    for (int idx = threadIdx.x; idx < KC * N; idx += nthreads) {
-        const int k = idx / N, n = idx - k * N;
+    for (int idx = threadIdx.x; idx < items * nsplit; idx += nthreads) {
+        const int part = idx / items, rem = idx - part * items;
+        const int k = rem / N, n = rem - k * N;
+        const int r0 = part * rpp, r1 = min(nrows, r0 + rpp);
         float a0 = 0.f, a1 = 0.f;
-        for (int r = 0; r < nrows; r += 2) {
+        for (int r = r0; r < r1; r += 2) {
             a0 = fmaf(sX[r * GN_BWD_LDX + k], sZ[r * GN_BWD_LDZ + n], a0);
             a1 = fmaf(sX[(r + 1) * GN_BWD_LDX + k], sZ[(r + 1) * GN_BWD_LDZ + n], a1);
         }

@@ -14,12 +14,11 @@
 #include "gn_weights.cuh"
 #include "../../include/graspnerf_b200.h"
 
-// Full-precision transcendental functions for the recomputed forward: the gradient of the compute_prob chain is
-// ill-conditioned (near/far CDF cancellation, ReLU gates of prob_embed at the switching point), so the 2^-21 fast-math
-// exp of the inference kernels would add avoidable noise on top of the fp32 accumulation noise the reference has too.
-__device__ __forceinline__ float kb_elu(float x) { return x > 0.f ? x : expm1f(x); }
-__device__ __forceinline__ float kb_sigmoid(float x) { return 1.f / (1.f + expf(-x)); }
-__device__ __forceinline__ float kb_softplus(float x) { return x > 20.f ? x : log1pf(expf(x)); }
+// Same fast-math activations as the inference kernels (a full-precision variant changed no gradient beyond the last digit:
+// the residual fp32 noise of the compute_prob chain comes from ReLU gates at the switching point, see tests/test_gpu_backward.py)
+__device__ __forceinline__ float kb_elu(float x) { return gn_elu(x); }
+__device__ __forceinline__ float kb_sigmoid(float x) { return gn_sigmoid(x); }
+__device__ __forceinline__ float kb_softplus(float x) { return gn_softplus(x); }
 
 #define KB_THREADS 256
 #define KB_WARPS (KB_THREADS / 32)
