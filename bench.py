@@ -117,6 +117,48 @@ def cpu_reference_volumes(n_volumes, warmup=1, budget_s=40.0):
     return n / dt, dt, n, best
 
 
+def make_train_data(seed, dev):
+    """One synthetic training sample of SURVEY.md 8d: configs[1]-sized scene + sdf_gt ~ U(-1,1), 64 random grasps."""
+    from graspnerf_b200.synth import make_scene, make_query
+    sc = make_scene(seed=seed, num_views=V, h=H, w=W)
+    rng = np.random.default_rng(1000 + seed)
+    ref = {k: (torch.from_numpy(v).to(dev) if isinstance(v, np.ndarray) else v) for k, v in sc.items() if k not in ('img_feats', 'ray_feats')}
+    ref['sdf_gt'] = torch.from_numpy(rng.uniform(-1, 1, (R, R, R)).astype(np.float32)).to(dev)
+    que = {k: torch.from_numpy(v).to(dev) for k, v in make_query(sc, 16, seed).items() if isinstance(v, np.ndarray)}
+    G = 64
+    quat = rng.standard_normal((G, 2, 4)).astype(np.float32)
+    quat /= np.linalg.norm(quat, axis=-1, keepdims=True)
+    grasp = [torch.from_numpy(rng.integers(0, R, (G, 3))).to(dev), torch.from_numpy((rng.random(G) < 0.5).astype(np.float32)).to(dev),
+             torch.from_numpy(quat).to(dev), torch.from_numpy(rng.uniform(0, 10, G).astype(np.float32)).to(dev)]
+    return {'step': 0, 'ref_imgs_info': ref, 'que_imgs_info': que, 'src_imgs_info': ref, 'grasp_info': grasp}
+
+
+def train_leg(args, dist, dev, world, rank, barrier, max_over_ranks):
+    """configs[2]/[3]-style optimizer step (reported as an extra key, not the headline metric): `train_batch` scenes per
+    GPU, GraspNeRF mirror forward (cuDNN encoders + CUDA hot path + VGN), SDF + VGN losses, backward through the hand-written
+    backward kernels, ONE all-reduce of the flat gradient bucket over the ranks, Adam.  render_rgb is off (the RGB head has
+    no backward kernels yet), so this is the volume-path share of the reference's training step."""
+    from graspnerf_b200.network import name2network, NRVGN_SDF_CFG
+    from graspnerf_b200.train import TrainStep
+    cfg = dict(NRVGN_SDF_CFG, render_rgb=False)
+    torch.manual_seed(0)
+    net = name2network[cfg['network']](cfg).to(dev).train()
+    step = TrainStep(net, lr=1e-4, dist=dist)
+    nb = args.train_batch
+    batch = [make_train_data(rank * nb + i, dev) for i in range(nb)]
+    step(batch)                                               # warm-up: cuDNN autotune, allocator pools, kernel attributes
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    losses = [step(batch) for _ in range(args.train_steps)]
+    ev1.record()
+    barrier()
+    ms = max_over_ranks([ev0.elapsed_time(ev1)], dist, dev)[0] / args.train_steps
+    return {'value': world * nb / (ms / 1e3), 'unit': 'scenes/s', 'ms_per_step': ms, 'scenes_per_gpu': nb, 'global_batch': world * nb,
+            'steps': args.train_steps, 'allreduce_bytes': step.bucket.nbytes if world > 1 else 0, 'loss': losses[-1],
+            'what': 'GraspNeRF mirror fwd+bwd (render_rgb off) + SDF/VGN losses + 1 NCCL all-reduce + Adam; 6x288x512, 40^3'}
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
@@ -143,6 +185,8 @@ def main():
     ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--cpu-volumes', type=int, default=12, help='size of the bounded CPU-baseline sample')
+    ap.add_argument('--train-batch', type=int, default=4, help='scenes per GPU of the extra training-step leg (0 = skip)')
+    ap.add_argument('--train-steps', type=int, default=2)
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg (profiling runs under ncu only)')
     args = ap.parse_args()
     if args.impl == 'reference':
@@ -243,6 +287,14 @@ def main():
 
     total_ms, e2e_ms = max_over_ranks([total_ms, e2e_ms], dist, dev)
     sampler.join(timeout=2)
+    train = None
+    if args.train_batch > 0:
+        del graphs, eng
+        torch.cuda.empty_cache()
+        try:
+            train = train_leg(args, dist, dev, world, rank, barrier, max_over_ranks)
+        except Exception as e:                                # the extra leg must never take the headline line down
+            train = {'error': f'{type(e).__name__}: {e}'[:300]}
     if rank == 0:
         peaks = load_peaks()
         traffic = load_traffic()
@@ -276,6 +328,7 @@ def main():
             'gpu_launches': 3 * K, 'launch_mode': 'CUDA graph of the 3 kernels per scene (cudaGraphLaunch per step); kernel_us from an eager instrumented pass',
             'clocks': sampler.summary(),
             'checksum': checksum,
+            'train_step': train,
         }
         if world == 1 and not args.no_cpu:
             vps, dt, nvol, nthr = cpu_reference_volumes(args.cpu_volumes, 1, budget_s=25.0)

@@ -85,7 +85,7 @@ static __device__ __noinline__ void gn_dw_flush(double* __restrict__ gW, int NP,
     const bool vec = (N & 3) == 0;
     const int items = vec ? KC * (N >> 2) : KC * N;
     int nsplit = 1;
-    if (items * 2 <= nthreads) { nsplit = nthreads / items; if (nsplit > (nrows >> 1)) nsplit = nrows >> 1; }
+    if (items * 8 <= nthreads) { nsplit = nthreads / (items * 4); if (nsplit > (nrows >> 1)) nsplit = nrows >> 1; }
     const int rpp = (((nrows + nsplit - 1) / nsplit) + 1) & ~1;              // rows per part, even
     if (vec) {
         const int n4 = N >> 2;
