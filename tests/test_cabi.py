@@ -97,3 +97,28 @@ def test_unpack_blob_grad_is_the_adjoint_of_pack_blob(lib):
     rhs = sum(float((w[k].double() * ug[k].double()).sum()) for k in ug)
     assert abs(lhs - rhs) <= 1e-9 * max(1.0, abs(lhs))
     assert all(ug[k].shape == w[k].shape for k in ug) and len(ug) == 56
+
+
+def test_launchers_reject_bad_arguments_before_touching_cuda(lib):
+    """Error convention of the C ABI (include/graspnerf_b200.h): 0 ok, < 0 argument error (checked before any CUDA call, so
+    this runs without a GPU), > 0 cudaError_t.  Nothing is launched here."""
+    from graspnerf_b200 import _lib
+    p = _lib.GnK1Params(); p.B, p.V, p.N = 1, 0, 10
+    assert lib.gn_k1_forward(ctypes.byref(p), None) == -1                       # V out of range
+    p.V, p.volume_mode, p.R, p.N = 6, 1, 40, 123
+    assert lib.gn_k1_forward(ctypes.byref(p), None) == -3                       # N != R^3 / missing tables
+    p.volume_mode, p.N = 0, 64
+    assert lib.gn_k1_forward(ctypes.byref(p), None) == -4                       # ray mode without pts / que_dir
+    a = _lib.GnK2aParams(); a.B, a.N, a.V = 1, 10, 40
+    assert lib.gn_k2a_forward(ctypes.byref(a), None) == -1 and lib.gn_k2a_forward_tc(ctypes.byref(a), None) < 0
+    b = _lib.GnK2bBwdParams(); b.B, b.N, b.dn = 1, 64000, 0
+    assert lib.gn_k2b_backward(ctypes.byref(b), None) == -1
+    b.dn = 40
+    assert lib.gn_k2b_backward(ctypes.byref(b), None) == -2                     # NULL buffers
+    c = _lib.GnK2aBwdParams(); c.B, c.N, c.V = 1, 10, 6
+    assert lib.gn_k2a_backward(ctypes.byref(c), None) == -2
+    d = _lib.GnK1BwdParams(); d.B, d.N, d.V = 1, 10, 6
+    assert lib.gn_k1_backward(ctypes.byref(d), None) == -2
+    assert lib.gn_sizeof_k2b_bwd_params() == ctypes.sizeof(_lib.GnK2bBwdParams)
+    assert lib.gn_sizeof_k2a_bwd_params() == ctypes.sizeof(_lib.GnK2aBwdParams)
+    assert lib.gn_sizeof_k1_bwd_params() == ctypes.sizeof(_lib.GnK1BwdParams)

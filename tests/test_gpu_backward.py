@@ -149,3 +149,28 @@ def test_mirror_trains_through_the_cuda_backward():
     with torch.no_grad():
         v1 = net(data)['volume']
     assert (v1 - v0).abs().max() > 0
+
+
+def test_batched_backward_equals_per_scene_backward():
+    """B = 2 scenes in one launch give each scene's feature-map gradients and the SUM of the two weight gradients."""
+    from graspnerf_b200 import ops
+    dev = torch.device('cuda:0')
+    sd = {k: v for k, v in golden_weights().items() if k.startswith(('agg_net.', 'dist_decoder.'))}
+    hw = ops.HeadWeights(sd, 'agg_net.', 'dist_decoder.', dev)
+    scs = [make_scene(seed=s, num_views=4, h=96, w=160, radius=0.45) for s in (3, 4)]
+    G = torch.from_numpy(np.random.default_rng(2).standard_normal((2, 1, R, R, R)).astype(np.float32)).to(dev)
+
+    def run(idx):
+        st = lambda k: torch.from_numpy(np.stack([scs[i][k] for i in idx])).to(dev)
+        scene = ops.Scene(st('imgs'), st('img_feats'), st('ray_feats'), st('poses'), st('Ks'), st('depth_range'))
+        bbox = torch.tensor([scs[i]['bbox3d'][0] for i in idx], device=dev)
+        rec, pt = ops.k1_forward(scene, hw, resolution=R, bbox_min=bbox)
+        pooled, _, _ = ops.k2a_forward(rec, pt, hw, scene.depth_range)
+        return ops.sample_volume_backward(scene, hw, bbox, rec, pt, pooled, G[idx].contiguous(), R)
+    di, dr, dw = run([0, 1])
+    di0, dr0, dw0 = run([0])
+    di1, dr1, dw1 = run([1])
+    assert_close(di[0].cpu(), di0[0].cpu(), what='d_img scene 0'); assert_close(di[1].cpu(), di1[0].cpu(), what='d_img scene 1')
+    assert_close(dr[0].cpu(), dr0[0].cpu(), rtol=1e-3, atol_scale=1e-3, what='d_ray scene 0')
+    assert_close(dr[1].cpu(), dr1[0].cpu(), rtol=1e-3, atol_scale=1e-3, what='d_ray scene 1')
+    assert_close(dw.cpu(), (dw0 + dw1).cpu(), rtol=1e-3, atol_scale=1e-3, what='weight gradient blob')
