@@ -229,16 +229,6 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step(i, evs=None):
-        """the three launches, eagerly; evs = 6 events recorded immediately around each launch"""
-        s, bb = scenes[i % POOL], bboxes[i % POOL]
-        e = (lambda j: (evs[2 * j], evs[2 * j + 1])) if evs is not None else (lambda j: None)
-        rec, pt = ops.k1_forward(s, hw, resolution=R, bbox_min=bb, ev=e(0))
-        _, _, _, tok = ops.k2a_forward(rec, pt, hw, s.depth_range, impl=ops.K2A_IMPL, want_pooled=False, want_tok=True,
-                                       resolution=R, bbox_min=bb, ev=e(1))
-        vol, _ = ops.k2b_forward(None, hw, dn=R, resolution=R, bbox_min=bb, tok=tok, ev=e(2))
-        return vol
-
     # ---------------- device-resident timing ----------------
     # one CUDA graph per pool scene (K1 -> K2a -> K2b captured once); a step = one graph launch
     graphs = [ops.VolumeGraph(scenes[i], hw, bboxes[i], R) for i in range(POOL)]
@@ -254,18 +244,38 @@ def main():
     ev1.record()
     barrier()
     total_ms = ev0.elapsed_time(ev1)
-    # per-kernel durations: the same launches issued eagerly on the same stream, CUDA events recorded immediately around each
-    # launch.  A 1 GiB fill is queued first so that (a) the launches are already queued when the GPU reaches them (no host
-    # gap inside an event pair) and (b) every kernel starts from a flushed L2.
-    KI = min(K, 32)
+    # per-kernel durations.  CUDA event timestamps on this GPU tick at 4.096 us, so a single ~50 us launch cannot be timed
+    # with its own event pair (round-1 numbers taken that way were quantised).  Each kernel is therefore launched 2*POOL
+    # times back to back, each launch on ANOTHER scene's buffers (inputs 8 x 25 MB, records 8 x 110 MB: the working set
+    # cycles past the 126 MB L2), between ONE event pair on the launching stream, behind a 1 GiB fill that flushes L2 and
+    # lets the launches queue up.
     filler = torch.empty(1 << 28, device=dev, dtype=torch.float32)
-    kev = [[torch.cuda.Event(enable_timing=True) for _ in range(6)] for _ in range(KI)]
-    for i in range(KI):
-        filler.fill_(float(i))
-        step(W_ + i, kev[i])
-    torch.cuda.synchronize()
-    del filler
-    kt = np.array([[e[2 * j].elapsed_time(e[2 * j + 1]) for j in range(3)] for e in kev]).mean(0)     # ms per launch: K1, K2a, K2b
+    inter = []
+    for i in range(POOL):
+        s_, bb_ = scenes[i], bboxes[i]
+        rec_, pt_ = ops.k1_forward(s_, hw, resolution=R, bbox_min=bb_)
+        tok_ = ops.k2a_forward(rec_, pt_, hw, s_.depth_range, impl=ops.K2A_IMPL, want_pooled=False, want_tok=True, resolution=R, bbox_min=bb_)[3]
+        inter.append((rec_, pt_, tok_))
+
+    def k_time(fn, reps=3):
+        out = []
+        for _ in range(reps):
+            for _f in range(6):           # ~1 ms of fills: the 16 launches below are queued before the GPU reaches them
+                filler.fill_(1.0)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(2 * POOL):
+                fn(i % POOL)
+            e1.record()
+            torch.cuda.synchronize()
+            out.append(e0.elapsed_time(e1) / (2 * POOL))
+        return float(np.median(out))
+    kt = np.array([
+        k_time(lambda i: ops.k1_forward(scenes[i], hw, resolution=R, bbox_min=bboxes[i])),
+        k_time(lambda i: ops.k2a_forward(inter[i][0], inter[i][1], hw, scenes[i].depth_range, impl=ops.K2A_IMPL, want_pooled=False,
+                                         want_tok=True, resolution=R, bbox_min=bboxes[i])),
+        k_time(lambda i: ops.k2b_forward(None, hw, dn=R, resolution=R, bbox_min=bboxes[i], tok=inter[i][2]))])     # ms per launch: K1, K2a, K2b
+    del filler, inter
 
     # ---------------- end-to-end timing (pinned host in, pinned host out) ----------------
     eng = VolumeEngine(hw, hosts[0], R, slots=3, device=dev)
@@ -325,7 +335,7 @@ def main():
             'kernel_us': {'k1': kt[0] * 1e3, 'k2a': kt[1] * 1e3, 'k2b': kt[2] * 1e3},
             'e2e': {'value': world * K / (e2e_ms / 1e3), 'unit': 'volumes/s', 'h2d_bytes_per_step': eng.h2d_bytes,
                     'd2h_bytes_per_step': eng.d2h_bytes, 'api': 'graspnerf_b200.engine.VolumeEngine.submit (pinned host buffers)'},
-            'gpu_launches': 3 * K, 'launch_mode': 'CUDA graph of the 3 kernels per scene (cudaGraphLaunch per step); kernel_us from an eager instrumented pass',
+            'gpu_launches': 3 * K, 'launch_mode': 'CUDA graph of the 3 kernels per scene (cudaGraphLaunch per step); kernel_us: each kernel launched 16x back to back over 8 scenes between one event pair (event clock ticks at 4.096 us)',
             'clocks': sampler.summary(),
             'checksum': checksum,
             'train_step': train,

@@ -12,26 +12,28 @@ from . import ops
 
 
 class HostScene:
-    """Pinned host buffers of one scene (the layout K1 consumes: channels-last feature maps)."""
+    """Pinned host buffers of one scene (the layout K1 consumes: the two channels-last feature maps [V,fh,fw,32]
+    interleaved per texel into one [V,fh,fw,64] buffer, ray_feats | img_feats)."""
 
     def __init__(self, imgs, img_feats_cl, ray_feats_cl, poses, Ks, depth_range, bbox_min):
         def pin(x):
             t = torch.as_tensor(x, dtype=torch.float32).contiguous()
             return t.pin_memory() if torch.cuda.is_available() else t
-        self.imgs, self.img_feats, self.ray_feats = pin(imgs), pin(img_feats_cl), pin(ray_feats_cl)
+        self.imgs = pin(imgs)
+        self.feats = pin(ops.fuse_feature_maps(torch.as_tensor(img_feats_cl, dtype=torch.float32),
+                                               torch.as_tensor(ray_feats_cl, dtype=torch.float32)))
         self.poses, self.Ks, self.depth_range, self.bbox_min = pin(poses), pin(Ks), pin(depth_range), pin(bbox_min)
 
     @property
     def nbytes(self):
-        return sum(t.numel() * 4 for t in (self.imgs, self.img_feats, self.ray_feats, self.poses, self.Ks,
-                                           self.depth_range, self.bbox_min))
+        return sum(t.numel() * 4 for t in (self.imgs, self.feats, self.poses, self.Ks, self.depth_range, self.bbox_min))
 
 
 class _Slot:
     def __init__(self, hs, resolution, device):
         def dev(t):
             return torch.empty(t.shape, dtype=torch.float32, device=device)
-        self.imgs, self.img_feats, self.ray_feats = dev(hs.imgs)[None], dev(hs.img_feats)[None], dev(hs.ray_feats)[None]
+        self.imgs, self.feats = dev(hs.imgs)[None], dev(hs.feats)[None]
         self.poses, self.Ks, self.depth_range = dev(hs.poses)[None], dev(hs.Ks)[None], dev(hs.depth_range)[None]
         self.bbox_min = dev(hs.bbox_min).reshape(1, 3)
         self.out_host = torch.empty((1, 1, resolution, resolution, resolution), dtype=torch.float32).pin_memory()
@@ -61,7 +63,7 @@ class VolumeEngine:
         s = self.slots[i]
         finished = self.collect(i) if s.busy else None
         with torch.cuda.stream(self.copy_stream):
-            for dst, src in ((s.imgs, hs.imgs), (s.img_feats, hs.img_feats), (s.ray_feats, hs.ray_feats),
+            for dst, src in ((s.imgs, hs.imgs), (s.feats, hs.feats),
                              (s.poses, hs.poses), (s.Ks, hs.Ks), (s.depth_range, hs.depth_range)):
                 dst[0].copy_(src, non_blocking=True)
             s.bbox_min.copy_(hs.bbox_min.reshape(1, 3), non_blocking=True)
@@ -70,7 +72,7 @@ class VolumeEngine:
             self.compute_stream.wait_event(s.ev_in)
             if s.graph is None:                   # first use of the slot: capture (layout prep + K1 + K2a + K2b) once
                 def prologue(s=s):
-                    return ops.Scene(s.imgs, s.img_feats, s.ray_feats, s.poses, s.Ks, s.depth_range, feats_channels_last=True)
+                    return ops.Scene(s.imgs, None, None, s.poses, s.Ks, s.depth_range, feats_fused=s.feats)
                 s.graph = ops.VolumeGraph(None, self.hw, s.bbox_min, self.R, self.vs, prologue=prologue)
             vol = s.graph.replay()
             s.out_host.copy_(vol, non_blocking=True)

@@ -88,13 +88,19 @@ def to_channels_last_maps(fmap):
 
 
 class Scene:
-    """Batched device-side inputs of the hot path (B scenes x V views)."""
+    """Batched device-side inputs of the hot path (B scenes x V views).
 
-    def __init__(self, imgs, img_feats, ray_feats, poses, Ks, depth_range, feats_channels_last=False):
+    Both feature maps are kept in ONE channels-last buffer `feats` [B,V,fh,fw,64] (ray_feats 32 | img_feats 32 per texel),
+    so a bilinear tap of K1 is one address and two adjacent 128-byte lines; `ray_feats` / `img_feats` are views of it."""
+
+    def __init__(self, imgs, img_feats, ray_feats, poses, Ks, depth_range, feats_channels_last=False, feats_fused=None):
         # accept single-scene [V,...] tensors like the reference's ref_imgs_info
         if imgs.dim() == 4:
-            imgs, img_feats, ray_feats = imgs[None], img_feats[None], ray_feats[None]
-            poses, Ks, depth_range = poses[None], Ks[None], depth_range[None]
+            imgs, poses, Ks, depth_range = imgs[None], poses[None], Ks[None], depth_range[None]
+            if feats_fused is not None:
+                feats_fused = feats_fused[None]
+            else:
+                img_feats, ray_feats = img_feats[None], ray_feats[None]
         _require_cuda(imgs, 'imgs')
         dev = imgs.device
         self.device = dev
@@ -102,16 +108,25 @@ class Scene:
         self.B, self.V, _, self.H, self.W = imgs.shape
         # RGBA-interleaved copy [B,V,H,W,4]: one bilinear tap = one 16-byte texel (layout change only, like channels-last)
         self.imgs = torch.cat([imgs.permute(0, 1, 3, 4, 2), imgs.new_zeros(self.B, self.V, self.H, self.W, 1)], -1).contiguous()
-        if feats_channels_last:       # already [B,V,fh,fw,32]
-            self.img_feats, self.ray_feats = _f32c(img_feats, dev), _f32c(ray_feats, dev)
-        else:                         # logical [B,V,32,fh,fw]; a channels_last-strided tensor converts without a copy
-            self.img_feats = to_channels_last_maps(img_feats.to(dev, torch.float32))
-            self.ray_feats = to_channels_last_maps(ray_feats.to(dev, torch.float32))
-        _, _, self.fh, self.fw, c = self.img_feats.shape
-        if c != 32 or self.ray_feats.shape != self.img_feats.shape:
-            raise ValueError('feature maps must be [B,V,fh,fw,32]')
+        if feats_fused is not None:   # already [B,V,fh,fw,64]
+            self.feats = _f32c(feats_fused, dev)
+        else:
+            if not feats_channels_last:   # logical [B,V,32,fh,fw] -> [B,V,fh,fw,32] views (no copy yet)
+                img_feats, ray_feats = img_feats.permute(0, 1, 3, 4, 2), ray_feats.permute(0, 1, 3, 4, 2)
+            if img_feats.shape[-1] != 32 or ray_feats.shape != img_feats.shape:
+                raise ValueError('feature maps must be [B,V,fh,fw,32]')
+            self.feats = torch.cat([ray_feats.to(dev, torch.float32), img_feats.to(dev, torch.float32)], -1).contiguous()
+        if self.feats.dim() != 5 or self.feats.shape[-1] != 64:
+            raise ValueError('fused feature buffer must be [B,V,fh,fw,64]')
+        _, _, self.fh, self.fw, _ = self.feats.shape
+        self.ray_feats, self.img_feats = self.feats[..., :32], self.feats[..., 32:]
         self.KRt, self.cam = camera_matrices(_f32c(poses, dev), _f32c(Ks, dev))
         self.depth_range = _f32c(depth_range, dev)
+
+
+def fuse_feature_maps(img_feats_cl, ray_feats_cl):
+    """Two channels-last maps [...,fh,fw,32] -> the fused buffer [...,fh,fw,64] (ray_feats | img_feats) K1 consumes."""
+    return torch.cat([ray_feats_cl, img_feats_cl], -1).contiguous()
 
 
 def k1_forward(scene, hw, *, resolution=None, bbox_min=None, volume_size=0.3, pts=None, que_dir=None, dn=None,
@@ -135,7 +150,8 @@ def k1_forward(scene, hw, *, resolution=None, bbox_min=None, volume_size=0.3, pt
     rec = torch.empty((scene.B, N, scene.V, REC_STRIDE), device=dev, dtype=torch.float32)
     pt = torch.empty((scene.B, N, PT_STRIDE), device=dev, dtype=torch.float32)
     dbg = torch.zeros((scene.B, N, scene.V, 2), device=dev, dtype=torch.int32) if debug_idx else None
-    p.imgs, p.img_feats, p.ray_feats = _ptr(scene.imgs).value, _ptr(scene.img_feats).value, _ptr(scene.ray_feats).value
+    p.imgs, p.ray_feats, p.img_feats = _ptr(scene.imgs).value, scene.feats.data_ptr(), scene.feats.data_ptr() + 128
+    p.feat_stride = 64
     p.KRt, p.cam = _ptr(scene.KRt).value, _ptr(scene.cam).value
     p.rec, p.pt, p.dbg_feat_idx = _ptr(rec).value, _ptr(pt).value, _ptr(dbg).value
     p.B, p.V, p.H, p.W, p.fh, p.fw = scene.B, scene.V, scene.H, scene.W, scene.fh, scene.fw
@@ -436,8 +452,8 @@ def k1_backward(scene, hw, d_rec, *, resolution=None, bbox_min=None, volume_size
     else:
         pts = _f32c(pts, dev)
         p.pts, p.R = _ptr(pts).value, 0
-    d_img = torch.zeros_like(scene.img_feats)
-    d_ray = torch.zeros_like(scene.ray_feats)
+    d_img = torch.zeros(tuple(scene.img_feats.shape), device=scene.device, dtype=torch.float32)
+    d_ray = torch.zeros(tuple(scene.ray_feats.shape), device=scene.device, dtype=torch.float32)
     p.KRt, p.d_rec, p.d_img_feats, p.d_ray_feats = _ptr(scene.KRt).value, _ptr(d_rec).value, _ptr(d_img).value, _ptr(d_ray).value
     p.B, p.V, p.H, p.W, p.fh, p.fw, p.N, p.volume_mode = B, V, scene.H, scene.W, scene.fh, scene.fw, N, 1 if vol else 0
     _lib.check(lib.gn_k1_backward(C.byref(p), _stream()), 'gn_k1_backward')

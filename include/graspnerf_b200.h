@@ -33,8 +33,8 @@ extern "C" {
  * in sample_volume's order (renderer.py:166-170).  volume_mode=0: explicit points (RGB head, render_ops.py:27-39). */
 typedef struct GnK1Params {
     const float* imgs;        /* [B,V,H,W,4] RGBA-interleaved (A unused) */
-    const float* img_feats;   /* [B,V,fh,fw,32] channels-last */
-    const float* ray_feats;   /* [B,V,fh,fw,32] channels-last */
+    const float* img_feats;   /* [B,V,fh,fw,32] channels-last, or ray_feats + 32 when feat_stride == 64 */
+    const float* ray_feats;   /* [B,V,fh,fw,32] channels-last, or the fused [B,V,fh,fw,64] buffer (ray_feats 32 | img_feats 32 per texel) */
     const float* KRt;         /* [B,V,3,4]  K @ [R|t]  (render_ops.py:94) */
     const float* cam;         /* [B,V,3]    camera centres -R^T t (render_ops.py:112) */
     const float* axis;        /* [R] voxel-centre table (volume mode) */
@@ -50,6 +50,7 @@ typedef struct GnK1Params {
     int dn;                   /* samples per ray */
     int volume_mode;
     int tiles_per_scene;      /* filled in by the launcher */
+    int feat_stride;          /* floats per feature-map texel: 32 (two maps, 0 means 32) or 64 (fused buffer: one address per bilinear tap) */
 } GnK1Params;
 
 int gn_k1_forward(const GnK1Params* params, void* stream);

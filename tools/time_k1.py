@@ -1,0 +1,48 @@
+"""K1 A/B timing (development aid): gn_k1_walk_kernel (GN_K1_IMPL=3) vs the round-1 tile kernel (GN_K1_IMPL=2).
+Each sample = 16 back-to-back launches cycling through 8 scenes (event timestamps on this GPU tick at 4.096 us, so single launches cannot be timed)."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+from graspnerf_b200 import ops
+from graspnerf_b200.synth import make_scene
+from tests.helpers import golden_weights
+
+
+def main():
+    iters = int(sys.argv[1]) if len(sys.argv) > 1 else 40
+    dev = torch.device('cuda:0')
+    hw = ops.HeadWeights(golden_weights(), 'agg_net.', 'dist_decoder.', dev)
+    scenes = []
+    for s in range(8):
+        sc = make_scene(seed=s)
+        t = {k: torch.from_numpy(v).to(dev) for k, v in sc.items() if isinstance(v, np.ndarray)}
+        scenes.append((ops.Scene(t['imgs'], t['img_feats'], t['ray_feats'], t['poses'], t['Ks'], t['depth_range']),
+                       torch.tensor([sc['bbox3d'][0]], device=dev)))
+    flush = torch.empty(512 * 1024 * 1024 // 4, device=dev)
+    cfgs = [dict(GN_K1_IMPL='2'),
+            dict(GN_K1_IMPL='3', GN_K1_STAGE='1', GN_K1_PIPE='0'), dict(GN_K1_IMPL='3', GN_K1_STAGE='1', GN_K1_PIPE='1'),
+            dict(GN_K1_IMPL='3', GN_K1_STAGE='0', GN_K1_PIPE='0'), dict(GN_K1_IMPL='3', GN_K1_STAGE='0', GN_K1_PIPE='1', GN_K1_MINB='6'),
+            dict(GN_K1_IMPL='3', GN_K1_STAGE='0', GN_K1_PIPE='1', GN_K1_MINB='5')]
+    for cfg in cfgs:
+        os.environ.update(cfg)
+        impl = ' '.join(f'{k[6:]}={v}' for k, v in cfg.items())
+        ts = []
+        for rep in range(iters // 8 + 2):
+            flush.fill_(1.0)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for it in range(16):          # 16 launches over 8 different scenes: inputs (8 x 28 MB) and records (8 x 110 MB) cycle past L2
+                sc, bb = scenes[it % 8]
+                rec, pt = ops.k1_forward(sc, hw, resolution=40, bbox_min=bb)
+            e1.record()
+            torch.cuda.synchronize()
+            if rep >= 2:
+                ts.append(e0.elapsed_time(e1) * 1e3 / 16)
+        ts = np.array(ts)
+        print(f'{impl}: K1 median {np.median(ts):.1f} us  min {ts.min():.1f}  mean {ts.mean():.1f} '
+              f'-> {135876608 / np.median(ts) / 1e3:.0f} GB/s (own bytes 135.9 MB)')
+
+
+if __name__ == '__main__':
+    main()
