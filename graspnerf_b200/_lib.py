@@ -41,7 +41,7 @@ class GnK2bBwdParams(C.Structure):
 
 
 class GnK2aBwdParams(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in ('rec', 'pt', 'weights', 'depth_range', 'que_dists', 'd_pooled', 'd_rec', 'd_weights')] + \
+    _fields_ = [(n, C.c_void_p) for n in ('rec', 'pt', 'weights', 'depth_range', 'que_dists', 'd_pooled', 'd_rec', 'd_weights', 'd_colors')] + \
                [(n, C.c_int) for n in ('B', 'N', 'V', 'dn')]
 
 

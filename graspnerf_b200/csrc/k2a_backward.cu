@@ -9,7 +9,8 @@
 // Reverse: d pooled[65] -> d rec.ray_feats[32], d rec.img_feats[32] per row, and the gradient of every weight of the chain
 // (dd.*, pe.*, nf.*, rd.*, bf.*, vf.*, v2.*), accumulated with coalesced atomics in the blob layout.
 // Activations live in thread-local arrays (registers / stack); weights sit in shared memory; the per-layer weight gradient
-// is a CTA-wide rows^T x rows product staged through shared memory (gn_bwd.cuh).  rgb_fc is not part of the volume path.
+// is a CTA-wide rows^T x rows product staged through shared memory (gn_bwd.cuh).  With d_colors (RGB head) the reverse of
+// rgb_fc + the softmax colour blend (ibrnet.py:507-511) is added: d colours -> d x, d vis2 and the rf.* weight gradients.
 #include "gn_bwd.cuh"
 #include "gn_weights.cuh"
 #include "../../include/graspnerf_b200.h"
@@ -252,6 +253,28 @@ gn_k2a_backward_kernel(const __grid_constant__ GnK2aBwdParams p, int num_tiles, 
             sig2 = kb_sigmoid(s);
             vis2 = sig2 * mask;
         }
+        // rgb_fc + softmax blend over the views (ibrnet.py:507-511), RGB head only
+        float rin[40], r16[16], r8[8], bw = 0.f;
+        const bool with_rgb = p.d_colors != nullptr;
+        if (with_rgb) {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) rin[c] = x[c];
+            rin[32] = vis2; rin[33] = dd[0]; rin[34] = dd[1]; rin[35] = dd[2]; rin[36] = dd[3]; rin[37] = rin[38] = rin[39] = 0.f;
+            load_bias<16>(sw + GN_OFF(RF_B0), r16);
+            mv_acc_rolled<37, 16, KB_THREADS>(sw + GN_OFF(RF_W0), rin, r16, scr);
+#pragma unroll
+            for (int c = 0; c < 16; ++c) r16[c] = kb_elu(r16[c]);
+            load_bias<8>(sw + GN_OFF(RF_B2), r8);
+            mv_acc_rolled<16, 8, KB_THREADS>(sw + GN_OFF(RF_W2), r16, r8, scr);
+            float logit = sw[GN_OFF(RF_B4)];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) { r8[c] = kb_elu(r8[c]); logit = fmaf(sw[GN_OFF(RF_W4) + c], r8[c], logit); }
+            if (mask == 0.f) logit = -1e9f;
+            float mx = -INFINITY;
+            for (int jv = 0; jv < V; ++jv) mx = fmaxf(mx, __shfl_sync(FULL, logit, (gb + jv) & 31));
+            const float e = __expf(logit - mx);
+            bw = __fdiv_rn(e, gsum(e, gb, V));
+        }
         const float Sv = gsum(vis2, gb, V) + 1e-8f;
         const float w2 = __fdiv_rn(vis2, Sv);
         const float S2 = gsum(w2, gb, V);
@@ -277,10 +300,33 @@ gn_k2a_backward_kernel(const __grid_constant__ GnK2aBwdParams p, int num_tiles, 
 #pragma unroll
         for (int c = 0; c < 32; ++c) dx[c] = 0.f;
         float dw2 = pool_bwd<32>(x, mu, dmu, dvar, w2, S2, dx) + dwm / (float)V;        // pooled[64] = mean_v(w2)
-        // w2 = vis2 / Sv
-        const float dvis2 = (dw2 - gsum(dw2 * w2, gb, V)) / Sv;
-        const float ds2 = dvis2 * mask * sig2 * (1.f - sig2);
         const float one = 1.f;
+        float dvis2_rgb = 0.f;
+        if (with_rgb) {
+            // colours = sum_v bw_v * rgb_v (rgb carries the mask); softmax over the views; rgb_fc 37 -> 16 -> 8 -> 1
+            const float4 dc = ldg4(p.d_colors + (size_t)pidx * 4);
+            const float dbw = valid ? (dc.x * tail.x + dc.y * tail.y + dc.z * tail.z) : 0.f;
+            const float dlogit = mask * bw * (dbw - gsum(bw * dbw, gb, V));             // a masked logit is the constant -1e9
+            dw_layer<1, 8, 8>(gw + GN_OFF(RF_W4), nullptr, &dlogit, r8, sX, sZ, KB_THREADS);
+            dw_layer<1, 1, 4>(gw + GN_OFF(RF_B4), nullptr, &one, &dlogit, sX, sZ, KB_THREADS);
+            float dr8[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) dr8[c] = sw[GN_OFF(RF_W4) + c] * dlogit * gn_delu(r8[c]);
+            dw_layer<16, 8, 8>(gw + GN_OFF(RF_W2), gw + GN_OFF(RF_B2), r16, dr8, sX, sZ, KB_THREADS);
+            float dr16[16];
+            mv_bwd_rolled<16, 8, false, KB_THREADS>(sw + GN_OFF(RF_W2), dr8, dr16, scr);
+#pragma unroll
+            for (int c = 0; c < 16; ++c) dr16[c] *= gn_delu(r16[c]);
+            dw_layer<37, 16, 16>(gw + GN_OFF(RF_W0), gw + GN_OFF(RF_B0), rin, dr16, sX, sZ, KB_THREADS);
+            float drin[37];
+            mv_bwd_rolled<37, 16, false, KB_THREADS>(sw + GN_OFF(RF_W0), dr16, drin, scr);
+#pragma unroll
+            for (int c = 0; c < 32; ++c) dx[c] += drin[c];
+            dvis2_rgb = drin[32];                                                       // dir_diff carries no gradient
+        }
+        // w2 = vis2 / Sv
+        const float dvis2 = (dw2 - gsum(dw2 * w2, gb, V)) / Sv + dvis2_rgb;
+        const float ds2 = dvis2 * mask * sig2 * (1.f - sig2);
         // vis_fc2.2 (row vector) and bias
         dw_layer<1, 32, 32>(gw + GN_OFF(V2_W2), nullptr, &ds2, v2h, sX, sZ, KB_THREADS);
         dw_layer<1, 1, 4>(gw + GN_OFF(V2_B2), nullptr, &one, &ds2, sX, sZ, KB_THREADS);

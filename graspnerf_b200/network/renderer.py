@@ -6,8 +6,9 @@ What runs where:
   * 2-D encoders, depth-mean head, VGN 3-D conv: PyTorch/cuDNN (out of the CUDA hot path, SURVEY.md section 8f);
   * sample_volume and the RGB head (render): the sm_100a kernels through graspnerf_b200.ops - no torch fallback.
 Training: sample_volume has a hand-written first-order backward (gn_k2b_backward -> gn_k2a_backward -> gn_k1_backward,
-ops.sample_volume_autograd), so forward() under autograd works with render_rgb off (losses on volume / vgn_pred /
-depth_mean).  The RGB head (render) has no backward yet: forward raises when gradients are required with render_rgb on."""
+ops.sample_volume_autograd).  The RGB head (render) trains through ops.ray_features_autograd (K1 / K2a forward kernels,
+gn_k2a_backward incl. rgb_fc / gn_k1_backward) plus the small per-ray head and compositing in torch (network/ray_head.py),
+which the eikonal loss differentiates twice exactly as the reference does (ibrnet.py:497-504)."""
 import numpy as np
 import torch
 import torch.nn as nn
@@ -15,6 +16,7 @@ import torch.nn as nn
 from .. import ops
 from .encoders import ResUNetLight, VgnConvNet, name2init_net, name2vis_encoder
 from .heads import name2agg_net, name2dist_decoder
+from . import ray_head
 
 
 class NeuralRayRenderer(nn.Module):
@@ -82,9 +84,12 @@ class NeuralRayRenderer(nn.Module):
 
     def render(self, que_imgs_info, ref_imgs_info, is_train):
         """renderer.py:201-220: chunk the query rays by ray_batch_num, coarse + fine pass per chunk (render_impl 152-162)."""
-        scene = self._scene(ref_imgs_info)
         coords = que_imgs_info['coords']
         dn, fdn = self.cfg['depth_sample_num'], self.cfg['fine_depth_sample_num']
+        autograd = torch.is_grad_enabled() and (ref_imgs_info['img_feats'].requires_grad or ref_imgs_info['ray_feats'].requires_grad
+                                                or any(p.requires_grad for p in self.agg_net.parameters()))
+        if not autograd:
+            scene = self._scene(ref_imgs_info)
         hw_c = self._head_weights(False)
         hw_f = self._head_weights(True) if self.cfg['use_hierarchical_sampling'] else None
         outs = {}
@@ -92,15 +97,19 @@ class NeuralRayRenderer(nn.Module):
             que = {'coords': coords[:, s:s + self.cfg['ray_batch_num']].contiguous(), 'poses': que_imgs_info['poses'],
                    'Ks': que_imgs_info['Ks'], 'depth_range': que_imgs_info['depth_range']}
             rn = que['coords'].shape[1]
-            if hw_f is not None:
+            if autograd:      # training: CUDA forward / reverse kernels for the per-(point,view) part, per-ray head in torch
+                u = torch.rand(1, rn, fdn, device=coords.device) if (is_train and hw_f is not None) else None
+                res = ray_head.render_rays_autograd(self, ref_imgs_info, que, dn, fdn, u, is_train)
+            elif hw_f is not None:
                 # sample_fine_depth uses torch.rand in training (render_ops.py:205), stratified midpoints in eval
                 u = torch.rand(1, rn, fdn, device=coords.device) if is_train else None
                 res = ops.render_rays(scene, hw_c, hw_f, que, dn, fdn, u)
             else:
                 res = ops.render_by_depth(scene, hw_c, que, ops.k3_coarse_depths(que['depth_range'], rn, dn))
-            res['s'] = torch.full((1, 1), hw_c.variance, device=coords.device)
-            if hw_f is not None:
-                res['s_fine'] = torch.full((1, 1), hw_f.variance, device=coords.device)
+            if not autograd:
+                res['s'] = torch.full((1, 1), hw_c.variance, device=coords.device)
+                if hw_f is not None:
+                    res['s_fine'] = torch.full((1, 1), hw_f.variance, device=coords.device)
             if 'imgs' in que_imgs_info:                     # renderer.py:125-127 (align_corners=True lookup of the GT colours)
                 gt = _bilinear_gt(que_imgs_info['imgs'], que['coords'])
                 res['pixel_colors_gt'] = gt
@@ -134,9 +143,6 @@ class NeuralRayRenderer(nn.Module):
 
     def forward(self, data):
         """renderer.py:268-291."""
-        if self.cfg['render_rgb'] and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError('the RGB head (render) has no backward kernels yet: train with render_rgb off, or call '
-                                      'under torch.no_grad(); the volume path (sample_volume) is differentiable')
         ref = data['ref_imgs_info'].copy()
         que = data['que_imgs_info'].copy()
         is_train = 'eval' not in data

@@ -418,9 +418,9 @@ def k2b_backward(pooled, hw, d_sdf, d_weights, *, dn, resolution=None, bbox_min=
     return d_pooled
 
 
-def k2a_backward(rec, pt, hw, depth_range, d_pooled, d_weights, *, que_dists=None, dn=1):
-    """Reverse of k2a_forward (volume-path part: no rgb_fc).  Accumulates into d_weights (float64); returns d_rec
-    [B,N,V,64] (gradient of the record's ray_feats | img_feats entries)."""
+def k2a_backward(rec, pt, hw, depth_range, d_pooled, d_weights, *, que_dists=None, dn=1, d_colors=None):
+    """Reverse of k2a_forward.  Accumulates into d_weights (float64); returns d_rec [B,N,V,64] (gradient of the record's
+    ray_feats | img_feats entries).  d_colors [B,N,4] (RGB head): also reverses rgb_fc + the softmax colour blend."""
     assert d_weights.dtype == torch.float64
     lib = _lib.load()
     B, N, V, _ = rec.shape
@@ -431,6 +431,10 @@ def k2a_backward(rec, pt, hw, depth_range, d_pooled, d_weights, *, que_dists=Non
         que_dists = _f32c(que_dists, dev)
     p.rec, p.pt, p.weights, p.depth_range = _ptr(rec).value, _ptr(pt).value, _ptr(hw.blob).value, _ptr(depth_range).value
     p.que_dists, p.d_pooled, p.d_rec, p.d_weights = _ptr(que_dists).value, _ptr(d_pooled).value, _ptr(d_rec).value, _ptr(d_weights).value
+    if d_colors is not None:
+        d_colors = _f32c(d_colors, dev)
+        assert d_colors.shape == (B, N, 4)
+    p.d_colors = _ptr(d_colors).value
     p.B, p.N, p.V, p.dn = B, N, V, int(dn)
     _lib.check(lib.gn_k2a_backward(C.byref(p), _stream()), 'gn_k2a_backward')
     return d_rec
@@ -501,7 +505,7 @@ class _SampleVolumeFn(torch.autograd.Function):
         if single:
             d_img, d_ray = d_img[0], d_ray[0]
         g = unpack_blob_grad(d_w, agg_prefix, dd_prefix)
-        pg = tuple(g[k].reshape(s) if k in g else None for k, s in zip(keys, shapes))
+        pg = tuple(g[k].reshape(s) if (k in g and '.rgb_fc.' not in k) else None for k, s in zip(keys, shapes))   # rgb_fc is not on the volume path
         ctx.scene = ctx.hw = ctx.saved = None
         return (d_img, d_ray, None, None) + pg
 
@@ -513,3 +517,55 @@ def sample_volume_autograd(imgs, img_feats, ray_feats, poses, Ks, depth_range, b
     keys = tuple(k for k in named_params if k.startswith(agg_prefix) or k.startswith(dd_prefix))
     static = (imgs, poses, Ks, depth_range, bbox_min, int(resolution), volume_size, agg_prefix, dd_prefix)
     return _SampleVolumeFn.apply(img_feats, ray_feats, static, keys, *[named_params[k] for k in keys])
+
+
+# ------------------------------------------------------------------------------------------------ training (RGB head)
+class _RayFeaturesFn(torch.autograd.Function):
+    """K1 (ray mode) -> K2a with colours, as an autograd node for the RGB head in training: returns the pooled per-point
+    features [B,N,68] (mean32 | var32 | mean_v(w) | nvalid ...) and the blended colours [B,N,4].  The per-ray geometry head
+    and the compositing that follow are torch ops (network/ray_head.py) because the reference differentiates them TWICE
+    (eikonal term, ibrnet.py:497-504); their cotangents d_pooled / d_colors come back here and go through
+    gn_k2a_backward (incl. rgb_fc + softmax blend) -> gn_k1_backward."""
+
+    @staticmethod
+    def forward(ctx, img_feats, ray_feats, static, keys, *params):
+        imgs, poses, Ks, depth_range, pts, que_dir, inv_dists, dn, agg_prefix, dd_prefix = static
+        sd = {k: p.detach() for k, p in zip(keys, params)}
+        hw = HeadWeights(sd, agg_prefix, dd_prefix, img_feats.device)
+        scene = Scene(imgs, img_feats.detach(), ray_feats.detach(), poses, Ks, depth_range)
+        rec, pt = k1_forward(scene, hw, pts=pts, que_dir=que_dir, dn=dn)
+        pooled, colors, _ = k2a_forward(rec, pt, hw, scene.depth_range, que_dists=inv_dists, dn=dn, want_colors=True)
+        ctx.scene, ctx.hw, ctx.saved = scene, hw, (rec, pt, pts, inv_dists)
+        ctx.meta = (dn, agg_prefix, dd_prefix, keys, img_feats.dim() == 4, [p.shape for p in params])
+        nvalid = pt[..., 0].clone()
+        ctx.mark_non_differentiable(nvalid)
+        return pooled, colors, nvalid
+
+    @staticmethod
+    def backward(ctx, d_pooled, d_colors, _d_nvalid):
+        from .weights import unpack_blob_grad
+        dn, agg_prefix, dd_prefix, keys, single, shapes = ctx.meta
+        rec, pt, pts, inv_dists = ctx.saved
+        scene, hw = ctx.scene, ctx.hw
+        d_w = torch.zeros(hw.blob.shape, dtype=torch.float64, device=hw.blob.device)
+        d_rec = k2a_backward(rec, pt, hw, scene.depth_range, d_pooled.contiguous(), d_w, que_dists=inv_dists, dn=dn,
+                             d_colors=d_colors.contiguous())
+        d_img, d_ray = k1_backward(scene, hw, d_rec, pts=pts)
+        d_img, d_ray = d_img.permute(0, 1, 4, 2, 3), d_ray.permute(0, 1, 4, 2, 3)
+        if single:
+            d_img, d_ray = d_img[0], d_ray[0]
+        g = unpack_blob_grad(d_w.float(), agg_prefix, dd_prefix)
+        skip = ('.geometry_fc.', '.ray_attention.', '.out_geometry_fc.')          # per-ray head: gradients come from the torch ops
+        pg = tuple(g[k].reshape(s) if (k in g and not any(t in k for t in skip)) else None for k, s in zip(keys, shapes))
+        ctx.scene = ctx.hw = ctx.saved = None
+        return (d_img, d_ray, None, None) + pg
+
+
+def ray_features_autograd(imgs, img_feats, ray_feats, poses, Ks, depth_range, pts, que_dir, inv_dists, dn, named_params,
+                          agg_prefix='agg_net.', dd_prefix='dist_decoder.'):
+    """Differentiable K1 -> K2a of the RGB head: pts [B,N,3] (N = rn*dn), que_dir [B,rn,3], inv_dists [B,N].
+    Returns (pooled [B,N,68], colors [B,N,4], nvalid [B,N])."""
+    keys = tuple(k for k in named_params if k.startswith(agg_prefix) or k.startswith(dd_prefix))
+    static = (imgs, poses, Ks, depth_range, pts.detach().contiguous(), que_dir.detach().contiguous(), inv_dists.detach().contiguous(),
+              int(dn), agg_prefix, dd_prefix)
+    return _RayFeaturesFn.apply(img_feats, ray_feats, static, keys, *[named_params[k] for k in keys])

@@ -96,7 +96,7 @@ def unpack_blob_grad(dblob, agg_prefix='agg_net.', dd_prefix='dist_decoder.'):
     """Adjoint of `pack_blob` over the raw (unfused) entries: a gradient in blob layout (torch tensor, any device)
     -> {reference state_dict key: gradient tensor of that parameter's shape}.  The packing is a linear map (transposes,
     the [rgb|img] <-> [img|rgb] permutation, the split of base_fc.0 into three blocks), so this is its transpose;
-    tests/test_cabi.py checks <pack(w), g> == <w, unpack(g)>.  rgb_fc (not on the volume path) is left out."""
+    tests/test_cabi.py checks <pack(w), g> == <w, unpack(g)>."""
     table = {name: (off, rows, cols, cp) for name, off, rows, cols, cp in _lib.weight_table()}
     A = agg_prefix + 'agg_impl.'
     perm = torch.as_tensor(PERM35, device=dblob.device)
@@ -136,6 +136,9 @@ def unpack_blob_grad(dblob, agg_prefix='agg_net.', dd_prefix='dist_decoder.'):
     lin('vf.w2', 'vf.b2', A + 'vis_fc.2')
     lin('v2.w0', 'v2.b0', A + 'vis_fc2.0')
     lin('v2.w2', 'v2.b2', A + 'vis_fc2.2', vector=True)
+    lin('rf.w0', 'rf.b0', A + 'rgb_fc.0')
+    lin('rf.w2', 'rf.b2', A + 'rgb_fc.2')
+    lin('rf.w4', 'rf.b4', A + 'rgb_fc.4', vector=True)
     lin('gf.w0', 'gf.b0', A + 'geometry_fc.0')
     lin('gf.w2', 'gf.b2', A + 'geometry_fc.2')
     for dst, src in (('at.wq', 'w_qs'), ('at.wk', 'w_ks'), ('at.wv', 'w_vs'), ('at.fc', 'fc')):

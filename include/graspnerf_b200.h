@@ -166,6 +166,8 @@ typedef struct GnK2aBwdParams {
     const float* d_pooled;     /* [B,N,68] from gn_k2b_backward */
     float* d_rec;              /* out [B,N,V,64]: gradient of the record's ray_feats (32) | img_feats (32) entries */
     double* d_weights;         /* accumulated (atomicAdd, fp64: the sum over ~10^5 rows loses no bits) [gn_weight_blob_floats()] */
+    const float* d_colors;     /* [B,N,4] upstream gradient of K2a's blended colours (rgb, pad), or NULL (volume path): adds the
+                                  reverse of rgb_fc + softmax blend (ibrnet.py:507-511) */
     int B, N, V, dn;
 } GnK2aBwdParams;
 int gn_k2a_backward(const GnK2aBwdParams* params, void* stream);

@@ -224,13 +224,14 @@ def ray_attention(sd, pfx, g, qmask):
                         sd[f'{pfx}ray_attention.layer_norm.bias'].to(dt), eps=1e-6)
 
 
-def aggregate(sd, agg_prefix, rec, que_pts, rn, dn, que_dir=None, want_grad=False, want_rgb=True):
+def aggregate(sd, agg_prefix, rec, que_pts, rn, dn, que_dir=None, want_grad=False, want_rgb=True, create_graph=False):
     """NeusAggregationNet._get_embedding (aggregate_net.py:35-70) + IBRNetWithNeuRayNeus.forward
     (ibrnet.py:447-513).  rec: dict of [N,V,*] with rgb, img_feats, ray_feats, dir, mask(float),
     hit_prob, vis (the latter two already mask-multiplied, renderer.py:76-77).
     que_pts [rn,dn,3]; que_dir [rn,dn,3] or None -> (0,0,1) (renderer.py:179).
     Returns dict with sdf [rn,dn], colors [rn,dn,3], grad [rn,dn,3] (if want_grad) and
-    intermediates."""
+    intermediates.  create_graph=True is the TRAINING form of ibrnet.py:497-504: sdf and grad stay attached to the
+    autograd graph (grad with create_graph=True), so losses on them can be differentiated (second order for grad)."""
     P = agg_prefix
     A = agg_prefix + 'agg_impl.'
     N, V = rec['mask'].shape[:2]
@@ -282,8 +283,8 @@ def aggregate(sd, agg_prefix, rec, que_pts, rn, dn, que_dir=None, want_grad=Fals
         sdf = sdf.masked_fill(nvalid.reshape(rn, dn) < 1, 1.0)
         grad = None
         if want_grad:
-            grad = torch.autograd.grad(sdf, pts, torch.ones_like(sdf))[0]
-    out = {'sdf': sdf if (torch.is_grad_enabled() and not want_grad) else sdf.detach(), 'grad': grad, 'prob_emb': prob_emb, 'dir_diff': dir_diff, 'f': f,
+            grad = torch.autograd.grad(sdf, pts, torch.ones_like(sdf), create_graph=create_graph, retain_graph=create_graph)[0]
+    out = {'sdf': sdf if (create_graph or (torch.is_grad_enabled() and not want_grad)) else sdf.detach(), 'grad': grad, 'prob_emb': prob_emb, 'dir_diff': dir_diff, 'f': f,
            'mean1': mean1[:, 0], 'var1': var1[:, 0], 'mean0': mean0[:, 0], 'var0': var0[:, 0],
            'x': x, 'vis2': vis2[..., 0], 'pooled': pooled, 'nvalid': nvalid, 'w0': w0[..., 0]}
     if want_rgb:
@@ -432,7 +433,7 @@ def fine_depths(depth, hit_prob, depth_range_q, fdn, u=None):
     return fd, inds
 
 
-def render_by_depth(sd, scene, que, que_depth, is_fine, ray_mask_view_num=2, ray_mask_point_num=8):
+def render_by_depth(sd, scene, que, que_depth, is_fine, ray_mask_view_num=2, ray_mask_point_num=8, train=False):
     """render_by_depth (renderer.py:110-138) + network_rendering (90-108), eval mode.
     que: dict coords [rn,2], pose [3,4], K [3,3], depth_range [2]; que_depth [rn,dn]."""
     rn, dn = que_depth.shape
@@ -444,7 +445,7 @@ def render_by_depth(sd, scene, que, que_depth, is_fine, ray_mask_view_num=2, ray
     que_dir = (-dirs / torch.norm(dirs, dim=1, keepdim=True))[:, None].expand(rn, dn, 3)
     rec = project_and_sample(scene, que_pts.reshape(-1, 3))
     rec = add_ray_probabilities(sd, dd, rec, scene['depth_range'], inv_dists)
-    agg = aggregate(sd, ag, rec, que_pts, rn, dn, que_dir, want_grad=True, want_rgb=True)
+    agg = aggregate(sd, ag, rec, que_pts, rn, dn, que_dir, want_grad=True, want_rgb=True, create_graph=train)
     dists = depth_to_dists(que_depth)
     inv_s = torch.exp(sd[ag + 'deviation_network.variance'] * 10.0).clip(1e-6, 1e6)   # neus.py:19, aggregate_net.py:107
     alpha = neus_alpha(agg['sdf'], agg['grad'], que_dir, dists, inv_s)
@@ -458,14 +459,16 @@ def render_by_depth(sd, scene, que, que_depth, is_fine, ray_mask_view_num=2, ray
     return out
 
 
-def render_rays(sd, scene, que, dn=40, fdn=40, u=None):
-    """render_impl + fine_render_impl (renderer.py:140-162), hierarchical sampling on."""
+def render_rays(sd, scene, que, dn=40, fdn=40, u=None, train=False, fine_depth=None):
+    """render_impl + fine_render_impl (renderer.py:140-162), hierarchical sampling on.  train=True keeps the outputs
+    attached to the autograd graph (the samplers see the detached hit probabilities, renderer.py:141)."""
     rn = que['coords'].shape[0]
     depth = coarse_depths(que['depth_range'], rn, dn)
-    out = render_by_depth(sd, scene, que, depth, False)
-    fd, inds = fine_depths(depth, out['hit_prob_nr'], que['depth_range'], fdn, u)
-    fdepth = torch.sort(fd, -1)[0]
-    fine = render_by_depth(sd, scene, que, fdepth, True)
+    out = render_by_depth(sd, scene, que, depth, False, train=train)
+    with torch.no_grad():
+        fd, inds = fine_depths(depth, out['hit_prob_nr'].detach(), que['depth_range'], fdn, u)
+        fdepth = torch.sort(fd, -1)[0] if fine_depth is None else fine_depth       # fine_depth: externally supplied samples
+    fine = render_by_depth(sd, scene, que, fdepth, True, train=train)
     out['depth'] = depth
     for k, v in fine.items():
         out[k + '_fine'] = v

@@ -168,3 +168,62 @@ def make_grad_golden():
 
 if __name__ == '__main__' and '--grads' in sys.argv:
     make_grad_golden()
+
+
+RENDER_GRAD_CASE = dict(scene=dict(seed=3, num_views=4, h=96, w=160, radius=0.45), num_rays=32, qseed=7, useed=11, gseed=77)
+
+
+def make_render_grad_golden():
+    """TRAINING-mode gradients of the RGB head from the UNMODIFIED reference (CPU autograd, is_train=True):
+    loss = sum(pixel_colors_nr * G1) + sum(pixel_colors_nr_fine * G2) + 0.1 * (sdf_gradient_error + sdf_gradient_error_fine)
+    (the eikonal terms need the second derivative of the per-ray head, ibrnet.py:497-504).  torch.rand inside
+    sample_fine_depth (render_ops.py:205) is replaced by a seeded u that is stored with the fixture.
+    -> tests/golden/render_grad_small_v4.npz"""
+    cfg, net = build_reference_net(0)
+    nr = net.nr_net
+    case = RENDER_GRAD_CASE
+    scene = make_scene(**case['scene'])
+    ref = to_torch(scene)
+    ref['img_feats'].requires_grad_(True)
+    ref['ray_feats'].requires_grad_(True)
+    que = to_torch(make_query(scene, case['num_rays'], case['qseed']))
+    rn, fdn = case['num_rays'], nr.cfg['fine_depth_sample_num']
+    u = torch.from_numpy(np.random.default_rng(case['useed']).random((1, rn, fdn), dtype=np.float32))
+    rng = np.random.default_rng(case['gseed'])
+    G1 = torch.from_numpy(rng.standard_normal((1, rn, 3)).astype(np.float32))
+    G2 = torch.from_numpy(rng.standard_normal((1, rn, 3)).astype(np.float32))
+    real_rand = torch.rand
+    torch.rand = lambda *a, **k: u.clone()
+    try:
+        res = nr.render_impl(que, ref, True)
+    finally:
+        torch.rand = real_rand
+    loss = (res['pixel_colors_nr'] * G1).sum() + (res['pixel_colors_nr_fine'] * G2).sum() \
+        + 0.1 * (res['sdf_gradient_error'].sum() + res['sdf_gradient_error_fine'].sum())
+    loss.backward()
+    # the fine pass's own sample depths (the inverse-CDF sampler is ill-conditioned where the coarse hit probability is ~0:
+    # parity tests feed THESE depths to both sides, like the eval fixtures do)
+    from network.render_ops import sample_depth, sample_fine_depth
+    with torch.no_grad():
+        depth, _ = sample_depth(que['depth_range'], que['coords'], nr.cfg['depth_sample_num'], False)
+        torch.rand = lambda *a, **k: u.clone()
+        try:
+            fd = sample_fine_depth(depth, res['hit_prob_nr'].detach(), que['depth_range'], fdn, True)
+        finally:
+            torch.rand = real_rand
+    out = {'depth_fine': torch.sort(fd, -1)[0].numpy(), 'u': u.numpy(), 'G1': G1.numpy(), 'G2': G2.numpy(), 'loss': np.float64(loss.item()),
+           'd_img_feats': ref['img_feats'].grad.numpy(), 'd_ray_feats': ref['ray_feats'].grad.numpy()}
+    for k in ('pixel_colors_nr', 'pixel_colors_nr_fine', 'sdf_gradient_error', 'sdf_gradient_error_fine', 'alpha_values',
+              'alpha_values_fine', 'hit_prob_nr', 'sdf_values', 'sdf_values_fine', 'render_depth', 'render_depth_fine'):
+        out[k] = res[k].detach().numpy()
+    n = 0
+    for k, v in nr.named_parameters():
+        if k.startswith(HOT_PREFIXES) and v.grad is not None:
+            out['dw/' + k] = v.grad.numpy(); n += 1
+    np.savez_compressed(os.path.join(HERE, 'render_grad_small_v4.npz'), **out)
+    print('render grad golden:', n, 'parameter grads; loss', loss.item(), '|d_img_feats|', float(ref['img_feats'].grad.abs().sum()),
+          '|d_ray_feats|', float(ref['ray_feats'].grad.abs().sum()), 'eik', res['sdf_gradient_error'].item(), res['sdf_gradient_error_fine'].item())
+
+
+if __name__ == '__main__' and '--render-grads' in sys.argv:
+    make_render_grad_golden()

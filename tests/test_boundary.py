@@ -53,10 +53,12 @@ def test_state_dict_matches_reference_layout_and_seed0_init():
         assert np.array_equal(sd['nr_net.' + k].numpy(), v), k
 
 
-def test_forward_refuses_autograd():
-    net = _build()
-    with pytest.raises(NotImplementedError):
-        net.nr_net({'ref_imgs_info': {}, 'que_imgs_info': {}})
+def test_hot_path_has_no_cpu_fallback():
+    """The mirror's hot path raises on host tensors instead of falling back to torch ops (ops._require_cuda)."""
+    from graspnerf_b200 import ops
+    z = torch.zeros(2, 3, 8, 8)
+    with pytest.raises(RuntimeError, match='no CPU path'):
+        ops.Scene(z, torch.zeros(2, 32, 2, 2), torch.zeros(2, 32, 2, 2), torch.zeros(2, 3, 4), torch.zeros(2, 3, 3), torch.zeros(2, 2))
 
 
 @pytest.mark.gpu

@@ -90,13 +90,13 @@ def test_unpack_blob_grad_is_the_adjoint_of_pack_blob(lib):
     blob = pack_blob(w)
     g = rng.standard_normal(blob.shape).astype(np.float32)
     for name, off, rows, cols, cp in _lib.weight_table():          # entries the backward kernels never write
-        if name.startswith(('nfc.', 'rf.')) or name in ('bf.wpc', 'bf.b0c'):
+        if name.startswith('nfc.') or name in ('bf.wpc', 'bf.b0c'):
             g[off:off + rows * cp] = 0
     ug = unpack_blob_grad(torch.from_numpy(g))
     lhs = float(np.dot(blob.astype(np.float64), g.astype(np.float64)))
     rhs = sum(float((w[k].double() * ug[k].double()).sum()) for k in ug)
     assert abs(lhs - rhs) <= 1e-9 * max(1.0, abs(lhs))
-    assert all(ug[k].shape == w[k].shape for k in ug) and len(ug) == 56
+    assert all(ug[k].shape == w[k].shape for k in ug) and len(ug) == 62
 
 
 def test_launchers_reject_bad_arguments_before_touching_cuda(lib):
