@@ -118,13 +118,15 @@ def cpu_reference_volumes(n_volumes, warmup=1, budget_s=40.0):
 
 
 def make_train_data(seed, dev):
-    """One synthetic training sample of SURVEY.md 8d: configs[1]-sized scene + sdf_gt ~ U(-1,1), 64 random grasps."""
+    """One synthetic training sample of SURVEY.md 8d: configs[1]-sized scene + sdf_gt ~ U(-1,1), true_depth ~ U(0.2,0.8),
+    512 query rays of view 0 with their colours (train_dataset.py:85), 64 random grasps."""
     from graspnerf_b200.synth import make_scene, make_query
     sc = make_scene(seed=seed, num_views=V, h=H, w=W)
     rng = np.random.default_rng(1000 + seed)
     ref = {k: (torch.from_numpy(v).to(dev) if isinstance(v, np.ndarray) else v) for k, v in sc.items() if k not in ('img_feats', 'ray_feats')}
     ref['sdf_gt'] = torch.from_numpy(rng.uniform(-1, 1, (R, R, R)).astype(np.float32)).to(dev)
-    que = {k: torch.from_numpy(v).to(dev) for k, v in make_query(sc, 16, seed).items() if isinstance(v, np.ndarray)}
+    ref['true_depth'] = torch.from_numpy(rng.uniform(0.2, 0.8, (V, 1, H, W)).astype(np.float32)).to(dev)
+    que = {k: torch.from_numpy(v).to(dev) for k, v in make_query(sc, 512, seed).items() if isinstance(v, np.ndarray)}
     G = 64
     quat = rng.standard_normal((G, 2, 4)).astype(np.float32)
     quat /= np.linalg.norm(quat, axis=-1, keepdims=True)
@@ -135,12 +137,12 @@ def make_train_data(seed, dev):
 
 def train_leg(args, dist, dev, world, rank, barrier, max_over_ranks):
     """configs[2]/[3]-style optimizer step (reported as an extra key, not the headline metric): `train_batch` scenes per
-    GPU, GraspNeRF mirror forward (cuDNN encoders + CUDA hot path + VGN), SDF + VGN losses, backward through the hand-written
-    backward kernels, ONE all-reduce of the flat gradient bucket over the ranks, Adam.  render_rgb is off (the RGB head has
-    no backward kernels yet), so this is the volume-path share of the reference's training step."""
+    GPU, GraspNeRF mirror forward with the SHIPPED configuration (render_rgb on: 512 rays x 40 coarse + 40 fine samples,
+    40^3 volume, depth-mean head, cuDNN encoders, VGN), the four losses of nrvgn_sdf.yaml (render, depth, sdf + eikonal,
+    vgn), backward through the hand-written reverse kernels, ONE all-reduce of the flat gradient bucket over the ranks, Adam."""
     from graspnerf_b200.network import name2network, NRVGN_SDF_CFG
     from graspnerf_b200.train import TrainStep
-    cfg = dict(NRVGN_SDF_CFG, render_rgb=False)
+    cfg = dict(NRVGN_SDF_CFG)
     torch.manual_seed(0)
     net = name2network[cfg['network']](cfg).to(dev).train()
     step = TrainStep(net, lr=1e-4, dist=dist)
@@ -156,7 +158,7 @@ def train_leg(args, dist, dev, world, rank, barrier, max_over_ranks):
     ms = max_over_ranks([ev0.elapsed_time(ev1)], dist, dev)[0] / args.train_steps
     return {'value': world * nb / (ms / 1e3), 'unit': 'scenes/s', 'ms_per_step': ms, 'scenes_per_gpu': nb, 'global_batch': world * nb,
             'steps': args.train_steps, 'allreduce_bytes': step.bucket.nbytes if world > 1 else 0, 'loss': losses[-1],
-            'what': 'GraspNeRF mirror fwd+bwd (render_rgb off) + SDF/VGN losses + 1 NCCL all-reduce + Adam; 6x288x512, 40^3'}
+            'what': 'GraspNeRF mirror fwd+bwd, shipped config (render_rgb on, 512 rays coarse+fine, 40^3 volume) + render/depth/sdf/eikonal/vgn losses + 1 NCCL all-reduce + Adam; 6x288x512'}
 
 
 def run_reference(args):
@@ -298,6 +300,7 @@ def main():
     total_ms, e2e_ms = max_over_ranks([total_ms, e2e_ms], dist, dev)
     sampler.join(timeout=2)
     train = None
+    h2d_bytes, d2h_bytes = eng.h2d_bytes, eng.d2h_bytes
     if args.train_batch > 0:
         del graphs, eng
         torch.cuda.empty_cache()
@@ -333,8 +336,8 @@ def main():
             'roofline': roof_k2 if dominant_k2 else roof_k1,
             'roofline_k1': roof_k1, 'roofline_k2': roof_k2,
             'kernel_us': {'k1': kt[0] * 1e3, 'k2a': kt[1] * 1e3, 'k2b': kt[2] * 1e3},
-            'e2e': {'value': world * K / (e2e_ms / 1e3), 'unit': 'volumes/s', 'h2d_bytes_per_step': eng.h2d_bytes,
-                    'd2h_bytes_per_step': eng.d2h_bytes, 'api': 'graspnerf_b200.engine.VolumeEngine.submit (pinned host buffers)'},
+            'e2e': {'value': world * K / (e2e_ms / 1e3), 'unit': 'volumes/s', 'h2d_bytes_per_step': h2d_bytes,
+                    'd2h_bytes_per_step': d2h_bytes, 'api': 'graspnerf_b200.engine.VolumeEngine.submit (pinned host buffers)'},
             'gpu_launches': 3 * K, 'launch_mode': 'CUDA graph of the 3 kernels per scene (cudaGraphLaunch per step); kernel_us: each kernel launched 16x back to back over 8 scenes between one event pair (event clock ticks at 4.096 us)',
             'clocks': sampler.summary(),
             'checksum': checksum,

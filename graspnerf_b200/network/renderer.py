@@ -88,19 +88,21 @@ class NeuralRayRenderer(nn.Module):
         dn, fdn = self.cfg['depth_sample_num'], self.cfg['fine_depth_sample_num']
         autograd = torch.is_grad_enabled() and (ref_imgs_info['img_feats'].requires_grad or ref_imgs_info['ray_feats'].requires_grad
                                                 or any(p.requires_grad for p in self.agg_net.parameters()))
+        hw_c = hw_f = None
         if not autograd:
             scene = self._scene(ref_imgs_info)
-        hw_c = self._head_weights(False)
-        hw_f = self._head_weights(True) if self.cfg['use_hierarchical_sampling'] else None
+            hw_c = self._head_weights(False)
+            hw_f = self._head_weights(True) if self.cfg['use_hierarchical_sampling'] else None
+        fine = self.cfg['use_hierarchical_sampling']
         outs = {}
         for s in range(0, coords.shape[1], self.cfg['ray_batch_num']):
             que = {'coords': coords[:, s:s + self.cfg['ray_batch_num']].contiguous(), 'poses': que_imgs_info['poses'],
                    'Ks': que_imgs_info['Ks'], 'depth_range': que_imgs_info['depth_range']}
             rn = que['coords'].shape[1]
             if autograd:      # training: CUDA forward / reverse kernels for the per-(point,view) part, per-ray head in torch
-                u = torch.rand(1, rn, fdn, device=coords.device) if (is_train and hw_f is not None) else None
+                u = torch.rand(1, rn, fdn, device=coords.device) if (is_train and fine) else None
                 res = ray_head.render_rays_autograd(self, ref_imgs_info, que, dn, fdn, u, is_train)
-            elif hw_f is not None:
+            elif fine:
                 # sample_fine_depth uses torch.rand in training (render_ops.py:205), stratified midpoints in eval
                 u = torch.rand(1, rn, fdn, device=coords.device) if is_train else None
                 res = ops.render_rays(scene, hw_c, hw_f, que, dn, fdn, u)
@@ -108,12 +110,12 @@ class NeuralRayRenderer(nn.Module):
                 res = ops.render_by_depth(scene, hw_c, que, ops.k3_coarse_depths(que['depth_range'], rn, dn))
             if not autograd:
                 res['s'] = torch.full((1, 1), hw_c.variance, device=coords.device)
-                if hw_f is not None:
+                if fine:
                     res['s_fine'] = torch.full((1, 1), hw_f.variance, device=coords.device)
             if 'imgs' in que_imgs_info:                     # renderer.py:125-127 (align_corners=True lookup of the GT colours)
                 gt = _bilinear_gt(que_imgs_info['imgs'], que['coords'])
                 res['pixel_colors_gt'] = gt
-                if hw_f is not None:
+                if fine:
                     res['pixel_colors_gt_fine'] = gt
             for k, v in res.items():
                 if k in ('depth', 'depth_fine', 'fine_inds', 'sdf_grad', 'sdf_grad_fine'):
@@ -127,7 +129,7 @@ class NeuralRayRenderer(nn.Module):
         ray_feats, imgs = ref_imgs_info['ray_feats'], ref_imgs_info['imgs']
         rfn, _, h, w = imgs.shape
         num = self.cfg['depth_loss_coords_num']
-        idx = torch.randperm(h * w)[:num].to(imgs.device)
+        idx = torch.randperm(h * w, device=imgs.device)[:num]
         coords = torch.stack([idx // w, idx % w], -1)        # the reference stacks (row, col) of meshgrid(arange(h), arange(w))
         coords = coords.unsqueeze(0).repeat(rfn, 1, 1)
         cf = coords.float()

@@ -9,7 +9,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .weights import pack_blob, positional_table, voxel_axis_table
+from .weights import DevicePacker, positional_table, voxel_axis_table
 
 REC_STRIDE, PT_STRIDE, POOL_STRIDE, TOK_STRIDE = 72, 2, 68, 20
 
@@ -33,16 +33,21 @@ def _require_cuda(t, what):
         raise RuntimeError(f'{what} must live on a CUDA device: graspnerf_b200 has no CPU path')
 
 
+_PACKERS = {}
+
+
 class HeadWeights:
     """Device-resident packed weights of one (agg_net, dist_decoder) pair + kernel constants.
 
-    `refresh(sd)` re-packs when any source tensor changed (training); inference packs once."""
+    `refresh(sd)` re-packs when any source tensor changed (training); inference packs once.  Packing runs on the device
+    (weights.DevicePacker: one gather + four tiny fp64 matmuls, no host synchronisation)."""
 
     def __init__(self, sd, agg_prefix='agg_net.', dd_prefix='dist_decoder.', device='cuda'):
         self.agg_prefix, self.dd_prefix, self.device = agg_prefix, dd_prefix, torch.device(device)
         self._versions = None
         self._pos = {}
         self._axis = {}
+        self._var = None
         self.refresh(sd)
 
     def _keys(self, sd):
@@ -52,15 +57,23 @@ class HeadWeights:
         vers = tuple((k, sd[k]._version, sd[k].data_ptr()) for k in self._keys(sd))
         if vers == self._versions:
             return
-        self.blob = torch.from_numpy(pack_blob(sd, self.agg_prefix, self.dd_prefix)).to(self.device)
+        key = (self.agg_prefix, self.dd_prefix, str(self.device))
+        if key not in _PACKERS:
+            _PACKERS[key] = DevicePacker(sd, self.agg_prefix, self.dd_prefix, self.device)
+        with torch.no_grad():
+            self.blob = _PACKERS[key].pack({k: sd[k].to(self.device) for k in _PACKERS[key].keys})
         # tensor-core operand images (fp16 hi/lo, K-major) + small constants, built on the device from the fp32 blob
         lib = _lib.load()
         self.tc_const = torch.empty(lib.gn_k2a_tc_const_bytes(), dtype=torch.uint8, device=self.device)
         with torch.cuda.device(self.device):
             _lib.check(lib.gn_k2a_tc_prepare(_ptr(self.blob), _ptr(self.tc_const), _stream()), 'gn_k2a_tc_prepare')
-        var = sd.get(self.agg_prefix + 'deviation_network.variance')
-        self.variance = float(var) if var is not None else 0.3
+        self._var = sd.get(self.agg_prefix + 'deviation_network.variance')
         self._versions = vers
+
+    @property
+    def variance(self):
+        """NeuS inverse-std parameter as a python float (inference compositing only: reading it synchronises)."""
+        return float(self._var.detach()) if self._var is not None else 0.3
 
     def pos_table(self, dn):
         if dn not in self._pos:

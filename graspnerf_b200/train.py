@@ -6,9 +6,10 @@ forward / backward kernels, the 2-D encoders and the VGN head through PyTorch/cu
 all-reduce (sum) of a flat fp32 bucket per step (NCCL over NVLink on GPUs, gloo in the CPU tests), divided by the number
 of scenes of the global batch; then every rank applies the same Adam update (trainer.py:120-123: Adam, lr 1e-4).
 
-Losses: the two of nrvgn_sdf.yaml that depend only on the volume path - SDFLoss' smooth-L1 term (loss.py:165-175) and VGNLoss
-(loss.py:194-252) - restated from their formulas.  The render / eikonal / depth terms need the RGB head's backward, which
-is not implemented yet (render_rgb must be off).
+Losses: the four of nrvgn_sdf.yaml (`loss: [render, depth, sdf, vgn]`) restated from their formulas - RenderLoss
+(loss.py:50-85, coarse + fine), DepthLoss (loss.py:87-144), SDFLoss' smooth-L1 and eikonal terms (loss.py:149-178) and VGNLoss
+(loss.py:194-252).  `training_losses` adds whichever terms the forward produced (render_rgb on / off, true_depth present or
+not); the reference's own loss classes work on the mirror's output dict unchanged as well.
 """
 import torch
 import torch.nn.functional as F
@@ -67,6 +68,50 @@ def vgn_loss(vgn_pred, grasp_info, weight=1e-2):
     return (l_qual + label * (l_rot + l_width)).mean() * weight
 
 
+def render_loss(out, weight=0.01, fine=True):
+    """RenderLoss (loss.py:50-85): ray-masked squared colour error of the coarse pass (+ fine pass, use_nr_fine_loss)."""
+    gt, m = out['pixel_colors_gt'], out['ray_mask'].float()
+
+    def one(pr):
+        return (torch.sum(((pr - gt) ** 2).sum(-1) * m, 1) / (torch.sum(m, 1) + 1e-3) * weight).sum()
+    loss = one(out['pixel_colors_nr'])
+    if fine and 'pixel_colors_nr_fine' in out:
+        loss = loss + one(out['pixel_colors_nr_fine'])
+    return loss
+
+
+def eikonal_loss(out, weight=0.1):
+    """SDFLoss eikonal term (loss.py:172-173): mean over the ray chunks of mean((|d sdf / d pts| - 1)^2), coarse pass."""
+    return out['sdf_gradient_error'].mean() * weight
+
+
+def depth_loss(out, ref, weight=1.0):
+    """DepthLoss (loss.py:87-144, l2, synthetic scenes): predicted mean inverse depth of the dist decoder at depth_coords
+    vs the ground-truth depth map, both in normalised inverse depth."""
+    coords = out['depth_coords'].float()
+    depth_maps = ref['true_depth']
+    _, _, h, w = depth_maps.shape
+    grid = torch.stack([coords[..., 0] / (w - 1) * 2 - 1, coords[..., 1] / (h - 1) * 2 - 1], -1).unsqueeze(1)
+    gt = F.grid_sample(depth_maps, grid, mode='bilinear', padding_mode='border', align_corners=True)[:, 0, 0]
+    dr = ref['depth_range']
+    near, far = -1 / dr[:, 0:1], -1 / dr[:, 1:2]
+    gt = torch.clamp((-1 / torch.clamp(gt, min=1e-5) - near) / (far - near), min=0, max=1.0)
+    loss = ((gt - out['depth_mean']) ** 2).mean()
+    if 'depth_mean_fine' in out:
+        loss = loss + ((gt - out['depth_mean_fine']) ** 2).mean()
+    return loss * weight
+
+
+def training_losses(out, data):
+    """Sum of the shipped configuration's loss terms that the forward produced."""
+    loss = volume_losses(out, data)
+    if 'pixel_colors_nr' in out and 'pixel_colors_gt' in out:
+        loss = loss + render_loss(out) + eikonal_loss(out)
+    if 'depth_mean' in out and 'true_depth' in data['ref_imgs_info']:
+        loss = loss + depth_loss(out, data['ref_imgs_info'])
+    return loss
+
+
 def volume_losses(out, data):
     loss = sdf_loss(out['volume'], data['ref_imgs_info']['sdf_gt'])
     if 'grasp_info' in data and 'full_vol' not in data:
@@ -77,7 +122,7 @@ def volume_losses(out, data):
 class TrainStep:
     """One optimizer step over a global batch of scenes, this rank's share passed in as a list of `data` dicts."""
 
-    def __init__(self, net, lr=1e-4, dist=None, loss_fn=volume_losses):
+    def __init__(self, net, lr=1e-4, dist=None, loss_fn=training_losses):
         self.net, self.dist, self.loss_fn = net, dist, loss_fn
         self.bucket = GradBucket(net.parameters())
         self.opt = torch.optim.Adam(self.bucket.params, lr=lr)

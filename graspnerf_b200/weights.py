@@ -92,6 +92,47 @@ def pack_blob(sd, agg_prefix='agg_net.', dd_prefix='dist_decoder.'):
     return blob
 
 
+class DevicePacker:
+    """pack_blob on the device, without host round trips (training re-packs the weights every step).
+
+    The raw entries of the blob are a fixed gather of the parameters (transposes, the [rgb|img] permutation, zero padding):
+    the gather index is built ONCE by running `pack_blob` on a state_dict of element ids.  The four host-fused composites
+    (nfc.w0, nfc.b0, bf.wpc, bf.b0c: products through the activation-free prob_embed.2) are evaluated with fp64 torch
+    matmuls on the device and rounded once, exactly like `_entries` does with numpy."""
+
+    def __init__(self, sd, agg_prefix, dd_prefix, device):
+        self.agg_prefix, self.dd_prefix, self.device = agg_prefix, dd_prefix, torch.device(device)
+        self.keys = sorted(k for k in sd if (k.startswith(agg_prefix) or k.startswith(dd_prefix)) and not k.endswith('deviation_network.variance'))
+        ids, n = {}, 1                                     # id 0 = "zero" (padding)
+        for k in self.keys:
+            m = sd[k].numel()
+            ids[k] = torch.arange(n, n + m, dtype=torch.float32).reshape(sd[k].shape)      # exact in fp32 (n << 2^24)
+            n += m
+        lab = pack_blob(ids, agg_prefix, dd_prefix)
+        table = {name: (off, rows, cols, cp) for name, off, rows, cols, cp in _lib.weight_table()}
+        self.fused = {name: table[name] for name in ('nfc.w0', 'nfc.b0', 'bf.wpc', 'bf.b0c')}
+        for off, rows, cols, cp in self.fused.values():
+            lab[off:off + rows * cp] = 0
+        assert float(lab.max()) < n and np.all(lab == np.round(lab))
+        self.index = torch.from_numpy(lab.astype(np.int64)).to(self.device)
+        self.A = agg_prefix + 'agg_impl.'
+
+    def pack(self, sd):
+        """sd: {key: device tensor}; returns the fp32 blob on the device (no synchronisation)."""
+        flat = torch.cat([sd[k].detach().reshape(-1).to(torch.float32) for k in self.keys])
+        blob = torch.cat([flat.new_zeros(1), flat])[self.index]
+        d = lambda k: sd[k].detach().to(torch.float64)
+        w_pe2, b_pe2 = d(self.agg_prefix + 'prob_embed.2.weight'), d(self.agg_prefix + 'prob_embed.2.bias')
+        w_nf0, b_nf0 = d(self.A + 'neuray_fc.0.weight'), d(self.A + 'neuray_fc.0.bias')
+        w_bfp, b_bf0 = d(self.A + 'base_fc.0.weight')[:, 175:207], d(self.A + 'base_fc.0.bias')
+        vals = {'nfc.w0': (w_nf0 @ w_pe2).t(), 'nfc.b0': b_pe2 @ w_nf0.t() + b_nf0,
+                'bf.wpc': (w_bfp @ w_pe2).t(), 'bf.b0c': b_pe2 @ w_bfp.t() + b_bf0}
+        for name, (off, rows, cols, cp) in self.fused.items():
+            assert cols == cp
+            blob[off:off + rows * cp] = vals[name].reshape(-1).to(torch.float32)
+        return blob
+
+
 def unpack_blob_grad(dblob, agg_prefix='agg_net.', dd_prefix='dist_decoder.'):
     """Adjoint of `pack_blob` over the raw (unfused) entries: a gradient in blob layout (torch tensor, any device)
     -> {reference state_dict key: gradient tensor of that parameter's shape}.  The packing is a linear map (transposes,

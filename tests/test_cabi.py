@@ -99,6 +99,25 @@ def test_unpack_blob_grad_is_the_adjoint_of_pack_blob(lib):
     assert all(ug[k].shape == w[k].shape for k in ug) and len(ug) == 62
 
 
+def test_device_packer_equals_host_packer(lib):
+    """weights.DevicePacker (gather index + fp64 torch matmuls for the fused composites; what training uses every step)
+    produces the blob of weights.pack_blob: raw entries bit for bit, composites to one fp32 ulp."""
+    import torch
+    from graspnerf_b200.weights import pack_blob, DevicePacker
+    from tests.helpers import golden_weights
+    sd = golden_weights()
+    for agg, dd in (('agg_net.', 'dist_decoder.'), ('fine_agg_net.', 'fine_dist_decoder.')):
+        ref = pack_blob(sd, agg, dd)
+        got = DevicePacker(sd, agg, dd, 'cpu').pack(sd).numpy()
+        assert got.shape == ref.shape
+        fused = np.zeros(ref.shape, bool)
+        for name, off, rows, cols, cp in __import__('graspnerf_b200')._lib.weight_table():
+            if name in ('nfc.w0', 'nfc.b0', 'bf.wpc', 'bf.b0c'):
+                fused[off:off + rows * cp] = True
+        assert np.array_equal(got[~fused], ref[~fused])
+        assert np.allclose(got[fused], ref[fused], rtol=2e-7, atol=1e-9) and np.abs(ref[fused]).sum() > 0
+
+
 def test_launchers_reject_bad_arguments_before_touching_cuda(lib):
     """Error convention of the C ABI (include/graspnerf_b200.h): 0 ok, < 0 argument error (checked before any CUDA call, so
     this runs without a GPU), > 0 cudaError_t.  Nothing is launched here."""
