@@ -6,7 +6,7 @@ OUT=gpurun_out
 mkdir -p $OUT
 timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3 > $OUT/pytest_gpu_$TAG.txt
 timeout 600 python bench.py > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err
-timeout 600 python bench.py --impl reference > $OUT/bench_ref_$TAG.json 2> $OUT/bench_ref_$TAG.err
+timeout 600 python bench.py --impl reference --steps 40 --warmup 3 > $OUT/bench_ref_$TAG.json 2> $OUT/bench_ref_$TAG.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_$TAG.csv \
     python bench.py --steps 4 --warmup 3 --no-cpu --train-batch 0 > /dev/null 2>&1
 for k in gn_k1_kernel gn_k2a_tc_kernel gn_k2b_attn_kernel; do
