@@ -204,3 +204,35 @@ def test_k1_walk_kernel_matches_tile_kernel(mode, monkeypatch):
     d = (r2[..., :64] - r3[..., :64]).abs().max().item()
     assert d <= 1e-6 * max(1.0, r2[..., :64].abs().max().item()), f'feature blends differ by {d:.3e}'
     assert (p2[0, :, 0] > 0).float().mean() > 0.3, 'test scene should have valid projections'
+
+
+def test_configs4_full_size_properties():
+    """BASELINE configs[4] at FULL size (12 views, 720x1280 images, 180x320 feature maps, 80^3 grid = 512 000 points,
+    6.1 M (point,view) rows): too large for the CPU oracle in a test, so the checks are size-independent properties:
+      * the tcgen05 path and the fp32 SIMT path (two independent implementations of K2a / K2b) agree to the parity tolerance;
+      * permuting the V views leaves the volume unchanged up to fp32 summation order (the model is view-symmetric:
+        ibrnet.py pools over the views with masks / weights only);
+      * the z flip: volume[..., k] is produced by sample R-1-k of ray (i, j) - checked on the validity pattern: voxels
+        seen by no view are exactly +1.0 (ibrnet.py:495) in both paths at the same places."""
+    from graspnerf_b200 import ops
+    dev = torch.device('cuda:0')
+    hw = ops.HeadWeights(golden_weights(), 'agg_net.', 'dist_decoder.', dev)
+    sc = _scene_t(dict(seed=31, num_views=12, h=720, w=1280, radius=0.55))
+    keys = ('imgs', 'img_feats', 'ray_feats', 'poses', 'Ks', 'depth_range')
+    scene = ops.Scene(*[sc[k].to(dev) for k in keys])
+    bbox = torch.tensor([sc['bbox3d'][0]], device=dev)
+    rec, pt = ops.k1_forward(scene, hw, resolution=80, bbox_min=bbox)
+    vol = ops.sample_volume(scene, hw, bbox, 80)
+    vol_simt = ops.sample_volume(scene, hw, bbox, 80, impl='simt')
+    perm = torch.tensor([5, 0, 11, 3, 8, 1, 10, 2, 7, 4, 9, 6])
+    scene_p = ops.Scene(*[sc[k][perm].to(dev) for k in keys])
+    vol_p = ops.sample_volume(scene_p, hw, bbox, 80)
+    torch.cuda.synchronize()
+    assert vol.shape == (1, 1, 80, 80, 80) and torch.isfinite(vol).all()
+    nvalid = pt[0, :, 0]
+    assert 0.5 < float((nvalid > 0).float().mean()) <= 1.0
+    assert_close(vol.cpu(), vol_simt.cpu(), what='80^3 / 12 x 720x1280: tensor-core vs SIMT path')
+    assert_close(vol_p.cpu(), vol.cpu(), rtol=2e-4, atol_scale=2e-4, what='view permutation invariance')
+    unseen = (nvalid.reshape(80, 80, 80).flip(-1) < 1)          # record order n = (i*R+j)*R + (R-1-k)
+    assert torch.equal(vol[0, 0][unseen], torch.ones_like(vol[0, 0][unseen]))
+    assert torch.equal(vol_simt[0, 0][unseen], torch.ones_like(vol[0, 0][unseen]))
