@@ -187,8 +187,8 @@ def main():
     ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--cpu-volumes', type=int, default=12, help='size of the bounded CPU-baseline sample')
-    ap.add_argument('--train-batch', type=int, default=4, help='scenes per GPU of the extra training-step leg (0 = skip)')
-    ap.add_argument('--train-steps', type=int, default=2)
+    ap.add_argument('--train-batch', type=int, default=32, help='scenes per GPU of the extra training-step leg (0 = skip); 32 = BASELINE configs[2], and configs[3] (256 scenes) at --gpus 8')
+    ap.add_argument('--train-steps', type=int, default=1)
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg (profiling runs under ncu only)')
     args = ap.parse_args()
     if args.impl == 'reference':

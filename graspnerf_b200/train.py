@@ -16,30 +16,43 @@ import torch.nn.functional as F
 
 
 class GradBucket:
-    """Flat fp32 view of all gradients: one collective per step, static layout (parameters that received no gradient in a
-    step - e.g. deviation_network.variance, rgb_fc - contribute zeros, so every rank sends the same bytes)."""
+    """Flat fp32 buffer holding ALL gradients: one collective per step, static layout (parameters that received no gradient
+    in a step - e.g. rgb_fc with render_rgb off - contribute zeros, so every rank sends the same bytes).  Every parameter's
+    `.grad` is a VIEW of the flat buffer, so autograd accumulates straight into it (no pack / unpack copies) and the
+    optimizer reads the reduced values in place."""
 
     def __init__(self, params):
-        self.params = [p for p in params if p.requires_grad]
+        # ALL parameters, also those that do not require a gradient yet: deviation_network.variance starts to after the first
+        # training forward (neus.py:16-19); it travels as zeros until then and the bucket layout never changes
+        self.params = list(params)
         self.sizes = [p.numel() for p in self.params]
         dev = self.params[0].device
         self.flat = torch.zeros(sum(self.sizes), dtype=torch.float32, device=dev)
         self.views = [v.view_as(p) for v, p in zip(self.flat.split(self.sizes), self.params)]
+        self.attach()
 
     @property
     def nbytes(self):
         return self.flat.numel() * 4
 
+    def attach(self):
+        for v, p in zip(self.views, self.params):
+            p.grad = v
+
+    def zero(self):
+        """Start of a step: zero the bucket and (re-)attach the views (something may have replaced a .grad)."""
+        self.flat.zero_()
+        self.attach()
+
     def pack(self):
         for v, p in zip(self.views, self.params):
             if p.grad is None:
                 v.zero_()
-            else:
+            elif p.grad.data_ptr() != v.data_ptr():
                 v.copy_(p.grad)
 
     def unpack(self):
-        for v, p in zip(self.views, self.params):
-            p.grad = v          # the optimizer reads the bucket's memory directly
+        self.attach()
 
     def allreduce(self, dist=None, scale=1.0):
         """sum over ranks (if a process group is given), then scale (1 / global number of scenes)."""
@@ -129,13 +142,13 @@ class TrainStep:
         self.world = dist.get_world_size() if (dist is not None and dist.is_initialized()) else 1
 
     def __call__(self, local_batch):
-        self.opt.zero_grad(set_to_none=True)
-        total = 0.0
+        self.bucket.zero()
+        total = torch.zeros((), device=self.bucket.flat.device)
         for data in local_batch:
             loss = self.loss_fn(self.net(data), data)
             loss.backward()
-            total += float(loss.detach())
+            total += loss.detach()              # no host synchronisation inside the scene loop
         n_global = len(local_batch) * self.world
         self.bucket.allreduce(self.dist, 1.0 / n_global)
         self.opt.step()
-        return total / max(len(local_batch), 1)
+        return float(total) / max(len(local_batch), 1)
