@@ -321,7 +321,7 @@ struct K1PairInfo {           // 80-byte stride: the four groups of a warp read 
 };
 #define K1_MISC 12            // floats per pair in s_misc: dd0..3, mask, depth, pad
 
-template <bool FUSED>
+template <bool FUSED, bool TEXPF>
 __global__ void __launch_bounds__(K1_THREADS, 4)
 gn_k1_kernel(const __grid_constant__ GnK1Params p)
 {
@@ -414,6 +414,15 @@ gn_k1_kernel(const __grid_constant__ GnK1Params p)
     const float* if_base = p.img_feats + (size_t)b * V * fmap_sz + 4 * j;
     const float* im_base = p.imgs + (size_t)b * V * plane * 4;
 
+    // image taps: lane j<4 fetches tap j as one RGBA texel and scales it; summed over lanes 0..3 with two xor-shuffles.
+    // The texels of view v+1 are requested while view v is blended: they are the gathers that miss to DRAM (the images are
+    // read once per scene), one full iteration ahead hides their latency behind the feature gathers of the current view.
+    float4 px = make_float4(0.f, 0.f, 0.f, 0.f);
+    float iw = 0.f;
+    if (TEXPF && j < 4) {
+        iw = s_info[pl * V].iw[j];
+        px = ldg4(im_base + (size_t)s_info[pl * V].io[j] * 4);
+    }
     for (int v = 0; v < V; ++v) {
         const int pair = pl * V + v;
         int4 fo = *reinterpret_cast<const int4*>(s_info[pair].fo);
@@ -423,14 +432,19 @@ gn_k1_kernel(const __grid_constant__ GnK1Params p)
         const float* imf = FUSED ? rf + GN_FEAT_C : if_base + (size_t)v * fmap_sz;
         const float4 r0 = ldg4(rf + fo.x), r1 = ldg4(rf + fo.y), r2 = ldg4(rf + fo.z), r3 = ldg4(rf + fo.w);
         const float4 g0 = ldg4(imf + fo.x), g1 = ldg4(imf + fo.y), g2 = ldg4(imf + fo.z), g3 = ldg4(imf + fo.w);
-        // image taps: lane j<4 fetches tap j as one RGBA texel and scales it; summed over lanes 0..3 with two xor-shuffles
-        float cr = 0.f, cg = 0.f, cb = 0.f;
-        if (j < 4) {
-            const int io = s_info[pair].io[j];
-            const float iw = s_info[pair].iw[j];
-            const float4 px = ldg4(im_base + ((size_t)v * plane + io) * 4);
-            cr = __fmul_rn(px.x, iw); cg = __fmul_rn(px.y, iw); cb = __fmul_rn(px.z, iw);
+        float4 px_n = make_float4(0.f, 0.f, 0.f, 0.f);
+        float iw_n = 0.f;
+        if (TEXPF) {
+            if (j < 4 && v + 1 < V) {
+                iw_n = s_info[pair + 1].iw[j];
+                px_n = ldg4(im_base + ((size_t)(v + 1) * plane + s_info[pair + 1].io[j]) * 4);
+            }
+        } else if (j < 4) {
+            iw = s_info[pair].iw[j];
+            px = ldg4(im_base + ((size_t)v * plane + s_info[pair].io[j]) * 4);
         }
+        float cr = __fmul_rn(px.x, iw), cg = __fmul_rn(px.y, iw), cb = __fmul_rn(px.z, iw);
+        if (TEXPF) { px = px_n; iw = iw_n; }
         float4 ray, img;
         ray.x = k1_blend(r0.x, r1.x, r2.x, r3.x, fwt); ray.y = k1_blend(r0.y, r1.y, r2.y, r3.y, fwt);
         ray.z = k1_blend(r0.z, r1.z, r2.z, r3.z, fwt); ray.w = k1_blend(r0.w, r1.w, r2.w, r3.w, fwt);
@@ -509,13 +523,12 @@ extern "C" int gn_k1_forward(const GnK1Params* hp, void* stream)
     if (smem > 227 * 1024) return -5;
     const long long grid = (long long)p.B * p.tiles_per_scene;
     if (grid > 0x7fffffffLL) return -6;
-    static size_t c2f[16] = {0}, c2s[16] = {0};
-    if (fused) {
-        e = gn_ensure_smem(gn_k1_kernel<true>, smem, c2f); if (e != cudaSuccess) return (int)e;
-        gn_k1_kernel<true><<<(unsigned)grid, K1_THREADS, smem, (cudaStream_t)stream>>>(p);
-    } else {
-        e = gn_ensure_smem(gn_k1_kernel<false>, smem, c2s); if (e != cudaSuccess) return (int)e;
-        gn_k1_kernel<false><<<(unsigned)grid, K1_THREADS, smem, (cudaStream_t)stream>>>(p);
-    }
+    const bool texpf = k1_env_int("GN_K1_TEXPF", 1) != 0;
+#define K1T_LAUNCH(FU, PF) { static size_t cache[16] = {0}; \
+        e = gn_ensure_smem(gn_k1_kernel<FU, PF>, smem, cache); if (e != cudaSuccess) return (int)e; \
+        gn_k1_kernel<FU, PF><<<(unsigned)grid, K1_THREADS, smem, (cudaStream_t)stream>>>(p); }
+    if (fused) { if (texpf) K1T_LAUNCH(true, true) else K1T_LAUNCH(true, false) }
+    else       { if (texpf) K1T_LAUNCH(false, true) else K1T_LAUNCH(false, false) }
+#undef K1T_LAUNCH
     return (int)cudaGetLastError();
 }

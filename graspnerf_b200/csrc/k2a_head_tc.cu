@@ -15,6 +15,7 @@
 //     as two more GEMMs on the pooled rows, so the per-ray kernel K2b only does attention + LayerNorm + output MLP.
 // Operand layouts were validated on B200 with tools/tc_probe.cu (profiles/tc_probe_r01.txt).
 #include "k2a_tc_common.cuh"
+#include <cstdlib>
 
 #define TC_THREADS 256
 #define TC_SLOTS 2
@@ -139,7 +140,7 @@ __device__ __forceinline__ void pool36(float* scr, int lane, int g, int v, int g
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
-gn_k2a_tc_kernel(const __grid_constant__ GnK2aParams p, int num_tiles, int G)
+gn_k2a_tc_kernel(const __grid_constant__ GnK2aParams p, int num_tiles, int G, int nslots)
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __half* s_img = reinterpret_cast<__half*>(smem_raw);
@@ -197,7 +198,8 @@ gn_k2a_tc_kernel(const __grid_constant__ GnK2aParams p, int num_tiles, int G)
     const unsigned FULL = 0xffffffffu;
     float* scr = s_pool + warp * (32 + G) * TC_POOL_STRIDE;
 
-    for (int tile = blockIdx.x * TC_SLOTS + slot; tile < num_tiles; tile += gridDim.x * TC_SLOTS) {
+    // nslots = TC_SLOTS in production; nslots = 1 (GN_K2A_SLOTS=1, measurement aid) leaves the second slot's warps idle
+    for (int tile = blockIdx.x * nslots + slot; slot < nslots && tile < num_tiles; tile += gridDim.x * nslots) {
         long long pidx = ((long long)tile * 4 + (warp & 3)) * G + g;
         const bool valid = lane_active && pidx < total_pts;
         pidx = pidx < total_pts ? pidx : total_pts - 1;
@@ -339,7 +341,7 @@ gn_k2a_tc_kernel(const __grid_constant__ GnK2aParams p, int num_tiles, int G)
         }
         TC_GEMM_BEGIN(cx) tc_issue<L_BF0B>(cx, 0, 0, true); TC_GEMM_END(cx)
         {   // next tile's first record line (ray_feats) and per-point word: hide their latency under S8..S11
-            const long long npidx = ((long long)(tile + gridDim.x * TC_SLOTS) * 4 + (warp & 3)) * G + g;
+            const long long npidx = ((long long)(tile + gridDim.x * nslots) * 4 + (warp & 3)) * G + g;
             if (npidx < total_pts) {
                 asm volatile("prefetch.global.L1 [%0];" :: "l"(p.rec + ((size_t)npidx * V + v) * GN_REC_STRIDE));
                 asm volatile("prefetch.global.L1 [%0];" :: "l"(p.rec + ((size_t)npidx * V + v) * GN_REC_STRIDE + GN_REC_RGB));
@@ -527,8 +529,10 @@ extern "C" int gn_k2a_forward_tc(const GnK2aParams* hp, void* stream)
     cudaError_t e = gn_ensure_smem(gn_k2a_tc_kernel, smem, smem_cache_gn_k2a_tc_kernel);
     if (e != cudaSuccess) return (int)e;
     const int sms = gn_sm_count();
-    const long long want = (tiles + TC_SLOTS - 1) / TC_SLOTS;
+    const char* es = getenv("GN_K2A_SLOTS");
+    const int nslots = (es && atoi(es) == 1) ? 1 : TC_SLOTS;
+    const long long want = (tiles + nslots - 1) / nslots;
     const int grid = (int)(want < sms ? want : sms);
-    gn_k2a_tc_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(p, (int)tiles, G);
+    gn_k2a_tc_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(p, (int)tiles, G, nslots);
     return (int)cudaGetLastError();
 }

@@ -20,10 +20,9 @@ def main():
         scenes.append((ops.Scene(t['imgs'], t['img_feats'], t['ray_feats'], t['poses'], t['Ks'], t['depth_range']),
                        torch.tensor([sc['bbox3d'][0]], device=dev)))
     flush = torch.empty(512 * 1024 * 1024 // 4, device=dev)
-    cfgs = [dict(GN_K1_IMPL='2'),
-            dict(GN_K1_IMPL='3', GN_K1_STAGE='1', GN_K1_PIPE='0'), dict(GN_K1_IMPL='3', GN_K1_STAGE='1', GN_K1_PIPE='1'),
-            dict(GN_K1_IMPL='3', GN_K1_STAGE='0', GN_K1_PIPE='0'), dict(GN_K1_IMPL='3', GN_K1_STAGE='0', GN_K1_PIPE='1', GN_K1_MINB='6'),
-            dict(GN_K1_IMPL='3', GN_K1_STAGE='0', GN_K1_PIPE='1', GN_K1_MINB='5')]
+    cfgs = [dict(GN_K1_IMPL='2', GN_K1_TEXPF='0'), dict(GN_K1_IMPL='2', GN_K1_TEXPF='1'),
+            dict(GN_K1_IMPL='3', GN_K1_STAGE='1'), dict(GN_K1_IMPL='3', GN_K1_STAGE='0'),
+            dict(GN_K1_IMPL='2', GN_K1_TEXPF='0'), dict(GN_K1_IMPL='2', GN_K1_TEXPF='1')]
     for cfg in cfgs:
         os.environ.update(cfg)
         impl = ' '.join(f'{k[6:]}={v}' for k, v in cfg.items())
