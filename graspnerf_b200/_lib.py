@@ -64,7 +64,7 @@ def load():
             'graspnerf_b200 has no CPU / PyTorch fallback for its CUDA kernels.')
     lib = C.CDLL(LIBPATH)
     lib.gn_version.restype = C.c_char_p
-    for name, st in (('gn_k1_forward', GnK1Params), ('gn_k2a_forward', GnK2aParams), ('gn_k2a_forward_tc', GnK2aParams), ('gn_k2b_forward', GnK2bParams),
+    for name, st in (('gn_k1_forward', GnK1Params), ('gn_k2a_forward', GnK2aParams), ('gn_k2a_forward_tc', GnK2aParams), ('gn_k2a_forward_tc3', GnK2aParams), ('gn_k2b_forward', GnK2bParams),
                      ('gn_k3_composite', GnK3Params), ('gn_k2b_backward', GnK2bBwdParams), ('gn_k2a_backward', GnK2aBwdParams),
                      ('gn_k1_backward', GnK1BwdParams)):
         fn = getattr(lib, name)

@@ -122,7 +122,7 @@ __device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigne
     unsigned long long r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r;
 }
 // split K fp32 values into fp16 hi/lo pairs and store them as the A operand (k0 = first k index, multiple of 16)
-template <int K> __device__ __forceinline__ void tm_store_a(uint32_t slot_lane_addr, int k0, const float* a) {
+template <int K, int AHI = TM_AHI, int ALO = TM_ALO> __device__ __forceinline__ void tm_store_a(uint32_t slot_lane_addr, int k0, const float* a) {
 #pragma unroll
     for (int c = 0; c < K / 2; c += 8) {
         uint32_t hi[8], lo[8];
@@ -137,8 +137,8 @@ template <int K> __device__ __forceinline__ void tm_store_a(uint32_t slot_lane_a
             hi[i] = *reinterpret_cast<const uint32_t*>(&h);
             lo[i] = *reinterpret_cast<const uint32_t*>(&l);
         }
-        tm_st8(slot_lane_addr + TM_AHI + k0 / 2 + c, hi);
-        tm_st8(slot_lane_addr + TM_ALO + k0 / 2 + c, lo);
+        tm_st8(slot_lane_addr + AHI + k0 / 2 + c, hi);
+        tm_st8(slot_lane_addr + ALO + k0 / 2 + c, lo);
     }
 }
 // ELU with one MUFU: ex2.approx.ftz (rel. err 2^-22)
@@ -174,4 +174,29 @@ template <int N> __device__ __forceinline__ void add_bias(const float* __restric
         y[n] += w.x; y[n + 1] += w.y; y[n + 2] += w.z; y[n + 3] += w.w;
     }
 }
+
+// ---- per-slot context and the GEMM round protocol shared by the tensor-core K2a kernels ----------------------------------
+struct TcCtx {
+    uint32_t tmem_slot;       // TMEM base of this slot (lane 0)
+    uint32_t lane_addr;       // tmem_slot + (warp%4 * 32 << 16)
+    uint32_t img_base16;      // (shared address of the image area) >> 4
+    uint32_t bar;             // shared address of this slot's mbarrier
+    uint32_t parity;
+    int bar_id;               // named barrier id of this slot
+    bool issuer;              // this warp issues the slot's MMAs (warp-uniform)
+    uint32_t elected;         // 1 on the one lane of the issuing warp that actually issues
+};
+
+// all 128 threads of the slot: A operand written -> (leader issues) -> accumulator ready
+#define TC_GEMM_BEGIN(cx)                                                            \
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");                     \
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");                 \
+    asm volatile("bar.sync %0, 128;" :: "r"((cx).bar_id) : "memory");                \
+    if ((cx).issuer) { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#define TC_GEMM_COMMIT(cx)                                                           \
+        tc_commit((cx).bar, (cx).elected); __syncwarp(); }
+#define TC_GEMM_WAIT(cx)                                                             \
+    mbar_wait((cx).bar, (cx).parity); (cx).parity ^= 1u;                             \
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#define TC_GEMM_END(cx) TC_GEMM_COMMIT(cx) TC_GEMM_WAIT(cx)
 

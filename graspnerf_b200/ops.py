@@ -178,7 +178,7 @@ def k1_forward(scene, hw, *, resolution=None, bbox_min=None, volume_size=0.3, pt
     return (rec, pt, dbg) if debug_idx else (rec, pt)
 
 
-K2A_IMPL = 'tc'      # 'tc' (tcgen05, default) or 'simt' (fp32 CUDA-core implementation kept as the on-GPU cross-check)
+K2A_IMPL = 'tc3'     # 'tc3' (tcgen05, three tiles per SM, default), 'tc' (tcgen05, two tiles per SM) or 'simt' (fp32 CUDA-core cross-check)
 
 
 def k2a_forward(rec, pt, hw, depth_range, *, que_dists=None, dn=1, want_colors=False, debug=False, impl=None,
@@ -199,7 +199,7 @@ def k2a_forward(rec, pt, hw, depth_range, *, que_dists=None, dn=1, want_colors=F
         que_dists = _f32c(que_dists, dev)
     p.que_dists, p.pooled, p.colors, p.dbg_rows = _ptr(que_dists).value, _ptr(pooled).value, _ptr(colors).value, _ptr(dbg).value
     p.B, p.N, p.V, p.dn, p.with_rgb = B, N, V, int(dn), 1 if want_colors else 0
-    if impl == 'tc':
+    if impl in ('tc', 'tc3'):
         p.tc_const = _ptr(hw.tc_const).value
         if want_tok:
             tok = torch.empty((B, N, TOK_STRIDE), device=dev, dtype=torch.float32)
@@ -214,7 +214,7 @@ def k2a_forward(rec, pt, hw, depth_range, *, que_dists=None, dn=1, want_colors=F
                 p.pts, p.R, p.volume_mode = _ptr(pts).value, 0, 0
     elif want_tok or not want_pooled:
         raise ValueError("tokens are produced by the tensor-core K2a only")
-    fn = {'tc': lib.gn_k2a_forward_tc, 'simt': lib.gn_k2a_forward}[impl]
+    fn = {'tc': lib.gn_k2a_forward_tc, 'tc3': lib.gn_k2a_forward_tc3, 'simt': lib.gn_k2a_forward}[impl]
     if ev is not None:
         ev[0].record()
     rc = fn(C.byref(p), _stream())
@@ -304,7 +304,7 @@ def sample_volume(scene, hw, bbox_min, resolution=40, volume_size=0.3, debug=Non
     impl 'tc' (default): tcgen05 K2a emits per-point tokens, K2b is attention-only.  'simt': fp32 CUDA-core K2a + full K2b."""
     impl = impl or K2A_IMPL
     rec, pt = k1_forward(scene, hw, resolution=resolution, bbox_min=bbox_min, volume_size=volume_size)
-    if impl == 'tc':
+    if impl in ('tc', 'tc3'):
         pooled, _, dbg, tok = k2a_forward(rec, pt, hw, scene.depth_range, debug=debug is not None, impl=impl,
                                           want_pooled=debug is not None, want_tok=True, resolution=resolution,
                                           bbox_min=bbox_min, volume_size=volume_size)

@@ -88,6 +88,7 @@ typedef struct GnK2aParams {
 } GnK2aParams;
 int gn_k2a_forward(const GnK2aParams* params, void* stream);      /* fp32 SIMT implementation (reference for the TC path) */
 int gn_k2a_forward_tc(const GnK2aParams* params, void* stream);   /* tcgen05 / TMEM implementation (fp16 hi/lo split, 3 MMAs per product) */
+int gn_k2a_forward_tc3(const GnK2aParams* params, void* stream);  /* same math re-scheduled into smaller GEMM rounds: 160 TMEM columns per tile, three tiles per SM */
 int gn_k2a_tc_const_bytes(void);
 int gn_k2a_tc_prepare(const float* weights, void* tc_const, void* stream);   /* fp32 blob -> fp16 hi/lo operand images + small constants */
 

@@ -28,7 +28,7 @@ def _setup(name):
     return ops, sd, sc, scene, que, oq, hw_c, hw_f, dev
 
 
-@pytest.mark.parametrize('impl', ['simt', 'tc'])
+@pytest.mark.parametrize('impl', ['simt', 'tc', 'tc3'])
 @pytest.mark.parametrize('name', list(RENDER_CASES))
 def test_render_coarse_and_fine(name, impl):
     from oracle import nr_oracle as O
@@ -62,4 +62,4 @@ def test_render_coarse_and_fine(name, impl):
         for k in keys:
             assert_close(fine[k].cpu(), g[k + '_fine'], what=f'{k}_fine vs reference golden')
     finally:
-        ops.K2A_IMPL = 'tc'
+        ops.K2A_IMPL = 'tc3'

@@ -24,7 +24,7 @@ def _dump(name, **arrs):
         np.savez_compressed(os.path.join(d, name + '.npz'), **{k: np.asarray(v) for k, v in arrs.items()})
 
 
-@pytest.mark.parametrize('impl', ['simt', 'tc'])
+@pytest.mark.parametrize('impl', ['simt', 'tc', 'tc3'])
 @pytest.mark.parametrize('name', list(VOLUME_CASES))
 def test_volume_path_vs_oracle_and_golden(name, impl):
     from graspnerf_b200 import ops
@@ -38,7 +38,7 @@ def test_volume_path_vs_oracle_and_golden(name, impl):
                       sc['Ks'].to(dev), sc['depth_range'].to(dev))
     bbox_min = torch.tensor([sc['bbox3d'][0]], device=dev)
     rec, pt, idx = ops.k1_forward(scene, hw, resolution=40, bbox_min=bbox_min, debug_idx=True)
-    if impl == 'tc':      # tensor-core K2a: pooled (checked below) AND per-point tokens -> attention-only K2b
+    if impl in ('tc', 'tc3'):      # tensor-core K2a: pooled (checked below) AND per-point tokens -> attention-only K2b
         pooled, _, rows, tok = ops.k2a_forward(rec, pt, hw, scene.depth_range, debug=True, impl=impl, want_tok=True,
                                                resolution=40, bbox_min=bbox_min)
         vol, _ = ops.k2b_forward(None, hw, dn=40, resolution=40, bbox_min=bbox_min, tok=tok)

@@ -21,7 +21,7 @@ def main():
         rec, pt = ops.k1_forward(scene, hw, resolution=40, bbox_min=bb)
         items.append((scene, bb, rec, pt))
     flush = torch.empty(512 * 1024 * 1024 // 4, device=dev)
-    for slots in ('2', '1', '2', '1'):
+    for slots, impl in (('2', 'tc'), ('2', 'tc3'), ('1', 'tc'), ('2', 'tc'), ('2', 'tc3')):
         os.environ['GN_K2A_SLOTS'] = slots
         ts = []
         for rep in range(5):
@@ -31,12 +31,12 @@ def main():
             e0.record()
             for it in range(16):
                 scene, bb, rec, pt = items[it % 8]
-                ops.k2a_forward(rec, pt, hw, scene.depth_range, want_pooled=False, want_tok=True, resolution=40, bbox_min=bb)
+                ops.k2a_forward(rec, pt, hw, scene.depth_range, want_pooled=False, want_tok=True, resolution=40, bbox_min=bb, impl=impl)
             e1.record()
             torch.cuda.synchronize()
             if rep >= 1:
                 ts.append(e0.elapsed_time(e1) * 1e3 / 16)
-        print(f'GN_K2A_SLOTS={slots}: K2a median {np.median(ts):.1f} us per 40^3 volume (384 000 rows)')
+        print(f'impl={impl} GN_K2A_SLOTS={slots}: K2a median {np.median(ts):.1f} us per 40^3 volume (384 000 rows)')
 
 
 if __name__ == '__main__':
