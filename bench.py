@@ -321,8 +321,8 @@ def main():
                    'achieved_survey_bytes': K1_BYTES_SURVEY / (kt[0] * 1e-3) / 1e9,
                    'note': 'achieved uses the bytes K1 itself must move (inputs once + 72-float record + 2 floats/point); '
                            'achieved_survey_bytes uses SURVEY 8d figure (153,284,608 B, counts mean/var that now live in K2a)'}
-        roof_k2 = {'kernel': 'gn_k2a_tc_kernel+gn_k2b_attn_kernel', 'bound': 'tensor', 'achieved': k2_tfs, 'peak': peaks['tf_sustained'],
-                   'unit': 'TFLOP/s', 'frac': k2_tfs / peaks['tf_sustained'], 'traffic': traffic.get('gn_k2a_tc_kernel'),
+        roof_k2 = {'kernel': 'gn_k2a_tc3_kernel+gn_k2b_attn_kernel', 'bound': 'tensor', 'achieved': k2_tfs, 'peak': peaks['tf_sustained'],
+                   'unit': 'TFLOP/s', 'frac': k2_tfs / peaks['tf_sustained'], 'traffic': traffic.get('gn_k2a_tc3_kernel'),
                    'us_per_launch': (kt[1] + kt[2]) * 1e3, 'peak_source': peaks['source'],
                    'note': 'algorithmic fp32 FLOPs of the reference semantics (SURVEY 8d: 23.2 GFLOP/volume) over the K2a+K2b time; '
                            'the kernel issues 3 fp16 MMAs per product (hi/lo split), so tensor-pipe activity is ~3x this fraction'}

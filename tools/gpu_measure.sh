@@ -9,7 +9,7 @@ timeout 600 python bench.py > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err
 timeout 600 python bench.py --impl reference --steps 40 --warmup 3 > $OUT/bench_ref_$TAG.json 2> $OUT/bench_ref_$TAG.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_$TAG.csv \
     python bench.py --steps 4 --warmup 3 --no-cpu --train-batch 0 > /dev/null 2>&1
-for k in gn_k1_kernel gn_k2a_tc_kernel gn_k2b_attn_kernel; do
+for k in gn_k1_kernel gn_k2a_tc3_kernel gn_k2b_attn_kernel; do
   timeout 300 ncu --set full --clock-control none --import-source on -k regex:$k -s 3 -c 1 -f -o $OUT/${k}_full_$TAG \
       python tools/time_volume.py 1 2 tc > /dev/null 2>&1
 done
