@@ -229,33 +229,38 @@ gn_k2a_tc3_kernel(const __grid_constant__ GnK2aParams p, int num_tiles, int G)
         t3_epilogue<1>(cx.lane_addr, 0, 4, sw + TS(DD_MEAN_B0), 0);        // D[0..63] -> ELU -> A[k 0..63]
         t3_epilogue<1>(cx.lane_addr, 64, 1, sw + TS(RD_B0), 64);           // ray_dir_fc hidden: D[64..79] -> ELU -> A[k 64..79]
         TC_GEMM_BEGIN(cx) t3_issue_full<L_DD2M>(cx, 0, 0, false); t3_issue_full<L_DD2V>(cx, 32, 32, false); TC_GEMM_END(cx)
-        // third layers of mean / var on CUDA cores
+        // ================= R3: aw first layer (rows 64..95 of the fused first-layer image), ray_dir_fc.2 (16 -> 35) ==========
+        // The second-layer outputs of mean / var are pulled into registers first; their third layers (CUDA cores) then run
+        // UNDER this round's MMAs instead of in front of them.
         float om0, om1, ov0, ov1;
         {
-            float h[32];
-            tm_ld<32>(cx.lane_addr + T3_D + 0, h);  bias_elu<32>(sw + TS(DD_MEAN_B2), h);
+            float hm[32], hvv[32];
+            tm_ld<32>(cx.lane_addr + T3_D + 0, hm);
+            tm_ld<32>(cx.lane_addr + T3_D + 32, hvv);
+            {
+                float ray[32];
+#pragma unroll
+                for (int c = 0; c < 32; c += 4) {
+                    const float4 t = ldg4(row + GN_REC_RAYF + c);   // L1-resident: read a moment ago
+                    ray[c] = t.x; ray[c + 1] = t.y; ray[c + 2] = t.z; ray[c + 3] = t.w;
+                }
+                t3_store_a<32>(cx.lane_addr, 0, ray);               // A[k 0..31] = ray_feats again (kept for R5)
+            }
+            TC_GEMM_BEGIN(cx) t3_issue<L_DD1, 64, 32, 0, 32>(cx, 0, 0, false); t3_issue_full<L_RD1>(cx, 32, 64, false); TC_GEMM_COMMIT(cx)
+            bias_elu<32>(sw + TS(DD_MEAN_B2), hm);
             om0 = sw[TS(DD_MEAN_B4)]; om1 = sw[TS(DD_MEAN_B4) + 1];
 #pragma unroll
-            for (int k = 0; k < 32; ++k) { const float2 w = *reinterpret_cast<const float2*>(sw + TS(DD_MEAN_W4) + k * 4); om0 = fmaf(h[k], w.x, om0); om1 = fmaf(h[k], w.y, om1); }
-            tm_ld<32>(cx.lane_addr + T3_D + 32, h); bias_elu<32>(sw + TS(DD_VAR_B2), h);
+            for (int k = 0; k < 32; ++k) { const float2 w = *reinterpret_cast<const float2*>(sw + TS(DD_MEAN_W4) + k * 4); om0 = fmaf(hm[k], w.x, om0); om1 = fmaf(hm[k], w.y, om1); }
+            bias_elu<32>(sw + TS(DD_VAR_B2), hvv);
             ov0 = sw[TS(DD_VAR_B4)]; ov1 = sw[TS(DD_VAR_B4) + 1];
 #pragma unroll
-            for (int k = 0; k < 32; ++k) { const float2 w = *reinterpret_cast<const float2*>(sw + TS(DD_VAR_W4) + k * 4); ov0 = fmaf(h[k], w.x, ov0); ov1 = fmaf(h[k], w.y, ov1); }
+            for (int k = 0; k < 32; ++k) { const float2 w = *reinterpret_cast<const float2*>(sw + TS(DD_VAR_W4) + k * 4); ov0 = fmaf(hvv[k], w.x, ov0); ov1 = fmaf(hvv[k], w.y, ov1); }
+            TC_GEMM_WAIT(cx)
         }
-        // ================= R3: aw first layer (rows 64..95 of the fused first-layer image), ray_dir_fc.2 (16 -> 35) ==========
-        {
-            float ray[32];
-#pragma unroll
-            for (int c = 0; c < 32; c += 4) {
-                const float4 t = ldg4(row + GN_REC_RAYF + c);   // L1-resident: read a moment ago
-                ray[c] = t.x; ray[c + 1] = t.y; ray[c + 2] = t.z; ray[c + 3] = t.w;
-            }
-            t3_store_a<32>(cx.lane_addr, 0, ray);               // A[k 0..31] = ray_feats again (kept for R5)
-        }
-        TC_GEMM_BEGIN(cx) t3_issue<L_DD1, 64, 32, 0, 32>(cx, 0, 0, false); t3_issue_full<L_RD1>(cx, 32, 64, false); TC_GEMM_END(cx)
         // ================= R4: aw second layer; f = [img_feats | rgb] + dir feature ==============================================
         t3_epilogue<1>(cx.lane_addr, 0, 2, sw + TS(DD_AW_B0), 32);          // D[0..31] -> ELU -> A[k 32..63]
-        float f[48];
+        TC_GEMM_BEGIN(cx) t3_issue_full<L_DD2A>(cx, 0, 32, false); TC_GEMM_COMMIT(cx)
+        float f[48];                                                        // D[32..79] (other columns than the running MMA's)
         tm_ld<48>(cx.lane_addr + T3_D + 32, f); bias_elu<36>(sw + TS(RD_B1), f);
 #pragma unroll
         for (int c = 0; c < 32; c += 4) {
@@ -265,7 +270,7 @@ gn_k2a_tc3_kernel(const __grid_constant__ GnK2aParams p, int num_tiles, int G)
         f[32] += tail.x; f[33] += tail.y; f[34] += tail.z;
 #pragma unroll
         for (int c = 35; c < 48; ++c) f[c] = 0.f;
-        TC_GEMM_BEGIN(cx) t3_issue_full<L_DD2A>(cx, 0, 32, false); TC_GEMM_END(cx)
+        TC_GEMM_WAIT(cx)
         // aw third layer, compute_prob (dist_decoder.py:109-142)
         float hit, vis;
         {
