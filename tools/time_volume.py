@@ -28,7 +28,7 @@ def main():
         ev[0].record()
         rec, pt = ops.k1_forward(scene, hw, resolution=40, bbox_min=bbox)
         ev[1].record()
-        if ops.K2A_IMPL == 'tc':
+        if ops.K2A_IMPL in ('tc', 'tc3'):
             _, _, _, tok = ops.k2a_forward(rec, pt, hw, scene.depth_range, want_pooled=False, want_tok=True, resolution=40, bbox_min=bbox)
             ev[2].record()
             vol, _ = ops.k2b_forward(None, hw, dn=40, resolution=40, bbox_min=bbox, tok=tok)
