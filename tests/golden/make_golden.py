@@ -227,3 +227,70 @@ def make_render_grad_golden():
 
 if __name__ == '__main__' and '--render-grads' in sys.argv:
     make_render_grad_golden()
+
+
+def loss_case(seed=5, rn=24, pn=64, rfn=3, h=20, w=28, G=16, R=8):
+    """Random (data_pr, data_gt) with the keys the four losses of nrvgn_sdf.yaml read; regenerated from the seed by the
+    test, so the fixture stores only the reference's loss values."""
+    rng = np.random.default_rng(seed)
+    f = lambda *s: torch.from_numpy(rng.random(s, dtype=np.float32))
+    quat = rng.standard_normal((G, 2, 4)).astype(np.float32); quat /= np.linalg.norm(quat, axis=-1, keepdims=True)
+    qp = rng.standard_normal((G, 4)).astype(np.float32); qp /= np.linalg.norm(qp, axis=-1, keepdims=True)
+    data_pr = {'pixel_colors_gt': f(1, rn, 3), 'pixel_colors_nr': f(1, rn, 3), 'pixel_colors_nr_fine': f(1, rn, 3),
+               'ray_mask': torch.from_numpy(rng.random((1, rn)) < 0.7),
+               'depth_coords': torch.from_numpy(np.stack([rng.integers(0, h, (rfn, pn)), rng.integers(0, w, (rfn, pn))], -1)),
+               'depth_mean': f(rfn, pn), 'depth_mean_fine': f(rfn, pn),
+               'volume': f(1, 1, R, R, R) * 2 - 1, 'sdf_gradient_error': f(1, 2), 's': f(1, 1),
+               'vgn_pred': (f(G) * 0.98 + 0.01, torch.from_numpy(qp), f(G) * 10)}
+    sdf_gt = f(R, R, R) * 2 - 1
+    sdf_gt[0, 0, :3] = -1.0                                   # masked voxels (loss.py:169)
+    data_gt = {'scene_name': 'vgn_syn/0', 'ref_imgs_info': {'true_depth': f(rfn, 1, h, w) * 0.6 + 0.2,
+               'depth_range': torch.tensor([[0.2, 0.8]] * rfn), 'sdf_gt': sdf_gt},
+               'grasp_info': [torch.from_numpy(rng.integers(0, R, (G, 3))), torch.from_numpy((rng.random(G) < 0.5).astype(np.float32)),
+                              torch.from_numpy(quat), f(G) * 10]}
+    return data_pr, data_gt
+
+
+def make_loss_golden():
+    """Values of the reference's own loss classes (network/loss.py: RenderLoss, DepthLoss, SDFLoss, VGNLoss with the shipped
+    yaml) on loss_case() -> tests/golden/losses.json.  pyquaternion / torchmetrics are stubbed (imported, unused here)."""
+    import json, types
+    class _Stub(types.ModuleType):                       # missing third-party modules: importable, every attribute is a stub
+        def __getattr__(self, k):
+            if k.startswith('__'):
+                raise AttributeError(k)
+            return _Stub(self.__name__ + '.' + k)
+
+        def __call__(self, *a, **k):
+            return self
+    import importlib.abc, importlib.machinery
+
+    class _Finder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
+        ROOTS = ('pyquaternion', 'torchmetrics', 'skimage', 'transforms3d', 'plyfile', 'h5py', 'open3d', 'inplace_abn', 'kornia', 'lpips')
+
+        def find_spec(self, name, path, target=None):
+            if name.split('.')[0] in self.ROOTS:
+                return importlib.machinery.ModuleSpec(name, self, is_package=True)
+            return None
+
+        def create_module(self, spec):
+            return _Stub(spec.name)
+
+        def exec_module(self, module):
+            module.__path__ = []
+    sys.meta_path.append(_Finder())
+    cfg, _ = __import__('ref_harness').load_reference()
+    from network.loss import name2loss
+    data_pr, data_gt = loss_case()
+    out = {}
+    for name in cfg['loss']:
+        res = name2loss[name](cfg)(data_pr, data_gt, 0, is_train=True)
+        for k, v in res.items():
+            out[k] = float(torch.as_tensor(v).reshape(-1)[0])
+    with open(os.path.join(HERE, 'losses.json'), 'w') as f:
+        json.dump(out, f, indent=1, sort_keys=True)
+    print('loss golden:', out)
+
+
+if __name__ == '__main__' and '--losses' in sys.argv:
+    make_loss_golden()

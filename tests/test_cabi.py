@@ -130,6 +130,7 @@ def test_launchers_reject_bad_arguments_before_touching_cuda(lib):
     assert lib.gn_k1_forward(ctypes.byref(p), None) == -4                       # ray mode without pts / que_dir
     a = _lib.GnK2aParams(); a.B, a.N, a.V = 1, 10, 40
     assert lib.gn_k2a_forward(ctypes.byref(a), None) == -1 and lib.gn_k2a_forward_tc(ctypes.byref(a), None) < 0
+    assert lib.gn_k2a_forward_tc3(ctypes.byref(a), None) < 0
     b = _lib.GnK2bBwdParams(); b.B, b.N, b.dn = 1, 64000, 0
     assert lib.gn_k2b_backward(ctypes.byref(b), None) == -1
     b.dn = 40
