@@ -91,3 +91,73 @@ def test_gradient_bucket_allreduce_two_ranks():
         for got, exp in zip(r[2][:4], mean):
             assert np.allclose(got, exp, rtol=1e-6, atol=1e-7)
         assert np.all(r[2][4] == 0)
+
+
+class _ToyNet:
+    """Stands in for the GraspNeRF mirror: a callable on a `data` dict with torch parameters (TrainStep only needs that)."""
+
+    def __init__(self):
+        import torch
+        torch.manual_seed(3)
+        self.mod = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 2))
+        self.frozen = torch.nn.Parameter(torch.ones(3), requires_grad=False)      # like deviation_network.variance before step 1
+
+    def parameters(self):
+        return list(self.mod.parameters()) + [self.frozen]
+
+    def __call__(self, data):
+        return {'y': self.mod(data['x'])}
+
+
+def _toy_loss(out, data):
+    return ((out['y'] - data['t']) ** 2).mean()
+
+
+def _toy_batch(n):
+    import torch
+    g = torch.Generator().manual_seed(11)
+    return [{'x': torch.randn(4, 6, generator=g), 't': torch.randn(4, 2, generator=g)} for _ in range(n)]
+
+
+def _trainstep_worker(rank, world, port, q):
+    import os
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from graspnerf_b200.train import TrainStep
+    from graspnerf_b200.shard import shard_scenes
+    net = _ToyNet()
+    step = TrainStep(net, lr=1e-2, dist=dist, loss_fn=_toy_loss)
+    batch = _toy_batch(4)
+    mine = [batch[i] for i in shard_scenes(4, rank, world)]
+    for _ in range(3):
+        step(mine)
+    q.put((rank, [p.detach().numpy().copy() for p in net.parameters()]))
+    dist.destroy_process_group()
+
+
+def test_trainstep_two_ranks_equals_one_rank_on_the_global_batch():
+    """Data-parallel equivalence: 2 ranks x 2 scenes with one gradient all-reduce per step == 1 process on the
+    4-scene batch, after three Adam steps; a parameter that does not require a gradient travels as zeros and stays put."""
+    import numpy as np
+    import torch.multiprocessing as mp
+    from graspnerf_b200.train import TrainStep
+    ref = _ToyNet()
+    step = TrainStep(ref, lr=1e-2, dist=None, loss_fn=_toy_loss)
+    batch = _toy_batch(4)
+    for _ in range(3):
+        step(batch)
+    want = [p.detach().numpy() for p in ref.parameters()]
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29800 + (os.getpid() % 150)
+    procs = [ctx.Process(target=_trainstep_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=180) for _ in range(2)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+    for r in res:
+        for got, exp in zip(r[1], want):
+            assert np.allclose(got, exp, rtol=1e-5, atol=1e-6)
+    assert np.array_equal(res[0][1][-1], np.ones(3, np.float32))
