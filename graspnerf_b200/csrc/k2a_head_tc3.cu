@@ -13,7 +13,9 @@
 //       R3  [aw first layer | ray_dir_fc.2]  (ray_feats re-stored) R4  [aw second layer]
 //       R5  [prob_embed.0]                                        R6  [neuray_fc.0 o prob_embed.2 | base_fc.0 per-view part]
 //       R7a [base_fc.0 on mean0|mean1]  R7b [base_fc.0 on var0|var1|tails]   R8 [base_fc.2]
-//       R9  [vis_fc.0]  R10 [vis_fc.2]  R11 [vis_fc2.0]           R13a/b [geometry_fc.0 on mean|var, then on embed]  R14 [geometry_fc.2]
+//       R9  [vis_fc.0]  R10 [vis_fc.2]  R11 [vis_fc2.0]
+//   * geometry_fc (per POINT, not per view) runs in a second phase of the same launch (t3_geometry_phase): the CTA re-reads
+//     the pooled rows of its own points and runs [geometry_fc.0 on mean|var, then on embed], [geometry_fc.2], one row per point;
 //   * tiles are handed out inside the CTA from a shared-memory counter (each CTA owns a contiguous range of tiles), so
 //     the three slots stay busy although a slot only sees ~7 tiles of a 40^3 volume.
 #include "k2a_tc_common.cuh"
@@ -121,6 +123,95 @@ __device__ __forceinline__ void t3_issue(const TcCtx& cx, int d_col, int a_k0, b
 template <int LAYER>
 __device__ __forceinline__ void t3_issue_full(const TcCtx& cx, int d_col, int a_k0, bool accumulate) {
     t3_issue<LAYER, 0, tc_layer(LAYER).N, 0, tc_layer(LAYER).K>(cx, d_col, a_k0, accumulate);
+}
+
+// Phase 2 of the launch: geometry_fc (ibrnet.py:487-489) once per POINT.  In the tile loop every point occupies V rows, so
+// running geometry_fc there repeats it V times (15 % of the kernel's instructions at V = 6).  The pooled features of this
+// CTA's points were written to `pooled` by the tile loop (L2 resident: ~120 KB per CTA); here a row is one point, 128 points
+// per tile.  NOT inlined: its register allocation must not disturb the tile loop's (which sits right at the 168-register
+// limit of 12 warps per SM).
+__device__ __noinline__ void t3_geometry_phase(const GnK2aParams& p, uint32_t tmem_slot, uint32_t img_base16, uint32_t bar, uint32_t parity,
+                                               const float* __restrict__ sw, int* s_ctr, int* s_tile, int slot, int warp, int lane,
+                                               long long pt_lo, long long pt_hi)
+{
+    TcCtx cx;                                           // rebuilt from scalars: a reference would pin the caller's copy in local memory
+    cx.tmem_slot = tmem_slot;
+    cx.lane_addr = tmem_slot + ((uint32_t)((warp & 3) * 32) << 16);
+    cx.img_base16 = img_base16;
+    cx.bar = bar;
+    cx.parity = parity;
+    cx.bar_id = 1 + slot;
+    cx.issuer = (warp & 3) == 0;
+    cx.elected = cx.issuer ? elect_one() : 0u;
+    const int n2 = (int)((pt_hi - pt_lo + 127) / 128);
+    for (;;) {
+        if ((warp & 3) == 0 && lane == 0) s_tile[slot] = atomicAdd(s_ctr, 1);
+        asm volatile("bar.sync %0, 128;" :: "r"(cx.bar_id) : "memory");
+        const int t2 = s_tile[slot];
+        asm volatile("bar.sync %0, 128;" :: "r"(cx.bar_id) : "memory");
+        if (t2 >= n2) break;
+        long long pidx = pt_lo + (long long)t2 * 128 + (warp & 3) * 32 + lane;
+        const bool valid2 = pidx < pt_hi;
+        pidx = valid2 ? pidx : pt_hi - 1;
+        const int b = (int)(pidx / p.N);
+        const int n = (int)(pidx - (long long)b * p.N);
+        const float* pr = p.pooled + (size_t)pidx * GN_POOL_STRIDE;
+        {
+            float mu[32];
+#pragma unroll
+            for (int c = 0; c < 32; c += 4) {
+                const float4 a4 = __ldcg(reinterpret_cast<const float4*>(pr + c));
+                mu[c] = a4.x; mu[c + 1] = a4.y; mu[c + 2] = a4.z; mu[c + 3] = a4.w;
+            }
+            t3_store_a<32>(cx.lane_addr, 0, mu);
+#pragma unroll
+            for (int c = 0; c < 32; c += 4) {
+                const float4 b4 = __ldcg(reinterpret_cast<const float4*>(pr + 32 + c));
+                mu[c] = b4.x; mu[c + 1] = b4.y; mu[c + 2] = b4.z; mu[c + 3] = b4.w;
+            }
+            t3_store_a<32>(cx.lane_addr, 32, mu);
+        }
+        const float4 wn = __ldcg(reinterpret_cast<const float4*>(pr + 64));       // wmean, nvalid
+        TC_GEMM_BEGIN(cx) t3_issue<L_GF0, 0, 64, 0, 64>(cx, 0, 0, false); TC_GEMM_COMMIT(cx)
+        float e[32];
+        {
+            float px, py, pz;
+            if (p.volume_mode) {   // same arithmetic as K1 (field_utils.py:17-27 + bbox3d[0]); n = (i*R+j)*R + (R-1-k)
+                const int R = p.R;
+                const int r = n / R, dsm = n - r * R;
+                const int i = r / R, j = r - i * R, k = R - 1 - dsm;
+                px = __fadd_rn(__ldg(p.axis + i), __ldg(p.bbox_min + b * 3 + 0));
+                py = __fadd_rn(__ldg(p.axis + j), __ldg(p.bbox_min + b * 3 + 1));
+                pz = __fadd_rn(__ldg(p.axis + k), __ldg(p.bbox_min + b * 3 + 2));
+            } else {
+                const float* q = p.pts + (size_t)pidx * 3;
+                px = __ldg(q); py = __ldg(q + 1); pz = __ldg(q + 2);
+            }
+            const float pv[3] = { px, py, pz };
+            e[0] = wn.x; e[1] = px; e[2] = py; e[3] = pz;                  // k 64 | embed (neus.py:21-66): p, sin/cos(p*{1,2,4})
+#pragma unroll
+            for (int q = 0; q < 3; ++q)
+#pragma unroll
+                for (int a = 0; a < 3; ++a) __sincosf(pv[a] * (float)(1 << q), &e[4 + 6 * q + a], &e[4 + 6 * q + 3 + a]);   // |arg| < 4: abs err ~1e-6
+#pragma unroll
+            for (int c = 22; c < 32; ++c) e[c] = 0.f;
+        }
+        TC_GEMM_WAIT(cx)
+        t3_store_a<32>(cx.lane_addr, 0, e);
+        TC_GEMM_BEGIN(cx) t3_issue<L_GF0, 0, 64, 64, 32>(cx, 0, 0, true); TC_GEMM_END(cx)
+        t3_epilogue<1>(cx.lane_addr, 0, 4, sw + TS(GF_B0), 0);
+        TC_GEMM_BEGIN(cx) t3_issue_full<L_GF2>(cx, 0, 0, false); TC_GEMM_END(cx)
+        {
+            float tk[16];
+            tm_ld<16>(cx.lane_addr + T3_D, tk); bias_elu<16>(sw + TS(GF_B2), tk);
+            if (valid2) {
+                float* out = p.tok + (size_t)pidx * GN_TOK_STRIDE;
+                st4(out, make_float4(tk[0], tk[1], tk[2], tk[3]));       st4(out + 4, make_float4(tk[4], tk[5], tk[6], tk[7]));
+                st4(out + 8, make_float4(tk[8], tk[9], tk[10], tk[11])); st4(out + 12, make_float4(tk[12], tk[13], tk[14], tk[15]));
+                st4(out + 16, make_float4(wn.y, 0.f, 0.f, 0.f));
+            }
+        }
+    }
 }
 
 __global__ void __launch_bounds__(T3_THREADS, 1)
@@ -428,50 +519,6 @@ gn_k2a_tc3_kernel(const __grid_constant__ GnK2aParams p, int num_tiles, int G)
             st4(dr, make_float4(hit, vis, w0, vis2));
             st4(dr + 4, make_float4(x[0], x[1], 0.f, 0.f));      // prob_embed is fused away in this kernel (not materialised)
         }
-        // ================= geometry_fc on the pooled rows (ibrnet.py:487-489) -> per-point token =================
-        if (p.tok) {            // uniform branch
-            t3_store_a<32>(cx.lane_addr, 0, mu);
-            t3_store_a<32>(cx.lane_addr, 32, vr);
-            TC_GEMM_BEGIN(cx) t3_issue<L_GF0, 0, 64, 0, 64>(cx, 0, 0, false); TC_GEMM_COMMIT(cx)
-            float e[32];
-            {
-                float px, py, pz;
-                if (p.volume_mode) {   // same arithmetic as K1 (field_utils.py:17-27 + bbox3d[0]); n = (i*R+j)*R + (R-1-k)
-                    const int R = p.R;
-                    const int r = n / R, dsm = n - r * R;
-                    const int i = r / R, j = r - i * R, k = R - 1 - dsm;
-                    px = __fadd_rn(__ldg(p.axis + i), __ldg(p.bbox_min + b * 3 + 0));
-                    py = __fadd_rn(__ldg(p.axis + j), __ldg(p.bbox_min + b * 3 + 1));
-                    pz = __fadd_rn(__ldg(p.axis + k), __ldg(p.bbox_min + b * 3 + 2));
-                } else {
-                    const float* q = p.pts + (size_t)pidx * 3;
-                    px = __ldg(q); py = __ldg(q + 1); pz = __ldg(q + 2);
-                }
-                const float pv[3] = { px, py, pz };
-                e[0] = wmean; e[1] = px; e[2] = py; e[3] = pz;                 // k 64 | embed (neus.py:21-66): p, sin/cos(p*{1,2,4})
-#pragma unroll
-                for (int q = 0; q < 3; ++q)
-#pragma unroll
-                    for (int a = 0; a < 3; ++a) __sincosf(pv[a] * (float)(1 << q), &e[4 + 6 * q + a], &e[4 + 6 * q + 3 + a]);   // |arg| < 4: abs err ~1e-6
-#pragma unroll
-                for (int c = 22; c < 32; ++c) e[c] = 0.f;
-            }
-            TC_GEMM_WAIT(cx)
-            t3_store_a<32>(cx.lane_addr, 0, e);
-            TC_GEMM_BEGIN(cx) t3_issue<L_GF0, 0, 64, 64, 32>(cx, 0, 0, true); TC_GEMM_END(cx)
-            t3_epilogue<1>(cx.lane_addr, 0, 4, sw + TS(GF_B0), 0);
-            TC_GEMM_BEGIN(cx) t3_issue_full<L_GF2>(cx, 0, 0, false); TC_GEMM_END(cx)
-            {
-                float t[16];
-                tm_ld<16>(cx.lane_addr + T3_D, t); bias_elu<16>(sw + TS(GF_B2), t);
-                if (writer) {
-                    float* out = p.tok + (size_t)pidx * GN_TOK_STRIDE;
-                    st4(out, make_float4(t[0], t[1], t[2], t[3]));       st4(out + 4, make_float4(t[4], t[5], t[6], t[7]));
-                    st4(out + 8, make_float4(t[8], t[9], t[10], t[11])); st4(out + 12, make_float4(t[12], t[13], t[14], t[15]));
-                    st4(out + 16, make_float4(nvalid, 0.f, 0.f, 0.f));
-                }
-            }
-        }
         // ================= rgb_fc + masked softmax over views (ibrnet.py:507-511), CUDA cores ================
         if (p.with_rgb && p.colors) {
             float r16[16], r8[8];
@@ -514,6 +561,15 @@ gn_k2a_tc3_kernel(const __grid_constant__ GnK2aParams p, int num_tiles, int G)
             if (writer) st4(p.colors + (size_t)pidx * 4, make_float4(c0, c1, c2, 0.f));
         }
     }
+    if (p.tok) {            // uniform branch: phase 2, geometry_fc per point
+        __syncthreads();                                                // every slot is done: all pooled rows of the CTA are written
+        if (tid == 0) *s_ctr = 0;
+        __syncthreads();
+        const long long pt_lo = (long long)tile_lo * 4 * G;
+        const long long pt_end = (long long)tile_hi * 4 * G;
+        t3_geometry_phase(p, cx.tmem_slot, cx.img_base16, cx.bar, cx.parity, sw, s_ctr, s_tile, slot, warp, lane, pt_lo,
+                          pt_end < total_pts ? pt_end : total_pts);
+    }
     // ---- teardown
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -529,6 +585,7 @@ extern "C" int gn_k2a_forward_tc3(const GnK2aParams* hp, void* stream)
     if (p.tok) {
         if (p.volume_mode && (p.R < 1 || p.N != p.R * p.R * p.R || !p.axis || !p.bbox_min)) return -3;
         if (!p.volume_mode && !p.pts) return -4;
+        if (!p.pooled) return -9;                     // phase 2 (geometry_fc per point) reads the pooled rows back
     }
     const int G = 32 / p.V;
     const long long total = (long long)p.B * p.N;

@@ -189,7 +189,8 @@ def k2a_forward(rec, pt, hw, depth_range, *, que_dists=None, dn=1, want_colors=F
     impl = impl or K2A_IMPL
     B, N, V, _ = rec.shape
     dev = rec.device
-    pooled = torch.empty((B, N, POOL_STRIDE), device=dev, dtype=torch.float32) if want_pooled else None
+    # the three-tile kernel runs geometry_fc in a second phase that re-reads the pooled rows: it always needs the buffer
+    pooled = torch.empty((B, N, POOL_STRIDE), device=dev, dtype=torch.float32) if (want_pooled or (impl == 'tc3' and want_tok)) else None
     colors = torch.empty((B, N, 4), device=dev, dtype=torch.float32) if want_colors else None
     dbg = torch.zeros((B, N, V, 8), device=dev, dtype=torch.float32) if debug else None
     tok = None
