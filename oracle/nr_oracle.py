@@ -10,7 +10,7 @@ Rules:
     legs may import this module; the product path never does;
   * pinned against the UNMODIFIED reference executed in the authoring container:
     tests/golden/make_golden.py generates tests/golden/*.npz from the real reference
-    and tests/test_oracle_vs_golden.py checks this file against them.  The reference
+    and tests/test_oracle_golden.py checks this file against them (forward values, first-order gradients of the volume path, training-mode gradients of the RGB head).  The reference
     ships no tests/golden vectors of its own, so "outputs of the
     reference itself run here" is the pin.
 
