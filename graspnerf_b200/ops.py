@@ -60,8 +60,9 @@ class HeadWeights:
         key = (self.agg_prefix, self.dd_prefix, str(self.device))
         if key not in _PACKERS:
             _PACKERS[key] = DevicePacker(sd, self.agg_prefix, self.dd_prefix, self.device)
+        self.packer = _PACKERS[key]
         with torch.no_grad():
-            self.blob = _PACKERS[key].pack({k: sd[k].to(self.device) for k in _PACKERS[key].keys})
+            self.blob = self.packer.pack({k: sd[k].to(self.device) for k in self.packer.keys})
         # tensor-core operand images (fp16 hi/lo, K-major) + small constants, built on the device from the fp32 blob
         lib = _lib.load()
         self.tc_const = torch.empty(lib.gn_k2a_tc_const_bytes(), dtype=torch.uint8, device=self.device)
@@ -496,7 +497,6 @@ class _SampleVolumeFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, img_feats, ray_feats, static, keys, *params):
-        from .weights import unpack_blob_grad  # noqa: F401  (import check before any launch)
         imgs, poses, Ks, depth_range, bbox_min, R, vs, agg_prefix, dd_prefix = static
         sd = {k: p.detach() for k, p in zip(keys, params)}
         hw = HeadWeights(sd, agg_prefix, dd_prefix, img_feats.device)
@@ -510,7 +510,6 @@ class _SampleVolumeFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, d_vol):
-        from .weights import unpack_blob_grad
         bbox_min, R, vs, agg_prefix, dd_prefix, keys, single, shapes = ctx.meta
         rec, pt, pooled = ctx.saved
         d_img, d_ray, d_w = sample_volume_backward(ctx.scene, ctx.hw, bbox_min, rec, pt, pooled, d_vol.contiguous(), R, vs)
@@ -518,7 +517,7 @@ class _SampleVolumeFn(torch.autograd.Function):
         d_ray = d_ray.permute(0, 1, 4, 2, 3)
         if single:
             d_img, d_ray = d_img[0], d_ray[0]
-        g = unpack_blob_grad(d_w, agg_prefix, dd_prefix)
+        g = ctx.hw.packer.unpack_grad(d_w)
         pg = tuple(g[k].reshape(s) if (k in g and '.rgb_fc.' not in k) else None for k, s in zip(keys, shapes))   # rgb_fc is not on the volume path
         ctx.scene = ctx.hw = ctx.saved = None
         return (d_img, d_ray, None, None) + pg
@@ -557,7 +556,6 @@ class _RayFeaturesFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, d_pooled, d_colors, _d_nvalid):
-        from .weights import unpack_blob_grad
         dn, agg_prefix, dd_prefix, keys, single, shapes = ctx.meta
         rec, pt, pts, inv_dists = ctx.saved
         scene, hw = ctx.scene, ctx.hw
@@ -568,7 +566,7 @@ class _RayFeaturesFn(torch.autograd.Function):
         d_img, d_ray = d_img.permute(0, 1, 4, 2, 3), d_ray.permute(0, 1, 4, 2, 3)
         if single:
             d_img, d_ray = d_img[0], d_ray[0]
-        g = unpack_blob_grad(d_w.float(), agg_prefix, dd_prefix)
+        g = hw.packer.unpack_grad(d_w)
         skip = ('.geometry_fc.', '.ray_attention.', '.out_geometry_fc.')          # per-ray head: gradients come from the torch ops
         pg = tuple(g[k].reshape(s) if (k in g and not any(t in k for t in skip)) else None for k, s in zip(keys, shapes))
         ctx.scene = ctx.hw = ctx.saved = None

@@ -116,6 +116,14 @@ class DevicePacker:
         assert float(lab.max()) < n and np.all(lab == np.round(lab))
         self.index = torch.from_numpy(lab.astype(np.int64)).to(self.device)
         self.A = agg_prefix + 'agg_impl.'
+        # adjoint of the gather (every parameter element sits at exactly one raw blob position): grad_flat = dblob[inverse]
+        inv = np.full(n - 1, -1, np.int64)
+        pos = np.nonzero(lab > 0)[0]
+        inv[lab[pos].astype(np.int64) - 1] = pos
+        assert (inv >= 0).all(), 'a parameter element is missing from the blob'
+        self.inverse = torch.from_numpy(inv).to(self.device)
+        self.shapes = [tuple(sd[k].shape) for k in self.keys]
+        self.sizes = [int(np.prod(s)) if len(s) else 1 for s in self.shapes]
 
     def pack(self, sd):
         """sd: {key: device tensor}; returns the fp32 blob on the device (no synchronisation)."""
@@ -131,6 +139,12 @@ class DevicePacker:
             assert cols == cp
             blob[off:off + rows * cp] = vals[name].reshape(-1).to(torch.float32)
         return blob
+
+    def unpack_grad(self, dblob):
+        """Adjoint of `pack` over the raw entries (= `unpack_blob_grad`, as ONE gather): blob-layout gradient -> {key: grad}.
+        The fused composites are never written by the reverse kernels (their gradient arrives through the raw entries)."""
+        flat = dblob.to(torch.float32)[self.inverse]
+        return {k: g.reshape(s) for k, g, s in zip(self.keys, flat.split(self.sizes), self.shapes)}
 
 
 def unpack_blob_grad(dblob, agg_prefix='agg_net.', dd_prefix='dist_decoder.'):

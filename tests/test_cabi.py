@@ -116,6 +116,11 @@ def test_device_packer_equals_host_packer(lib):
                 fused[off:off + rows * cp] = True
         assert np.array_equal(got[~fused], ref[~fused])
         assert np.allclose(got[fused], ref[fused], rtol=2e-7, atol=1e-9) and np.abs(ref[fused]).sum() > 0
+        # the one-gather adjoint equals weights.unpack_blob_grad (the transposed packing) entry by entry
+        from graspnerf_b200.weights import unpack_blob_grad
+        g = torch.from_numpy(np.random.default_rng(1).standard_normal(ref.shape).astype(np.float32))
+        a, b = DevicePacker(sd, agg, dd, 'cpu').unpack_grad(g), unpack_blob_grad(g, agg, dd)
+        assert set(a) == set(b) and all(torch.equal(a[k], b[k]) for k in a)
 
 
 def test_launchers_reject_bad_arguments_before_touching_cuda(lib):
