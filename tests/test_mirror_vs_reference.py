@@ -1,0 +1,54 @@
+"""The torch-side modules of the mirror (2-D encoders, depth-mean head, VGN 3-D conv: SURVEY.md section 8f, kept in
+PyTorch/cuDNN by design) against the UNMODIFIED reference, live, on CPU.  Runs only where /root/reference exists (the authoring
+container, where the driver runs the CPU suite); skipped on the GPU box.  The hot path itself is covered by the fixtures."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, 'golden'))
+from ref_harness import reference_available, build_reference_net      # noqa: E402
+from graspnerf_b200.synth import make_scene                            # noqa: E402
+from tests.test_boundary import CFG                                    # noqa: E402
+
+pytestmark = pytest.mark.skipif(not reference_available(), reason='needs the reference checkout (/root/reference)')
+
+
+def test_torch_side_modules_match_the_live_reference():
+    from graspnerf_b200.network import name2network
+    orig_cuda, orig_to = torch.Tensor.cuda, torch.Tensor.to   # the harness shims these two for the reference's hard-coded .cuda()
+    try:
+        _, ref_net = build_reference_net(0)                   # torch.manual_seed(0) inside
+    finally:
+        torch.Tensor.cuda, torch.Tensor.to = orig_cuda, orig_to
+    torch.manual_seed(0)
+    net = name2network[CFG['network']](dict(CFG)).eval()
+    sd_ref = ref_net.state_dict()
+    assert all(torch.equal(v, sd_ref[k]) for k, v in net.state_dict().items())       # same init -> same weights (also test_boundary)
+    scene = make_scene(seed=3, num_views=4, h=96, w=160, radius=0.45)
+    imgs = torch.from_numpy(scene['imgs'])
+    ref = {'imgs': imgs}
+    with torch.no_grad():
+        # image_encoder / init_net / vis_encoder (renderer.py:275-279)
+        a_img, b_img = net.nr_net.image_encoder(imgs), ref_net.nr_net.image_encoder(imgs)
+        a_ray = net.nr_net.vis_encoder(net.nr_net.init_net(ref, ref, False), a_img)
+        b_ray = ref_net.nr_net.vis_encoder(ref_net.nr_net.init_net(ref, ref, False), b_img)
+        assert a_img.shape == (4, 32, 24, 40) and torch.allclose(a_img, b_img, rtol=1e-5, atol=1e-6)
+        assert torch.allclose(a_ray, b_ray, rtol=1e-5, atol=1e-6)
+        # depth-mean head (renderer.py:222-266): same pixels under the same RNG state, same decoders
+        info = {'imgs': imgs, 'ray_feats': b_ray}
+        torch.manual_seed(7)
+        da = net.nr_net.predict_mean_for_depth_loss(info)
+        torch.manual_seed(7)
+        db = ref_net.nr_net.predict_mean_for_depth_loss(info)
+        assert set(da) == set(db)
+        assert torch.equal(da['depth_coords'], db['depth_coords'])
+        for k in ('depth_mean', 'depth_mean_2', 'depth_mean_fine', 'depth_mean_fine_2'):
+            assert torch.allclose(da[k], db[k], rtol=1e-5, atol=1e-6), k
+        # VGN head on a volume (gd/networks.py:39-97, renderer.py:323-330)
+        vol = torch.from_numpy(np.random.default_rng(0).uniform(-1, 1, (1, 1, 40, 40, 40)).astype(np.float32))
+        for x, y in zip(net.vgn_net(vol), ref_net.vgn_net(vol)):
+            assert torch.allclose(x, y, rtol=1e-5, atol=1e-6)
