@@ -22,23 +22,31 @@ def reference_available():
 _loaded = {}
 
 
-def load_reference():
-    """Returns (cfg dict, name2network) with the shims installed."""
-    if 'mods' in _loaded:
-        return _loaded['mods']
+def install_shims():
+    """(Re-)installs the three shims; idempotent (a caller may have restored torch.Tensor.cuda / .to in between)."""
     import torch
-    import yaml
     if 'easydict' not in sys.modules:
         m = types.ModuleType('easydict')
         m.EasyDict = dict
         sys.modules['easydict'] = m
-    torch.Tensor.cuda = lambda self, *a, **k: self
-    _to = torch.Tensor.to
+    if '_to' not in _loaded:
+        _loaded['_to'] = torch.Tensor.to
+    _to = _loaded['_to']
 
     def _to_cpu(self, *a, **k):
         a = ['cpu' if isinstance(x, str) and x.startswith('cuda') else x for x in a]
         return _to(self, *a, **k)
+    torch.Tensor.cuda = lambda self, *a, **k: self
     torch.Tensor.to = _to_cpu
+
+
+def load_reference():
+    """Returns (cfg dict, name2network) with the shims installed."""
+    install_shims()
+    if 'mods' in _loaded:
+        return _loaded['mods']
+    import torch
+    import yaml
     for p in (os.path.join(REF_ROOT, 'src'), os.path.join(REF_ROOT, 'src', 'nr')):
         if p not in sys.path:
             sys.path.insert(0, p)

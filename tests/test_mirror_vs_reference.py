@@ -52,3 +52,24 @@ def test_torch_side_modules_match_the_live_reference():
         vol = torch.from_numpy(np.random.default_rng(0).uniform(-1, 1, (1, 1, 40, 40, 40)).astype(np.float32))
         for x, y in zip(net.vgn_net(vol), ref_net.vgn_net(vol)):
             assert torch.allclose(x, y, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize('kw', [dict(seed=41, num_views=5, h=80, w=112, radius=0.4), dict(seed=42, num_views=2, h=64, w=64, radius=0.25, theta=1.0)])
+def test_oracle_sample_volume_matches_the_live_reference_on_fresh_scenes(kw):
+    """Beyond the committed fixtures: the oracle against the reference's sample_volume on scenes that are in no fixture
+    (other view counts / image sizes / camera rings, incl. a 2-view close-up with many invalid projections)."""
+    from oracle import nr_oracle as O
+    from tests.helpers import assert_close
+    orig_cuda, orig_to = torch.Tensor.cuda, torch.Tensor.to
+    try:
+        _, ref_net = build_reference_net(0)
+        scene = make_scene(**kw)
+        sc = {k: (torch.from_numpy(v) if isinstance(v, np.ndarray) else v) for k, v in scene.items()}
+        with torch.no_grad():
+            want = ref_net.nr_net.sample_volume(dict(sc))
+    finally:
+        torch.Tensor.cuda, torch.Tensor.to = orig_cuda, orig_to
+    sd = {k: v for k, v in ref_net.nr_net.state_dict().items()}
+    got = O.sample_volume(sd, sc)
+    rel = assert_close(got, want, what=f'volume {kw}')
+    assert rel < 1e-5
