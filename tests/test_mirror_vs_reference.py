@@ -73,3 +73,34 @@ def test_oracle_sample_volume_matches_the_live_reference_on_fresh_scenes(kw):
     got = O.sample_volume(sd, sc)
     rel = assert_close(got, want, what=f'volume {kw}')
     assert rel < 1e-5
+
+
+def test_oracle_render_rays_matches_the_live_reference_on_a_fresh_scene():
+    """RGB head (coarse + fine, eval) on a scene / query that is in no fixture.  The fine pass gets the reference's own fine
+    sample depths (the inverse-CDF sampler is ill-conditioned where the coarse hit probability vanishes, see make_golden.py)."""
+    from oracle import nr_oracle as O
+    from graspnerf_b200.synth import make_query
+    from tests.helpers import assert_close
+    kw = dict(seed=43, num_views=3, h=64, w=96, radius=0.5)
+    scene = make_scene(**kw)
+    sc = {k: (torch.from_numpy(v) if isinstance(v, np.ndarray) else v) for k, v in scene.items()}
+    q = make_query(scene, 20, 5)
+    que_ref = {k: torch.from_numpy(v) for k, v in q.items()}
+    orig_cuda, orig_to = torch.Tensor.cuda, torch.Tensor.to
+    try:
+        _, ref_net = build_reference_net(0)
+        nr = ref_net.nr_net
+        res = nr.render_impl(que_ref, dict(sc), False)
+        from network.render_ops import sample_depth, sample_fine_depth
+        with torch.no_grad():
+            depth, _ = sample_depth(que_ref['depth_range'], que_ref['coords'], nr.cfg['depth_sample_num'], False)
+            fd = sample_fine_depth(depth, res['hit_prob_nr'].detach(), que_ref['depth_range'], nr.cfg['fine_depth_sample_num'], False)
+    finally:
+        torch.Tensor.cuda, torch.Tensor.to = orig_cuda, orig_to
+    sd = dict(nr.state_dict())
+    que = {'coords': que_ref['coords'][0], 'pose': que_ref['poses'][0], 'K': que_ref['Ks'][0], 'depth_range': que_ref['depth_range'][0]}
+    out = O.render_rays(sd, sc, que, 40, 40, fine_depth=torch.sort(fd, -1)[0][0])
+    for k in ('sdf_values', 'alpha_values', 'hit_prob_nr', 'colors_nr', 'pixel_colors_nr', 'render_depth'):
+        for sfx in ('', '_fine'):
+            assert_close(out[k + sfx].detach(), res[k + sfx][0].detach(), what=k + sfx)
+    assert torch.equal(out['ray_mask'], res['ray_mask'][0]) and torch.equal(out['ray_mask_fine'], res['ray_mask_fine'][0])
