@@ -63,3 +63,24 @@ def test_render_coarse_and_fine(name, impl):
             assert_close(fine[k].cpu(), g[k + '_fine'], what=f'{k}_fine vs reference golden')
     finally:
         ops.K2A_IMPL = 'tc3'
+
+
+@pytest.mark.parametrize('impl', ['simt', 'tc', 'tc3'])
+def test_ragged_ray_batch(impl):
+    """37 rays x 11 samples = 407 points: not a multiple of any tile size on the path (K1 32 / 16 points, K2a 16-20 points per
+    128-row tile, K2b 11 rays per CTA), sample count != 40 (positional table, attention length) - against the oracle."""
+    from oracle import nr_oracle as O
+    ops, sd, sc, scene, que, oq, hw_c, hw_f, dev = _setup('rays48_small')
+    ops.K2A_IMPL = impl
+    try:
+        rn, dn = 37, 11
+        que = {k: (v[:, :rn].contiguous() if k == 'coords' else v) for k, v in que.items()}
+        oq = dict(oq, coords=oq['coords'][:rn])
+        depth = ops.k3_coarse_depths(que['depth_range'], rn, dn)
+        out = ops.render_by_depth(scene, hw_c, que, depth)
+        oc = O.render_by_depth(sd, sc, oq, depth[0].cpu(), False)
+        for k in ('sdf_values', 'alpha_values', 'hit_prob_nr', 'colors_nr', 'pixel_colors_nr', 'render_depth'):
+            assert_close(out[k][0].cpu(), oc[k], what=f'{k} vs oracle (ragged)')
+        assert torch.equal(out['ray_mask'][0].cpu(), oc['ray_mask'])
+    finally:
+        ops.K2A_IMPL = 'tc3'
