@@ -147,3 +147,26 @@ def test_launchers_reject_bad_arguments_before_touching_cuda(lib):
     assert lib.gn_sizeof_k2b_bwd_params() == ctypes.sizeof(_lib.GnK2bBwdParams)
     assert lib.gn_sizeof_k2a_bwd_params() == ctypes.sizeof(_lib.GnK2aBwdParams)
     assert lib.gn_sizeof_k1_bwd_params() == ctypes.sizeof(_lib.GnK1BwdParams)
+
+
+def test_sass_contains_the_blackwell_instructions_the_design_claims():
+    """Static check on the built objects (cuobjdump, no GPU needed): the tensor-core K2a kernels really issue tcgen05 MMAs from
+    tensor memory (UTCHMMA, LDTM / STTM), commit on mbarriers (UTCBAR) and fetch their weights with bulk async copies (UBLKCP);
+    the K1 walking kernel's staged store is a bulk async copy shared -> global (UBLKCP.G.S)."""
+    import shutil
+    import subprocess
+    from graspnerf_b200.build import LIBDIR
+    cuobjdump = shutil.which('cuobjdump') or '/usr/local/cuda/bin/cuobjdump'
+    if not os.path.exists(cuobjdump):
+        pytest.skip('cuobjdump not available')
+
+    def sass(obj):
+        path = os.path.join(LIBDIR, obj)
+        if not os.path.exists(path):
+            pytest.skip(f'{obj} not built in-tree')
+        return subprocess.run([cuobjdump, '-sass', path], capture_output=True, text=True).stdout
+    for obj in ('k2a_head_tc3.o', 'k2a_head_tc.o'):
+        s = sass(obj)
+        assert s.count('UTCHMMA') >= 100 and 'LDTM' in s and 'STTM' in s and 'UTCBAR' in s and 'UBLKCP.S.G' in s, obj
+        assert 'sm_100a' in s
+    assert 'UBLKCP.G.S' in sass('k1_project_sample.o')
