@@ -14,7 +14,7 @@ class GnK1Params(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ('imgs', 'img_feats', 'ray_feats', 'KRt', 'cam', 'axis', 'bbox_min', 'pts',
                                           'que_dir', 'rec', 'pt', 'dbg_feat_idx')] + \
                [(n, C.c_int) for n in ('B', 'V', 'H', 'W', 'fh', 'fw', 'R', 'N', 'dn', 'volume_mode',
-                                       'tiles_per_scene', 'feat_stride')]
+                                       'tiles_per_scene', 'feat_stride', 'img_u8')]
 
 
 class GnK2aParams(C.Structure):
@@ -58,13 +58,14 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIBPATH):
+    libpath = LIBPATH[:-3] + os.environ.get('GN_LIB_TAG', '') + '.so'      # GN_LIB_TAG: development A/B builds (build.py)
+    if not os.path.exists(libpath):
         raise RuntimeError(
-            f'{LIBPATH} not found: build it with `python -m graspnerf_b200.build` (or __graft_entry__.build()). '
+            f'{libpath} not found: build it with `python -m graspnerf_b200.build` (or __graft_entry__.build()). '
             'graspnerf_b200 has no CPU / PyTorch fallback for its CUDA kernels.')
-    lib = C.CDLL(LIBPATH)
+    lib = C.CDLL(libpath)
     lib.gn_version.restype = C.c_char_p
-    for name, st in (('gn_k1_forward', GnK1Params), ('gn_k2a_forward', GnK2aParams), ('gn_k2a_forward_tc', GnK2aParams), ('gn_k2a_forward_tc3', GnK2aParams), ('gn_k2b_forward', GnK2bParams),
+    for name, st in (('gn_k1_forward', GnK1Params), ('gn_k2a_forward', GnK2aParams), ('gn_k2a_forward_tc', GnK2aParams), ('gn_k2b_forward', GnK2bParams),
                      ('gn_k3_composite', GnK3Params), ('gn_k2b_backward', GnK2bBwdParams), ('gn_k2a_backward', GnK2aBwdParams),
                      ('gn_k1_backward', GnK1BwdParams)):
         fn = getattr(lib, name)

@@ -40,33 +40,36 @@ def nvcc_path():
     return 'nvcc'
 
 
-def build_library(force=False, verbose=True):
+def build_library(force=False, verbose=True, tag='', defs=()):
+    """tag / defs: development builds of kernel variants (tools/ab_build.py): lib/libgraspnerf_b200<tag>.so compiled with
+    extra -D flags, loaded instead of the product library when GN_LIB_TAG=<tag> is set (A/B timing in one GPU call)."""
     os.makedirs(LIBDIR, exist_ok=True)
-    stamp = os.path.join(LIBDIR, 'build.sha256')
-    dig = _digest()
-    if not force and os.path.exists(LIBPATH) and os.path.exists(stamp) and open(stamp).read().strip() == dig:
-        return LIBPATH
+    libpath = LIBPATH[:-3] + tag + '.so'
+    stamp = os.path.join(LIBDIR, 'build%s.sha256' % tag)
+    dig = _digest() + ' ' + ' '.join(defs)
+    if not force and os.path.exists(libpath) and os.path.exists(stamp) and open(stamp).read().strip() == dig:
+        return libpath
     nvcc = nvcc_path()
     objs = []
 
     def compile_one(src):
-        obj = os.path.join(LIBDIR, src[:-3] + '.o')
-        cmd = [nvcc] + NVCC_FLAGS + ['-c', os.path.join(CSRC, src), '-o', obj]
+        obj = os.path.join(LIBDIR, src[:-3] + tag + '.o')
+        cmd = [nvcc] + NVCC_FLAGS + list(defs) + ['-c', os.path.join(CSRC, src), '-o', obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError('nvcc failed for %s:\n%s\n%s' % (src, r.stdout, r.stderr))
         return obj
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 2)) as ex:
         objs = list(ex.map(compile_one, _sources()))
-    cmd = [nvcc, '-shared', '--cudart', 'shared', '-gencode', 'arch=compute_100a,code=sm_100a', '-o', LIBPATH] + objs
+    cmd = [nvcc, '-shared', '--cudart', 'shared', '-gencode', 'arch=compute_100a,code=sm_100a', '-o', libpath] + objs
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError('link failed:\n%s\n%s' % (r.stdout, r.stderr))
     with open(stamp, 'w') as f:
         f.write(dig)
     if verbose:
-        print('built', LIBPATH, file=sys.stderr)
-    return LIBPATH
+        print('built', libpath, file=sys.stderr)
+    return libpath
 
 
 if __name__ == '__main__':

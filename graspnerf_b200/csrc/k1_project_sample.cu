@@ -10,29 +10,21 @@
 // mean/variance poolings of ibrnet.py:457-471 are GEMM / epilogue work and live in K2a: with them inside this
 // kernel it was issue-bound at 25 % of the HBM roofline, see profiles/.)
 //
-// Two implementations of the same arithmetic (cross-checked on the GPU, tests/test_gpu_volume.py):
-//
-//  gn_k1_kernel (default)  one CTA = 256 threads = a 2x2x8 voxel tile (32 points) x V views.
+//  gn_k1_kernel  one CTA = 256 threads = a 2x2x8 voxel tile (32 points) x V views.
 //    phase A  thread <-> (point, view): projection, mask, view direction, dir_diff, bilinear tap offsets/weights -> shared memory.
 //    phase B  8 lanes <-> one point, lane j <-> channels 4j..4j+3: each bilinear tap is ONE 256-byte texel of the fused
 //             channels-last feature buffer (2 x LDG.128 per lane, the second at an immediate +128 B), the 4 image taps are
-//             4 RGBA texels on lanes 0..3, records leave as coalesced float4 streaming stores.
+//             4 RGBA texels on lanes 0..3 (fp32, or uint8 divided by 255 in the kernel: main.py:170 color_map_forward),
+//             records leave as coalesced float4 streaming stores.
 //
-//  gn_k1_walk_kernel (GN_K1_IMPL=3, experiment kept as the on-GPU cross-check)  one CTA = a tile of 16 CONSECUTIVE points
-//    of the record order (two z-runs of 8 samples) x V views; an 8-lane group WALKS one (run, view) and keeps the 2x2 tap
-//    window of both maps in registers, stored by texel parity so that a window that moved by one texel reloads only the
-//    column/row that changed (4.1 instead of 8 gathered lines per (point,view) on the bench scene).  GN_K1_STAGE=1 also
-//    assembles the tile's records (16 x V x 288 B, contiguous in HBM) in shared memory and writes them with ONE bulk async
-//    copy (cp.async.bulk.global.shared::cta, `UBLKCP` in SASS).  It executes 28 % fewer instructions and half the gathers,
-//    but measured SLOWER on B200 (49 / 53 us vs 45 us per 40^3 volume, profiles/k1_variants_r01e.txt): the register window
-//    (and, staged, the 27 KB tile buffer) cuts the resident warps from 32 to 24 (18) per SM and the kernel is bound by
-//    exposed latency per resident warp, not by the number of gathers.
+// Variants that were built, measured on B200 and found slower are kept as source records under profiles/experiments/
+// (k1_project_sample_bulk_walk_r02a.cu.txt): a register-window "walk" along z (4.1 instead of 8 gathered lines per (point,view),
+// 49 us vs 45 us: occupancy), records staged in shared memory and written by cp.async.bulk (53 us per tile / 49 us per warp row).
 #include "gn_common.cuh"
 #include "../../include/graspnerf_b200.h"
-#include <cstdlib>
 
 // ----------------------------------------------------------------------------------------------------------------------
-// per-(point,view) set-up shared by both kernels
+// per-(point,view) set-up
 struct K1Pair {
     int   fo[4];              // feature-map tap texel indices (y*fw + x) within the view's [fh,fw] map
     float fw_[4];             // feature tap weights * mask   (nw, ne, sw, se)
@@ -86,7 +78,7 @@ __device__ __forceinline__ void k1_pair_setup(const float (&Hm)[12], const float
     }
 }
 
-// bilinear blend in the fixed order both kernels share: ((t0*w0) then fma t1, t2, t3)
+// bilinear blend in a fixed order: ((t0*w0) then fma t1, t2, t3)
 __device__ __forceinline__ float k1_blend(float t0, float t1, float t2, float t3, const float4 w) {
     float a = __fmul_rn(t0, w.x);
     a = __fmaf_rn(t1, w.y, a); a = __fmaf_rn(t2, w.z, a); a = __fmaf_rn(t3, w.w, a);
@@ -94,220 +86,7 @@ __device__ __forceinline__ float k1_blend(float t0, float t1, float t2, float t3
 }
 
 // ======================================================================================================================
-// walking kernel
-#define K1W_TILE_P 16          // points per CTA (two runs of 8)
-#define K1W_RUN 8
-#define K1W_CST_VIEW 20        // floats per view in the constant block: KRt 12 | cam 3 | pad (80-byte stride: conflict-free float4 reads)
-
-// Per (point,view) tap table.  The 2x2 bilinear window is stored by TEXEL PARITY: slot s = (y&1)<<1 | (x&1).  A window that
-// moves by one texel replaces exactly the slots of the column/row that left; the others keep their registers - no data moves.
-struct K1WInfo {
-    unsigned fo[4];           // byte offset of the slot's texel within the scene's feature buffer (view offset included)
-    float    fw_[4];          // slot weight * mask
-    unsigned io[4];           // byte offset of image tap t's RGBA texel within the scene's images (view offset included)
-    float    iw[4];           // image tap weight * mask
-    float    dd[4];           // dir_diff            (read back by phase B only in the direct-store variant)
-    float    depth, pad[3];
-};
-
-__device__ __forceinline__ float4 k1_ld4(const char* base, unsigned off) { return __ldg(reinterpret_cast<const float4*>(base + (size_t)off)); }
-__device__ __forceinline__ float4 k1_blend4(const float4 a, const float4 b, const float4 c, const float4 d, const float4 w) {
-    float4 o;
-    o.x = k1_blend(a.x, b.x, c.x, d.x, w); o.y = k1_blend(a.y, b.y, c.y, d.y, w);
-    o.z = k1_blend(a.z, b.z, c.z, d.z, w); o.w = k1_blend(a.w, b.w, c.w, d.w, w);
-    return o;
-}
-
-// FUSED: both feature maps live in one [B,V,fh,fw,64] buffer (ray_feats | img_feats per texel): one address per tap.
-// blockDim.x = 8 * (2V rounded up to a multiple of 4): one 8-lane group per (run, view) unit; NT = its compile-time bound.
-// STAGE: records are assembled in shared memory and leave as one bulk async copy per tile; !STAGE: float4 streaming stores
-// straight from registers (no staging buffer: more resident CTAs, larger L1).
-template <int NT, int MINB, bool FUSED, bool STAGE>
-__global__ void __launch_bounds__(NT, MINB)
-gn_k1_walk_kernel(const __grid_constant__ GnK1Params p)
-{
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int V = p.V, R = p.R;
-    const int npair = K1W_TILE_P * V;
-    float*   rec_s  = reinterpret_cast<float*>(smem_raw);                                  // [npair][72]  (= the HBM layout)
-    K1WInfo* s_info = reinterpret_cast<K1WInfo*>(rec_s + (STAGE ? (size_t)npair * GN_REC_STRIDE : 0));   // [npair]
-    float*   s_mask = reinterpret_cast<float*>(s_info + npair);                            // [npair]
-    float*   s_cst  = s_mask + npair;                                                      // [V][20] | bbox 4 | axis R
-
-    const int tiles_per_scene = p.tiles_per_scene;
-    const int b = blockIdx.x / tiles_per_scene;
-    const int tile = blockIdx.x - b * tiles_per_scene;
-    const int tid = threadIdx.x, nthr = blockDim.x;
-    const int n0 = tile * K1W_TILE_P;
-
-    // ---- constants to shared memory ---------------------------------------------------------------------------------
-    for (int i = tid; i < V * 12; i += nthr) {
-        const int v = i / 12;
-        s_cst[v * K1W_CST_VIEW + (i - v * 12)] = __ldg(p.KRt + (size_t)b * V * 12 + i);
-    }
-    for (int i = tid; i < V * 3; i += nthr) {
-        const int v = i / 3;
-        s_cst[v * K1W_CST_VIEW + 12 + (i - v * 3)] = __ldg(p.cam + (size_t)b * V * 3 + i);
-    }
-    if (p.volume_mode) {
-        if (tid < 3) s_cst[V * K1W_CST_VIEW + tid] = __ldg(p.bbox_min + b * 3 + tid);
-        for (int i = tid; i < R; i += nthr) s_cst[V * K1W_CST_VIEW + 4 + i] = __ldg(p.axis + i);
-    }
-    __syncthreads();
-
-    // =============================== phase A ==========================================================================
-    for (int q = tid; q < npair; q += nthr) {
-        const int pl = q / V;
-        const int v = q - pl * V;
-        int n = n0 + pl;
-        const bool live = n < p.N;
-        n = min(n, p.N - 1);
-        float px, py, pz, qx = 0.f, qy = 0.f, qz = 1.f;   // que_dir = (0,0,1) in volume mode, renderer.py:179
-        if (p.volume_mode) {
-            // record index n = (i*R + j)*R + (R-1-k)   (renderer.py:169-170: reshape (1,R*R,R,3), flip the sample axis)
-            const int ij = n / R, kk = n - ij * R;
-            const int i = ij / R, j = ij - i * R, k = R - 1 - kk;
-            const float* ax = s_cst + V * K1W_CST_VIEW + 4;
-            // field_utils.py:17-27 table (host-built, fp32) + bbox3d[0] in fp32 (renderer.py:167-168)
-            px = __fadd_rn(ax[i], s_cst[V * K1W_CST_VIEW + 0]);
-            py = __fadd_rn(ax[j], s_cst[V * K1W_CST_VIEW + 1]);
-            pz = __fadd_rn(ax[k], s_cst[V * K1W_CST_VIEW + 2]);
-        } else {
-            const float* pp = p.pts + ((size_t)b * p.N + n) * 3;
-            px = __ldg(pp); py = __ldg(pp + 1); pz = __ldg(pp + 2);
-            const float* d = p.que_dir + ((size_t)b * (p.N / p.dn) + n / p.dn) * 3;
-            qx = __ldg(d); qy = __ldg(d + 1); qz = __ldg(d + 2);
-        }
-        float Hm[12], cc[3];
-        {
-            const float4* c4 = reinterpret_cast<const float4*>(s_cst + v * K1W_CST_VIEW);
-            const float4 a0 = c4[0], a1 = c4[1], a2 = c4[2], a3 = c4[3];
-            Hm[0] = a0.x; Hm[1] = a0.y; Hm[2] = a0.z; Hm[3] = a0.w; Hm[4] = a1.x; Hm[5] = a1.y; Hm[6] = a1.z; Hm[7] = a1.w;
-            Hm[8] = a2.x; Hm[9] = a2.y; Hm[10] = a2.z; Hm[11] = a2.w; cc[0] = a3.x; cc[1] = a3.y; cc[2] = a3.z;
-        }
-        K1Pair o;
-        k1_pair_setup(Hm, cc, px, py, pz, qx, qy, qz, live, p.H, p.W, p.fh, p.fw, o);
-        {
-            // tap t -> parity slot t ^ s0, s0 = parity of the window corner.  (At the border a clamped tap repeats its
-            // neighbour's texel with weight exactly 0; it still gets its own slot, so the mapping stays a permutation.)
-            const unsigned tb = (unsigned)p.feat_stride * 4u, vb = (unsigned)v * (unsigned)(p.fh * p.fw) * tb;
-            const bool sx = o.x0 & 1, sy = o.y0 & 1;
-            unsigned f0 = vb + (unsigned)o.fo[0] * tb, f1 = vb + (unsigned)o.fo[1] * tb, f2 = vb + (unsigned)o.fo[2] * tb, f3 = vb + (unsigned)o.fo[3] * tb;
-            float w0 = o.fw_[0], w1 = o.fw_[1], w2 = o.fw_[2], w3 = o.fw_[3];
-            if (sx) { unsigned t; float u; t = f0; f0 = f1; f1 = t; t = f2; f2 = f3; f3 = t; u = w0; w0 = w1; w1 = u; u = w2; w2 = w3; w3 = u; }
-            if (sy) { unsigned t; float u; t = f0; f0 = f2; f2 = t; t = f1; f1 = f3; f3 = t; u = w0; w0 = w2; w2 = u; u = w1; w1 = w3; w3 = u; }
-            *reinterpret_cast<uint4*>(s_info[q].fo) = make_uint4(f0, f1, f2, f3);
-            *reinterpret_cast<float4*>(s_info[q].fw_) = make_float4(w0, w1, w2, w3);
-            const unsigned ib = (unsigned)v * (unsigned)(p.H * p.W) * 16u;
-            *reinterpret_cast<uint4*>(s_info[q].io) = make_uint4(ib + (unsigned)o.io[0] * 16u, ib + (unsigned)o.io[1] * 16u,
-                                                                 ib + (unsigned)o.io[2] * 16u, ib + (unsigned)o.io[3] * 16u);
-            *reinterpret_cast<float4*>(s_info[q].iw) = *reinterpret_cast<const float4*>(o.iw);
-        }
-        s_mask[q] = o.mask;
-        if (STAGE) {
-            float* row = rec_s + (size_t)q * GN_REC_STRIDE;
-            st4(row + GN_REC_RGB, make_float4(0.f, 0.f, 0.f, o.depth));       // rgb is filled in by phase B
-            st4(row + GN_REC_DD, make_float4(o.dd[0], o.dd[1], o.dd[2], o.dd[3]));
-        } else {
-            *reinterpret_cast<float4*>(s_info[q].dd) = make_float4(o.dd[0], o.dd[1], o.dd[2], o.dd[3]);
-            s_info[q].depth = o.depth;
-        }
-        if (p.dbg_feat_idx && live) {   // optional index-table dump for the bit-exactness tests
-            int* od = p.dbg_feat_idx + (((size_t)b * p.N + n) * V + v) * 2;
-            od[0] = o.x0; od[1] = o.y0;
-        }
-    }
-    __syncthreads();
-
-    // per-point valid count / view bit mask (ibrnet.py:466,490)
-    if (tid < K1W_TILE_P && n0 + tid < p.N) {
-        float nvalid = 0.f;
-        unsigned bits = 0u;
-        for (int v = 0; v < V; ++v) {
-            const float m = s_mask[tid * V + v];
-            nvalid += m;
-            bits |= (m != 0.f ? 1u : 0u) << v;
-        }
-        float2 o2; o2.x = nvalid; o2.y = __uint_as_float(bits);
-        *reinterpret_cast<float2*>(p.pt + ((size_t)b * p.N + n0 + tid) * GN_PT_STRIDE) = o2;
-    }
-
-    // =============================== phase B ==========================================================================
-    // 8-lane group <-> unit u = (view v = u >> 1, run = u & 1); lane j <-> channels 4j..4j+3 of both maps.
-    // The tap table and the image texels of sample z+1 are fetched while sample z is blended.
-    {
-        const int unit = tid >> 3, j = tid & 7;
-        const bool on = unit < 2 * V;
-        const int v = on ? (unit >> 1) : 0, run = unit & 1;
-        const size_t fmap_bytes = (size_t)p.fh * p.fw * p.feat_stride * 4;
-        const char* rf_scene = reinterpret_cast<const char*>(p.ray_feats) + (size_t)b * V * fmap_bytes + j * 16;
-        const char* if_scene = FUSED ? rf_scene + 128 : reinterpret_cast<const char*>(p.img_feats) + (size_t)b * V * fmap_bytes + j * 16;
-        const char* im_scene = reinterpret_cast<const char*>(p.imgs) + (size_t)b * V * p.H * p.W * 16;   // RGBA-interleaved [B,V,H,W,4]
-        int q = run * K1W_RUN * V + v;
-        const int nrow0 = n0 + run * K1W_RUN;                      // first point of the run
-        float* grow = p.rec + (((size_t)b * p.N + nrow0) * V + v) * GN_REC_STRIDE;      // (!STAGE) HBM row of the current sample
-        unsigned c0 = 0xffffffffu, c1 = 0xffffffffu, c2 = 0xffffffffu, c3 = 0xffffffffu;
-        float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0, r2 = r0, r3 = r0, g0 = r0, g1 = r0, g2 = r0, g3 = r0;
-        uint4 fo = *reinterpret_cast<const uint4*>(s_info[q].fo);
-        float4 w = *reinterpret_cast<const float4*>(s_info[q].fw_);
-        float4 tx = make_float4(0.f, 0.f, 0.f, 0.f);
-        float iw = 0.f;
-        if (j < 4) { iw = s_info[q].iw[j]; tx = k1_ld4(im_scene, s_info[q].io[j]); }
-#pragma unroll 2
-        for (int z = 0; z < K1W_RUN; ++z) {
-            // this sample's window: load only the slots whose texel changed
-            if (fo.x != c0) { r0 = k1_ld4(rf_scene, fo.x); g0 = k1_ld4(if_scene, fo.x); c0 = fo.x; }
-            if (fo.y != c1) { r1 = k1_ld4(rf_scene, fo.y); g1 = k1_ld4(if_scene, fo.y); c1 = fo.y; }
-            if (fo.z != c2) { r2 = k1_ld4(rf_scene, fo.z); g2 = k1_ld4(if_scene, fo.z); c2 = fo.z; }
-            if (fo.w != c3) { r3 = k1_ld4(rf_scene, fo.w); g3 = k1_ld4(if_scene, fo.w); c3 = fo.w; }
-            // next sample's tap table and image texels
-            const int qn = q + (z + 1 < K1W_RUN ? V : 0);
-            const uint4 fo_n = *reinterpret_cast<const uint4*>(s_info[qn].fo);
-            const float4 w_n = *reinterpret_cast<const float4*>(s_info[qn].fw_);
-            float4 tx_n = make_float4(0.f, 0.f, 0.f, 0.f);
-            float iw_n = 0.f;
-            if (j < 4) { iw_n = s_info[qn].iw[j]; tx_n = k1_ld4(im_scene, s_info[qn].io[j]); }
-            // image taps: lane j<4 holds tap j as one RGBA texel; scaled and summed over lanes 0..3 with two xor-shuffles
-            float cr = __fmul_rn(tx.x, iw), cg = __fmul_rn(tx.y, iw), cb = __fmul_rn(tx.z, iw);
-            cr = __fadd_rn(cr, __shfl_xor_sync(0xffffffffu, cr, 1)); cg = __fadd_rn(cg, __shfl_xor_sync(0xffffffffu, cg, 1)); cb = __fadd_rn(cb, __shfl_xor_sync(0xffffffffu, cb, 1));
-            cr = __fadd_rn(cr, __shfl_xor_sync(0xffffffffu, cr, 2)); cg = __fadd_rn(cg, __shfl_xor_sync(0xffffffffu, cg, 2)); cb = __fadd_rn(cb, __shfl_xor_sync(0xffffffffu, cb, 2));
-            const float4 ray = k1_blend4(r0, r1, r2, r3, w), img = k1_blend4(g0, g1, g2, g3, w);
-            if (STAGE) {
-                if (on) {
-                    float* row = rec_s + (size_t)q * GN_REC_STRIDE;
-                    st4(row + GN_REC_RAYF + 4 * j, ray);
-                    st4(row + GN_REC_IMGF + 4 * j, img);
-                    if (j == 0) { *reinterpret_cast<float2*>(row + GN_REC_RGB) = make_float2(cr, cg); row[GN_REC_RGB + 2] = cb; }
-                }
-            } else if (on && nrow0 + z < p.N) {
-                st4_cs(grow + GN_REC_RAYF + 4 * j, ray);
-                st4_cs(grow + GN_REC_IMGF + 4 * j, img);
-                // tail: lanes 0 and 1 write the two adjacent 16-byte chunks [64,68) and [68,72) with ONE store instruction
-                if (j < 2) st4_cs(grow + GN_REC_RGB + 4 * j, j == 0 ? make_float4(cr, cg, cb, s_info[q].depth) : *reinterpret_cast<const float4*>(s_info[q].dd));
-            }
-            grow += (size_t)V * GN_REC_STRIDE;
-            q = qn; fo = fo_n; w = w_n; tx = tx_n; iw = iw_n;
-        }
-    }
-    if (!STAGE) return;
-
-    // =============================== store ============================================================================
-    // generic-proxy writes to shared memory -> visible to the async proxy, then one bulk copy of the live prefix
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncthreads();
-    if (tid == 0) {
-        const int nlive = min(K1W_TILE_P, p.N - n0);
-        const unsigned bytes = (unsigned)nlive * (unsigned)V * GN_REC_STRIDE * 4u;
-        float* dst = p.rec + ((size_t)b * p.N + n0) * V * GN_REC_STRIDE;
-        const unsigned src = (unsigned)__cvta_generic_to_shared(rec_s);
-        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(dst), "r"(src), "r"(bytes) : "memory");
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // shared memory must outlive the copy's reads
-    }
-}
-
-// ======================================================================================================================
-// round-1 kernel (GN_K1_IMPL=2): one CTA = 256 threads = a 2x2x8 voxel tile (32 points) x V views
+// one CTA = 256 threads = a 2x2x8 voxel tile (32 points) x V views
 //   phase A  thread <-> (point, view) -> shared memory;  phase B  8 lanes <-> one point, lane j <-> channels 4j..4j+3
 #define K1_THREADS 256
 #define K1_TILE_P 32
@@ -321,7 +100,17 @@ struct K1PairInfo {           // 80-byte stride: the four groups of a warp read 
 };
 #define K1_MISC 12            // floats per pair in s_misc: dd0..3, mask, depth, pad
 
-template <bool FUSED, bool TEXPF>
+// one image tap as (r,g,b,-): fp32 RGBA texel, or uint8 RGBA texel / 255 (exactly np.float32(u8) / 255, main.py:170)
+template <bool U8>
+__device__ __forceinline__ float4 k1_img_texel(const void* imgs, size_t texel) {
+    if (U8) {
+        const uchar4 t = __ldg(reinterpret_cast<const uchar4*>(imgs) + texel);
+        return make_float4(__fdiv_rn((float)t.x, 255.f), __fdiv_rn((float)t.y, 255.f), __fdiv_rn((float)t.z, 255.f), 0.f);
+    }
+    return __ldg(reinterpret_cast<const float4*>(imgs) + texel);
+}
+
+template <bool FUSED, bool U8>
 __global__ void __launch_bounds__(K1_THREADS, 4)
 gn_k1_kernel(const __grid_constant__ GnK1Params p)
 {
@@ -347,10 +136,12 @@ gn_k1_kernel(const __grid_constant__ GnK1Params p)
     for (int pair = tid; pair < npair; pair += K1_THREADS) {
         const int pl = pair / V;
         const int v = pair - pl * V;
-        float px, py, pz, qx = 0.f, qy = 0.f, qz = 1.f;
+        float px, py, pz, qx = 0.f, qy = 0.f, qz = 1.f;   // que_dir = (0,0,1) in volume mode, renderer.py:179
         bool live = true;
         int n;
         if (p.volume_mode) {
+            // record index n = (i*R + j)*R + (R-1-k)   (renderer.py:169-170: reshape (1,R*R,R,3), flip the sample axis);
+            // point = field_utils.py:17-27 table (host-built, fp32) + bbox3d[0] in fp32 (renderer.py:167-168)
             const int i = ti * 2 + (pl >> 4), j = tj * 2 + ((pl >> 3) & 1), k = tk * 8 + (pl & 7);
             px = __fadd_rn(__ldg(p.axis + i), __ldg(p.bbox_min + b * 3 + 0));
             py = __fadd_rn(__ldg(p.axis + j), __ldg(p.bbox_min + b * 3 + 1));
@@ -372,7 +163,7 @@ gn_k1_kernel(const __grid_constant__ GnK1Params p)
         for (int i = 0; i < 3; ++i) cc[i] = __ldg(p.cam + ((size_t)b * V + v) * 3 + i);
         K1Pair o;
         k1_pair_setup(Hm, cc, px, py, pz, qx, qy, qz, live, p.H, p.W, p.fh, p.fw, o);
-        if (p.dbg_feat_idx && live) {
+        if (p.dbg_feat_idx && live) {   // optional index-table dump for the bit-exactness tests
             int* od = p.dbg_feat_idx + (((size_t)b * p.N + n) * V + v) * 2;
             od[0] = o.x0; od[1] = o.y0;
         }
@@ -399,6 +190,7 @@ gn_k1_kernel(const __grid_constant__ GnK1Params p)
         live = n < p.N;
         n = min(n, p.N - 1);
     }
+    // per-point valid count / view bit mask (ibrnet.py:466,490)
     float nvalid = 0.f;
     unsigned bits = 0u;
     for (int v = 0; v < V; ++v) {
@@ -412,16 +204,16 @@ gn_k1_kernel(const __grid_constant__ GnK1Params p)
     const size_t plane = (size_t)p.H * p.W;
     const float* rf_base = p.ray_feats + (size_t)b * V * fmap_sz + 4 * j;
     const float* if_base = p.img_feats + (size_t)b * V * fmap_sz + 4 * j;
-    const float* im_base = p.imgs + (size_t)b * V * plane * 4;
+    const size_t im_base = (size_t)b * V * plane;      // texel index of this scene's first view
 
     // image taps: lane j<4 fetches tap j as one RGBA texel and scales it; summed over lanes 0..3 with two xor-shuffles.
     // The texels of view v+1 are requested while view v is blended: they are the gathers that miss to DRAM (the images are
     // read once per scene), one full iteration ahead hides their latency behind the feature gathers of the current view.
     float4 px = make_float4(0.f, 0.f, 0.f, 0.f);
     float iw = 0.f;
-    if (TEXPF && j < 4) {
+    if (j < 4) {
         iw = s_info[pl * V].iw[j];
-        px = ldg4(im_base + (size_t)s_info[pl * V].io[j] * 4);
+        px = k1_img_texel<U8>(p.imgs, im_base + (size_t)s_info[pl * V].io[j]);
     }
     for (int v = 0; v < V; ++v) {
         const int pair = pl * V + v;
@@ -434,17 +226,12 @@ gn_k1_kernel(const __grid_constant__ GnK1Params p)
         const float4 g0 = ldg4(imf + fo.x), g1 = ldg4(imf + fo.y), g2 = ldg4(imf + fo.z), g3 = ldg4(imf + fo.w);
         float4 px_n = make_float4(0.f, 0.f, 0.f, 0.f);
         float iw_n = 0.f;
-        if (TEXPF) {
-            if (j < 4 && v + 1 < V) {
-                iw_n = s_info[pair + 1].iw[j];
-                px_n = ldg4(im_base + ((size_t)(v + 1) * plane + s_info[pair + 1].io[j]) * 4);
-            }
-        } else if (j < 4) {
-            iw = s_info[pair].iw[j];
-            px = ldg4(im_base + ((size_t)v * plane + s_info[pair].io[j]) * 4);
+        if (j < 4 && v + 1 < V) {
+            iw_n = s_info[pair + 1].iw[j];
+            px_n = k1_img_texel<U8>(p.imgs, im_base + (size_t)(v + 1) * plane + (size_t)s_info[pair + 1].io[j]);
         }
         float cr = __fmul_rn(px.x, iw), cg = __fmul_rn(px.y, iw), cb = __fmul_rn(px.z, iw);
-        if (TEXPF) { px = px_n; iw = iw_n; }
+        px = px_n; iw = iw_n;
         float4 ray, img;
         ray.x = k1_blend(r0.x, r1.x, r2.x, r3.x, fwt); ray.y = k1_blend(r0.y, r1.y, r2.y, r3.y, fwt);
         ray.z = k1_blend(r0.z, r1.z, r2.z, r3.z, fwt); ray.w = k1_blend(r0.w, r1.w, r2.w, r3.w, fwt);
@@ -456,7 +243,7 @@ gn_k1_kernel(const __grid_constant__ GnK1Params p)
         if (live) {
             st4_cs(row + GN_REC_RAYF + 4 * j, ray);
             st4_cs(row + GN_REC_IMGF + 4 * j, img);
-            if (j < 2) {
+            if (j < 2) {       // tail: lanes 0 and 1 write the two adjacent 16-byte chunks [64,68) and [68,72) with ONE store instruction
                 const float4 ddq = *reinterpret_cast<const float4*>(s_misc + pair * K1_MISC);
                 st4_cs(row + GN_REC_RGB + 4 * j, j == 0 ? make_float4(cr, cg, cb, s_misc[pair * K1_MISC + 5]) : ddq);
             }
@@ -469,11 +256,6 @@ gn_k1_kernel(const __grid_constant__ GnK1Params p)
 }
 
 // ----------------------------------------------------------------------------------------------------------------------
-static int k1_env_int(const char* name, int dflt) {
-    const char* e = getenv(name);
-    return e ? atoi(e) : dflt;
-}
-
 extern "C" int gn_k1_forward(const GnK1Params* hp, void* stream)
 {
     GnK1Params p = *hp;
@@ -486,36 +268,7 @@ extern "C" int gn_k1_forward(const GnK1Params* hp, void* stream)
     if (p.feat_stride == 0) p.feat_stride = GN_FEAT_C;
     const bool fused = p.feat_stride == 2 * GN_FEAT_C;
     if (p.feat_stride != GN_FEAT_C && !(fused && p.img_feats == p.ray_feats + GN_FEAT_C)) return -7;
-    const int impl = k1_env_int("GN_K1_IMPL", 2) == 3 ? 3 : 2;          // read per call: tests switch it at run time
-    cudaError_t e;
-    if (impl == 3) {
-        p.tiles_per_scene = (p.N + K1W_TILE_P - 1) / K1W_TILE_P;
-        const int npair = K1W_TILE_P * p.V;
-        const bool stage = k1_env_int("GN_K1_STAGE", 0) != 0;
-        const size_t smem = (size_t)npair * ((stage ? GN_REC_STRIDE * 4 : 0) + sizeof(K1WInfo) + 4)
-                          + (size_t)(p.V * K1W_CST_VIEW + 4 + (p.volume_mode ? p.R : 0)) * 4 + 16;
-        const unsigned nthr = 32u * (unsigned)((2 * p.V + 3) / 4);          // one 8-lane group per (run, view) unit
-        if (smem > 227 * 1024) return -5;
-        if ((double)p.V * p.fh * p.fw * p.feat_stride * 4.0 >= 4294967296.0 || (double)p.V * p.H * p.W * 16.0 >= 4294967296.0) return -8;   // 32-bit tap byte offsets
-        const long long grid = (long long)p.B * p.tiles_per_scene;
-        if (grid > 0x7fffffffLL) return -6;
-#define K1W_LAUNCH(NT, MINB, FU, ST) { static size_t cache[16] = {0}; \
-            e = gn_ensure_smem(gn_k1_walk_kernel<NT, MINB, FU, ST>, smem, cache); if (e != cudaSuccess) return (int)e; \
-            gn_k1_walk_kernel<NT, MINB, FU, ST><<<(unsigned)grid, nthr, smem, (cudaStream_t)stream>>>(p); }
-#define K1W_LAUNCH_F(NT, MINB, ST) { if (fused) K1W_LAUNCH(NT, MINB, true, ST) else K1W_LAUNCH(NT, MINB, false, ST) }
-        if (stage) {
-            if (nthr <= 96)       K1W_LAUNCH_F(96, 6, true)
-            else if (nthr <= 192) K1W_LAUNCH_F(192, 3, true)
-            else                  K1W_LAUNCH_F(512, 1, true)
-        } else {
-            if (nthr <= 96)       K1W_LAUNCH_F(96, 8, false)
-            else if (nthr <= 192) K1W_LAUNCH_F(192, 4, false)
-            else                  K1W_LAUNCH_F(512, 1, false)
-        }
-#undef K1W_LAUNCH_F
-#undef K1W_LAUNCH
-        return (int)cudaGetLastError();
-    }
+    if (p.img_u8 != 0 && p.img_u8 != 1) return -8;
     if (p.volume_mode) p.tiles_per_scene = (p.R / 2) * (p.R / 2) * (p.R / 8);
     else               p.tiles_per_scene = (p.N + K1_TILE_P - 1) / K1_TILE_P;
     const int npair = K1_TILE_P * p.V;
@@ -523,12 +276,12 @@ extern "C" int gn_k1_forward(const GnK1Params* hp, void* stream)
     if (smem > 227 * 1024) return -5;
     const long long grid = (long long)p.B * p.tiles_per_scene;
     if (grid > 0x7fffffffLL) return -6;
-    const bool texpf = k1_env_int("GN_K1_TEXPF", 1) != 0;
-#define K1T_LAUNCH(FU, PF) { static size_t cache[16] = {0}; \
-        e = gn_ensure_smem(gn_k1_kernel<FU, PF>, smem, cache); if (e != cudaSuccess) return (int)e; \
-        gn_k1_kernel<FU, PF><<<(unsigned)grid, K1_THREADS, smem, (cudaStream_t)stream>>>(p); }
-    if (fused) { if (texpf) K1T_LAUNCH(true, true) else K1T_LAUNCH(true, false) }
-    else       { if (texpf) K1T_LAUNCH(false, true) else K1T_LAUNCH(false, false) }
+    cudaError_t e;
+#define K1T_LAUNCH(FU, U8) { static size_t cache[16] = {0}; \
+        e = gn_ensure_smem(gn_k1_kernel<FU, U8>, smem, cache); if (e != cudaSuccess) return (int)e; \
+        gn_k1_kernel<FU, U8><<<(unsigned)grid, K1_THREADS, smem, (cudaStream_t)stream>>>(p); }
+    if (fused) { if (p.img_u8) K1T_LAUNCH(true, true) else K1T_LAUNCH(true, false) }
+    else       { if (p.img_u8) K1T_LAUNCH(false, true) else K1T_LAUNCH(false, false) }
 #undef K1T_LAUNCH
     return (int)cudaGetLastError();
 }

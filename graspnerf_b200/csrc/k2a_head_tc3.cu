@@ -1,11 +1,12 @@
-// K2a, three resident tiles per SM ("tc3"): the tensor-core head of k2a_head_tc.cu re-scheduled so that a tile needs
-// 160 instead of 256 tensor-memory columns, which lets THREE 128-row tiles (12 warps, 3 per scheduler) share an SM.
+// K2a on tcgen05 / TMEM, three resident 128-row tiles per SM: the GEMM chain is scheduled so that a tile needs 160
+// tensor-memory columns, which lets THREE tiles (12 warps, 3 per scheduler) share an SM.  (The first version, two tiles of
+// 256 columns, was 15 % slower and is gone; profiles/ keeps its measurements.)
 //
 // Why: the kernel is bound by exposed latency per resident warp, not by the tensor pipe or the instruction count
 // (profiles/: one tile per SM 455 us, two tiles 275 us per 40^3 volume; T(n) ~ 95 + 360/n us).  Registers allow 12 warps
 // (168 per thread); tensor memory (512 columns) and shared memory (153 KB of weight images) are what limit the tile count.
 //
-// Same math, same operand images (gn_k2a_tc_prepare) and same reference lines as k2a_head_tc.cu.  What changes:
+// Operand images: gn_k2a_tc_prepare (k2a_tc_prepare.cu).  Layout of a tile:
 //   * TMEM map per tile: D 80 columns | A hi 40 | A lo 40  (K <= 80 per GEMM issue);
 //   * the GEMM chain is cut into smaller rounds that fit that map - sub-ranges of the prepared images are addressed through
 //     the descriptor (row offset n0, k offset k0), so no new images are needed:
@@ -19,7 +20,6 @@
 //   * tiles are handed out inside the CTA from a shared-memory counter (each CTA owns a contiguous range of tiles), so
 //     the three slots stay busy although a slot only sees ~7 tiles of a 40^3 volume.
 #include "k2a_tc_common.cuh"
-#include <cstdlib>
 
 #define T3_THREADS 384
 #define T3_SLOTS 3
@@ -37,7 +37,7 @@ static_assert(t3_smem_bytes(5) <= 227 * 1024, "K2a-TC3 shared memory budget at V
 
 template <int K> __device__ __forceinline__ void t3_store_a(uint32_t lane_addr, int k0, const float* a) { tm_store_a<K, T3_AHI, T3_ALO>(lane_addr, k0, a); }
 
-// Generic layer epilogue (see k2a_head_tc.cu): A[k0 ..) = act(D[d_col ..) + bias), 16 columns per step, next load in flight.
+// Generic layer epilogue: A[k0 ..) = act(D[d_col ..) + bias), 16 columns per step, next load in flight.
 template <int ACT>
 __device__ __noinline__ void t3_epilogue(uint32_t lane_addr, int d_col, int nchunk, const float* __restrict__ bias, int k0)
 {
@@ -64,21 +64,41 @@ __device__ __noinline__ void t3_epilogue(uint32_t lane_addr, int d_col, int nchu
     }
 }
 
+// sum of the V rows of a point, float4 chunk `ch` (packed FADD2 accumulation)
+template <int VV>
+__device__ __forceinline__ void t3_pool_chunk(const float* q, float* dst, int V, bool lane_active)
+{
+    unsigned long long s0 = 0ull, s1 = 0ull;              // (+0, +0) pairs
+    if (VV > 0) {
+#pragma unroll
+        for (int jv = 0; jv < VV; ++jv) {
+            const float4 t = *reinterpret_cast<const float4*>(q + jv * T3_POOL_STRIDE);
+            s0 = add2(s0, pk2(t.x, t.y)); s1 = add2(s1, pk2(t.z, t.w));
+        }
+    } else {
+#pragma unroll 2
+        for (int jv = 0; jv < V; ++jv) {
+            const float4 t = *reinterpret_cast<const float4*>(q + jv * T3_POOL_STRIDE);
+            s0 = add2(s0, pk2(t.x, t.y)); s1 = add2(s1, pk2(t.z, t.w));
+        }
+    }
+    float4 s;
+    upk2(s0, s.x, s.y); upk2(s1, s.z, s.w);
+    if (lane_active) st4(dst, s);
+}
 __device__ __noinline__ void t3_pool_rows(float* scr, int g, int v, int gb, int V, bool lane_active)
 {
     __syncwarp();
     float* sums = scr + (32 + g) * T3_POOL_STRIDE;
     const float* base = scr + gb * T3_POOL_STRIDE;
+    // lane (g,v) sums the float4 chunks v, v+V, ... of its point's V rows.  V = 6 (the shipped configuration): chunk v for
+    // every lane, chunk v+6 for v < 3, fully unrolled.
+    if (V == 6) {
+        t3_pool_chunk<6>(base + 4 * v, sums + 4 * v, V, lane_active);
+        if (v < 3) t3_pool_chunk<6>(base + 4 * (v + 6), sums + 4 * (v + 6), V, lane_active);
+    } else {
 #pragma unroll 1
-    for (int ch = v; ch < 9; ch += V) {                 // lane (g,v) sums the float4 chunks v, v+V, ... of its point's V rows
-        const float* q = base + 4 * ch;
-        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 2
-        for (int jv = 0; jv < V; ++jv) {
-            const float4 t = *reinterpret_cast<const float4*>(q + jv * T3_POOL_STRIDE);
-            s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
-        }
-        if (lane_active) st4(sums + 4 * ch, s);
+        for (int ch = v; ch < 9; ch += V) t3_pool_chunk<0>(base + 4 * ch, sums + 4 * ch, V, lane_active);
     }
     __syncwarp();
 }
@@ -576,7 +596,7 @@ gn_k2a_tc3_kernel(const __grid_constant__ GnK2aParams p, int num_tiles, int G)
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(*s_tmem), "r"(512));
 }
 
-extern "C" int gn_k2a_forward_tc3(const GnK2aParams* hp, void* stream)
+extern "C" int gn_k2a_forward_tc(const GnK2aParams* hp, void* stream)
 {
     const GnK2aParams& p = *hp;
     if (p.V < 2 || p.V > 32 || p.B < 1 || p.N < 1) return -1;

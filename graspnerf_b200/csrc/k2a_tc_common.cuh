@@ -1,4 +1,4 @@
-// Shared pieces of the tensor-core K2a kernel (k2a_head_tc.cu) and its prepare step (k2a_tc_prepare.cu):
+// Shared pieces of the tensor-core K2a kernel (k2a_head_tc3.cu) and its prepare step (k2a_tc_prepare.cu):
 // TMEM column map, fp16 operand-image table, small-constant table, tcgen05 / mbarrier PTX wrappers, the prepare kernel.
 #pragma once
 #include "gn_common.cuh"
@@ -129,6 +129,15 @@ template <int K, int AHI = TM_AHI, int ALO = TM_ALO> __device__ __forceinline__ 
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const float a0 = a[2 * (c + i)], a1 = a[2 * (c + i) + 1];
+#ifndef GN_SPLIT_CVT
+            // hi = rn_f16(a) packed (low 16 bits = even k, tc_probe variant 0); lo = rn_f16(a - hi) with the residual taken by
+            // the mixed-precision FMA (fma.rn.f32.f16: a - 1*hi in ONE instruction, `FHFMA` in SASS) - 4 instructions per pair
+            asm("{\n\t.reg .b16 h0, h1, m1;\n\t.reg .f32 d0, d1;\n\t"
+                "cvt.rn.f16x2.f32 %0, %3, %2;\n\t"
+                "mov.b32 {h0, h1}, %0;\n\tmov.b16 m1, 0xBC00;\n\t"
+                "fma.rn.f32.f16 d0, h0, m1, %2;\n\tfma.rn.f32.f16 d1, h1, m1, %3;\n\t"
+                "cvt.rn.f16x2.f32 %1, d1, d0;\n\t}" : "=&r"(hi[i]), "=r"(lo[i]) : "f"(a0), "f"(a1));
+#else
             const __half2 h = __floats2half2_rn(a0, a1);                 // .x (low 16 bits) = even k  (tc_probe variant 0)
             const float2 hf = __half22float2(h);
             float d0, d1;
@@ -136,6 +145,7 @@ template <int K, int AHI = TM_AHI, int ALO = TM_ALO> __device__ __forceinline__ 
             const __half2 l = __floats2half2_rn(d0, d1);
             hi[i] = *reinterpret_cast<const uint32_t*>(&h);
             lo[i] = *reinterpret_cast<const uint32_t*>(&l);
+#endif
         }
         tm_st8(slot_lane_addr + AHI + k0 / 2 + c, hi);
         tm_st8(slot_lane_addr + ALO + k0 / 2 + c, lo);

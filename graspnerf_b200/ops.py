@@ -179,19 +179,19 @@ def k1_forward(scene, hw, *, resolution=None, bbox_min=None, volume_size=0.3, pt
     return (rec, pt, dbg) if debug_idx else (rec, pt)
 
 
-K2A_IMPL = 'tc3'     # 'tc3' (tcgen05, three tiles per SM, default), 'tc' (tcgen05, two tiles per SM) or 'simt' (fp32 CUDA-core cross-check)
+K2A_IMPL = 'tc'      # the tcgen05 kernel.  impl='simt' (fp32 CUDA-core restatement of the same math) exists for the GPU tests only
 
 
 def k2a_forward(rec, pt, hw, depth_range, *, que_dists=None, dn=1, want_colors=False, debug=False, impl=None,
                 want_pooled=True, want_tok=False, resolution=None, bbox_min=None, volume_size=0.3, pts=None, ev=None):
-    """K2a launch.  impl 'tc' (tcgen05) or 'simt'.  want_tok (tc only): also run geometry_fc and emit per-point tokens
+    """K2a launch.  impl 'tc' (tcgen05, the product path) or 'simt' (test cross-check).  want_tok (tc only): also run geometry_fc and emit per-point tokens
     [B,N,20] for the attention-only K2b; needs the points: (resolution, bbox_min) in volume mode or pts [B,N,3]."""
     lib = _lib.load()
-    impl = impl or K2A_IMPL
+    impl = 'tc' if (impl or K2A_IMPL) in ('tc', 'tc3') else 'simt'
     B, N, V, _ = rec.shape
     dev = rec.device
     # the three-tile kernel runs geometry_fc in a second phase that re-reads the pooled rows: it always needs the buffer
-    pooled = torch.empty((B, N, POOL_STRIDE), device=dev, dtype=torch.float32) if (want_pooled or (impl == 'tc3' and want_tok)) else None
+    pooled = torch.empty((B, N, POOL_STRIDE), device=dev, dtype=torch.float32) if (want_pooled or (impl == 'tc' and want_tok)) else None
     colors = torch.empty((B, N, 4), device=dev, dtype=torch.float32) if want_colors else None
     dbg = torch.zeros((B, N, V, 8), device=dev, dtype=torch.float32) if debug else None
     tok = None
@@ -201,7 +201,7 @@ def k2a_forward(rec, pt, hw, depth_range, *, que_dists=None, dn=1, want_colors=F
         que_dists = _f32c(que_dists, dev)
     p.que_dists, p.pooled, p.colors, p.dbg_rows = _ptr(que_dists).value, _ptr(pooled).value, _ptr(colors).value, _ptr(dbg).value
     p.B, p.N, p.V, p.dn, p.with_rgb = B, N, V, int(dn), 1 if want_colors else 0
-    if impl in ('tc', 'tc3'):
+    if impl == 'tc':
         p.tc_const = _ptr(hw.tc_const).value
         if want_tok:
             tok = torch.empty((B, N, TOK_STRIDE), device=dev, dtype=torch.float32)
@@ -216,7 +216,7 @@ def k2a_forward(rec, pt, hw, depth_range, *, que_dists=None, dn=1, want_colors=F
                 p.pts, p.R, p.volume_mode = _ptr(pts).value, 0, 0
     elif want_tok or not want_pooled:
         raise ValueError("tokens are produced by the tensor-core K2a only")
-    fn = {'tc': lib.gn_k2a_forward_tc, 'tc3': lib.gn_k2a_forward_tc3, 'simt': lib.gn_k2a_forward}[impl]
+    fn = {'tc': lib.gn_k2a_forward_tc, 'simt': lib.gn_k2a_forward}[impl]
     if ev is not None:
         ev[0].record()
     rc = fn(C.byref(p), _stream())
@@ -304,9 +304,9 @@ def k3_fine_depths(depth, hit_prob, depth_range_q, u, want_inds=False):
 def sample_volume(scene, hw, bbox_min, resolution=40, volume_size=0.3, debug=None, impl=None):
     """NeuralRayRenderer.sample_volume (renderer.py:164-199) for B scenes: K1 -> K2a -> K2b.  Returns [B,1,R,R,R].
     impl 'tc' (default): tcgen05 K2a emits per-point tokens, K2b is attention-only.  'simt': fp32 CUDA-core K2a + full K2b."""
-    impl = impl or K2A_IMPL
+    impl = 'tc' if (impl or K2A_IMPL) in ('tc', 'tc3') else 'simt'
     rec, pt = k1_forward(scene, hw, resolution=resolution, bbox_min=bbox_min, volume_size=volume_size)
-    if impl in ('tc', 'tc3'):
+    if impl == 'tc':
         pooled, _, dbg, tok = k2a_forward(rec, pt, hw, scene.depth_range, debug=debug is not None, impl=impl,
                                           want_pooled=debug is not None, want_tok=True, resolution=resolution,
                                           bbox_min=bbox_min, volume_size=volume_size)

@@ -220,3 +220,28 @@ def voxel_axis_table(resolution, volume_size=0.3):
     voxel = volume_size / resolution
     half = voxel / 2
     return np.array([i * voxel + half for i in range(resolution)]).astype(np.float32)
+
+
+_SEED0 = {}
+
+
+def seed0_model(cfg=None, seed=0):
+    """The mirror `GraspNeRF` constructed under torch.manual_seed(seed): same construction order and initialisers as the
+    reference (renderer.py:298-303, ibrnet.py:427-432), so seed 0 reproduces the reference's random init bit for bit
+    (tests/test_boundary.py checks it against checksums of the real reference).  The caller's RNG state is preserved."""
+    import torch
+    from .network import name2network, NRVGN_SDF_CFG
+    cfg = dict(NRVGN_SDF_CFG if cfg is None else cfg)
+    with torch.random.fork_rng(devices=[]):
+        torch.manual_seed(seed)
+        return name2network[cfg['network']](cfg).eval()
+
+
+def seed0_weights(seed=0):
+    """Hot-path state_dict ('agg_net.*', 'dist_decoder.*', 'fine_*' ... without the 'nr_net.' prefix) of seed0_model():
+    random-init weights of the reference architecture for bench.py / smoke() / tools (no file, no dependency on tests/)."""
+    if seed not in _SEED0:
+        sd = seed0_model(seed=seed).state_dict()
+        _SEED0[seed] = {k[len('nr_net.'):]: v.detach().clone() for k, v in sd.items()
+                        if k.startswith('nr_net.') and ('agg_net.' in k or 'dist_decoder.' in k)}
+    return _SEED0[seed]

@@ -32,7 +32,7 @@ extern "C" {
  * (aggregate_net.py:11-17) and the per-point valid-view count / mask (ibrnet.py:466,490).  volume_mode=1: points are the voxel centres of utils/field_utils.py:12-27 plus bbox_min,
  * in sample_volume's order (renderer.py:166-170).  volume_mode=0: explicit points (RGB head, render_ops.py:27-39). */
 typedef struct GnK1Params {
-    const float* imgs;        /* [B,V,H,W,4] RGBA-interleaved (A unused) */
+    const void* imgs;         /* [B,V,H,W,4] RGBA-interleaved (A unused): fp32 in [0,1], or uint8 when img_u8 = 1 */
     const float* img_feats;   /* [B,V,fh,fw,32] channels-last, or ray_feats + 32 when feat_stride == 64 */
     const float* ray_feats;   /* [B,V,fh,fw,32] channels-last, or the fused [B,V,fh,fw,64] buffer (ray_feats 32 | img_feats 32 per texel) */
     const float* KRt;         /* [B,V,3,4]  K @ [R|t]  (render_ops.py:94) */
@@ -51,6 +51,8 @@ typedef struct GnK1Params {
     int volume_mode;
     int tiles_per_scene;      /* filled in by the launcher */
     int feat_stride;          /* floats per feature-map texel: 32 (two maps, 0 means 32) or 64 (fused buffer: one address per bilinear tap) */
+    int img_u8;               /* 1: imgs holds uint8 texels; the kernel divides by 255 exactly as color_map_forward does (main.py:170,
+                                 utils/base_utils.py:492-493), so the planner's PNG bytes cross PCIe as bytes */
 } GnK1Params;
 
 int gn_k1_forward(const GnK1Params* params, void* stream);
@@ -86,9 +88,8 @@ typedef struct GnK2aParams {
     int with_rgb;              /* 1: also evaluate rgb_fc + blend into `colors` */
     int R, volume_mode;        /* (tok) */
 } GnK2aParams;
-int gn_k2a_forward(const GnK2aParams* params, void* stream);      /* fp32 SIMT implementation (reference for the TC path) */
-int gn_k2a_forward_tc(const GnK2aParams* params, void* stream);   /* tcgen05 / TMEM implementation (fp16 hi/lo split, 3 MMAs per product) */
-int gn_k2a_forward_tc3(const GnK2aParams* params, void* stream);  /* same math re-scheduled into smaller GEMM rounds: 160 TMEM columns per tile, three tiles per SM */
+int gn_k2a_forward_tc(const GnK2aParams* params, void* stream);   /* THE product kernel: tcgen05 / TMEM (fp16 hi/lo split, 3 MMAs per product; 160 TMEM columns per tile, three tiles per SM) */
+int gn_k2a_forward(const GnK2aParams* params, void* stream);      /* fp32 CUDA-core implementation of the same math: on-GPU cross-check for tests, never selected by the host code */
 int gn_k2a_tc_const_bytes(void);
 int gn_k2a_tc_prepare(const float* weights, void* tc_const, void* stream);   /* fp32 blob -> fp16 hi/lo operand images + small constants */
 

@@ -28,7 +28,7 @@ def _setup(name):
     return ops, sd, sc, scene, que, oq, hw_c, hw_f, dev
 
 
-@pytest.mark.parametrize('impl', ['simt', 'tc', 'tc3'])
+@pytest.mark.parametrize('impl', ['simt', 'tc'])
 @pytest.mark.parametrize('name', list(RENDER_CASES))
 def test_render_coarse_and_fine(name, impl):
     from oracle import nr_oracle as O
@@ -65,7 +65,7 @@ def test_render_coarse_and_fine(name, impl):
         ops.K2A_IMPL = 'tc3'
 
 
-@pytest.mark.parametrize('impl', ['simt', 'tc', 'tc3'])
+@pytest.mark.parametrize('impl', ['simt', 'tc'])
 def test_ragged_ray_batch(impl):
     """37 rays x 11 samples = 407 points: not a multiple of any tile size on the path (K1 32 / 16 points, K2a 16-20 points per
     128-row tile, K2b 11 rays per CTA), sample count != 40 (positional table, attention length) - against the oracle."""

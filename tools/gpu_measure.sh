@@ -11,7 +11,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
     python bench.py --steps 4 --warmup 3 --no-cpu --train-batch 0 > /dev/null 2>&1
 for k in gn_k1_kernel gn_k2a_tc3_kernel gn_k2b_attn_kernel; do
   timeout 300 ncu --set full --clock-control none --import-source on -k regex:$k -s 3 -c 1 -f -o $OUT/${k}_full_$TAG \
-      python tools/time_volume.py 1 2 tc3 > /dev/null 2>&1
+      python tools/time_volume.py 1 2 tc > /dev/null 2>&1
 done
 if [ -x tools/tc_probe ]; then timeout 60 tools/tc_probe > $OUT/tc_probe_$TAG.txt 2>&1; fi
 nvidia-smi --query-gpu=name,clocks.max.sm,clocks.max.mem,power.limit --format=csv > $OUT/gpu_$TAG.csv

@@ -1,18 +1,20 @@
-"""K1 A/B timing (development aid): gn_k1_walk_kernel (GN_K1_IMPL=3) vs the round-1 tile kernel (GN_K1_IMPL=2).
-Each sample = 16 back-to-back launches cycling through 8 scenes (event timestamps on this GPU tick at 4.096 us, so single launches cannot be timed)."""
+"""K1 timing aid (development): variants selected by environment (GN_K1_BULK=0/1, GN_K1_TEXPF=0/1; GN_LIB_TAG picks a
+tagged library build).  Each sample = 16 back-to-back launches cycling through 8 scenes behind an L2-flushing fill (event
+timestamps on this GPU tick at 4.096 us, so single launches cannot be timed)."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
 from graspnerf_b200 import ops
 from graspnerf_b200.synth import make_scene
-from tests.helpers import golden_weights
+from graspnerf_b200.weights import seed0_weights
 
 
 def main():
     iters = int(sys.argv[1]) if len(sys.argv) > 1 else 40
+    cfgs = [dict(kv.split('=') for kv in a.split(',')) for a in sys.argv[2:]] or [dict(GN_K1_BULK='0'), dict(GN_K1_BULK='1'), dict(GN_K1_BULK='0'), dict(GN_K1_BULK='1')]
     dev = torch.device('cuda:0')
-    hw = ops.HeadWeights(golden_weights(), 'agg_net.', 'dist_decoder.', dev)
+    hw = ops.HeadWeights(seed0_weights(), 'agg_net.', 'dist_decoder.', dev)
     scenes = []
     for s in range(8):
         sc = make_scene(seed=s)
@@ -20,15 +22,13 @@ def main():
         scenes.append((ops.Scene(t['imgs'], t['img_feats'], t['ray_feats'], t['poses'], t['Ks'], t['depth_range']),
                        torch.tensor([sc['bbox3d'][0]], device=dev)))
     flush = torch.empty(512 * 1024 * 1024 // 4, device=dev)
-    cfgs = [dict(GN_K1_IMPL='2', GN_K1_TEXPF='0'), dict(GN_K1_IMPL='2', GN_K1_TEXPF='1'),
-            dict(GN_K1_IMPL='3', GN_K1_STAGE='1'), dict(GN_K1_IMPL='3', GN_K1_STAGE='0'),
-            dict(GN_K1_IMPL='2', GN_K1_TEXPF='0'), dict(GN_K1_IMPL='2', GN_K1_TEXPF='1')]
     for cfg in cfgs:
         os.environ.update(cfg)
-        impl = ' '.join(f'{k[6:]}={v}' for k, v in cfg.items())
+        impl = ' '.join(f'{k}={v}' for k, v in cfg.items())
         ts = []
         for rep in range(iters // 8 + 2):
-            flush.fill_(1.0)
+            for _ in range(3):
+                flush.fill_(1.0)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for it in range(16):          # 16 launches over 8 different scenes: inputs (8 x 28 MB) and records (8 x 110 MB) cycle past L2
@@ -39,7 +39,7 @@ def main():
             if rep >= 2:
                 ts.append(e0.elapsed_time(e1) * 1e3 / 16)
         ts = np.array(ts)
-        print(f'{impl}: K1 median {np.median(ts):.1f} us  min {ts.min():.1f}  mean {ts.mean():.1f} '
+        print(f'[{os.environ.get("GN_LIB_TAG", "")}] {impl}: K1 median {np.median(ts):.1f} us  min {ts.min():.1f}  mean {ts.mean():.1f} '
               f'-> {135876608 / np.median(ts) / 1e3:.0f} GB/s (own bytes 135.9 MB)')
 
 

@@ -5,7 +5,7 @@ import numpy as np
 import torch
 from graspnerf_b200 import ops
 from graspnerf_b200.synth import make_scene
-from tests.helpers import golden_weights
+from graspnerf_b200.weights import seed0_weights as golden_weights
 
 
 def main():

@@ -5,13 +5,13 @@ import numpy as np
 import torch
 from graspnerf_b200 import ops
 from graspnerf_b200.synth import make_scene
-from tests.helpers import golden_weights
+from graspnerf_b200.weights import seed0_weights as golden_weights
 
 
 def main():
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 1
     iters = int(sys.argv[2]) if len(sys.argv) > 2 else 20
-    ops.K2A_IMPL = sys.argv[3] if len(sys.argv) > 3 else 'tc'
+    ops.K2A_IMPL = 'simt' if (len(sys.argv) > 3 and sys.argv[3] == 'simt') else 'tc'
     dev = torch.device('cuda:0')
     sd = golden_weights()
     hw = ops.HeadWeights(sd, 'agg_net.', 'dist_decoder.', dev)
