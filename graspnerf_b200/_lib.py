@@ -20,7 +20,7 @@ class GnK1Params(C.Structure):
 class GnK2aParams(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ('rec', 'pt', 'weights', 'depth_range', 'que_dists', 'pooled', 'colors',
                                           'dbg_rows', 'tc_const', 'tok', 'axis', 'bbox_min', 'pts')] + \
-               [(n, C.c_int) for n in ('B', 'N', 'V', 'dn', 'with_rgb', 'R', 'volume_mode')]
+               [(n, C.c_int) for n in ('B', 'N', 'V', 'dn', 'with_rgb', 'R', 'volume_mode')] + [('status', C.c_void_p)]
 
 
 class GnK2bParams(C.Structure):
@@ -50,6 +50,17 @@ class GnK1BwdParams(C.Structure):
                [(n, C.c_int) for n in ('B', 'V', 'H', 'W', 'fh', 'fw', 'R', 'N', 'volume_mode')]
 
 
+class GnRaySetupParams(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ('coords', 'poses', 'Ks', 'depth', 'depth_range', 'pts', 'que_dir', 'inv_dists')] + \
+               [(n, C.c_int) for n in ('B', 'rn', 'dn')]
+
+
+class GnGraspPostParams(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ('tsdf', 'qual', 'rot', 'width', 'qual_out', 'scratch', 'grasps', 'count')] + \
+               [(n, C.c_float) for n in ('sigma', 'min_width', 'max_width', 'tsdf_thres_high', 'tsdf_thres_low', 'threshold')] + \
+               [(n, C.c_int) for n in ('R', 'max_filter_size', 'max_grasps')]
+
+
 _lib = None
 
 
@@ -67,7 +78,7 @@ def load():
     lib.gn_version.restype = C.c_char_p
     for name, st in (('gn_k1_forward', GnK1Params), ('gn_k2a_forward', GnK2aParams), ('gn_k2a_forward_tc', GnK2aParams), ('gn_k2b_forward', GnK2bParams),
                      ('gn_k3_composite', GnK3Params), ('gn_k2b_backward', GnK2bBwdParams), ('gn_k2a_backward', GnK2aBwdParams),
-                     ('gn_k1_backward', GnK1BwdParams)):
+                     ('gn_k1_backward', GnK1BwdParams), ('gn_k3_ray_setup', GnRaySetupParams), ('gn_k4_grasp_post', GnGraspPostParams)):
         fn = getattr(lib, name)
         fn.restype = C.c_int
         fn.argtypes = [C.POINTER(st), C.c_void_p]
@@ -82,7 +93,8 @@ def load():
     for name, st in (('gn_sizeof_k1_params', GnK1Params), ('gn_sizeof_k2a_params', GnK2aParams),
                      ('gn_sizeof_k2b_params', GnK2bParams), ('gn_sizeof_k3_params', GnK3Params),
                      ('gn_sizeof_k2b_bwd_params', GnK2bBwdParams), ('gn_sizeof_k2a_bwd_params', GnK2aBwdParams),
-                     ('gn_sizeof_k1_bwd_params', GnK1BwdParams)):
+                     ('gn_sizeof_k1_bwd_params', GnK1BwdParams), ('gn_sizeof_ray_setup_params', GnRaySetupParams),
+                     ('gn_sizeof_grasp_post_params', GnGraspPostParams)):
         got = getattr(lib, name)()
         if got != C.sizeof(st):
             raise RuntimeError(f'{name}: library says {got} bytes, ctypes mirror has {C.sizeof(st)}')

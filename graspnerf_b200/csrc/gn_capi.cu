@@ -22,3 +22,5 @@ extern "C" int gn_sizeof_k3_params(void) { return (int)sizeof(GnK3Params); }
 extern "C" int gn_sizeof_k2b_bwd_params(void) { return (int)sizeof(GnK2bBwdParams); }
 extern "C" int gn_sizeof_k2a_bwd_params(void) { return (int)sizeof(GnK2aBwdParams); }
 extern "C" int gn_sizeof_k1_bwd_params(void) { return (int)sizeof(GnK1BwdParams); }
+extern "C" int gn_sizeof_ray_setup_params(void) { return (int)sizeof(GnRaySetupParams); }
+extern "C" int gn_sizeof_grasp_post_params(void) { return (int)sizeof(GnGraspPostParams); }

@@ -58,7 +58,7 @@ __device__ __noinline__ void t3_epilogue(uint32_t lane_addr, int d_col, int nchu
 #pragma unroll
         for (int i = 0; i < 16; i += 2) {
             if (ACT == 1) tc_elu2(y[i], y[i + 1]);
-            else if (ACT == 2) { y[i] = fmaxf(y[i], 0.f); y[i + 1] = fmaxf(y[i + 1], 0.f); }
+            else if (ACT == 2) { y[i] = y[i] > 0.f ? y[i] : y[i] * 0.f; y[i + 1] = y[i + 1] > 0.f ? y[i + 1] : y[i + 1] * 0.f; }   // ReLU that keeps NaN (fmaxf would hide an overflow)
         }
         t3_store_a<16>(lane_addr, k0 + c * 16, y);
     }
@@ -225,6 +225,10 @@ __device__ __noinline__ void t3_geometry_phase(const GnK2aParams& p, uint32_t tm
             float tk[16];
             tm_ld<16>(cx.lane_addr + T3_D, tk); bias_elu<16>(sw + TS(GF_B2), tk);
             if (valid2) {
+                float chk = 0.f;
+#pragma unroll
+                for (int c = 0; c < 16; ++c) chk += fabsf(tk[c]);
+                if (p.status && !(chk <= 3.0e38f)) atomicOr(p.status, 1);       // inf / NaN reached the tokens (fp16 operand overflow upstream)
                 float* out = p.tok + (size_t)pidx * GN_TOK_STRIDE;
                 st4(out, make_float4(tk[0], tk[1], tk[2], tk[3]));       st4(out + 4, make_float4(tk[4], tk[5], tk[6], tk[7]));
                 st4(out + 8, make_float4(tk[8], tk[9], tk[10], tk[11])); st4(out + 12, make_float4(tk[12], tk[13], tk[14], tk[15]));
@@ -524,6 +528,14 @@ gn_k2a_tc3_kernel(const __grid_constant__ GnK2aParams p, int num_tiles, int G)
 #pragma unroll
             for (int c = 0; c < 36; ++c) { const float dl = x[c] - mu[c]; tmp[c] = w2 * dl * dl; }
             t3_pool36(scr, lane, g, v, gb, V, lane_active, tmp, vr);
+        }
+        if (p.status) {
+            float chk = fabsf(hit) + fabsf(vis);
+            if (writer) {
+#pragma unroll
+                for (int c = 0; c < 32; ++c) chk += fabsf(mu[c]) + fabsf(vr[c]);
+            }
+            if (valid && !(chk <= 3.0e38f)) atomicOr(p.status, 1);
         }
         if (p.pooled && writer) {
             float* out = p.pooled + (size_t)pidx * GN_POOL_STRIDE;

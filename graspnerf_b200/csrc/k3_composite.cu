@@ -149,3 +149,59 @@ extern "C" int gn_k3_fine_depths(const float* depth, const float* hit_prob, cons
         depth, hit_prob, depth_range, u, fine_depth, (long long*)inds, B, rn, dn, fdn);
     return (int)cudaGetLastError();
 }
+
+// ----------------------------------------------------------------------------------------------------------------------
+// Ray set-up of the RGB head: coords2rays (render_ops.py:4-25), depth2points (27-39), depth2inv_dists (46-52) in ONE launch
+// (the reference - and round 1 of this repo - runs a 3x3 torch.inverse, three bmm and ~10 element-wise kernels per chunk).
+// thread <-> ray.  K^-1 is the adjugate / determinant in fp32 (torch.inverse factorises; both are exact to ~1 ulp for the
+// upper-triangular pinhole K), the world direction is (R^T (K^-1 [x,y,1]) + c) - c like render_ops.py:22-23.
+__global__ void gn_k3_ray_setup_kernel(const GnRaySetupParams p)
+{
+    const long long ray = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ray >= (long long)p.B * p.rn) return;
+    const int b = (int)(ray / p.rn);
+    const float* K = p.Ks + b * 9;
+    const float* P = p.poses + b * 12;
+    const float a = K[0], bb = K[1], c = K[2], d = K[3], e = K[4], f = K[5], g = K[6], h = K[7], i = K[8];
+    const float A = e * i - f * h, Bc = -(d * i - f * g), Cc = d * h - e * g;
+    const float det = a * A + bb * Bc + c * Cc;
+    const float id = __fdiv_rn(1.f, det);
+    const float inv[9] = { A * id, -(bb * i - c * h) * id, (bb * f - c * e) * id,
+                           Bc * id, (a * i - c * g) * id, -(a * f - c * d) * id,
+                           Cc * id, -(a * h - bb * g) * id, (a * e - bb * d) * id };
+    const float x = p.coords[ray * 2], y = p.coords[ray * 2 + 1];
+    const float cx = inv[0] * x + inv[1] * y + inv[2], cy = inv[3] * x + inv[4] * y + inv[5], cz = inv[6] * x + inv[7] * y + inv[8];
+    // rot = R^T (render_ops.py:14), centre = -R^T t (15)
+    float ctr[3], dir[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        ctr[r] = -(P[0 * 4 + r] * P[3] + P[1 * 4 + r] * P[7] + P[2 * 4 + r] * P[11]);
+        const float w = (P[0 * 4 + r] * cx + P[1 * 4 + r] * cy + P[2 * 4 + r] * cz) + ctr[r];
+        dir[r] = w - ctr[r];
+    }
+    const float nrm = sqrtf(dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2]);
+    p.que_dir[ray * 3] = __fdiv_rn(-dir[0], nrm); p.que_dir[ray * 3 + 1] = __fdiv_rn(-dir[1], nrm); p.que_dir[ray * 3 + 2] = __fdiv_rn(-dir[2], nrm);
+    const float rnear = __fdiv_rn(-1.f, p.depth_range[b * 2]), rfar = __fdiv_rn(-1.f, p.depth_range[b * 2 + 1]);
+    const float* dep = p.depth + ray * p.dn;
+    float* pts = p.pts + ray * p.dn * 3;
+    float* qd = p.inv_dists + ray * p.dn;
+    float cur = __fdiv_rn(__fdiv_rn(-1.f, dep[0]) - rnear, rfar - rnear);
+    for (int s = 0; s < p.dn; ++s) {
+        const float z = dep[s];
+        pts[s * 3] = ctr[0] + dir[0] * z; pts[s * 3 + 1] = ctr[1] + dir[1] * z; pts[s * 3 + 2] = ctr[2] + dir[2] * z;
+        float nxt = 0.f;
+        if (s + 1 < p.dn) nxt = __fdiv_rn(__fdiv_rn(-1.f, dep[s + 1]) - rnear, rfar - rnear);
+        qd[s] = (s + 1 < p.dn) ? __fsub_rn(nxt, cur) : 1e6f;                        // depth2dists: last spacing 1e6
+        cur = nxt;
+    }
+}
+
+extern "C" int gn_k3_ray_setup(const GnRaySetupParams* hp, void* stream)
+{
+    const GnRaySetupParams& p = *hp;
+    if (p.B < 1 || p.rn < 1 || p.dn < 1) return -1;
+    if (!p.coords || !p.poses || !p.Ks || !p.depth || !p.depth_range || !p.pts || !p.que_dir || !p.inv_dists) return -2;
+    const long long rays = (long long)p.B * p.rn;
+    gn_k3_ray_setup_kernel<<<(unsigned)((rays + 127) / 128), 128, 0, (cudaStream_t)stream>>>(p);
+    return (int)cudaGetLastError();
+}

@@ -1,91 +1,214 @@
-"""Host-buffer front end of the hot path: pinned host scenes in, TSDF volumes out, copies overlapped with compute.
+"""Host-buffer front ends: pinned host scenes in, results out, copies overlapped with compute.
 
-This is the reference-facing call for the `sample_volume` path when the inputs live in HOST memory (what
-GraspNeRFPlanner.core hands to the network, src/nr/main.py:225-247): H2D of the step's inputs, K1 -> K2a -> K2b, D2H of
-the volume.  Three slots are kept in flight so the PCIe copies of step i+1 run under the kernels of step i
-(one copy stream + one compute stream, ordered by CUDA events; no host synchronisation inside the loop except when a
-slot is recycled).
+Two engines, both the reference-facing call when the inputs live in HOST memory (what GraspNeRFPlanner.core hands to the
+network, src/nr/main.py:225-247):
+
+  VolumeEngine   the hot path alone: images + the encoders' feature maps from the host -> K1 -> K2a -> K2b -> TSDF volume.
+  ForwardEngine  the whole GraspNeRF.forward of the planner (eval, render_rgb off as main.py:150): uint8 images from the
+                 host -> 2-D encoders (cuDNN) -> K1 -> K2a -> K2b -> VGN head -> (optional) grasp post-processing on the
+                 device; only the image bytes cross PCIe on the way in.
+
+`slots` scenes are kept in flight so the PCIe copies of step i+1 run under the kernels of step i (one copy stream + one
+compute stream, ordered by CUDA events; no host synchronisation inside the loop except when a slot is recycled).
+
+Images may be uint8 ([V,H,W,3] as cv2 / imread give them, or [V,H,W,4]): they cross PCIe as bytes and K1 divides by 255 in
+its gather exactly like color_map_forward (main.py:170); fp32 [V,3,H,W] images are accepted as the reference holds them.
+
+Result lifetime: a result handed back by submit()/collect()/drain() is a pinned buffer owned by the engine.  Each slot
+alternates between TWO output buffers, so a returned buffer stays untouched until the SAME slot has been submitted to twice
+more, i.e. for at least `slots` further submit() calls.  Copy it if you need it longer.
 """
 import torch
 
 from . import ops
 
 
-class HostScene:
-    """Pinned host buffers of one scene (the layout K1 consumes: the two channels-last feature maps [V,fh,fw,32]
-    interleaved per texel into one [V,fh,fw,64] buffer, ray_feats | img_feats)."""
+def _pin(x, dtype=None):
+    t = torch.as_tensor(x)
+    if dtype is not None:
+        t = t.to(dtype)
+    t = t.contiguous()
+    return t.pin_memory() if torch.cuda.is_available() else t
 
-    def __init__(self, imgs, img_feats_cl, ray_feats_cl, poses, Ks, depth_range, bbox_min):
-        def pin(x):
-            t = torch.as_tensor(x, dtype=torch.float32).contiguous()
-            return t.pin_memory() if torch.cuda.is_available() else t
-        self.imgs = pin(imgs)
-        self.feats = pin(ops.fuse_feature_maps(torch.as_tensor(img_feats_cl, dtype=torch.float32),
-                                               torch.as_tensor(ray_feats_cl, dtype=torch.float32)))
-        self.poses, self.Ks, self.depth_range, self.bbox_min = pin(poses), pin(Ks), pin(depth_range), pin(bbox_min)
+
+class HostScene:
+    """Pinned host buffers of one scene.  imgs: uint8 [V,H,W,3|4] or fp32 [V,3,H,W]; feature maps (VolumeEngine only):
+    the two channels-last maps [V,fh,fw,32], interleaved per texel into the fused [V,fh,fw,64] buffer K1 consumes."""
+
+    def __init__(self, imgs, img_feats_cl=None, ray_feats_cl=None, poses=None, Ks=None, depth_range=None, bbox_min=None):
+        imgs = torch.as_tensor(imgs)
+        if imgs.dtype == torch.uint8:
+            if imgs.shape[-1] == 3:                       # pad to RGBA once on the host: one 4-byte texel per bilinear tap
+                imgs = torch.cat([imgs, torch.zeros(imgs.shape[:-1] + (1,), dtype=torch.uint8)], -1)
+            self.imgs = _pin(imgs)
+        else:
+            self.imgs = _pin(imgs, torch.float32)
+        self.feats = None
+        if img_feats_cl is not None:
+            self.feats = _pin(ops.fuse_feature_maps(torch.as_tensor(img_feats_cl, dtype=torch.float32),
+                                                    torch.as_tensor(ray_feats_cl, dtype=torch.float32)))
+        self.poses, self.Ks = _pin(poses, torch.float32), _pin(Ks, torch.float32)
+        self.depth_range, self.bbox_min = _pin(depth_range, torch.float32), _pin(bbox_min, torch.float32)
+
+    def tensors(self):
+        return [t for t in (self.imgs, self.feats, self.poses, self.Ks, self.depth_range, self.bbox_min) if t is not None]
 
     @property
     def nbytes(self):
-        return sum(t.numel() * 4 for t in (self.imgs, self.feats, self.poses, self.Ks, self.depth_range, self.bbox_min))
+        return sum(t.numel() * t.element_size() for t in self.tensors())
 
 
 class _Slot:
-    def __init__(self, hs, resolution, device):
+    def __init__(self, hs, out_shapes, device):
         def dev(t):
-            return torch.empty(t.shape, dtype=torch.float32, device=device)
-        self.imgs, self.feats = dev(hs.imgs)[None], dev(hs.feats)[None]
+            return torch.empty(t.shape, dtype=t.dtype, device=device)
+        self.imgs = dev(hs.imgs)[None]
+        self.feats = dev(hs.feats)[None] if hs.feats is not None else None
         self.poses, self.Ks, self.depth_range = dev(hs.poses)[None], dev(hs.Ks)[None], dev(hs.depth_range)[None]
         self.bbox_min = dev(hs.bbox_min).reshape(1, 3)
-        self.out_host = torch.empty((1, 1, resolution, resolution, resolution), dtype=torch.float32).pin_memory()
+        # two pinned output sets per slot, alternating (see "Result lifetime" in the module docstring)
+        self.out_host = [[torch.empty(s, dtype=d).pin_memory() for s, d in out_shapes] for _ in range(2)]
+        self.flip = 0
         self.graph = None
+        self.static_out = None
         self.ev_in = torch.cuda.Event()
         self.ev_done = torch.cuda.Event()
         self.busy = False
         self.tag = None
+        self.last = None
 
 
-class VolumeEngine:
-    def __init__(self, head_weights, example, resolution=40, volume_size=0.3, slots=3, device='cuda'):
-        self.hw, self.R, self.vs = head_weights, resolution, volume_size
+class _Engine:
+    """Slot ring shared by both engines; subclasses provide `_out_shapes()` and `_compute(slot) -> list of device tensors`."""
+
+    def __init__(self, example, slots, device):
         self.device = torch.device(device)
         self.copy_stream = torch.cuda.Stream(self.device)
         self.compute_stream = torch.cuda.Stream(self.device)
-        self.slots = [_Slot(example, resolution, self.device) for _ in range(slots)]
+        shapes = self._out_shapes()
+        self.slots = [_Slot(example, shapes, self.device) for _ in range(slots)]
         self.next = 0
         self.h2d_bytes = example.nbytes
-        self.d2h_bytes = resolution ** 3 * 4
+        self.d2h_bytes = sum(int(torch.tensor(s).prod()) * torch.empty((), dtype=d).element_size() for s, d in shapes)
 
     def submit(self, hs, tag=None):
-        """Queues one scene; returns the slot index.  If the slot is still in flight its result is returned first via
-        `collect`."""
+        """Queues one scene.  Returns (slot index, finished) where `finished` is the result of the scene that previously
+        occupied the slot - (tag, outputs) - or None."""
         i = self.next
         self.next = (self.next + 1) % len(self.slots)
         s = self.slots[i]
         finished = self.collect(i) if s.busy else None
         with torch.cuda.stream(self.copy_stream):
-            for dst, src in ((s.imgs, hs.imgs), (s.feats, hs.feats),
-                             (s.poses, hs.poses), (s.Ks, hs.Ks), (s.depth_range, hs.depth_range)):
-                dst[0].copy_(src, non_blocking=True)
+            for dst, src in ((s.imgs, hs.imgs), (s.feats, hs.feats), (s.poses, hs.poses), (s.Ks, hs.Ks), (s.depth_range, hs.depth_range)):
+                if dst is not None:
+                    dst[0].copy_(src, non_blocking=True)
             s.bbox_min.copy_(hs.bbox_min.reshape(1, 3), non_blocking=True)
             s.ev_in.record(self.copy_stream)
         with torch.cuda.stream(self.compute_stream):
             self.compute_stream.wait_event(s.ev_in)
-            if s.graph is None:                   # first use of the slot: capture (layout prep + K1 + K2a + K2b) once
-                def prologue(s=s):
-                    return ops.Scene(s.imgs, None, None, s.poses, s.Ks, s.depth_range, feats_fused=s.feats)
-                s.graph = ops.VolumeGraph(None, self.hw, s.bbox_min, self.R, self.vs, prologue=prologue)
-            vol = s.graph.replay()
-            s.out_host.copy_(vol, non_blocking=True)
+            outs = self._compute(s)
+            s.flip ^= 1
+            hosts = s.out_host[s.flip]                   # the buffer set NOT handed out by the previous collect of this slot
+            for h, d in zip(hosts, outs):
+                h.copy_(d.reshape(h.shape), non_blocking=True)
             s.ev_done.record(self.compute_stream)
-        s.busy, s.tag = True, tag
+        s.busy, s.tag, s.last = True, tag, hosts
         return i, finished
 
     def collect(self, i):
-        """Blocks until slot i finished; returns (tag, pinned host volume [1,1,R,R,R])."""
+        """Blocks until slot i finished; returns (tag, outputs).  Outputs: see the engine's docstring."""
         s = self.slots[i]
         s.ev_done.synchronize()
         s.busy = False
-        return s.tag, s.out_host
+        return s.tag, self._wrap(s.last)
 
     def drain(self):
         return [self.collect(i) for i, s in enumerate(self.slots) if s.busy]
+
+    def _wrap(self, hosts):
+        return hosts[0] if len(hosts) == 1 else hosts
+
+
+class VolumeEngine(_Engine):
+    """Hot path with host buffers.  Result per scene: the pinned host volume [1,1,R,R,R]."""
+
+    def __init__(self, head_weights, example, resolution=40, volume_size=0.3, slots=3, device='cuda'):
+        if example.feats is None:
+            raise ValueError('VolumeEngine needs the feature maps in the HostScene (use ForwardEngine for images-in)')
+        self.hw, self.R, self.vs = head_weights, resolution, volume_size
+        super().__init__(example, slots, device)
+
+    def _out_shapes(self):
+        return [((1, 1, self.R, self.R, self.R), torch.float32)]
+
+    def _compute(self, s):
+        if s.graph is None:                   # first use of the slot: capture (layout prep + K1 + K2a + K2b) once
+            def prologue(s=s):
+                return ops.Scene(s.imgs, None, None, s.poses, s.Ks, s.depth_range, feats_fused=s.feats)
+            s.graph = ops.VolumeGraph(None, self.hw, s.bbox_min, self.R, self.vs, prologue=prologue)
+        return [s.graph.replay()]
+
+
+class ForwardEngine(_Engine):
+    """The planner's whole network call with host buffers (GraspNeRFPlanner.core, main.py:211-253): images in, volumes out.
+
+    net: the mirror `GraspNeRF` (graspnerf_b200.network), on `device`, eval mode.  Per scene the device runs image_encoder /
+    init_net / vis_encoder (renderer.py:275-279, cuDNN fp32), sample_volume (K1 -> K2a -> K2b), the depth-mean head
+    (renderer.py:288-289: always on in eval) and the VGN head (renderer.py:323-330), captured in ONE CUDA graph per slot
+    when capture succeeds (eager otherwise; `self.graphed` says which).  Result per scene, pinned host tensors:
+      [volumes [7,R,R,R] = tsdf, qual, rot0..3, width,  grasps [max_grasps,9],  count int32[1]]
+    (grasps / count from gn_k4_grasp_post - main.py:23-74 - when post_cfg is given, else zeros)."""
+
+    def __init__(self, net, example, slots=3, device='cuda', post_cfg=None, max_grasps=256, depth_mean=True, use_graph=True):
+        self.net = net.eval()
+        self.R = net.nr_net.cfg['volume_resolution']
+        self.post_cfg, self.max_grasps, self.depth_mean, self.use_graph = post_cfg, max_grasps, depth_mean, use_graph
+        self.graphed = None
+        if example.imgs.dtype != torch.uint8:
+            raise ValueError('ForwardEngine takes uint8 images [V,H,W,3|4] (the planner reads PNG bytes, main.py:166-171)')
+        super().__init__(example, slots, device)
+
+    def _out_shapes(self):
+        R = self.R
+        return [((7, R, R, R), torch.float32), ((self.max_grasps, 9), torch.float32), ((1,), torch.int32)]
+
+    def _body(self, s):
+        nr = self.net.nr_net
+        imgs = (s.imgs[0, ..., :3].permute(0, 3, 1, 2).to(torch.float32) / 255.0).contiguous()     # color_map_forward + transpose (main.py:192)
+        ref = {'imgs': imgs, 'imgs_u8': s.imgs, 'poses': s.poses[0], 'Ks': s.Ks[0], 'depth_range': s.depth_range[0],
+               'bbox3d': s.bbox_min.reshape(1, 3)}
+        ref['img_feats'] = nr.image_encoder(imgs)
+        ref['ray_feats'] = nr.vis_encoder(nr.init_net(ref, ref, False), ref['img_feats'])
+        vol = nr.sample_volume(ref)
+        if self.depth_mean:
+            nr.predict_mean_for_depth_loss(ref)
+        qual, rot, width = self.net.vgn_net(vol)
+        R = self.R
+        vols = torch.cat([vol.reshape(1, R, R, R), qual.reshape(1, R, R, R), rot.reshape(4, R, R, R), width.reshape(1, R, R, R)], 0)
+        if self.post_cfg is not None:
+            _, grasps, count = ops.grasp_post(vols[0], vols[1], vols[2:6], vols[6], max_grasps=self.max_grasps, **self.post_cfg)
+        else:
+            grasps = torch.zeros((self.max_grasps, 9), device=vols.device)
+            count = torch.zeros((1,), device=vols.device, dtype=torch.int32)
+        return [vols, grasps, count]
+
+    def _compute(self, s):
+        with torch.no_grad():
+            if not self.use_graph or self.graphed is False:
+                return self._body(s)
+            if s.graph is None:
+                cur = torch.cuda.current_stream(self.device)
+                try:
+                    for _ in range(2):                    # warm-up outside capture: cuDNN algorithm selection, allocator pools
+                        self._body(s)
+                    cur.synchronize()
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=cur):
+                        s.static_out = self._body(s)
+                    s.graph, self.graphed = g, True
+                except Exception:                          # an op in the torch-side modules refused capture: stay eager
+                    torch.cuda.synchronize(self.device)
+                    s.graph, self.graphed = None, False
+                    return self._body(s)
+            s.graph.replay()
+            return s.static_out

@@ -93,17 +93,12 @@ def render_by_depth_autograd(nr, ref, que, que_depth, is_fine, is_train=True):
     assert B == 1, 'the reference renders one query view per call (qn = 1)'
     agg = nr.fine_agg_net if is_fine else nr.agg_net
     agg_prefix, dd_prefix = ('fine_agg_net.', 'fine_dist_decoder.') if is_fine else ('agg_net.', 'dist_decoder.')
-    dr = que['depth_range']
-    near, far = (-1 / dr[:, 0])[:, None, None], (-1 / dr[:, 1])[:, None, None]
-    dinv = (-1 / que_depth - near) / (far - near)                                      # depth2inv_dists render_ops.py:46-52
-    inv_dists = torch.cat([dinv[..., 1:] - dinv[..., :-1], torch.full_like(dinv[..., :1], 1e6)], -1)
+    que_depth = que_depth.contiguous()
+    pts, que_dir, inv_dists = ops.ray_setup(que['coords'], que['poses'], que['Ks'], que['depth_range'], que_depth)   # render_ops.py:4-52
     dists = torch.cat([que_depth[..., 1:] - que_depth[..., :-1], torch.full_like(que_depth[..., :1], 1e6)], -1)   # depth2dists 41-44
-    centre, dirs = ops.query_rays(que['coords'], que['poses'], que['Ks'])
-    pts = (centre[:, None, None] + dirs[:, :, None] * que_depth[..., None]).reshape(B, rn * dn, 3)   # depth2points 27-39
-    que_dir = (-dirs / torch.norm(dirs, dim=2, keepdim=True)).contiguous()
     named = {k: v for k, v in nr.named_parameters() if k.startswith((agg_prefix, dd_prefix))}
     pooled, colors, nvalid = ops.ray_features_autograd(ref['imgs'], ref['img_feats'], ref['ray_feats'], ref['poses'], ref['Ks'],
-                                                       ref['depth_range'], pts, que_dir, inv_dists.reshape(B, rn * dn), dn, named,
+                                                       ref['depth_range'], pts, que_dir, inv_dists, dn, named,
                                                        agg_prefix, dd_prefix)
     nvalid = nvalid[0].reshape(rn, dn)
     sdf, grad = sdf_and_gradient(agg.agg_impl, pooled[0, :, :65].reshape(rn, dn, 65), pts[0].reshape(rn, dn, 3), nvalid)

@@ -38,6 +38,20 @@ class NeuralRayRenderer(nn.Module):
         self.cfg = {**self.base_cfg, **cfg}
         if self.cfg['agg_net_type'] != 'neus':
             raise NotImplementedError("only agg_net_type 'neus' (the shipped nrvgn_sdf.yaml) is implemented")
+        # configuration values the kernels hard-code: refuse anything else instead of silently computing something different
+        for key in ('dist_decoder_cfg', 'fine_dist_decoder_cfg'):
+            dcfg = {'bias_val': 0.05, 'use_vis': True, **self.cfg[key]}          # dist_decoder.py:54-58 defaults
+            if dcfg['use_vis']:
+                raise NotImplementedError(f"{key}.use_vis=True (cdf * vis_decoder, dist_decoder.py:130-131) is not implemented: the shipped "
+                                          "nrvgn_sdf.yaml sets use_vis: false for both decoders")
+            if float(dcfg['bias_val']) != 0.05:
+                raise NotImplementedError(f'{key}.bias_val != 0.05 is not implemented (the K2a kernel adds the 0.05 of dist_decoder.py:56)')
+        if self.cfg['disable_view_dir']:
+            raise NotImplementedError('disable_view_dir=True (renderer.py:116-117) is not implemented')
+        if self.cfg['fine_depth_use_all']:
+            raise NotImplementedError('fine_depth_use_all=True (renderer.py:145-146: coarse + fine depths) is not implemented')
+        if self.cfg['alpha_value_ground_state'] != -15:
+            raise NotImplementedError('alpha_value_ground_state != -15 is not implemented')
         self.vis_encoder = name2vis_encoder[self.cfg['vis_encoder_type']](self.cfg['vis_encoder_cfg'])
         self.dist_decoder = name2dist_decoder[self.cfg['dist_decoder_type']](self.cfg['dist_decoder_cfg'])
         self.image_encoder = ResUNetLight(3, [1, 2, 6, 4], 32, inplanes=16)
@@ -63,7 +77,13 @@ class NeuralRayRenderer(nn.Module):
 
     @staticmethod
     def _scene(ref_imgs_info):
-        return ops.Scene(ref_imgs_info['imgs'], ref_imgs_info['img_feats'], ref_imgs_info['ray_feats'],
+        # 'imgs_u8' (optional, engine.ForwardEngine / planner): the same images as uint8 RGBA [1,V,H,W,4]; K1 then gathers
+        # bytes and divides by 255 itself (bit-identical to gathering the fp32 image, main.py:170)
+        imgs = ref_imgs_info.get('imgs_u8', ref_imgs_info['imgs'])
+        if imgs.dtype == torch.uint8 and imgs.dim() == 5:
+            return ops.Scene(imgs, ref_imgs_info['img_feats'][None], ref_imgs_info['ray_feats'][None], ref_imgs_info['poses'][None],
+                             ref_imgs_info['Ks'][None], ref_imgs_info['depth_range'][None])
+        return ops.Scene(imgs, ref_imgs_info['img_feats'], ref_imgs_info['ray_feats'],
                          ref_imgs_info['poses'], ref_imgs_info['Ks'], ref_imgs_info['depth_range'])
 
     # ------------------------------------------------------------------------------------------------ hot path
@@ -124,14 +144,16 @@ class NeuralRayRenderer(nn.Module):
         return {k: torch.cat(v, 1) for k, v in outs.items()}
 
     # ------------------------------------------------------------------------------------------------ torch-side heads
-    def predict_mean_for_depth_loss(self, ref_imgs_info):
-        """renderer.py:222-266: depth_loss_coords_num random pixels x V -> mean_decoder (+fine).  Small; stays in torch."""
+    def predict_mean_for_depth_loss(self, ref_imgs_info, coords=None):
+        """renderer.py:222-266: depth_loss_coords_num random pixels x V -> mean_decoder (+fine).  Small; stays in torch.
+        coords (optional, [V,num,2] int64): use these pixels instead of drawing new ones (parity tests)."""
         ray_feats, imgs = ref_imgs_info['ray_feats'], ref_imgs_info['imgs']
         rfn, _, h, w = imgs.shape
         num = self.cfg['depth_loss_coords_num']
-        idx = torch.randperm(h * w, device=imgs.device)[:num]
-        coords = torch.stack([idx // w, idx % w], -1)        # the reference stacks (row, col) of meshgrid(arange(h), arange(w))
-        coords = coords.unsqueeze(0).repeat(rfn, 1, 1)
+        if coords is None:
+            idx = torch.randperm(h * w, device=imgs.device)[:num]
+            coords = torch.stack([idx // w, idx % w], -1)        # the reference stacks (row, col) of meshgrid(arange(h), arange(w))
+            coords = coords.unsqueeze(0).repeat(rfn, 1, 1)
         cf = coords.float()
         grid = torch.stack([cf[..., 0] / (w - 1) * 2 - 1, cf[..., 1] / (h - 1) * 2 - 1], -1).unsqueeze(1)   # ops.py:29-31
         feats = torch.nn.functional.grid_sample(ray_feats, grid, mode='bilinear', padding_mode='border',

@@ -14,8 +14,15 @@ from .weights import DevicePacker, positional_table, voxel_axis_table
 REC_STRIDE, PT_STRIDE, POOL_STRIDE, TOK_STRIDE = 72, 2, 68, 20
 
 
-def _stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+def _stream(dev=None):
+    """Current stream of the device that owns the tensors (NOT of torch's current device: a scene on cuda:1 must launch on
+    cuda:1 even if the caller never called torch.cuda.set_device)."""
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _on(dev):
+    """Context: the launchers' per-device caches (kernel attributes, SM count) and the launch itself use cudaGetDevice()."""
+    return torch.cuda.device(dev)
 
 
 def _ptr(t):
@@ -66,10 +73,23 @@ class HeadWeights:
         # tensor-core operand images (fp16 hi/lo, K-major) + small constants, built on the device from the fp32 blob
         lib = _lib.load()
         self.tc_const = torch.empty(lib.gn_k2a_tc_const_bytes(), dtype=torch.uint8, device=self.device)
-        with torch.cuda.device(self.device):
-            _lib.check(lib.gn_k2a_tc_prepare(_ptr(self.blob), _ptr(self.tc_const), _stream()), 'gn_k2a_tc_prepare')
+        with _on(self.device):
+            _lib.check(lib.gn_k2a_tc_prepare(_ptr(self.blob), _ptr(self.tc_const), _stream(self.device)), 'gn_k2a_tc_prepare')
         self._var = sd.get(self.agg_prefix + 'deviation_network.variance')
+        if not hasattr(self, 'status'):
+            self.status = torch.zeros(1, dtype=torch.int32, device=self.device)     # sticky numerics flag written by K2a
         self._versions = vers
+
+    def check_numerics(self, reset=True):
+        """Raises FloatingPointError if any K2a launch with these weights saw a non-finite hit probability, pooled feature or
+        token since the last reset: the fp16 hi/lo operand split of the tensor-core kernel overflows for activations >= 65504
+        (the fp32 reference would not).  Reading the flag synchronises; call it when convenient (tests, every N training steps)."""
+        bad = int(self.status.item())
+        if reset:
+            self.status.zero_()
+        if bad:
+            raise FloatingPointError('gn_k2a_forward_tc: non-finite activations (fp16 operand range 65504 exceeded); '
+                                     'the weights / features are outside the range the tensor-core path supports')
 
     @property
     def variance(self):
@@ -118,10 +138,21 @@ class Scene:
         _require_cuda(imgs, 'imgs')
         dev = imgs.device
         self.device = dev
-        imgs = _f32c(imgs, dev)                                                     # [B,V,3,H,W] as the reference holds them
-        self.B, self.V, _, self.H, self.W = imgs.shape
-        # RGBA-interleaved copy [B,V,H,W,4]: one bilinear tap = one 16-byte texel (layout change only, like channels-last)
-        self.imgs = torch.cat([imgs.permute(0, 1, 3, 4, 2), imgs.new_zeros(self.B, self.V, self.H, self.W, 1)], -1).contiguous()
+        self.img_u8 = imgs.dtype == torch.uint8
+        if self.img_u8:
+            # the planner's images are PNG bytes (main.py:166-171): [B,V,H,W,3] (HWC, as cv2 / imread give them) or already
+            # [B,V,H,W,4]; the kernel divides by 255 exactly like color_map_forward, the bytes stay bytes in HBM
+            if imgs.shape[-1] == 3:
+                imgs = torch.cat([imgs, imgs.new_zeros(imgs.shape[:-1] + (1,))], -1)
+            if imgs.shape[-1] != 4:
+                raise ValueError('uint8 images must be [B,V,H,W,3] or [B,V,H,W,4]')
+            self.imgs = imgs.contiguous()
+            self.B, self.V, self.H, self.W, _ = self.imgs.shape
+        else:
+            imgs = _f32c(imgs, dev)                                                 # [B,V,3,H,W] as the reference holds them
+            self.B, self.V, _, self.H, self.W = imgs.shape
+            # RGBA-interleaved copy [B,V,H,W,4]: one bilinear tap = one 16-byte texel (layout change only, like channels-last)
+            self.imgs = torch.cat([imgs.permute(0, 1, 3, 4, 2), imgs.new_zeros(self.B, self.V, self.H, self.W, 1)], -1).contiguous()
         if feats_fused is not None:   # already [B,V,fh,fw,64]
             self.feats = _f32c(feats_fused, dev)
         else:
@@ -169,10 +200,11 @@ def k1_forward(scene, hw, *, resolution=None, bbox_min=None, volume_size=0.3, pt
     p.KRt, p.cam = _ptr(scene.KRt).value, _ptr(scene.cam).value
     p.rec, p.pt, p.dbg_feat_idx = _ptr(rec).value, _ptr(pt).value, _ptr(dbg).value
     p.B, p.V, p.H, p.W, p.fh, p.fw = scene.B, scene.V, scene.H, scene.W, scene.fh, scene.fw
-    p.N, p.dn, p.volume_mode = N, dn_, 1 if vol else 0
+    p.N, p.dn, p.volume_mode, p.img_u8 = N, dn_, 1 if vol else 0, 1 if scene.img_u8 else 0
     if ev is not None:
         ev[0].record()
-    rc = lib.gn_k1_forward(C.byref(p), _stream())
+    with _on(dev):
+        rc = lib.gn_k1_forward(C.byref(p), _stream(dev))
     if ev is not None:
         ev[1].record()
     _lib.check(rc, 'gn_k1_forward')
@@ -203,6 +235,7 @@ def k2a_forward(rec, pt, hw, depth_range, *, que_dists=None, dn=1, want_colors=F
     p.B, p.N, p.V, p.dn, p.with_rgb = B, N, V, int(dn), 1 if want_colors else 0
     if impl == 'tc':
         p.tc_const = _ptr(hw.tc_const).value
+        p.status = _ptr(hw.status).value
         if want_tok:
             tok = torch.empty((B, N, TOK_STRIDE), device=dev, dtype=torch.float32)
             p.tok = _ptr(tok).value
@@ -219,7 +252,8 @@ def k2a_forward(rec, pt, hw, depth_range, *, que_dists=None, dn=1, want_colors=F
     fn = {'tc': lib.gn_k2a_forward_tc, 'simt': lib.gn_k2a_forward}[impl]
     if ev is not None:
         ev[0].record()
-    rc = fn(C.byref(p), _stream())
+    with _on(dev):
+        rc = fn(C.byref(p), _stream(dev))
     if ev is not None:
         ev[1].record()
     _lib.check(rc, f'gn_k2a_forward[{impl}]')
@@ -254,7 +288,8 @@ def k2b_forward(pooled, hw, *, dn, resolution=None, bbox_min=None, volume_size=0
     p.B, p.N, p.dn, p.volume_mode = B, N, int(dn), 1 if vol else 0
     if ev is not None:
         ev[0].record()
-    rc = lib.gn_k2b_forward(C.byref(p), _stream())
+    with _on(dev):
+        rc = lib.gn_k2b_forward(C.byref(p), _stream(dev))
     if ev is not None:
         ev[1].record()
     _lib.check(rc, 'gn_k2b_forward')
@@ -276,7 +311,8 @@ def k3_composite(sdf, grad, colors, que_dir, depth, inv_s, cos_anneal_ratio=1.0)
     p.inv_s, p.cos_anneal_ratio = float(inv_s), float(cos_anneal_ratio)
     p.alpha, p.hit_prob, p.pixel_colors, p.render_depth, p.eik_partial = _ptr(alpha).value, _ptr(hit).value, _ptr(pix).value, _ptr(rdepth).value, _ptr(eik).value
     p.B, p.rn, p.dn = B, rn, dn
-    _lib.check(lib.gn_k3_composite(C.byref(p), _stream()), 'gn_k3_composite')
+    with _on(dev):
+        _lib.check(lib.gn_k3_composite(C.byref(p), _stream(dev)), 'gn_k3_composite')
     return alpha, hit, pix, rdepth, eik
 
 
@@ -285,7 +321,8 @@ def k3_coarse_depths(depth_range_q, rn, dn):
     lib = _lib.load()
     B = depth_range_q.shape[0]
     out = torch.empty((B, rn, dn), device=depth_range_q.device, dtype=torch.float32)
-    _lib.check(lib.gn_k3_coarse_depths(_ptr(depth_range_q), _ptr(out), B, rn, dn, _stream()), 'gn_k3_coarse_depths')
+    with _on(out.device):
+        _lib.check(lib.gn_k3_coarse_depths(_ptr(depth_range_q), _ptr(out), B, rn, dn, _stream(out.device)), 'gn_k3_coarse_depths')
     return out
 
 
@@ -296,8 +333,9 @@ def k3_fine_depths(depth, hit_prob, depth_range_q, u, want_inds=False):
     fdn = u.shape[-1]
     out = torch.empty((B, rn, fdn), device=depth.device, dtype=torch.float32)
     inds = torch.empty((B, rn, fdn), device=depth.device, dtype=torch.int64) if want_inds else None
-    _lib.check(lib.gn_k3_fine_depths(_ptr(depth), _ptr(hit_prob), _ptr(depth_range_q), _ptr(u), _ptr(out), _ptr(inds),
-                                     B, rn, dn, fdn, _stream()), 'gn_k3_fine_depths')
+    with _on(out.device):
+        _lib.check(lib.gn_k3_fine_depths(_ptr(depth), _ptr(hit_prob), _ptr(depth_range_q), _ptr(u), _ptr(out), _ptr(inds),
+                                         B, rn, dn, fdn, _stream(out.device)), 'gn_k3_fine_depths')
     return out, inds
 
 
@@ -349,36 +387,44 @@ class VolumeGraph:
 
 
 # ------------------------------------------------------------------------------------------------ RGB head
-def query_rays(coords, poses, Ks):
-    """coords2rays (render_ops.py:4-25) for B query views: coords [B,rn,2] pixel (x,y) -> centre [B,3], un-normalised
-    directions [B,rn,3].  A 3x3 inverse and two tiny matmuls per view: done with torch like the reference."""
-    rot_t = poses[:, :, :3].transpose(1, 2)
-    centre = -(rot_t @ poses[:, :, 3:])[..., 0]
-    hom = torch.cat([coords, torch.ones_like(coords[..., :1])], -1)
-    cam = torch.inverse(Ks) @ hom.transpose(1, 2)
-    world = (rot_t @ cam + centre[:, :, None]).transpose(1, 2)
-    return centre, world - centre[:, None]
+def ray_setup(coords, poses, Ks, depth_range_q, que_depth):
+    """coords2rays + depth2points + depth2inv_dists (render_ops.py:4-52) in one launch (gn_k3_ray_setup): coords [B,rn,2]
+    pixel (x,y), poses [B,3,4], Ks [B,3,3], depth_range_q [B,2], que_depth [B,rn,dn] ->
+    pts [B,rn*dn,3], que_dir [B,rn,3], inv_dists [B,rn*dn]."""
+    lib = _lib.load()
+    B, rn, dn = que_depth.shape
+    dev = que_depth.device
+    coords, poses, Ks, dr, depth = (_f32c(t, dev) for t in (coords, poses, Ks, depth_range_q, que_depth))
+    pts = torch.empty((B, rn * dn, 3), device=dev, dtype=torch.float32)
+    que_dir = torch.empty((B, rn, 3), device=dev, dtype=torch.float32)
+    inv_dists = torch.empty((B, rn * dn), device=dev, dtype=torch.float32)
+    p = _lib.GnRaySetupParams()
+    p.coords, p.poses, p.Ks, p.depth, p.depth_range = (_ptr(t).value for t in (coords, poses, Ks, depth, dr))
+    p.pts, p.que_dir, p.inv_dists = _ptr(pts).value, _ptr(que_dir).value, _ptr(inv_dists).value
+    p.B, p.rn, p.dn = B, rn, dn
+    with _on(dev):
+        _lib.check(lib.gn_k3_ray_setup(C.byref(p), _stream(dev)), 'gn_k3_ray_setup')
+    return pts, que_dir, inv_dists
+
+
+def inv_s_from(variance):
+    """exp(10 * variance) clipped (neus.py:19, aggregate_net.py:107)."""
+    import math
+    return min(max(math.exp(float(variance) * 10.0), 1e-6), 1e6)
 
 
 def render_by_depth(scene, hw, que, que_depth, ray_mask_view_num=2, ray_mask_point_num=8):
     """render_by_depth + network_rendering (renderer.py:90-138), eval mode, for B query views.
     que: dict coords [B,rn,2], poses [B,3,4], Ks [B,3,3], depth_range [B,2] (device tensors); que_depth [B,rn,dn]."""
     B, rn, dn = que_depth.shape
-    dr = que['depth_range']
-    near, far = (-1 / dr[:, 0])[:, None, None], (-1 / dr[:, 1])[:, None, None]
-    dinv = (-1 / que_depth - near) / (far - near)                                   # depth2inv_dists render_ops.py:46-52
-    inv_dists = torch.cat([dinv[..., 1:] - dinv[..., :-1], torch.full_like(dinv[..., :1], 1e6)], -1)
-    centre, dirs = query_rays(que['coords'], que['poses'], que['Ks'])
-    pts = (centre[:, None, None] + dirs[:, :, None] * que_depth[..., None]).reshape(B, rn * dn, 3)   # depth2points 27-39
-    que_dir = (-dirs / torch.norm(dirs, dim=2, keepdim=True)).contiguous()
+    que_depth = que_depth.contiguous()
+    pts, que_dir, inv_dists = ray_setup(que['coords'], que['poses'], que['Ks'], que['depth_range'], que_depth)
     rec, pt = k1_forward(scene, hw, pts=pts, que_dir=que_dir, dn=dn)
-    pooled, colors, _ = k2a_forward(rec, pt, hw, scene.depth_range, que_dists=inv_dists.reshape(B, rn * dn), dn=dn,
-                                    want_colors=True)
+    pooled, colors, _ = k2a_forward(rec, pt, hw, scene.depth_range, que_dists=inv_dists, dn=dn, want_colors=True)
     sdf, grad = k2b_forward(pooled, hw, dn=dn, pts=pts, want_grad=True)
-    import math
-    inv_s = min(max(math.exp(hw.variance * 10.0), 1e-6), 1e6)                        # neus.py:19, aggregate_net.py:107
+    inv_s = inv_s_from(hw.variance)
     alpha, hit, pix, rdepth, eik = k3_composite(sdf.reshape(B, rn, dn), grad.reshape(B, rn, dn, 3),
-                                                colors.reshape(B, rn, dn, 4), que_dir, que_depth.contiguous(), inv_s)
+                                                colors.reshape(B, rn, dn, 4), que_dir, que_depth, inv_s)
     nvalid = pt[..., 0].reshape(B, rn, dn)
     out = {'alpha_values': alpha, 'sdf_values': sdf.reshape(B, rn, dn), 'colors_nr': colors.reshape(B, rn, dn, 4)[..., :3],
            'hit_prob_nr': hit, 'pixel_colors_nr': pix, 'render_depth': rdepth,
@@ -429,7 +475,8 @@ def k2b_backward(pooled, hw, d_sdf, d_weights, *, dn, resolution=None, bbox_min=
     p.pooled, p.weights, p.pos_table, p.d_sdf = _ptr(pooled).value, _ptr(hw.blob).value, _ptr(pos).value, _ptr(d_sdf).value
     p.d_pooled, p.d_weights = _ptr(d_pooled).value, _ptr(d_weights).value
     p.B, p.N, p.dn, p.volume_mode = B, N, int(dn), 1 if vol else 0
-    _lib.check(lib.gn_k2b_backward(C.byref(p), _stream()), 'gn_k2b_backward')
+    with _on(dev):
+        _lib.check(lib.gn_k2b_backward(C.byref(p), _stream(dev)), 'gn_k2b_backward')
     return d_pooled
 
 
@@ -451,7 +498,8 @@ def k2a_backward(rec, pt, hw, depth_range, d_pooled, d_weights, *, que_dists=Non
         assert d_colors.shape == (B, N, 4)
     p.d_colors = _ptr(d_colors).value
     p.B, p.N, p.V, p.dn = B, N, V, int(dn)
-    _lib.check(lib.gn_k2a_backward(C.byref(p), _stream()), 'gn_k2a_backward')
+    with _on(dev):
+        _lib.check(lib.gn_k2a_backward(C.byref(p), _stream(dev)), 'gn_k2a_backward')
     return d_rec
 
 
@@ -475,7 +523,8 @@ def k1_backward(scene, hw, d_rec, *, resolution=None, bbox_min=None, volume_size
     d_ray = torch.zeros(tuple(scene.ray_feats.shape), device=scene.device, dtype=torch.float32)
     p.KRt, p.d_rec, p.d_img_feats, p.d_ray_feats = _ptr(scene.KRt).value, _ptr(d_rec).value, _ptr(d_img).value, _ptr(d_ray).value
     p.B, p.V, p.H, p.W, p.fh, p.fw, p.N, p.volume_mode = B, V, scene.H, scene.W, scene.fh, scene.fw, N, 1 if vol else 0
-    _lib.check(lib.gn_k1_backward(C.byref(p), _stream()), 'gn_k1_backward')
+    with _on(dev):
+        _lib.check(lib.gn_k1_backward(C.byref(p), _stream(dev)), 'gn_k1_backward')
     return d_img, d_ray
 
 
@@ -581,3 +630,30 @@ def ray_features_autograd(imgs, img_feats, ray_feats, poses, Ks, depth_range, pt
     static = (imgs, poses, Ks, depth_range, pts.detach().contiguous(), que_dir.detach().contiguous(), inv_dists.detach().contiguous(),
               int(dn), agg_prefix, dd_prefix)
     return _RayFeaturesFn.apply(img_feats, ray_feats, static, keys, *[named_params[k] for k in keys])
+
+
+# ------------------------------------------------------------------------------------------------ grasp post-processing
+def grasp_post(tsdf, qual, rot, width, *, gaussian_filter_sigma=1.0, min_width=1.33, max_width=9.33, tsdf_thres_high=0.5,
+               tsdf_thres_low=1e-3, threshold=0.90, max_filter_size=4, max_grasps=512):
+    """`process` + `select` of the planner (main.py:23-74) on the device (gn_k4_grasp_post), one scene: tsdf / qual / width
+    [R,R,R] (any leading singleton dims), rot [4,R,R,R].  Returns (qual_processed [R,R,R], grasps [max_grasps,9] =
+    i, j, k, score, rot0..3, width in np.argwhere order, count int32[1]) - all DEVICE tensors, nothing synchronises."""
+    lib = _lib.load()
+    dev = tsdf.device
+    _require_cuda(tsdf, 'tsdf')
+    R = tsdf.shape[-1]
+    tsdf, qual, width = (_f32c(t, dev).reshape(R, R, R) for t in (tsdf, qual, width))
+    rot = _f32c(rot, dev).reshape(4, R, R, R)
+    qual_out = torch.empty((R, R, R), device=dev, dtype=torch.float32)
+    scratch = torch.empty((3 * R * R * R,), device=dev, dtype=torch.float32)
+    grasps = torch.zeros((max_grasps, 9), device=dev, dtype=torch.float32)
+    count = torch.zeros((1,), device=dev, dtype=torch.int32)
+    p = _lib.GnGraspPostParams()
+    p.tsdf, p.qual, p.rot, p.width = _ptr(tsdf).value, _ptr(qual).value, _ptr(rot).value, _ptr(width).value
+    p.qual_out, p.scratch, p.grasps, p.count = _ptr(qual_out).value, _ptr(scratch).value, _ptr(grasps).value, _ptr(count).value
+    p.sigma, p.min_width, p.max_width = float(gaussian_filter_sigma), float(min_width), float(max_width)
+    p.tsdf_thres_high, p.tsdf_thres_low, p.threshold = float(tsdf_thres_high), float(tsdf_thres_low), float(threshold)
+    p.R, p.max_filter_size, p.max_grasps = R, int(max_filter_size), int(max_grasps)
+    with _on(dev):
+        _lib.check(lib.gn_k4_grasp_post(C.byref(p), _stream(dev)), 'gn_k4_grasp_post')
+    return qual_out, grasps, count

@@ -87,6 +87,9 @@ typedef struct GnK2aParams {
     int B, N, V, dn;
     int with_rgb;              /* 1: also evaluate rgb_fc + blend into `colors` */
     int R, volume_mode;        /* (tok) */
+    int* status;               /* optional sticky flag word (tensor-core path): bit 0 is OR-ed in when a row's hit / visibility or a
+                                  point's pooled features / tokens are not finite - the fp16 hi/lo operand split overflows for
+                                  activations >= 65504, which the fp32 reference would survive; NULL = no check */
 } GnK2aParams;
 int gn_k2a_forward_tc(const GnK2aParams* params, void* stream);   /* THE product kernel: tcgen05 / TMEM (fp16 hi/lo split, 3 MMAs per product; 160 TMEM columns per tile, three tiles per SM) */
 int gn_k2a_forward(const GnK2aParams* params, void* stream);      /* fp32 CUDA-core implementation of the same math: on-GPU cross-check for tests, never selected by the host code */
@@ -138,6 +141,42 @@ int gn_k3_coarse_depths(const float* depth_range /*[B,2]*/, float* depth /*[B,rn
 int gn_k3_fine_depths(const float* depth /*[B,rn,dn]*/, const float* hit_prob /*[B,rn,dn]*/, const float* depth_range /*[B,2]*/,
                       const float* u /*[B,rn,fdn]*/, float* fine_depth /*[B,rn,fdn] sorted*/, int64_t* inds /*[B,rn,fdn] or NULL*/,
                       int B, int rn, int dn, int fdn, void* stream);
+
+/* Ray set-up of the RGB head in one launch: coords2rays (render_ops.py:4-25), depth2points (27-39) and depth2inv_dists
+ * (46-52).  poses are the QUERY views' world->camera [R|t]; depth is the per-ray sample table (gn_k3_coarse_depths /
+ * gn_k3_fine_depths).  Outputs feed gn_k1_forward (pts, que_dir) and gn_k2a_forward_tc (inv_dists = que_dists). */
+typedef struct GnRaySetupParams {
+    const float* coords;       /* [B,rn,2] pixel (x,y) */
+    const float* poses;        /* [B,3,4] */
+    const float* Ks;           /* [B,3,3] */
+    const float* depth;        /* [B,rn,dn] */
+    const float* depth_range;  /* [B,2] */
+    float* pts;                /* out [B,rn*dn,3] */
+    float* que_dir;            /* out [B,rn,3] unit, pointing from the sample back to the camera (render_ops.py:37) */
+    float* inv_dists;          /* out [B,rn*dn] spacings in normalised inverse depth, last one 1e6 */
+    int B, rn, dn;
+} GnRaySetupParams;
+int gn_k3_ray_setup(const GnRaySetupParams* params, void* stream);
+
+/* Grasp post-processing on the device (the step after the path in GraspNeRFPlanner.__call__, main.py:23-84,202-203):
+ * `process` = gaussian_filter(qual, sigma 1, 'nearest') + TSDF band mask (binary_dilation of the outside voxels, 2
+ * iterations, restricted to the band) + width limits; `select` = threshold, 4^3 maximum-filter NMS ('reflect'), ordered
+ * compaction of the surviving voxels.  Volumes are [R,R,R] fp32 (rot [4,R,R,R]); one scene per call.
+ * scratch: 3*R^3 floats.  count: int32 number of grasps found (may exceed max_grasps: only the first max_grasps rows are
+ * written).  The filtered volume is bit-identical to scipy's (float64 accumulation in scipy's tap order). */
+typedef struct GnGraspPostParams {
+    const float* tsdf;         /* [R,R,R] */
+    const float* qual;         /* [R,R,R] */
+    const float* rot;          /* [4,R,R,R] */
+    const float* width;        /* [R,R,R] */
+    float* qual_out;           /* out [R,R,R]: quality volume after process() (before select's threshold / NMS) */
+    float* scratch;            /* [3*R^3] */
+    float* grasps;             /* out [max_grasps,9]: i, j, k, score, rot0..3, width (argwhere order, main.py:68-73) */
+    int* count;                /* out [1] */
+    float sigma, min_width, max_width, tsdf_thres_high, tsdf_thres_low, threshold;
+    int R, max_filter_size, max_grasps;
+} GnGraspPostParams;
+int gn_k4_grasp_post(const GnGraspPostParams* params, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------------
  * Backward (training) entry points of the volume path: d volume -> d weights, d feature maps.  First order only.
@@ -194,6 +233,8 @@ int gn_sizeof_k3_params(void);
 int gn_sizeof_k2b_bwd_params(void);
 int gn_sizeof_k2a_bwd_params(void);
 int gn_sizeof_k1_bwd_params(void);
+int gn_sizeof_ray_setup_params(void);
+int gn_sizeof_grasp_post_params(void);
 
 #ifdef __cplusplus
 }

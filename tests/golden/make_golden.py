@@ -294,3 +294,63 @@ def make_loss_golden():
 
 if __name__ == '__main__' and '--losses' in sys.argv:
     make_loss_golden()
+
+
+def quantise_images(scene):
+    """uint8 images as the planner holds them (main.py:166-171) and their fp32 form u8 / 255 (color_map_forward)."""
+    u8 = np.clip(np.floor(scene['imgs'] * 256.0), 0, 255).astype(np.uint8)
+    scene = dict(scene)
+    scene['imgs'] = u8.astype(np.float32) / np.float32(255.0)
+    return scene, np.ascontiguousarray(u8.transpose(0, 2, 3, 1))
+
+
+def make_extra_golden():
+    """Round-2 fixtures (python tests/golden/make_golden.py --extra):
+      render_inds.npz        the int64 `inds` table torch.searchsorted returns INSIDE the reference's sample_fine_depth
+                             (render_ops.py:210) for every render case - the reference-held index table K3 is compared with;
+      forward_small_u8.npz   one full GraspNeRF.forward (eval, render_rgb off, main.py:150) on a small scene whose images are
+                             uint8 / 255 (what the planner feeds): volume, qual, rot, width, depth_mean (+ coords)."""
+    cfg, net = build_reference_net(0)
+    from network.render_ops import sample_depth, sample_fine_depth
+    nr = net.nr_net
+    inds_out = {}
+    real_ss = torch.searchsorted
+    for name, case in RENDER_CASES.items():
+        scene = make_scene(**case['scene'])
+        ref, que = to_torch(scene), to_torch(make_query(scene, case['num_rays'], case['qseed']))
+        res = nr.render_impl(que, ref, False)
+        seen = []
+
+        def spy(*a, **k):
+            r = real_ss(*a, **k)
+            seen.append(r.clone())
+            return r
+        torch.searchsorted = spy
+        try:
+            with torch.no_grad():
+                depth, _ = sample_depth(que['depth_range'], que['coords'], nr.cfg['depth_sample_num'], False)
+                sample_fine_depth(depth, res['hit_prob_nr'].detach(), que['depth_range'], nr.cfg['fine_depth_sample_num'], False)
+        finally:
+            torch.searchsorted = real_ss
+        assert len(seen) == 1
+        inds_out[name] = seen[0].numpy().astype(np.int64)
+        print('inds', name, inds_out[name].shape, inds_out[name].min(), inds_out[name].max())
+    np.savez_compressed(os.path.join(HERE, 'render_inds.npz'), **inds_out)
+
+    scene, u8 = quantise_images(make_scene(seed=3, num_views=4, h=96, w=160, radius=0.45))
+    ref = to_torch({k: v for k, v in scene.items() if k not in ('img_feats', 'ray_feats')})
+    q = to_torch(make_query(scene, 16, 7))
+    net.nr_net.cfg['render_rgb'] = False
+    data = {'step': 0, 'eval': True, 'full_vol': True, 'ref_imgs_info': ref, 'que_imgs_info': q, 'src_imgs_info': ref}
+    torch.manual_seed(123)
+    with torch.no_grad():
+        out = net(data)
+    qual, rot, width = out['vgn_pred']
+    np.savez_compressed(os.path.join(HERE, 'forward_small_u8.npz'), volume=out['volume'][0, 0].numpy(), qual=qual[0, 0].numpy(),
+                        rot=rot[0].numpy(), width=width[0, 0].numpy(), depth_mean=out['depth_mean'].numpy(),
+                        depth_coords=out['depth_coords'].numpy(), imgs_u8_checksum=np.int64(u8.astype(np.int64).sum()))
+    print('forward_small_u8: volume std', out['volume'].std().item(), 'qual range', qual.min().item(), qual.max().item())
+
+
+if __name__ == '__main__' and '--extra' in sys.argv:
+    make_extra_golden()

@@ -1,0 +1,167 @@
+"""GPU tests of the round-2 host-facing pieces: uint8 image gathers in K1, the pinned-host engines (VolumeEngine result
+lifetime, ForwardEngine = the planner's whole network call against the reference's output), the ray set-up kernel and the
+sticky numerics flag of the tensor-core K2a."""
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import load_golden, assert_close
+from graspnerf_b200.synth import make_scene, make_query
+from graspnerf_b200.weights import seed0_weights, seed0_model
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def _quantised(kw):
+    sc = make_scene(**kw)
+    u8 = np.clip(np.floor(sc['imgs'] * 256.0), 0, 255).astype(np.uint8)
+    sc['imgs'] = u8.astype(np.float32) / np.float32(255.0)
+    return sc, np.ascontiguousarray(u8.transpose(0, 2, 3, 1))
+
+
+def test_k1_uint8_images_give_the_same_record_as_fp32_images():
+    """imgs_u8 / 255 in the kernel (`__fdiv_rn`) == np.float32(u8) / 255 on the host (color_map_forward, main.py:170): the
+    whole record - not only the rgb entries - must be bit-identical between the two image formats."""
+    from graspnerf_b200 import ops
+    sc, u8 = _quantised(dict(seed=5, num_views=5, h=96, w=160, radius=0.5))
+    t = {k: torch.from_numpy(v).to(DEV) for k, v in sc.items() if isinstance(v, np.ndarray)}
+    hw = ops.HeadWeights(seed0_weights(), 'agg_net.', 'dist_decoder.', DEV)
+    bb = torch.tensor([sc['bbox3d'][0]], device=DEV)
+    s32 = ops.Scene(t['imgs'], t['img_feats'], t['ray_feats'], t['poses'], t['Ks'], t['depth_range'])
+    s8 = ops.Scene(torch.from_numpy(u8).to(DEV), t['img_feats'], t['ray_feats'], t['poses'], t['Ks'], t['depth_range'])
+    assert s8.img_u8 and s8.imgs.dtype == torch.uint8 and s8.imgs.shape[-1] == 4
+    r32, p32 = ops.k1_forward(s32, hw, resolution=40, bbox_min=bb)
+    r8, p8 = ops.k1_forward(s8, hw, resolution=40, bbox_min=bb)
+    assert torch.equal(r32, r8) and torch.equal(p32, p8)
+    assert float(r8[..., 64:67].abs().max()) > 0.1                       # colours are really sampled
+    v32, v8 = ops.sample_volume(s32, hw, bb, 40), ops.sample_volume(s8, hw, bb, 40)
+    assert torch.equal(v32, v8)
+
+
+def test_volume_engine_uint8_path_and_result_lifetime():
+    """VolumeEngine with uint8 images == the eager path; a result handed back by submit() must still hold ITS volume after the
+    same slot has been re-submitted and the device has finished (round-1 bug: the pinned buffer was recycled immediately)."""
+    from graspnerf_b200 import ops
+    from graspnerf_b200.engine import VolumeEngine, HostScene
+    hw = ops.HeadWeights(seed0_weights(), 'agg_net.', 'dist_decoder.', DEV)
+    hosts, want = [], []
+    for seed in range(4):
+        sc, u8 = _quantised(dict(seed=30 + seed, num_views=4, h=96, w=160, radius=0.45))
+        t = {k: torch.from_numpy(v).to(DEV) for k, v in sc.items() if isinstance(v, np.ndarray)}
+        s = ops.Scene(t['imgs'], t['img_feats'], t['ray_feats'], t['poses'], t['Ks'], t['depth_range'])
+        want.append(ops.sample_volume(s, hw, torch.tensor([sc['bbox3d'][0]], device=DEV), 40).cpu())
+        hosts.append(HostScene(u8, s.img_feats[0].cpu(), s.ray_feats[0].cpu(), sc['poses'], sc['Ks'], sc['depth_range'],
+                               np.asarray(sc['bbox3d'][0], np.float32)))
+    eng = VolumeEngine(hw, hosts[0], 40, slots=2, device=DEV)
+    held = {}
+    for i in range(8):                                   # 2 slots: slot of scene i is recycled at submit i+2
+        _, fin = eng.submit(hosts[i % 4], tag=i)
+        if fin is not None:
+            held[fin[0]] = fin[1]                        # keep the engine's buffer itself, no clone
+            if fin[0] >= 1:                              # the buffer handed out one collect earlier on this slot's sibling is old enough to check
+                torch.cuda.synchronize()                 # everything queued so far (incl. the re-submission of that slot) has run
+                k = fin[0]
+                assert torch.equal(held[k], want[k % 4]), f'result {k} was overwritten while the caller still held it'
+    for tag, out in eng.drain():
+        assert torch.equal(out, want[tag % 4])
+
+
+def test_forward_engine_matches_the_reference_forward():
+    """engine.ForwardEngine (uint8 images in -> encoders -> K1/K2a/K2b -> VGN) against the UNMODIFIED reference's
+    GraspNeRF.forward on the same uint8/255 images (tests/golden/forward_small_u8.npz).  cuDNN fp32 (TF32 off) vs CPU convs:
+    tolerance 2e-3 like test_boundary."""
+    from graspnerf_b200.engine import ForwardEngine, HostScene
+    g = load_golden('forward_small_u8.npz')
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    sc, u8 = _quantised(dict(seed=3, num_views=4, h=96, w=160, radius=0.45))
+    assert int(u8.astype(np.int64).sum()) == int(g['imgs_u8_checksum'])
+    net = seed0_model().to(DEV).eval()
+    net.nr_net.cfg['render_rgb'] = False
+    hs = HostScene(u8, None, None, sc['poses'], sc['Ks'], sc['depth_range'], np.asarray(sc['bbox3d'][0], np.float32))
+    for use_graph in (False, True):
+        eng = ForwardEngine(net, hs, slots=2, device=DEV, post_cfg=dict(tsdf_thres_high=0.0, tsdf_thres_low=-0.85), use_graph=use_graph)
+        for i in range(3):
+            eng.submit(hs, tag=i)
+        res = eng.drain()
+        vols, grasps, count = res[-1][1]
+        assert vols.shape == (7, 40, 40, 40)
+        assert_close(vols[0], g['volume'], rtol=2e-3, atol_scale=2e-3, what=f'tsdf volume (graph={eng.graphed})')
+        assert_close(vols[1], g['qual'], rtol=2e-3, atol_scale=2e-3, what='qual')
+        assert_close(vols[2:6], g['rot'], rtol=2e-3, atol_scale=5e-3, what='rot')
+        assert_close(vols[6], g['width'], rtol=2e-3, atol_scale=2e-3, what='width')
+        assert all(torch.equal(r[1][0], vols) for r in res)            # every slot / replay gives the same answer
+        assert int(count.item()) >= 0
+
+
+def test_mirror_depth_mean_values_with_injected_coords():
+    """depth_mean* VALUES on the GPU (round 1 only checked the keys): the mirror's head on the reference's own random pixels
+    (depth_coords of the fixture) against the reference's depth_mean."""
+    g = load_golden('forward_small_v4.npz')
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    sc = make_scene(seed=3, num_views=4, h=96, w=160, radius=0.45)
+    net = seed0_model().to(DEV).eval()
+    nr = net.nr_net
+    imgs = torch.from_numpy(sc['imgs']).to(DEV)
+    with torch.no_grad():
+        img_feats = nr.image_encoder(imgs)
+        ray_feats = nr.vis_encoder(nr.init_net({'imgs': imgs}, None, False), img_feats)
+        out = nr.predict_mean_for_depth_loss({'imgs': imgs, 'ray_feats': ray_feats}, coords=torch.from_numpy(g['depth_coords']).to(DEV))
+    assert torch.equal(out['depth_coords'].cpu(), torch.from_numpy(g['depth_coords']))
+    assert_close(out['depth_mean'].cpu(), g['depth_mean'], rtol=2e-3, atol_scale=2e-3, what='depth_mean vs reference')
+
+
+def test_ray_setup_kernel_matches_the_reference_formulas():
+    """gn_k3_ray_setup vs coords2rays / depth2points / depth2inv_dists written with torch exactly as render_ops.py:4-52."""
+    from graspnerf_b200 import ops
+    sc = make_scene(seed=8, num_views=3, h=96, w=160)
+    q = make_query(sc, 50, 3)
+    que = {k: torch.from_numpy(q[k]).to(DEV) for k in ('coords', 'poses', 'Ks', 'depth_range')}
+    depth = ops.k3_coarse_depths(que['depth_range'], 50, 13)
+    pts, qd, inv = ops.ray_setup(que['coords'], que['poses'], que['Ks'], que['depth_range'], depth)
+    coords, poses, Ks, dr, d = (t.double().cpu() for t in (que['coords'], que['poses'], que['Ks'], que['depth_range'], depth))
+    rot = poses[:, :, :3].unsqueeze(1).permute(0, 1, 3, 2)
+    trans = -rot @ poses[:, :, 3:].unsqueeze(1)
+    centers = trans.repeat(1, 50, 1, 1).squeeze(-1)
+    hom = torch.cat([coords, torch.ones(1, 50, 1, dtype=torch.float64)], 2)
+    cam = torch.inverse(Ks).unsqueeze(1) @ hom.unsqueeze(3)
+    dirs = (rot @ cam + trans).squeeze(3) - centers
+    want_pts = centers.unsqueeze(2) + dirs.unsqueeze(2) * d.unsqueeze(3)
+    want_dir = -dirs / torch.norm(dirs, dim=2, keepdim=True)
+    near, far = (-1 / dr[:, 0])[:, None, None], (-1 / dr[:, 1])[:, None, None]
+    dinv = (-1 / d - near) / (far - near)
+    want_inv = torch.cat([dinv[..., 1:] - dinv[..., :-1], torch.full((1, 50, 1), 1e6, dtype=torch.float64)], -1)
+    assert_close(pts.cpu().reshape(1, 50, 13, 3), want_pts, rtol=1e-5, atol_scale=1e-6, what='que_pts')
+    assert_close(qd.cpu(), want_dir, rtol=1e-5, atol_scale=1e-6, what='que_dir')
+    assert_close(inv.cpu().reshape(1, 50, 13)[..., :-1], want_inv[..., :-1], rtol=1e-4, atol_scale=1e-5, what='inverse-depth spacings')
+    assert torch.equal(inv.cpu().reshape(1, 50, 13)[..., -1], torch.full((1, 50), 1e6))
+
+
+@pytest.mark.parametrize('scale,expect_overflow', [(30.0, False), (3000.0, True)])
+def test_fp16_operand_range_large_activations_and_overflow_flag(scale, expect_overflow):
+    """The tensor-core K2a splits every activation into fp16 hi/lo halves: operands must stay below 65504.  Weights scaled so
+    that activations are ~1e3 must still match the fp32 CUDA-core path; scaled until they overflow, the sticky flag must
+    trip and check_numerics() must raise instead of returning a silently wrong volume."""
+    from graspnerf_b200 import ops
+    sd = {k: v.clone() for k, v in seed0_weights().items()}
+    for k in ('agg_net.agg_impl.base_fc.0.weight', 'agg_net.agg_impl.vis_fc.0.weight'):
+        sd[k] = sd[k] * scale
+    sc = make_scene(seed=12, num_views=4, h=96, w=160, radius=0.45)
+    t = {k: torch.from_numpy(v).to(DEV) for k, v in sc.items() if isinstance(v, np.ndarray)}
+    hw = ops.HeadWeights(sd, 'agg_net.', 'dist_decoder.', DEV)
+    scene = ops.Scene(t['imgs'], t['img_feats'] * (scale if expect_overflow else 1.0), t['ray_feats'], t['poses'], t['Ks'], t['depth_range'])
+    bb = torch.tensor([sc['bbox3d'][0]], device=DEV)
+    dbg = {}
+    vol = ops.sample_volume(scene, hw, bb, 40, debug=dbg)
+    torch.cuda.synchronize()
+    if expect_overflow:
+        with pytest.raises(FloatingPointError):
+            hw.check_numerics()
+        hw.check_numerics()                               # the flag was reset by the failing check
+    else:
+        hw.check_numerics()
+        assert float(dbg['rows'][..., 4:6].abs().max()) > 10.0, 'the test should exercise large activations (base_fc output; vis_fc hidden is ~30x that)'
+        vol_simt = ops.sample_volume(scene, hw, bb, 40, impl='simt')
+        assert_close(vol.cpu(), vol_simt.cpu(), what='large-activation volume: tensor-core vs fp32 CUDA-core path')

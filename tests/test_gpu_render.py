@@ -54,6 +54,9 @@ def test_render_coarse_and_fine(name, impl):
         fd, inds = ops.k3_fine_depths(torch.from_numpy(g['depth']).to(dev), hp, que['depth_range'], u.to(dev), want_inds=True)
         ofd, oinds = O.fine_depths(torch.from_numpy(g['depth'][0]), torch.from_numpy(g['hit_prob_nr'][0]), oq['depth_range'], 40)
         assert torch.equal(inds[0].cpu(), oinds), 'searchsorted index table differs from the oracle'
+        # ... and vs the table torch.searchsorted returned INSIDE the unmodified reference's sample_fine_depth (render_ops.py:210)
+        ref_inds = load_golden('render_inds.npz')[name]
+        assert np.array_equal(inds.cpu().numpy(), ref_inds), 'searchsorted index table differs from the reference-held table'
         assert_close(fd[0].cpu(), torch.sort(ofd, -1)[0], rtol=1e-5, atol_scale=1e-6, what='fine depths vs oracle')
         assert_close(fd.cpu(), g['depth_fine'], what='fine depths vs reference')
         # ---- fine pass on the reference's fine depths
@@ -61,8 +64,17 @@ def test_render_coarse_and_fine(name, impl):
         assert np.array_equal(fine['ray_mask'].cpu().numpy(), g['ray_mask_fine'])
         for k in keys:
             assert_close(fine[k].cpu(), g[k + '_fine'], what=f'{k}_fine vs reference golden')
+        # ---- the chain's OWN fine pass (own coarse hit_prob -> own sampler -> fine kernels): the inverse-CDF sampler is
+        # ill-conditioned where the coarse hit probability vanishes, so an index may legitimately flip; report, bound loosely
+        full = ops.render_rays(scene, hw_c, hw_f, que, 40, 40)
+        flips = int((full['fine_inds'].cpu().numpy() != ref_inds).sum())
+        dmax = float((full['depth_fine'].cpu() - torch.from_numpy(g['depth_fine'])).abs().max())
+        print(f'[{name}/{impl}] own-chain fine pass: {flips}/{ref_inds.size} searchsorted flips vs the reference, max |d depth| {dmax:.2e}')
+        assert flips <= ref_inds.size // 100
+        pc = full['pixel_colors_nr_fine'].cpu().numpy()
+        assert np.isfinite(pc).all() and np.abs(pc - g['pixel_colors_nr_fine']).max() < 5e-3
     finally:
-        ops.K2A_IMPL = 'tc3'
+        ops.K2A_IMPL = 'tc'
 
 
 @pytest.mark.parametrize('impl', ['simt', 'tc'])
@@ -83,4 +95,4 @@ def test_ragged_ray_batch(impl):
             assert_close(out[k][0].cpu(), oc[k], what=f'{k} vs oracle (ragged)')
         assert torch.equal(out['ray_mask'][0].cpu(), oc['ray_mask'])
     finally:
-        ops.K2A_IMPL = 'tc3'
+        ops.K2A_IMPL = 'tc'
