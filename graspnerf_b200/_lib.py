@@ -51,7 +51,7 @@ class GnK1BwdParams(C.Structure):
 
 
 class GnRaySetupParams(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in ('coords', 'poses', 'Ks', 'depth', 'depth_range', 'pts', 'que_dir', 'inv_dists')] + \
+    _fields_ = [(n, C.c_void_p) for n in ('coords', 'poses', 'Ks', 'depth', 'depth_range', 'pts', 'que_dir', 'inv_dists', 'centers', 'dirs')] + \
                [(n, C.c_int) for n in ('B', 'rn', 'dn')]
 
 

@@ -179,6 +179,8 @@ __global__ void gn_k3_ray_setup_kernel(const GnRaySetupParams p)
         const float w = (P[0 * 4 + r] * cx + P[1 * 4 + r] * cy + P[2 * 4 + r] * cz) + ctr[r];
         dir[r] = w - ctr[r];
     }
+    if (p.centers) { p.centers[ray * 3] = ctr[0]; p.centers[ray * 3 + 1] = ctr[1]; p.centers[ray * 3 + 2] = ctr[2]; }
+    if (p.dirs) { p.dirs[ray * 3] = dir[0]; p.dirs[ray * 3 + 1] = dir[1]; p.dirs[ray * 3 + 2] = dir[2]; }
     const float nrm = sqrtf(dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2]);
     p.que_dir[ray * 3] = __fdiv_rn(-dir[0], nrm); p.que_dir[ray * 3 + 1] = __fdiv_rn(-dir[1], nrm); p.que_dir[ray * 3 + 2] = __fdiv_rn(-dir[2], nrm);
     const float rnear = __fdiv_rn(-1.f, p.depth_range[b * 2]), rfar = __fdiv_rn(-1.f, p.depth_range[b * 2 + 1]);

@@ -1,9 +1,13 @@
-"""Parameter containers of the hot-path heads.  They own the reference's parameters under the reference's key names
-(dist_decoder.py:53-98, aggregate_net.py:19-33,87-104, ibrnet.py:373-432, neus.py:6-19) but have NO torch forward for the
-heavy part: the math runs in the CUDA kernels (graspnerf_b200.ops).  Initialisation follows the reference (kaiming on
-base_fc / vis_fc / vis_fc2 / geometry_fc / rgb_fc / neuray_fc, ibrnet.py:105-109,427-432)."""
+"""The hot-path heads under the reference's class names, parameter names and call signatures (dist_decoder.py:53-153,
+aggregate_net.py:19-140, ibrnet.py:373-432, neus.py:6-19).  The modules own the reference's parameters; the heavy math runs
+in the CUDA kernels: `NeusAggregationNet.forward(prj_dict, que_dir, que_pts, que_dists, is_train)` launches K1 (dir_diff
+with the caller's que_dir) -> K2a -> K2b -> K3 on the record that graspnerf_b200.network.render_ops.project_points_dict
+attached to prj_dict.  Initialisation follows the reference (kaiming on base_fc / vis_fc / vis_fc2 / geometry_fc / rgb_fc /
+neuray_fc, ibrnet.py:105-109,427-432)."""
 import torch
 import torch.nn as nn
+
+from .. import ops
 
 
 def _mlp3(cin, hid, cout, last):
@@ -37,7 +41,29 @@ class MixtureLogisticsDistDecoder(nn.Module):
         return self.mean_decoder(prj_ray_feats)
 
     def forward(self, feats):
-        raise RuntimeError('MixtureLogisticsDistDecoder.forward is fused into the K2a kernel; call NeuralRayRenderer instead')
+        """dist_decoder.py:99-107 -> (mean, var, vis=None, aw).  Stand-alone calls evaluate the three 32->32->32->{2,2,1}
+        MLPs with the module's own torch layers; the renderer never calls this - predict_proj_ray_prob / render /
+        sample_volume run the decoders fused inside K2a (gn_k2a_forward_tc)."""
+        return self.mean_decoder(feats), self.var_decoder(feats), None, self.aw_decoder(feats)
+
+    def compute_prob(self, depth, interval, mean, var, vis, aw, is_ref, depth_range):
+        """dist_decoder.py:109-142 (use_vis False, is_ref True): mixture-of-logistics visibility / hit probability in
+        normalised inverse depth.  Same remark as forward(): the product path has this fused in K2a."""
+        near_r, far_r = -1 / depth_range[:, 0], -1 / depth_range[:, 1]
+        shape = [-1] + [1] * (depth.dim() - 1)
+        d = (-1 / torch.clamp_min(depth, 1e-5) - near_r.reshape(shape)) / (far_r.reshape(shape) - near_r.reshape(shape))   # dist_decoder.py:18-24
+        if tuple(interval.shape) != (1, 0):
+            half = interval / 2                                                                   # dist_decoder.py:33-38
+            first = half[..., 0:1]
+            near, far = d - torch.cat([first, half[..., :-1]], -1), d + half
+        else:
+            near, far = d - 0.005, d + 0.005                                                      # fixed_interval_val 0.01 (121-124, 47-49)
+        mix = torch.cat([aw, 1 - aw], -1)
+        cdf0 = 0.5 + 0.5 * torch.tanh((near[..., None] - mean) * var)
+        cdf1 = 0.5 + 0.5 * torch.tanh((far[..., None] - mean) * var)
+        visibility = torch.sum((1 - cdf0) * mix, -1)
+        hit_prob = torch.sum((cdf1 - cdf0) * mix, -1)
+        return torch.log(hit_prob / (visibility - hit_prob + 1e-5) + 1e-5), visibility, hit_prob
 
 
 class _Attention(nn.Module):                      # ibrnet.py:52-70 parameters
@@ -99,8 +125,53 @@ class NeusAggregationNet(nn.Module):
         self.step = 0
         self.cos_anneal_ratio = 1.0
 
-    def forward(self, *a, **k):
-        raise RuntimeError('NeusAggregationNet.forward is fused into the K2a/K2b/K3 kernels; call NeuralRayRenderer instead')
+    def pair_with(self, dist_decoder, agg_prefix, dd_prefix):
+        """The kernels fuse this net with its dist decoder (K2a evaluates both); the renderer tells each agg net which decoder
+        it is paired with.  Plain attribute (not a sub-module): the decoder's parameters stay under their own keys."""
+        object.__setattr__(self, '_paired', (dist_decoder, agg_prefix, dd_prefix))
+        self._hw = None
+
+    def _head_weights(self):
+        dd, agg_prefix, dd_prefix = self._paired
+        sd = {agg_prefix + k: v for k, v in self.named_parameters()}
+        sd.update({dd_prefix + k: v for k, v in dd.named_parameters()})
+        dev = next(self.parameters()).device
+        if self._hw is None or self._hw.device != dev:
+            self._hw = ops.HeadWeights(sd, agg_prefix, dd_prefix, dev)
+        else:
+            self._hw.refresh(sd)
+        return self._hw
+
+    def forward(self, prj_dict, que_dir, que_pts, que_dists, is_train):
+        """aggregate_net.py:125-140, evaluation only (training goes through network.ray_head / ops.*_autograd).
+        prj_dict: from graspnerf_b200.network.render_ops.project_points_dict (it carries the kernel record);
+        que_dir [qn,rn,dn,3]; que_pts [qn,rn,dn,3]; que_dists [qn,rn,dn] metric spacings (depth2dists) or None.
+        Returns (alpha, sdf, colors, grad_error, variance) or, with que_dists None, (None, sdf, colors, None, None)."""
+        if '_rec' not in prj_dict:
+            raise ValueError('prj_dict must come from graspnerf_b200.network.render_ops.project_points_dict (it carries the '
+                             'per-(point,view) record the kernels consume)')
+        if que_dir is None:
+            raise NotImplementedError('que_dir=None (disable_view_dir) is not implemented')
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and is_train:
+            raise NotImplementedError('training goes through NeuralRayRenderer.render / sample_volume (autograd nodes), not this call')
+        qn, rn, dn, _ = que_pts.shape
+        hw = self._head_weights()
+        scene, pts = prj_dict['_scene'], prj_dict['_que_pts']
+        qd = que_dir[:, :, 0].to(pts.device, torch.float32).contiguous()                   # the same direction for every sample of a ray
+        rec, pt = ops.k1_forward(scene, hw, pts=pts, que_dir=qd, dn=dn)                   # dir_diff with the caller's que_dir (aggregate_net.py:11-17)
+        inv_dists = prj_dict.get('_inv_dists')
+        pooled, colors, _ = ops.k2a_forward(rec, pt, hw, scene.depth_range, que_dists=inv_dists, dn=dn, want_colors=True)
+        sdf, grad = ops.k2b_forward(pooled, hw, dn=dn, pts=pts, want_grad=que_dists is not None)
+        colors = colors.reshape(qn, rn, dn, 4)[..., :3]
+        if que_dists is None:
+            return None, sdf.reshape(qn, rn, dn), colors, None, None
+        depth = prj_dict.get('_que_depth')
+        if depth is None:                                   # differences of the running sum reproduce the spacings
+            depth = torch.cumsum(torch.cat([torch.zeros_like(que_dists[..., :1]), que_dists[..., :-1]], -1), -1)
+        alpha, _, _, _, eik = ops.k3_composite(sdf.reshape(qn, rn, dn), grad.reshape(qn, rn, dn, 3), torch.cat(
+            [colors, torch.zeros_like(colors[..., :1])], -1).contiguous(), qd, depth.contiguous(), ops.inv_s_from(hw.variance), self.cos_anneal_ratio)
+        grad_error = (eik.sum(1) / (rn * dn)).reshape(1, 1)
+        return alpha, sdf.reshape(qn, rn, dn), colors, grad_error, self.deviation_network.variance.reshape(1, 1)
 
 
 name2dist_decoder = {'mixture_logistics': MixtureLogisticsDistDecoder}

@@ -17,6 +17,7 @@ from .. import ops
 from .encoders import ResUNetLight, VgnConvNet, name2init_net, name2vis_encoder
 from .heads import name2agg_net, name2dist_decoder
 from . import ray_head
+from . import render_ops
 
 
 class NeuralRayRenderer(nn.Module):
@@ -60,6 +61,9 @@ class NeuralRayRenderer(nn.Module):
         if self.cfg['use_hierarchical_sampling']:
             self.fine_dist_decoder = name2dist_decoder[self.cfg['dist_decoder_type']](self.cfg['fine_dist_decoder_cfg'])
             self.fine_agg_net = name2agg_net[self.cfg['agg_net_type']](self.cfg['fine_agg_net_cfg'])
+        self.agg_net.pair_with(self.dist_decoder, 'agg_net.', 'dist_decoder.')
+        if self.cfg['use_hierarchical_sampling']:
+            self.fine_agg_net.pair_with(self.fine_dist_decoder, 'fine_agg_net.', 'fine_dist_decoder.')
         self.use_sdf = True
         self._hw = {}
 
@@ -101,6 +105,77 @@ class NeuralRayRenderer(nn.Module):
                                               ref_imgs_info['poses'], ref_imgs_info['Ks'], ref_imgs_info['depth_range'],
                                               bbox_min, named, self.cfg['volume_resolution'])
         return ops.sample_volume(self._scene(ref_imgs_info), self._head_weights(False), bbox_min, self.cfg['volume_resolution'])
+
+    # ------------------------------------------------------------------------------------------------ the reference's stage API
+    # renderer.py:62-162 under the reference's names.  render() / sample_volume() use the fused launch sequences in ops
+    # directly; these methods expose the same stages one by one (parity tests, diagnostics, external callers).
+    def predict_proj_ray_prob(self, prj_dict, ref_imgs_info, que_dists, is_fine):
+        """renderer.py:62-78: adds 'alpha', 'vis', 'hit_prob' ([rfn,qn,rn,dn,1]) to prj_dict.  The three decoder MLPs and
+        compute_prob run inside K2a; que_dists: [qn,rn,dn] inverse-depth spacings, or an empty tensor (fixed interval)."""
+        hw = self._head_weights(is_fine)
+        rec, pt, scene = prj_dict['_rec'], prj_dict['_pt'], prj_dict['_scene']
+        rfn, qn, rn, dn, _ = prj_dict['mask'].shape
+        inv = None if que_dists.numel() == 0 else que_dists.reshape(1, rn * dn).to(rec.device, torch.float32).contiguous()
+        _, _, rows = ops.k2a_forward(rec, pt, hw, scene.depth_range, que_dists=inv, dn=dn, debug=True)
+        hit = rows[0, :, :, 0].t().reshape(rfn, qn, rn, dn, 1)                               # already x mask (renderer.py:76-77)
+        vis = rows[0, :, :, 1].t().reshape(rfn, qn, rn, dn, 1)
+        m = prj_dict['mask']
+        prj_dict['alpha'] = torch.log(hit / (vis - hit + 1e-5) + 1e-5) * m + (1 - m) * self.cfg['alpha_value_ground_state']
+        prj_dict['vis'], prj_dict['hit_prob'], prj_dict['_inv_dists'] = vis, hit, inv
+        return prj_dict
+
+    def get_img_feats(self, ref_imgs_info, prj_dict):
+        """renderer.py:80-88: the img_feats tap is fused into K1 (one gather serves both feature maps), so project_points_dict
+        already produced it; this keeps the reference's call sequence working."""
+        if 'img_feats' not in prj_dict:
+            raise ValueError('prj_dict must come from graspnerf_b200.network.render_ops.project_points_dict')
+        return prj_dict
+
+    def network_rendering(self, prj_dict, que_dir, que_pts, que_depth, is_fine, is_train, is_sdf=False, sdf_only=False):
+        """renderer.py:90-108 (is_sdf: the NeuS aggregation net is the only one implemented)."""
+        net = self.fine_agg_net if is_fine else self.agg_net
+        dists = None
+        if que_depth is not None:
+            dists = torch.cat([que_depth[..., 1:] - que_depth[..., :-1], torch.full_like(que_depth[..., :1], 1e6)], -1)   # depth2dists
+            prj_dict['_que_depth'] = que_depth
+        alpha, sdf, colors, grad_err, s = net(prj_dict, que_dir, que_pts, dists, is_train)
+        outputs = {'sdf_values': sdf, 'sdf_gradient_error': grad_err, 's': s}
+        if sdf_only:
+            return outputs
+        T = torch.cumprod(torch.cat([torch.ones_like(alpha[..., :1]), 1.0 - alpha + 1e-10], -1), -1)[..., :-1]          # render_ops.py:72-80
+        outputs.update(alpha_values=alpha, colors_nr=colors, hit_prob_nr=alpha * T)
+        outputs['pixel_colors_nr'] = torch.sum(outputs['hit_prob_nr'].unsqueeze(-1) * colors, 2)
+        return outputs
+
+    def render_by_depth(self, que_depth, que_imgs_info, ref_imgs_info, is_train, is_fine):
+        """renderer.py:110-138, the fused launch sequence (ray set-up -> K1 -> K2a -> K2b -> K3)."""
+        que = {k: que_imgs_info[k] for k in ('coords', 'poses', 'Ks', 'depth_range')}
+        if torch.is_grad_enabled() and is_train and any(p.requires_grad for p in self.agg_net.parameters()):
+            out = ray_head.render_by_depth_autograd(self, ref_imgs_info, que, que_depth, is_fine, is_train)
+        else:
+            out = ops.render_by_depth(self._scene(ref_imgs_info), self._head_weights(is_fine), que, que_depth,
+                                      self.cfg['ray_mask_view_num'], self.cfg['ray_mask_point_num'])
+            out['s'] = torch.full((1, 1), self._head_weights(is_fine).variance, device=que_depth.device)
+        out.pop('sdf_grad', None)
+        if 'imgs' in que_imgs_info:
+            out['pixel_colors_gt'] = _bilinear_gt(que_imgs_info['imgs'], que_imgs_info['coords'])
+        return out
+
+    def fine_render_impl(self, coarse_render_info, que_imgs_info, ref_imgs_info, is_train):
+        """renderer.py:140-150."""
+        fd = render_ops.sample_fine_depth(coarse_render_info['depth'], coarse_render_info['hit_prob'], que_imgs_info['depth_range'],
+                                          self.cfg['fine_depth_sample_num'], is_train)
+        return self.render_by_depth(fd, que_imgs_info, ref_imgs_info, is_train, True)     # the kernel returns them sorted (renderer.py:148)
+
+    def render_impl(self, que_imgs_info, ref_imgs_info, is_train):
+        """renderer.py:152-162."""
+        que_depth, _ = render_ops.sample_depth(que_imgs_info['depth_range'], que_imgs_info['coords'], self.cfg['depth_sample_num'], False)
+        outputs = self.render_by_depth(que_depth, que_imgs_info, ref_imgs_info, is_train, False)
+        if self.cfg['use_hierarchical_sampling']:
+            fine = self.fine_render_impl({'depth': que_depth, 'hit_prob': outputs['hit_prob_nr']}, que_imgs_info, ref_imgs_info, is_train)
+            for k, v in fine.items():
+                outputs[k + '_fine'] = v
+        return outputs
 
     def render(self, que_imgs_info, ref_imgs_info, is_train):
         """renderer.py:201-220: chunk the query rays by ray_batch_num, coarse + fine pass per chunk (render_impl 152-162)."""

@@ -387,10 +387,10 @@ class VolumeGraph:
 
 
 # ------------------------------------------------------------------------------------------------ RGB head
-def ray_setup(coords, poses, Ks, depth_range_q, que_depth):
+def ray_setup(coords, poses, Ks, depth_range_q, que_depth, want_rays=False):
     """coords2rays + depth2points + depth2inv_dists (render_ops.py:4-52) in one launch (gn_k3_ray_setup): coords [B,rn,2]
     pixel (x,y), poses [B,3,4], Ks [B,3,3], depth_range_q [B,2], que_depth [B,rn,dn] ->
-    pts [B,rn*dn,3], que_dir [B,rn,3], inv_dists [B,rn*dn]."""
+    pts [B,rn*dn,3], que_dir [B,rn,3], inv_dists [B,rn*dn]  (+ centers [B,rn,3], un-normalised dirs [B,rn,3] with want_rays)."""
     lib = _lib.load()
     B, rn, dn = que_depth.shape
     dev = que_depth.device
@@ -402,9 +402,13 @@ def ray_setup(coords, poses, Ks, depth_range_q, que_depth):
     p.coords, p.poses, p.Ks, p.depth, p.depth_range = (_ptr(t).value for t in (coords, poses, Ks, depth, dr))
     p.pts, p.que_dir, p.inv_dists = _ptr(pts).value, _ptr(que_dir).value, _ptr(inv_dists).value
     p.B, p.rn, p.dn = B, rn, dn
+    centers = dirs = None
+    if want_rays:
+        centers, dirs = torch.empty((B, rn, 3), device=dev, dtype=torch.float32), torch.empty((B, rn, 3), device=dev, dtype=torch.float32)
+        p.centers, p.dirs = _ptr(centers).value, _ptr(dirs).value
     with _on(dev):
         _lib.check(lib.gn_k3_ray_setup(C.byref(p), _stream(dev)), 'gn_k3_ray_setup')
-    return pts, que_dir, inv_dists
+    return (pts, que_dir, inv_dists, centers, dirs) if want_rays else (pts, que_dir, inv_dists)
 
 
 def inv_s_from(variance):

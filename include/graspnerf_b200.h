@@ -154,6 +154,8 @@ typedef struct GnRaySetupParams {
     float* pts;                /* out [B,rn*dn,3] */
     float* que_dir;            /* out [B,rn,3] unit, pointing from the sample back to the camera (render_ops.py:37) */
     float* inv_dists;          /* out [B,rn*dn] spacings in normalised inverse depth, last one 1e6 */
+    float* centers;            /* optional out [B,rn,3]: ray origins (coords2rays' first result), or NULL */
+    float* dirs;               /* optional out [B,rn,3]: un-normalised ray directions (coords2rays' second result), or NULL */
     int B, rn, dn;
 } GnRaySetupParams;
 int gn_k3_ray_setup(const GnRaySetupParams* params, void* stream);

@@ -139,11 +139,13 @@ def test_ray_setup_kernel_matches_the_reference_formulas():
     assert torch.equal(inv.cpu().reshape(1, 50, 13)[..., -1], torch.full((1, 50), 1e6))
 
 
-@pytest.mark.parametrize('scale,expect_overflow', [(30.0, False), (3000.0, True)])
+@pytest.mark.parametrize('scale,expect_overflow', [(6.0, False), (3000.0, True)])
 def test_fp16_operand_range_large_activations_and_overflow_flag(scale, expect_overflow):
-    """The tensor-core K2a splits every activation into fp16 hi/lo halves: operands must stay below 65504.  Weights scaled so
-    that activations are ~1e3 must still match the fp32 CUDA-core path; scaled until they overflow, the sticky flag must
-    trip and check_numerics() must raise instead of returning a silently wrong volume."""
+    """The tensor-core K2a splits every activation into fp16 hi/lo halves: operands must stay below 65504 - and the pooled
+    VARIANCE features are operands too, so the 32-channel features x must stay below ~250 (250^2 ~ 65504; measured on B200:
+    weights scaled x30 give |x| ~ 1.5e3, variances ~ 2e6 and trip the flag).  Weights scaled so that |x| is O(100) must still
+    match the fp32 CUDA-core path; scaled until they overflow, the sticky flag must trip and check_numerics() must raise
+    instead of returning a silently wrong volume."""
     from graspnerf_b200 import ops
     sd = {k: v.clone() for k, v in seed0_weights().items()}
     for k in ('agg_net.agg_impl.base_fc.0.weight', 'agg_net.agg_impl.vis_fc.0.weight'):
@@ -162,6 +164,8 @@ def test_fp16_operand_range_large_activations_and_overflow_flag(scale, expect_ov
         hw.check_numerics()                               # the flag was reset by the failing check
     else:
         hw.check_numerics()
-        assert float(dbg['rows'][..., 4:6].abs().max()) > 10.0, 'the test should exercise large activations (base_fc output; vis_fc hidden is ~30x that)'
+        xmax = float(dbg['rows'][..., 4:6].abs().max())
+        print(f'large-activation test: max |x[0:2]| = {xmax:.1f}')
+        assert xmax > 10.0, 'the test should exercise large activations'
         vol_simt = ops.sample_volume(scene, hw, bb, 40, impl='simt')
         assert_close(vol.cpu(), vol_simt.cpu(), what='large-activation volume: tensor-core vs fp32 CUDA-core path')

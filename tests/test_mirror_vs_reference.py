@@ -104,3 +104,26 @@ def test_oracle_render_rays_matches_the_live_reference_on_a_fresh_scene():
         for sfx in ('', '_fine'):
             assert_close(out[k + sfx].detach(), res[k + sfx][0].detach(), what=k + sfx)
     assert torch.equal(out['ray_mask'], res['ray_mask'][0]) and torch.equal(out['ray_mask_fine'], res['ray_mask_fine'][0])
+
+
+def test_install_swaps_the_reference_registry():
+    """graspnerf_b200.install(): the reference's own registry (renderer.py:333-335) hands out the mirror class, which loads a
+    reference state_dict unchanged - what train.sh / sim_grasp.py need to run with zero source edits."""
+    import graspnerf_b200
+    from graspnerf_b200.network import GraspNeRF as Mirror
+    orig_cuda, orig_to = torch.Tensor.cuda, torch.Tensor.to
+    try:
+        cfg, ref_net = build_reference_net(0)
+        import network.renderer as ref_mod
+        saved = (ref_mod.name2network['grasp_nerf'], ref_mod.GraspNeRF, ref_mod.NeuralRayRenderer)
+        try:
+            reg = graspnerf_b200.install()
+            assert reg is ref_mod.name2network and reg['grasp_nerf'] is Mirror
+            net = reg[cfg['network']](cfg)                     # the reference's cfg (yaml) builds the mirror
+            missing, unexpected = net.load_state_dict(ref_net.state_dict(), strict=True)
+            assert not missing and not unexpected
+        finally:
+            ref_mod.name2network['grasp_nerf'], ref_mod.GraspNeRF, ref_mod.NeuralRayRenderer = saved
+            ref_mod.__graspnerf_b200__ = False
+    finally:
+        torch.Tensor.cuda, torch.Tensor.to = orig_cuda, orig_to

@@ -1,7 +1,7 @@
 """Pretty-print the interesting fields of a bench.py JSON line (development aid)."""
 import json, sys
 d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
-keys = ('impl', 'value', 'unit', 'n_gpus', 'ms_per_step', 'kernel_us', 'e2e', 'train_step', 'clocks', 'cpu_baseline')
+keys = ('impl', 'value', 'unit', 'n_gpus', 'ms_per_step', 'kernel_us', 'e2e', 'full_forward', 'highres', 'train_step', 'clocks', 'cpu_baseline')
 for k in keys:
     if k in d:
         print(k, '=', d[k])
