@@ -61,6 +61,10 @@ class GnGraspPostParams(C.Structure):
                [(n, C.c_int) for n in ('R', 'max_filter_size', 'max_grasps')]
 
 
+class GnVgnParams(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ('volume', 'weights', 'workspace', 'out')] + [(n, C.c_int) for n in ('B', 'R', 'out_scene_stride')]
+
+
 _lib = None
 
 
@@ -78,7 +82,7 @@ def load():
     lib.gn_version.restype = C.c_char_p
     for name, st in (('gn_k1_forward', GnK1Params), ('gn_k2a_forward', GnK2aParams), ('gn_k2a_forward_tc', GnK2aParams), ('gn_k2b_forward', GnK2bParams),
                      ('gn_k3_composite', GnK3Params), ('gn_k2b_backward', GnK2bBwdParams), ('gn_k2a_backward', GnK2aBwdParams),
-                     ('gn_k1_backward', GnK1BwdParams), ('gn_k3_ray_setup', GnRaySetupParams), ('gn_k4_grasp_post', GnGraspPostParams)):
+                     ('gn_k1_backward', GnK1BwdParams), ('gn_k3_ray_setup', GnRaySetupParams), ('gn_k4_grasp_post', GnGraspPostParams), ('gn_vgn_forward', GnVgnParams)):
         fn = getattr(lib, name)
         fn.restype = C.c_int
         fn.argtypes = [C.POINTER(st), C.c_void_p]
@@ -88,13 +92,16 @@ def load():
     lib.gn_k3_fine_depths.argtypes = [C.c_void_p] * 6 + [C.c_int] * 4 + [C.c_void_p]
     lib.gn_k2a_tc_prepare.restype = C.c_int
     lib.gn_k2a_tc_prepare.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.gn_vgn_layer_info.restype = C.c_int
+    lib.gn_vgn_layer_info.argtypes = [C.c_int] + [C.POINTER(C.c_int)] * 7
+    lib.gn_vgn_workspace_floats.argtypes = [C.c_int]
     lib.gn_weight_entry.restype = C.c_int
     lib.gn_weight_entry.argtypes = [C.c_int, C.POINTER(C.c_char_p)] + [C.POINTER(C.c_int)] * 4
     for name, st in (('gn_sizeof_k1_params', GnK1Params), ('gn_sizeof_k2a_params', GnK2aParams),
                      ('gn_sizeof_k2b_params', GnK2bParams), ('gn_sizeof_k3_params', GnK3Params),
                      ('gn_sizeof_k2b_bwd_params', GnK2bBwdParams), ('gn_sizeof_k2a_bwd_params', GnK2aBwdParams),
                      ('gn_sizeof_k1_bwd_params', GnK1BwdParams), ('gn_sizeof_ray_setup_params', GnRaySetupParams),
-                     ('gn_sizeof_grasp_post_params', GnGraspPostParams)):
+                     ('gn_sizeof_grasp_post_params', GnGraspPostParams), ('gn_sizeof_vgn_params', GnVgnParams)):
         got = getattr(lib, name)()
         if got != C.sizeof(st):
             raise RuntimeError(f'{name}: library says {got} bytes, ctypes mirror has {C.sizeof(st)}')

@@ -182,9 +182,10 @@ class ForwardEngine(_Engine):
         vol = nr.sample_volume(ref)
         if self.depth_mean:
             nr.predict_mean_for_depth_loss(ref)
-        qual, rot, width = self.net.vgn_net(vol)
         R = self.R
-        vols = torch.cat([vol.reshape(1, R, R, R), qual.reshape(1, R, R, R), rot.reshape(4, R, R, R), width.reshape(1, R, R, R)], 0)
+        vols = torch.empty((7, R, R, R), device=vol.device, dtype=torch.float32)
+        vols[0].copy_(vol.reshape(R, R, R))
+        self.net.vgn_net(vol, out=vols[1:].unsqueeze(0))             # K5 writes qual | rot | width straight into the result buffer
         if self.post_cfg is not None:
             _, grasps, count = ops.grasp_post(vols[0], vols[1], vols[2:6], vols[6], max_grasps=self.max_grasps, **self.post_cfg)
         else:

@@ -144,7 +144,7 @@ class _VgnEncoder(nn.Module):                     # gd/networks.py:57-74
         return F.relu(self.conv3(F.relu(self.conv2(F.relu(self.conv1(x))))))
 
 
-class _VgnDecoder(nn.Module):                     # gd/networks.py:77-97 (hard-coded 10/20/40 grids)
+class _VgnDecoder(nn.Module):                     # gd/networks.py:77-97
     def __init__(self):
         super().__init__()
         self.conv1 = nn.Conv3d(64, 64, 3, padding=1)
@@ -152,9 +152,12 @@ class _VgnDecoder(nn.Module):                     # gd/networks.py:77-97 (hard-c
         self.conv3 = nn.Conv3d(32, 16, 5, padding=2)
 
     def forward(self, x):
-        x = F.interpolate(F.relu(self.conv1(x)), 10)
-        x = F.interpolate(F.relu(self.conv2(x)), 20)
-        return F.interpolate(F.relu(self.conv3(x)), 40)
+        # the reference hard-codes the grids 10 / 20 / 40 (networks.py:88-96) = x2 per stage for its 40^3 volume; written as
+        # x2 here so that the 80^3 volumes of BASELINE configs[4] work too
+        n = x.shape[-1]
+        x = F.interpolate(F.relu(self.conv1(x)), 2 * n)
+        x = F.interpolate(F.relu(self.conv2(x)), 4 * n)
+        return F.interpolate(F.relu(self.conv3(x)), 8 * n)
 
 
 class VgnConvNet(nn.Module):                      # gd/networks.py:39-54
@@ -165,6 +168,16 @@ class VgnConvNet(nn.Module):                      # gd/networks.py:39-54
         self.conv_rot = nn.Conv3d(16, 4, 5, padding=2)
         self.conv_width = nn.Conv3d(16, 1, 5, padding=2)
 
-    def forward(self, x):
+    def forward(self, x, out=None):
+        """networks.py:47-54.  Inference on a CUDA volume: seven direct-convolution launches (csrc/k5_vgn_conv.cu, upsampling
+        folded into the weights).  With autograd recording (training) the same layers run through torch / cuDNN."""
+        if x.is_cuda and not (torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters()))):
+            from .. import ops
+            if getattr(self, '_vw', None) is None:
+                object.__setattr__(self, '_vw', ops.VgnWeights(self))
+            return ops.vgn_forward(x, self._vw, out=out)
+        return self.forward_torch(x)
+
+    def forward_torch(self, x):
         x = self.decoder(self.encoder(x))
         return torch.sigmoid(self.conv_qual(x)), F.normalize(self.conv_rot(x), dim=1), self.conv_width(x)

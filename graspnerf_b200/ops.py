@@ -661,3 +661,45 @@ def grasp_post(tsdf, qual, rot, width, *, gaussian_filter_sigma=1.0, min_width=1
     with _on(dev):
         _lib.check(lib.gn_k4_grasp_post(C.byref(p), _stream(dev)), 'gn_k4_grasp_post')
     return qual_out, grasps, count
+
+
+# ------------------------------------------------------------------------------------------------ VGN head (K5)
+class VgnWeights:
+    """Prepared weights of the VGN ConvNet for gn_vgn_forward; re-packed when a source tensor changed (like HeadWeights)."""
+
+    def __init__(self, module):
+        self.module, self._versions, self.blob, self._ws = module, None, None, {}
+
+    def refresh(self):
+        sd = dict(self.module.named_parameters())
+        vers = tuple((k, v._version, v.data_ptr()) for k, v in sd.items())
+        if vers != self._versions:
+            from .weights import pack_vgn
+            with torch.no_grad():
+                self.blob = pack_vgn(sd)
+            self._versions = vers
+        return self.blob
+
+    def workspace(self, R, dev):
+        if (R, dev) not in self._ws:
+            self._ws[(R, dev)] = torch.empty(_lib.load().gn_vgn_workspace_floats(R), dtype=torch.float32, device=dev)
+        return self._ws[(R, dev)]
+
+
+def vgn_forward(volume, vw, out=None):
+    """gd/networks.py ConvNet.forward on the device kernels: volume [B,1,R,R,R] -> (qual [B,1,R,R,R], rot [B,4,R,R,R],
+    width [B,1,R,R,R]) as views of one [B,6,R,R,R] buffer (`out` optional: [B,>=6,R,R,R]-strided destination)."""
+    lib = _lib.load()
+    _require_cuda(volume, 'volume')
+    dev = volume.device
+    B, R = volume.shape[0], volume.shape[-1]
+    vol = _f32c(volume, dev).reshape(B, R, R, R)
+    blob = vw.refresh()
+    if out is None:
+        out = torch.empty((B, 6, R, R, R), device=dev, dtype=torch.float32)
+    p = _lib.GnVgnParams()
+    p.volume, p.weights, p.workspace, p.out = _ptr(vol).value, _ptr(blob).value, _ptr(vw.workspace(R, dev)).value, _ptr(out).value
+    p.B, p.R, p.out_scene_stride = B, R, out.stride(0)
+    with _on(dev):
+        _lib.check(lib.gn_vgn_forward(C.byref(p), _stream(dev)), 'gn_vgn_forward')
+    return out[:, 0:1], out[:, 1:5], out[:, 5:6]

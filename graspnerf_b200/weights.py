@@ -245,3 +245,53 @@ def seed0_weights(seed=0):
         _SEED0[seed] = {k[len('nr_net.'):]: v.detach().clone() for k, v in sd.items()
                         if k.startswith('nr_net.') and ('agg_net.' in k or 'dist_decoder.' in k)}
     return _SEED0[seed]
+
+
+# ------------------------------------------------------------------------------------------------ VGN 3-D ConvNet (K5)
+_VGN_LAYERS = ('encoder.conv1', 'encoder.conv2', 'encoder.conv3', 'decoder.conv1', 'decoder.conv2', 'decoder.conv3', 'heads')
+
+
+def _fold_upsampled(w):
+    """Folds `nearest x2 upsample -> Conv3d(K, padding=K//2)` into 8 parity classes of 3x3x3 kernels on the low-resolution
+    grid (csrc/k5_vgn_conv.cu): output voxel o = 2m + parity reads high-res taps o + d, d in [-r, r], which live in low-res
+    cells m + floor((parity + d) / 2) in {m-1, m, m+1}; taps sharing a cell share their input, so their weights add up.
+    w [cout, cin, K, K, K] (fp64) -> [8, cout, cin, 27], class index = px*4 + py*2 + pz."""
+    import torch
+    K = w.shape[-1]
+    r = K // 2
+    M = torch.zeros(2, 3, K, dtype=torch.float64)
+    for par in range(2):
+        for d in range(-r, r + 1):
+            M[par, (par + d) // 2 + 1, d + r] = 1.0
+    eff = torch.einsum('pad,qbe,rcf,oidef->pqroiabc', M, M, M, w.double())
+    return eff.reshape(8, w.shape[0], w.shape[1], 27)
+
+
+def pack_vgn(sd, prefix=''):
+    """VGN state_dict (src/gd/networks.py:39-97 key names: encoder.conv{1,2,3}, decoder.conv{1,2,3}, conv_qual / conv_rot /
+    conv_width) -> the fp32 blob gn_vgn_forward consumes.  Layout per layer comes from the library (gn_vgn_layer_info)."""
+    import ctypes as C
+    import torch
+    from . import _lib
+    lib = _lib.load()
+    dev = sd[prefix + 'encoder.conv1.weight'].device
+    blob = torch.zeros(lib.gn_vgn_blob_floats(), dtype=torch.float32, device=dev)
+    for li, name in enumerate(_VGN_LAYERS):
+        v = [C.c_int() for _ in range(7)]
+        assert lib.gn_vgn_layer_info(li, *[C.byref(x) for x in v]) == 0
+        cin, cout, cout_t, taps, classes, w_off, b_off = (x.value for x in v)
+        if name == 'heads':
+            w = torch.cat([sd[prefix + k + '.weight'] for k in ('conv_qual', 'conv_rot', 'conv_width')], 0)
+            b = torch.cat([sd[prefix + k + '.bias'] for k in ('conv_qual', 'conv_rot', 'conv_width')], 0)
+        else:
+            w, b = sd[prefix + name + '.weight'], sd[prefix + name + '.bias']
+        w, b = w.detach().double(), b.detach().double()
+        assert w.shape[0] == cout and w.shape[1] == cin
+        w = _fold_upsampled(w).to(dev) if classes == 8 else w.reshape(1, cout, cin, taps)
+        assert w.shape[-1] == taps
+        nb = (cout + cout_t - 1) // cout_t
+        wk = w.permute(0, 2, 3, 1).reshape(classes, cin * taps, cout)                    # [class][cin*tap][cout]
+        wk = torch.nn.functional.pad(wk, (0, nb * cout_t - cout)).reshape(classes, cin * taps, nb, cout_t).permute(0, 2, 1, 3)
+        blob[w_off:w_off + wk.numel()] = wk.reshape(-1).float()
+        blob[b_off:b_off + cout] = b.float()
+    return blob

@@ -180,6 +180,24 @@ typedef struct GnGraspPostParams {
 } GnGraspPostParams;
 int gn_k4_grasp_post(const GnGraspPostParams* params, void* stream);
 
+/* K5: the VGN 3-D ConvNet that consumes the TSDF volume (src/gd/networks.py:39-97, called at renderer.py:323-330): three
+ * strided encoder convolutions, three decoder convolutions with nearest x2 upsampling in between (folded exactly into 8
+ * parity classes of 3x3x3 kernels on the low-resolution grid) and the three 5^3 heads (sigmoid / F.normalize / identity)
+ * as seven direct fp32 convolutions.  weights: blob prepared by the host (graspnerf_b200.weights.pack_vgn, layout from
+ * gn_vgn_layer_info); out per scene: qual [R^3] | rot [4,R^3] | width [R^3] (6 consecutive volumes). */
+typedef struct GnVgnParams {
+    const float* volume;       /* [B,R,R,R] TSDF volume (K2b's output) */
+    const float* weights;      /* [gn_vgn_blob_floats()] */
+    float* workspace;          /* [gn_vgn_workspace_floats(R)] */
+    float* out;                /* [B] scenes, out_scene_stride floats apart, 6*R^3 floats each */
+    int B, R;
+    int out_scene_stride;
+} GnVgnParams;
+int gn_vgn_forward(const GnVgnParams* params, void* stream);
+int gn_vgn_layer_info(int layer, int* cin, int* cout, int* cout_t, int* taps, int* classes, int* w_offset, int* b_offset);
+int gn_vgn_blob_floats(void);
+int gn_vgn_workspace_floats(int R);
+
 /* ---------------------------------------------------------------------------------------------------------------------
  * Backward (training) entry points of the volume path: d volume -> d weights, d feature maps.  First order only.
  * The reference gets these from torch autograd through renderer.py:164-199; here each forward kernel has a hand-derived
@@ -237,6 +255,7 @@ int gn_sizeof_k2a_bwd_params(void);
 int gn_sizeof_k1_bwd_params(void);
 int gn_sizeof_ray_setup_params(void);
 int gn_sizeof_grasp_post_params(void);
+int gn_sizeof_vgn_params(void);
 
 #ifdef __cplusplus
 }

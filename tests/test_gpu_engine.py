@@ -168,4 +168,71 @@ def test_fp16_operand_range_large_activations_and_overflow_flag(scale, expect_ov
         print(f'large-activation test: max |x[0:2]| = {xmax:.1f}')
         assert xmax > 10.0, 'the test should exercise large activations'
         vol_simt = ops.sample_volume(scene, hw, bb, 40, impl='simt')
-        assert_close(vol.cpu(), vol_simt.cpu(), what='large-activation volume: tensor-core vs fp32 CUDA-core path')
+        # large weights amplify rounding differences between two fp32-accurate evaluations (measured on B200: 9 of 64 000 voxels at
+        # 4.4e-4, rel-L2 9.4e-6): element-wise bound relaxed to 1e-3, rel-L2 kept tight
+        rel = assert_close(vol.cpu(), vol_simt.cpu(), rtol=1e-3, atol_scale=1e-3, what='large-activation volume: tensor-core vs fp32 CUDA-core path')
+        assert rel < 5e-5
+
+
+def test_planner_core_and_plan():
+    """planner.GraspPlanner: core() has the reference's signature / return layout (main.py:211-253) and matches the
+    reference's forward (fixture); plan() = core + process + select equals the oracle's scipy post-processing of the SAME
+    volumes (bit-exact quality volume, same grasp rows in np.argwhere order)."""
+    from graspnerf_b200.planner import GraspPlanner
+    from oracle import grasp_post as G
+    g = load_golden('forward_small_u8.npz')
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    sc, u8 = _quantised(dict(seed=3, num_views=4, h=96, w=160, radius=0.45))
+    net = seed0_model().to(DEV).eval()
+    pl = GraspPlanner(net, DEV, max_grasps=512)
+    ext = np.concatenate([sc['poses'], np.tile(np.array([[[0, 0, 0, 1]]], np.float32), (4, 1, 1))], 1)      # [V,4,4] like main.py:196
+    vol, label, rot, width, t = pl.core(sc['imgs'], ext, sc['Ks'], sc['depth_range'], sc['bbox3d'])          # float images [V,3,H,W] = u8 / 255
+    assert vol.shape == (1, 1, 40, 40, 40) and label.shape == (1, 1, 40, 40, 40) and rot.shape == (1, 4, 40, 40, 40) and width.shape == (1, 1, 40, 40, 40)
+    assert_close(vol[0, 0], g['volume'], rtol=2e-3, atol_scale=2e-3, what='planner.core volume vs reference')
+    assert_close(label[0, 0], g['qual'], rtol=2e-3, atol_scale=2e-3, what='planner.core qual vs reference')
+    pl.tsdf_thres_high, pl.tsdf_thres_low = 0.0, -0.85
+    pl._engines.clear()
+    # seed-0 random weights give qual ~ 0.5 everywhere: lower select()'s threshold through a custom post_cfg so grasps exist
+    from graspnerf_b200.engine import ForwardEngine, HostScene
+    hs = HostScene(u8, None, None, sc['poses'], sc['Ks'], sc['depth_range'], np.asarray(sc['bbox3d'][0], np.float32))
+    post = dict(tsdf_thres_high=0.0, tsdf_thres_low=-0.85, threshold=0.5, min_width=-1e9, max_width=1e9)
+    eng = ForwardEngine(net, hs, slots=2, device=DEV, post_cfg=post, max_grasps=2048)
+    i, _ = eng.submit(hs)
+    _, (vols, grasps, count) = eng.collect(i)
+    v = vols.numpy()
+    q_or, r_or, w_or = G.process(v[0], v[1].copy(), v[2:6], v[6], tsdf_thres_high=0.0, tsdf_thres_low=-0.85, min_width=-1e9, max_width=1e9)
+    idx, scs, ro, wi = G.select(q_or, r_or, w_or, threshold=0.5)
+    n = int(count.item())
+    assert n == len(idx) and n > 0, (n, len(idx))
+    gr = grasps[:min(n, 2048)].numpy()
+    m = len(gr)
+    assert np.array_equal(gr[:, :3].astype(np.int64), idx[:m]) and np.array_equal(gr[:, 3], scs[:m].astype(np.float32))
+    assert np.array_equal(gr[:, 4:8], ro[:m]) and np.array_equal(gr[:, 8], wi[:m])
+    out = pl.plan(u8, ext, sc['Ks'])
+    assert set(out) >= {'index', 'score', 'rot', 'width', 'planning_time'} and out['index'].shape[1] == 3
+
+
+@pytest.mark.parametrize('R,B', [(40, 1), (40, 3), (80, 1)])
+def test_vgn_kernels_match_the_torch_modules(R, B):
+    """gn_vgn_forward (seven direct convolutions, nearest x2 upsampling folded into the weights) against the same layers in
+    torch / cuDNN fp32 (the mirror's training path, itself pinned to the reference's VGN by tests/test_mirror_vs_reference.py)."""
+    torch.backends.cudnn.allow_tf32 = False
+    net = seed0_model().to(DEV).eval().vgn_net
+    g = torch.Generator().manual_seed(R + B)
+    vol = (torch.rand(B, 1, R, R, R, generator=g) * 2 - 1).to(DEV)
+    with torch.no_grad():
+        q, r, w = net(vol)
+        qt, rt, wt = net.forward_torch(vol)
+    assert q.shape == qt.shape and r.shape == rt.shape and w.shape == wt.shape
+    assert_close(q.cpu(), qt.cpu(), rtol=1e-5, atol_scale=1e-5, what='qual')
+    assert_close(w.cpu(), wt.cpu(), rtol=1e-4, atol_scale=1e-5, what='width')
+    assert_close(r.cpu(), rt.cpu(), rtol=1e-4, atol_scale=1e-4, what='rot')
+    # and with trained-looking (non-tiny) weights: scale every layer so activations do not vanish
+    with torch.no_grad():
+        for p in net.parameters():
+            p.mul_(3.0)
+        q, r, w = net(vol)
+        qt, rt, wt = net.forward_torch(vol)
+    assert_close(q.cpu(), qt.cpu(), rtol=1e-4, atol_scale=1e-5, what='qual (scaled weights)')
+    assert_close(w.cpu(), wt.cpu(), rtol=1e-4, atol_scale=1e-4, what='width (scaled weights)')
