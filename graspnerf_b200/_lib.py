@@ -65,6 +65,11 @@ class GnVgnParams(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ('volume', 'weights', 'workspace', 'out')] + [(n, C.c_int) for n in ('B', 'R', 'out_scene_stride')]
 
 
+class GnNormActPadParams(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ('x', 'gamma', 'beta', 'res', 'res_gamma', 'res_beta', 'out_padded', 'out_unpadded')] + \
+               [(n, C.c_int) for n in ('N', 'C', 'H', 'W', 'pad', 'x_pad', 'res_pad', 'act')] + [('eps', C.c_float)]
+
+
 _lib = None
 
 
@@ -82,7 +87,7 @@ def load():
     lib.gn_version.restype = C.c_char_p
     for name, st in (('gn_k1_forward', GnK1Params), ('gn_k2a_forward', GnK2aParams), ('gn_k2a_forward_tc', GnK2aParams), ('gn_k2b_forward', GnK2bParams),
                      ('gn_k3_composite', GnK3Params), ('gn_k2b_backward', GnK2bBwdParams), ('gn_k2a_backward', GnK2aBwdParams),
-                     ('gn_k1_backward', GnK1BwdParams), ('gn_k3_ray_setup', GnRaySetupParams), ('gn_k4_grasp_post', GnGraspPostParams), ('gn_vgn_forward', GnVgnParams)):
+                     ('gn_k1_backward', GnK1BwdParams), ('gn_k3_ray_setup', GnRaySetupParams), ('gn_k4_grasp_post', GnGraspPostParams), ('gn_vgn_forward', GnVgnParams), ('gn_k6_norm_act_pad', GnNormActPadParams)):
         fn = getattr(lib, name)
         fn.restype = C.c_int
         fn.argtypes = [C.POINTER(st), C.c_void_p]
@@ -92,6 +97,8 @@ def load():
     lib.gn_k3_fine_depths.argtypes = [C.c_void_p] * 6 + [C.c_int] * 4 + [C.c_void_p]
     lib.gn_k2a_tc_prepare.restype = C.c_int
     lib.gn_k2a_tc_prepare.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.gn_k6_upsample2x_pad.restype = C.c_int
+    lib.gn_k6_upsample2x_pad.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
     lib.gn_vgn_layer_info.restype = C.c_int
     lib.gn_vgn_layer_info.argtypes = [C.c_int] + [C.POINTER(C.c_int)] * 7
     lib.gn_vgn_workspace_floats.argtypes = [C.c_int]
@@ -101,7 +108,8 @@ def load():
                      ('gn_sizeof_k2b_params', GnK2bParams), ('gn_sizeof_k3_params', GnK3Params),
                      ('gn_sizeof_k2b_bwd_params', GnK2bBwdParams), ('gn_sizeof_k2a_bwd_params', GnK2aBwdParams),
                      ('gn_sizeof_k1_bwd_params', GnK1BwdParams), ('gn_sizeof_ray_setup_params', GnRaySetupParams),
-                     ('gn_sizeof_grasp_post_params', GnGraspPostParams), ('gn_sizeof_vgn_params', GnVgnParams)):
+                     ('gn_sizeof_grasp_post_params', GnGraspPostParams), ('gn_sizeof_vgn_params', GnVgnParams),
+                     ('gn_sizeof_norm_act_pad_params', GnNormActPadParams)):
         got = getattr(lib, name)()
         if got != C.sizeof(st):
             raise RuntimeError(f'{name}: library says {got} bytes, ctypes mirror has {C.sizeof(st)}')

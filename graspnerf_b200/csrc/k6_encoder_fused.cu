@@ -1,0 +1,128 @@
+// K6: fused element-wise stages of the 2-D encoders (src/nr/network/ops.py:78-230, init_net.py:8-35, vis_encoder.py:6-21).
+// The reference's ResUNetLight / residual blocks run, per 3x3 convolution, a reflection-pad kernel, the convolution, an
+// InstanceNorm (two kernels + a `repeat` of the affine parameters), an activation and often a residual add: ~6 launches
+// whose cost at batch 6 is launch / latency, not bytes (profiles/profile_forward_r02e.txt: pad 12 %, instance norm + its
+// repeat / copy 18 %, bilinear upsampling 11 %, ReLU 2 % of the encoders' GPU time).  Here ONE kernel per layer does
+//   out = reflect_pad( act( InstanceNorm(x) * gamma + beta  [+ residual | + InstanceNorm(residual) * g_r + b_r] ), p )
+// and writes the tensor already padded for the NEXT convolution (which then runs with padding 0), plus the un-padded copy
+// when a 1x1 / skip consumer needs it.  The convolutions themselves stay in cuDNN (fp32).
+//   gn_k6_norm_act_pad   one CTA per (image, channel) plane; mean / biased variance in two passes (fp32, like at::native).
+//   gn_k6_upsample2x_pad F.interpolate(scale_factor=2, mode='bilinear', align_corners=True) (ops.py:142-150) + reflect pad.
+#include "gn_common.cuh"
+#include "../../include/graspnerf_b200.h"
+
+#define K6_THREADS 256
+
+__device__ __forceinline__ float k6_block_sum(float v, float* s_red)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();
+    if (lane == 0) s_red[warp] = v;
+    __syncthreads();
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < K6_THREADS / 32; ++w) t += s_red[w];
+    return t;
+}
+
+__device__ __forceinline__ void k6_plane_stats(const float* __restrict__ x, int n, int row_len, int row_stride, float eps,
+                                               float* s_red, float& mean, float& rstd)
+{
+    // x: plane of n = rows*row_len elements, row r starts at x + r*row_stride (a padded tensor's interior is such a view)
+    float s = 0.f;
+    for (int i = threadIdx.x; i < n; i += K6_THREADS) s += x[(i / row_len) * row_stride + (i % row_len)];
+    mean = k6_block_sum(s, s_red) / (float)n;
+    float q = 0.f;
+    for (int i = threadIdx.x; i < n; i += K6_THREADS) { const float d = x[(i / row_len) * row_stride + (i % row_len)] - mean; q = fmaf(d, d, q); }
+    const float var = k6_block_sum(q, s_red) / (float)n;                 // biased, like InstanceNorm
+    rstd = rsqrtf(var + eps);
+}
+
+__device__ __forceinline__ int k6_reflect(int i, int n) { return i < 0 ? -i : (i >= n ? 2 * n - 2 - i : i); }
+
+__global__ void __launch_bounds__(K6_THREADS)
+gn_k6_norm_act_pad_kernel(const GnNormActPadParams p)
+{
+    __shared__ float s_red[K6_THREADS / 32];
+    const int plane = blockIdx.x;                        // n * C + c
+    const int c = plane % p.C;
+    const int H = p.H, W = p.W, hw = H * W;
+    const int xs = W + 2 * p.x_pad;                      // row stride of the (possibly padded) input
+    const float* x = p.x + (size_t)plane * (size_t)(H + 2 * p.x_pad) * xs + (size_t)p.x_pad * xs + p.x_pad;
+    float mean = 0.f, rstd = 1.f, g = 1.f, b = 0.f;
+    if (p.gamma) {
+        k6_plane_stats(x, hw, W, xs, p.eps, s_red, mean, rstd);
+        g = __ldg(p.gamma + c) * rstd; b = __ldg(p.beta + c) - mean * g;          // y = (x - mean) * rstd * gamma + beta
+    }
+    const float* r = nullptr;
+    int rs = 0;
+    float rg = 1.f, rb = 0.f;
+    if (p.res) {
+        rs = W + 2 * p.res_pad;
+        r = p.res + (size_t)plane * (size_t)(H + 2 * p.res_pad) * rs + (size_t)p.res_pad * rs + p.res_pad;
+        if (p.res_gamma) {
+            float rm, rr;
+            k6_plane_stats(r, hw, W, rs, p.eps, s_red, rm, rr);
+            rg = __ldg(p.res_gamma + c) * rr; rb = __ldg(p.res_beta + c) - rm * rg;
+        }
+    }
+    const int P = p.pad, Hp = H + 2 * P, Wp = W + 2 * P;
+    float* op = p.out_padded ? p.out_padded + (size_t)plane * Hp * Wp : nullptr;
+    float* ou = p.out_unpadded ? p.out_unpadded + (size_t)plane * hw : nullptr;
+    const int total = Hp * Wp;
+    for (int i = threadIdx.x; i < total; i += K6_THREADS) {
+        const int hp = i / Wp, wp = i - hp * Wp;
+        const int h = k6_reflect(hp - P, H), w = k6_reflect(wp - P, W);
+        float v = fmaf(x[h * xs + w], g, b);
+        if (r) v += fmaf(r[h * rs + w], rg, rb);
+        if (p.act == 1) v = fmaxf(v, 0.f);
+        else if (p.act == 2) v = v > 0.f ? v : expm1f(v);                          // F.elu
+        if (op) op[i] = v;
+        if (ou && hp >= P && hp < P + H && wp >= P && wp < P + W) ou[(hp - P) * W + (wp - P)] = v;
+    }
+    if (!op && ou) { /* only the un-padded copy was requested and P == 0: handled by the loop above (op null) */ }
+}
+
+extern "C" int gn_k6_norm_act_pad(const GnNormActPadParams* hp, void* stream)
+{
+    const GnNormActPadParams& p = *hp;
+    if (p.N < 1 || p.C < 1 || p.H < 1 || p.W < 1 || p.pad < 0 || p.pad >= p.H || p.pad >= p.W || p.x_pad < 0 || p.res_pad < 0) return -1;
+    if (!p.x || (!p.out_padded && !p.out_unpadded) || ((p.gamma == nullptr) != (p.beta == nullptr)) || ((p.res_gamma == nullptr) != (p.res_beta == nullptr))) return -2;
+    if (p.res_gamma && !p.res) return -2;
+    if (p.act < 0 || p.act > 2) return -3;
+    if (!p.out_padded && p.pad != 0) return -3;
+    gn_k6_norm_act_pad_kernel<<<(unsigned)(p.N * p.C), K6_THREADS, 0, (cudaStream_t)stream>>>(p);
+    return (int)cudaGetLastError();
+}
+
+// F.interpolate(x, scale_factor=2, mode='bilinear', align_corners=True) then reflection padding by `pad`
+// (at::native upsample_bilinear2d: scale = (in-1)/(out-1) in fp32, src = scale*dst, lambda1 = src - floor(src)).
+__global__ void __launch_bounds__(K6_THREADS)
+gn_k6_upsample2x_pad_kernel(const float* __restrict__ x, float* __restrict__ out, int planes, int H, int W, int pad)
+{
+    const int Ho = 2 * H, Wo = 2 * W, Hp = Ho + 2 * pad, Wp = Wo + 2 * pad;
+    const long long total = (long long)planes * Hp * Wp;
+    const float sh = Ho > 1 ? (float)(H - 1) / (float)(Ho - 1) : 0.f, sw = Wo > 1 ? (float)(W - 1) / (float)(Wo - 1) : 0.f;
+    for (long long i = (long long)blockIdx.x * K6_THREADS + threadIdx.x; i < total; i += (long long)gridDim.x * K6_THREADS) {
+        const int wp = (int)(i % Wp), hp = (int)((i / Wp) % Hp);
+        const long long pl = i / ((long long)Wp * Hp);
+        const int ho = k6_reflect(hp - pad, Ho), wo = k6_reflect(wp - pad, Wo);
+        const float fh = sh * (float)ho, fw = sw * (float)wo;
+        const int h0 = (int)fh, w0 = (int)fw;
+        const int h1 = h0 + (h0 < H - 1 ? 1 : 0), w1 = w0 + (w0 < W - 1 ? 1 : 0);
+        const float lh1 = fh - (float)h0, lw1 = fw - (float)w0, lh0 = 1.f - lh1, lw0 = 1.f - lw1;
+        const float* xp = x + pl * (long long)H * W;
+        out[i] = lh0 * (lw0 * __ldg(xp + h0 * W + w0) + lw1 * __ldg(xp + h0 * W + w1)) + lh1 * (lw0 * __ldg(xp + h1 * W + w0) + lw1 * __ldg(xp + h1 * W + w1));
+    }
+}
+
+extern "C" int gn_k6_upsample2x_pad(const float* x, float* out, int planes, int H, int W, int pad, void* stream)
+{
+    if (!x || !out || planes < 1 || H < 1 || W < 1 || pad < 0 || pad >= 2 * H || pad >= 2 * W) return -1;
+    const long long total = (long long)planes * (2 * H + 2 * pad) * (2 * W + 2 * pad);
+    const long long blocks = (total + K6_THREADS - 1) / K6_THREADS;
+    gn_k6_upsample2x_pad_kernel<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), K6_THREADS, 0, (cudaStream_t)stream>>>(x, out, planes, H, W, pad);
+    return (int)cudaGetLastError();
+}

@@ -1,10 +1,29 @@
-"""2-D feature encoders and the VGN 3-D head: plain PyTorch/cuDNN modules (out of the CUDA hot path),
-re-stated here only so that the boundary class owns every parameter of the reference checkpoint under the reference's
-key names.  Architectures follow src/nr/network/ops.py:78-230, init_net.py:8-35, vis_encoder.py:6-21 and
-src/gd/networks.py:39-97; the key/shape table is pinned by tests/golden/state_dict_keys.json."""
+"""2-D feature encoders and the VGN 3-D head (the steps right before / after the hot path).  The modules
+own every parameter of the reference checkpoint under the reference's key names; architectures follow
+src/nr/network/ops.py:78-230, init_net.py:8-35, vis_encoder.py:6-21 and src/gd/networks.py:39-97 (key/shape table pinned by
+tests/golden/state_dict_keys.json).
+
+Two execution paths per module, same parameters:
+  * `forward`       plain PyTorch/cuDNN, differentiable: training;
+  * `forward_fused` inference on CUDA tensors: convolutions in cuDNN fp32, everything between two convolutions (reflection
+                    pad, InstanceNorm, activation, residual add, bilinear x2 upsampling) in ONE launch of csrc/k6_encoder_fused.cu
+                    per layer; the VGN head entirely in csrc/k5_vgn_conv.cu.
+`use_fused(x)` picks the path."""
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
+
+FUSED = True          # module-level switch for the fused inference path (tests compare both paths)
+
+
+def use_fused(x, module):
+    return FUSED and x.is_cuda and x.dtype == torch.float32 and not (
+        torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in module.parameters())))
+
+
+def _conv0(xp, conv):
+    """A convolution whose (reflection) padding has already been applied by the producer of `xp`."""
+    return F.conv2d(xp, conv.weight, conv.bias, conv.stride, 0)
 
 
 def _inorm(c):
@@ -32,6 +51,18 @@ class BasicBlock(nn.Module):                      # ops.py:86-125
         y = self.bn2(self.conv2(y))
         return self.relu(y + (x if self.downsample is None else self.downsample(x)))
 
+    def forward_fused(self, xp, xu, want_padded=True, want_unpadded=False):
+        """xp: block input reflection-padded by 1; xu: the same tensor un-padded (only read by a 1x1 downsample branch).
+        -> (output padded by 1 or None, output un-padded or None)."""
+        from .. import ops
+        a_p, _ = ops.norm_act_pad(_conv0(xp, self.conv1), self.bn1, 'relu', pad=1)
+        raw2 = _conv0(a_p, self.conv2)
+        if self.downsample is None:          # identity residual = interior of the padded input
+            return ops.norm_act_pad(raw2, self.bn2, 'relu', pad=1, res=xp, res_pad=1, want_padded=want_padded, want_unpadded=want_unpadded)
+        rawd = _conv0(xu, self.downsample[0])
+        return ops.norm_act_pad(raw2, self.bn2, 'relu', pad=1, res=rawd, res_norm=self.downsample[1],
+                                want_padded=want_padded, want_unpadded=want_unpadded)
+
 
 class ConvNormELU(nn.Module):                     # ops.py `conv` 127-140
     def __init__(self, cin, cout, k, stride):
@@ -42,6 +73,11 @@ class ConvNormELU(nn.Module):                     # ops.py `conv` 127-140
     def forward(self, x):
         return F.elu(self.bn(self.conv(x)))
 
+    def forward_fused(self, xp, pad=0, want_padded=False, want_unpadded=True):
+        """xp: input already reflection-padded for self.conv."""
+        from .. import ops
+        return ops.norm_act_pad(_conv0(xp, self.conv), self.bn, 'elu', pad=pad, want_padded=want_padded, want_unpadded=want_unpadded)
+
 
 class UpConv(nn.Module):                          # ops.py `upconv` 142-150
     def __init__(self, cin, cout, k, scale):
@@ -51,6 +87,11 @@ class UpConv(nn.Module):                          # ops.py `upconv` 142-150
 
     def forward(self, x):
         return self.conv(F.interpolate(x, scale_factor=self.scale, mode='bilinear', align_corners=True))
+
+    def forward_fused(self, xu):
+        from .. import ops
+        assert self.scale == 2
+        return self.conv.forward_fused(ops.upsample2x_pad(xu.contiguous(), pad=(self.conv.conv.kernel_size[0] - 1) // 2))[1]
 
 
 class ResUNetLight(nn.Module):                    # ops.py:150-230
@@ -83,6 +124,8 @@ class ResUNetLight(nn.Module):                    # ops.py:150-230
         return torch.cat([x, skip], 1)
 
     def forward(self, x):
+        if use_fused(x, self):
+            return self.forward_fused(x)
         x = self.relu(self.bn1(self.conv1(x)))
         x1 = self.layer1(x)
         x2 = self.layer2(x1)
@@ -90,6 +133,31 @@ class ResUNetLight(nn.Module):                    # ops.py:150-230
         x = self.iconv3(self._skip(x2, self.upconv3(x3)))
         x = self.iconv2(self._skip(x1, self.upconv2(x)))
         return self.out_conv(x)
+
+    @staticmethod
+    def _stage_fused(stage, xp, xu, last_padded, last_unpadded):
+        n = len(stage)
+        for i, blk in enumerate(stage):
+            last = i == n - 1
+            xp, xu = blk.forward_fused(xp, xu, want_padded=(not last) or last_padded, want_unpadded=last and last_unpadded)
+        return xp, xu
+
+    def forward_fused(self, x):
+        """Same math as forward(), inference only: every tensor between two convolutions is produced by one K6 launch,
+        already reflection-padded for its consumer."""
+        from .. import ops
+        xin, _ = ops.norm_act_pad(x.contiguous(), None, None, pad=3)                                  # reflection pad for the 7x7 stem
+        x0p, x0u = ops.norm_act_pad(_conv0(xin, self.conv1), self.bn1, 'relu', pad=1, want_unpadded=True)
+        x1p, x1u = self._stage_fused(self.layer1, x0p, x0u, True, True)
+        x2p, x2u = self._stage_fused(self.layer2, x1p, x1u, True, True)
+        _, x3u = self._stage_fused(self.layer3, x2p, x2u, False, True)
+        y = self._skip(x2u, self.upconv3.forward_fused(x3u))
+        yp, _ = ops.norm_act_pad(y.contiguous(), None, None, pad=1)
+        y = self.iconv3.forward_fused(yp)[1]
+        y = self._skip(x1u, self.upconv2.forward_fused(y))
+        yp, _ = ops.norm_act_pad(y.contiguous(), None, None, pad=1)
+        y = self.iconv2.forward_fused(yp)[1]
+        return self.out_conv(y)
 
 
 class ResidualBlock(nn.Module):                   # ops.py:43-76 (use_norm branch)
@@ -102,6 +170,13 @@ class ResidualBlock(nn.Module):                   # ops.py:43-76 (use_norm branc
     def forward(self, x):
         y = self.conv(x)
         return y + (x if self.short_cut is None else self.short_cut(x))
+
+    def forward_fused(self, x):
+        """pre-activation residual block: IN -> ReLU -> conv3x3 -> IN -> ReLU -> conv3x3, + x."""
+        from .. import ops
+        t, _ = ops.norm_act_pad(x.contiguous(), self.conv[0], 'relu', pad=1)
+        t, _ = ops.norm_act_pad(_conv0(t, self.conv[2]), self.conv[3], 'relu', pad=1)
+        return _conv0(t, self.conv[5]) + (x if self.short_cut is None else self.short_cut(x))
 
 
 class CostVolumeInitNet(nn.Module):               # init_net.py:8-35 (no cost volume despite the name)
@@ -116,7 +191,12 @@ class CostVolumeInitNet(nn.Module):               # init_net.py:8-35 (no cost vo
         self.out_conv = nn.Sequential(_c3(32, 32), ResidualBlock(32, 32), _c1(32, 32))
 
     def forward(self, ref_imgs_info, src_imgs_info, is_train):
-        return self.out_conv(self.res_net(ref_imgs_info['imgs']))
+        x = self.res_net(ref_imgs_info['imgs'])
+        if use_fused(x, self):
+            from .. import ops
+            xp, _ = ops.norm_act_pad(x.contiguous(), None, None, pad=1)
+            return self.out_conv[2](self.out_conv[1].forward_fused(_conv0(xp, self.out_conv[0])))
+        return self.out_conv(x)
 
 
 class DefaultVisEncoder(nn.Module):               # vis_encoder.py:6-21
@@ -126,7 +206,13 @@ class DefaultVisEncoder(nn.Module):               # vis_encoder.py:6-21
         self.out_conv = nn.Sequential(_c3(64, 32), ResidualBlock(32, 32), ResidualBlock(32, 32), _c1(32, 32))
 
     def forward(self, ray_feats, imgs_feats):
-        return self.out_conv(torch.cat([imgs_feats, ray_feats], 1))
+        x = torch.cat([imgs_feats, ray_feats], 1)
+        if use_fused(x, self):
+            from .. import ops
+            xp, _ = ops.norm_act_pad(x, None, None, pad=1)
+            y = self.out_conv[1].forward_fused(_conv0(xp, self.out_conv[0]))
+            return self.out_conv[3](self.out_conv[2].forward_fused(y))
+        return self.out_conv(x)
 
 
 name2init_net = {'cost_volume': CostVolumeInitNet}

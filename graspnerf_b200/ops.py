@@ -5,6 +5,7 @@ hand-written sm_100a kernels.  Nothing in this module has a CPU or eager-PyTorch
 built library these functions raise.
 """
 import ctypes as C
+from ctypes import byref as C_byref
 import numpy as np
 import torch
 
@@ -703,3 +704,46 @@ def vgn_forward(volume, vw, out=None):
     with _on(dev):
         _lib.check(lib.gn_vgn_forward(C.byref(p), _stream(dev)), 'gn_vgn_forward')
     return out[:, 0:1], out[:, 1:5], out[:, 5:6]
+
+
+# ------------------------------------------------------------------------------------------------ fused encoder stages (K6)
+_ACT = {None: 0, 'none': 0, 'relu': 1, 'elu': 2}
+
+
+def norm_act_pad(x, norm=None, act=None, pad=0, res=None, res_norm=None, x_pad=0, res_pad=0, want_padded=True, want_unpadded=False):
+    """gn_k6_norm_act_pad: out = reflect_pad(act(IN(x) [+ res | + IN(res)]), pad).  x [N,C,H+2*x_pad,W+2*x_pad] (NCHW fp32,
+    contiguous); norm / res_norm: nn.InstanceNorm2d modules (affine) or None.  Returns (padded or None, un-padded or None)."""
+    lib = _lib.load()
+    dev = x.device
+    N, C = x.shape[0], x.shape[1]
+    H, W = x.shape[2] - 2 * x_pad, x.shape[3] - 2 * x_pad
+    assert x.is_contiguous() and x.dtype == torch.float32
+    outp = torch.empty((N, C, H + 2 * pad, W + 2 * pad), device=dev, dtype=torch.float32) if want_padded else None
+    outu = torch.empty((N, C, H, W), device=dev, dtype=torch.float32) if want_unpadded else None
+    p = _lib.GnNormActPadParams()
+    p.x = _ptr(x).value
+    if norm is not None:
+        p.gamma, p.beta, p.eps = _ptr(norm.weight).value, _ptr(norm.bias).value, float(norm.eps)
+    else:
+        p.eps = 1e-5
+    if res is not None:
+        assert res.is_contiguous() and res.shape[2] - 2 * res_pad == H and res.shape[3] - 2 * res_pad == W and res.shape[1] == C
+        p.res = _ptr(res).value
+        if res_norm is not None:
+            p.res_gamma, p.res_beta = _ptr(res_norm.weight).value, _ptr(res_norm.bias).value
+    p.out_padded, p.out_unpadded = _ptr(outp).value, _ptr(outu).value
+    p.N, p.C, p.H, p.W, p.pad, p.x_pad, p.res_pad, p.act = N, C, H, W, int(pad), int(x_pad), int(res_pad), _ACT[act]
+    with _on(dev):
+        _lib.check(lib.gn_k6_norm_act_pad(C_byref(p), _stream(dev)), 'gn_k6_norm_act_pad')
+    return outp, outu
+
+
+def upsample2x_pad(x, pad=0):
+    """gn_k6_upsample2x_pad: F.interpolate(x, scale_factor=2, mode='bilinear', align_corners=True) + reflection pad."""
+    lib = _lib.load()
+    N, C, H, W = x.shape
+    assert x.is_contiguous() and x.dtype == torch.float32
+    out = torch.empty((N, C, 2 * H + 2 * pad, 2 * W + 2 * pad), device=x.device, dtype=torch.float32)
+    with _on(x.device):
+        _lib.check(lib.gn_k6_upsample2x_pad(_ptr(x), _ptr(out), N * C, H, W, int(pad), _stream(x.device)), 'gn_k6_upsample2x_pad')
+    return out

@@ -259,7 +259,7 @@ def _fold_upsampled(w):
     import torch
     K = w.shape[-1]
     r = K // 2
-    M = torch.zeros(2, 3, K, dtype=torch.float64)
+    M = torch.zeros(2, 3, K, dtype=torch.float64, device=w.device)
     for par in range(2):
         for d in range(-r, r + 1):
             M[par, (par + d) // 2 + 1, d + r] = 1.0
@@ -287,7 +287,7 @@ def pack_vgn(sd, prefix=''):
             w, b = sd[prefix + name + '.weight'], sd[prefix + name + '.bias']
         w, b = w.detach().double(), b.detach().double()
         assert w.shape[0] == cout and w.shape[1] == cin
-        w = _fold_upsampled(w).to(dev) if classes == 8 else w.reshape(1, cout, cin, taps)
+        w = _fold_upsampled(w) if classes == 8 else w.reshape(1, cout, cin, taps)
         assert w.shape[-1] == taps
         nb = (cout + cout_t - 1) // cout_t
         wk = w.permute(0, 2, 3, 1).reshape(classes, cin * taps, cout)                    # [class][cin*tap][cout]

@@ -198,6 +198,29 @@ int gn_vgn_layer_info(int layer, int* cin, int* cout, int* cout_t, int* taps, in
 int gn_vgn_blob_floats(void);
 int gn_vgn_workspace_floats(int R);
 
+/* K6: fused element-wise stages of the 2-D encoders (src/nr/network/ops.py:78-230: ResUNetLight / BasicBlock / conv /
+ * upconv; init_net.py:8-35; vis_encoder.py:6-21), inference only.  One launch per layer replaces reflection pad +
+ * InstanceNorm (+ affine repeat) + activation + residual add:
+ *   out = reflect_pad( act( IN(x)*gamma+beta [+ res | + IN(res)*res_gamma+res_beta] ), pad )
+ * x / res may themselves be interiors of padded tensors (x_pad / res_pad = their border width).  NCHW fp32. */
+typedef struct GnNormActPadParams {
+    const float* x;            /* [N,C,H+2*x_pad,W+2*x_pad] */
+    const float* gamma;        /* [C] or NULL (no normalisation of x) */
+    const float* beta;         /* [C] or NULL */
+    const float* res;          /* [N,C,H+2*res_pad,W+2*res_pad] or NULL */
+    const float* res_gamma;    /* [C] or NULL: instance-normalise the residual too (BasicBlock downsample branch, ops.py:96-124) */
+    const float* res_beta;
+    float* out_padded;         /* [N,C,H+2*pad,W+2*pad] or NULL */
+    float* out_unpadded;       /* [N,C,H,W] or NULL */
+    int N, C, H, W;
+    int pad, x_pad, res_pad;
+    int act;                   /* 0 none, 1 ReLU, 2 ELU */
+    float eps;
+} GnNormActPadParams;
+int gn_k6_norm_act_pad(const GnNormActPadParams* params, void* stream);
+/* F.interpolate(scale_factor=2, bilinear, align_corners=True) (ops.py:142-150) + reflection pad: x [planes,H,W] -> out [planes,2H+2pad,2W+2pad] */
+int gn_k6_upsample2x_pad(const float* x, float* out, int planes, int H, int W, int pad, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------------------
  * Backward (training) entry points of the volume path: d volume -> d weights, d feature maps.  First order only.
  * The reference gets these from torch autograd through renderer.py:164-199; here each forward kernel has a hand-derived
@@ -256,6 +279,7 @@ int gn_sizeof_k1_bwd_params(void);
 int gn_sizeof_ray_setup_params(void);
 int gn_sizeof_grasp_post_params(void);
 int gn_sizeof_vgn_params(void);
+int gn_sizeof_norm_act_pad_params(void);
 
 #ifdef __cplusplus
 }

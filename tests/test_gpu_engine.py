@@ -236,3 +236,56 @@ def test_vgn_kernels_match_the_torch_modules(R, B):
         qt, rt, wt = net.forward_torch(vol)
     assert_close(q.cpu(), qt.cpu(), rtol=1e-4, atol_scale=1e-5, what='qual (scaled weights)')
     assert_close(w.cpu(), wt.cpu(), rtol=1e-4, atol_scale=1e-4, what='width (scaled weights)')
+
+
+@pytest.mark.parametrize('shape', [(6, 288, 512), (4, 96, 160), (2, 64, 96)])
+def test_fused_encoder_path_matches_the_torch_modules(shape):
+    """network/encoders.py forward_fused (cuDNN convolutions + one gn_k6_* launch per layer for reflection pad / InstanceNorm
+    / activation / residual / bilinear upsampling) against the plain torch modules with the same parameters (which are pinned
+    to the reference's encoders by tests/test_mirror_vs_reference.py)."""
+    from graspnerf_b200.network import encoders as E
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    nr = seed0_model().to(DEV).eval().nr_net
+    n, h, w = shape
+    x = torch.rand(n, 3, h, w, generator=torch.Generator().manual_seed(h)).to(DEV)
+    out = {}
+    with torch.no_grad():
+        for fused in (False, True):
+            E.FUSED = fused
+            try:
+                f = nr.image_encoder(x)
+                r0 = nr.init_net({'imgs': x}, None, False)
+                out[fused] = (f, r0, nr.vis_encoder(r0, f))
+            finally:
+                E.FUSED = True
+    for name, a, b in zip(('image_encoder', 'init_net', 'vis_encoder'), out[True], out[False]):
+        assert a.shape == b.shape
+        assert_close(a.cpu(), b.cpu(), rtol=1e-4, atol_scale=2e-5, what=f'{name} fused vs torch')
+
+
+def test_k6_kernels_against_torch_ops():
+    """gn_k6_norm_act_pad / gn_k6_upsample2x_pad one by one against the torch ops they replace."""
+    import torch.nn.functional as F
+    from graspnerf_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    x = (torch.randn(3, 5, 14, 22, generator=g) * 2 + 1).to(DEV)
+    r = torch.randn(3, 5, 14, 22, generator=g).to(DEV)
+    n1 = torch.nn.InstanceNorm2d(5, affine=True).to(DEV); n2 = torch.nn.InstanceNorm2d(5, affine=True).to(DEV)
+    with torch.no_grad():
+        for m in (n1, n2):
+            m.weight.uniform_(0.5, 1.5); m.bias.uniform_(-0.5, 0.5)
+        for act, fn in (('relu', F.relu), ('elu', F.elu), (None, lambda t: t)):
+            for pad in (0, 1, 3):
+                want = F.pad(fn(n1(x) + n2(r)), (pad,) * 4, mode='reflect') if pad else fn(n1(x) + n2(r))
+                gp, gu = ops.norm_act_pad(x, n1, act, pad=pad, res=r, res_norm=n2, want_unpadded=True)
+                assert_close(gp.cpu(), want.cpu(), rtol=1e-5, atol_scale=1e-5, what=f'norm_act_pad {act} pad {pad}')
+                assert_close(gu.cpu(), fn(n1(x) + n2(r)).cpu(), rtol=1e-5, atol_scale=1e-5, what='un-padded copy')
+        xp = F.pad(x, (1, 1, 1, 1), mode='reflect').contiguous()                  # x / res given as interiors of padded tensors
+        gp, _ = ops.norm_act_pad(xp, n1, 'relu', pad=1, res=xp, x_pad=1, res_pad=1)
+        assert_close(gp.cpu(), F.pad(F.relu(n1(x) + x), (1, 1, 1, 1), mode='reflect').cpu(), rtol=1e-5, atol_scale=1e-5, what='padded inputs')
+        gp, _ = ops.norm_act_pad(x, None, None, pad=2)
+        assert torch.equal(gp, F.pad(x, (2, 2, 2, 2), mode='reflect'))
+        up = ops.upsample2x_pad(x, pad=1)
+        want = F.pad(F.interpolate(x, scale_factor=2, mode='bilinear', align_corners=True), (1, 1, 1, 1), mode='reflect')
+        assert_close(up.cpu(), want.cpu(), rtol=1e-6, atol_scale=1e-6, what='bilinear x2 + reflect pad')
