@@ -177,8 +177,7 @@ class ForwardEngine(_Engine):
         imgs = (s.imgs[0, ..., :3].permute(0, 3, 1, 2).to(torch.float32) / 255.0).contiguous()     # color_map_forward + transpose (main.py:192)
         ref = {'imgs': imgs, 'imgs_u8': s.imgs, 'poses': s.poses[0], 'Ks': s.Ks[0], 'depth_range': s.depth_range[0],
                'bbox3d': s.bbox_min.reshape(1, 3)}
-        ref['img_feats'] = nr.image_encoder(imgs)
-        ref['ray_feats'] = nr.vis_encoder(nr.init_net(ref, ref, False), ref['img_feats'])
+        ref['img_feats'], ref['ray_feats'] = nr.encode(ref, ref, False)
         vol = nr.sample_volume(ref)
         if self.depth_mean:
             nr.predict_mean_for_depth_loss(ref)

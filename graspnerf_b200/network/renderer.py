@@ -66,6 +66,8 @@ class NeuralRayRenderer(nn.Module):
             self.fine_agg_net.pair_with(self.fine_dist_decoder, 'fine_agg_net.', 'fine_dist_decoder.')
         self.use_sdf = True
         self._hw = {}
+        self._side = None
+        self.two_stream_encoders = True
 
     # ------------------------------------------------------------------------------------------------ plumbing
     def _head_weights(self, fine=False):
@@ -240,15 +242,32 @@ class NeuralRayRenderer(nn.Module):
             out['depth_mean_fine'], out['depth_mean_fine_2'] = mf[..., 0], mf[..., 1]
         return out
 
+    def encode(self, ref, src=None, is_train=False):
+        """renderer.py:275-279: image_encoder, init_net, vis_encoder -> (img_feats, ray_feats).  In inference on a CUDA device
+        the two independent ResUNets (image_encoder and init_net: ~150 small launches each at batch V, latency- not
+        throughput-bound) run CONCURRENTLY on two streams (fork / join with events, also under CUDA-graph capture)."""
+        imgs = ref['imgs']
+        if imgs.is_cuda and not torch.is_grad_enabled() and self.two_stream_encoders:
+            cur = torch.cuda.current_stream(imgs.device)
+            if self._side is None or self._side.device != imgs.device:
+                self._side = torch.cuda.Stream(imgs.device)
+            self._side.wait_stream(cur)
+            with torch.cuda.stream(self._side):
+                ray0 = self.init_net(ref, src, is_train)
+            img_feats = self.image_encoder(imgs)
+            cur.wait_stream(self._side)
+        else:
+            img_feats = self.image_encoder(imgs)
+            ray0 = self.init_net(ref, src, is_train)
+        return img_feats, self.vis_encoder(ray0, img_feats)
+
     def forward(self, data):
         """renderer.py:268-291."""
         ref = data['ref_imgs_info'].copy()
         que = data['que_imgs_info'].copy()
         is_train = 'eval' not in data
         src = data['src_imgs_info'].copy() if 'src_imgs_info' in data else None
-        ref['img_feats'] = self.image_encoder(ref['imgs'])
-        ref['ray_feats'] = self.init_net(ref, src, is_train)
-        ref['ray_feats'] = self.vis_encoder(ref['ray_feats'], ref['img_feats'])
+        ref['img_feats'], ref['ray_feats'] = self.encode(ref, src, is_train)
         out = {}
         if self.cfg['render_rgb']:
             out = self.render(que, ref, is_train)

@@ -718,6 +718,8 @@ def norm_act_pad(x, norm=None, act=None, pad=0, res=None, res_norm=None, x_pad=0
     N, C = x.shape[0], x.shape[1]
     H, W = x.shape[2] - 2 * x_pad, x.shape[3] - 2 * x_pad
     assert x.is_contiguous() and x.dtype == torch.float32
+    if not want_padded:
+        pad = 0
     outp = torch.empty((N, C, H + 2 * pad, W + 2 * pad), device=dev, dtype=torch.float32) if want_padded else None
     outu = torch.empty((N, C, H, W), device=dev, dtype=torch.float32) if want_unpadded else None
     p = _lib.GnNormActPadParams()

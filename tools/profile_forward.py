@@ -33,10 +33,20 @@ def main():
     ref = {k: (torch.from_numpy(v).to(dev) if isinstance(v, np.ndarray) else v) for k, v in sc.items() if k not in ('img_feats', 'ray_feats')}
 
     def encoders(x):
-        f = nr.image_encoder(x)
-        return f, nr.vis_encoder(nr.init_net({'imgs': x}, None, False), f)
+        return nr.encode({'imgs': x}, None, False)
     with torch.no_grad():
-        print(f'encoders eager fp32 NCHW          : {timeit(lambda: encoders(imgs)):.3f} ms')
+        from graspnerf_b200.network import encoders as E
+        for fused in (False, True):
+            for two in (False, True):
+                E.FUSED, nr.two_stream_encoders = fused, two
+                print(f'encoders eager fp32 fused={fused} two_stream={two}: {timeit(lambda: encoders(imgs)):.3f} ms')
+                g0 = torch.cuda.CUDAGraph(); s0 = torch.cuda.Stream()
+                with torch.cuda.stream(s0):
+                    encoders(imgs); torch.cuda.synchronize()
+                    with torch.cuda.graph(g0, stream=s0):
+                        o0 = encoders(imgs)
+                print(f'encoders GRAPH fp32 fused={fused} two_stream={two}: {timeit(lambda: g0.replay()):.3f} ms')
+                del g0
         print(f'  image_encoder only              : {timeit(lambda: nr.image_encoder(imgs)):.3f} ms')
         print(f'  init_net only                   : {timeit(lambda: nr.init_net({"imgs": imgs}, None, False)):.3f} ms')
         f = nr.image_encoder(imgs); r = nr.init_net({'imgs': imgs}, None, False)
