@@ -28,8 +28,14 @@ __device__ __forceinline__ float gn_softplus(float x) {
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
-// streaming store: the record is written once and read once by the next kernel
+// record store: written once by K1, read once by K2a right after.  Default: streaming (evict-first) store.
+// GN_K1_STORE_DEFAULT (experiment): normal write-back policy, so the 110 MB record of a 40^3 scene can stay in the 126 MB L2
+// until K2a reads it.
+#ifdef GN_K1_STORE_DEFAULT
+__device__ __forceinline__ void st4_cs(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+#else
 __device__ __forceinline__ void st4_cs(float* p, float4 v) { __stcs(reinterpret_cast<float4*>(p), v); }
+#endif
 
 __device__ __forceinline__ float4 f4_fma(float4 a, float w, float4 acc) {
     acc.x = fmaf(a.x, w, acc.x); acc.y = fmaf(a.y, w, acc.y);

@@ -315,6 +315,16 @@ gn_k2a_tc3_kernel(const __grid_constant__ GnK2aParams p, int num_tiles, int G)
         const int b = (int)(pidx / p.N);
         const int n = (int)(pidx - (long long)b * p.N);
         const float* row = p.rec + ((size_t)pidx * V + v) * GN_REC_STRIDE;
+#ifdef GN_K2A_PREFETCH
+        {   // the slot's next tile is (most likely) three tiles ahead: pull this thread's row of it towards L2 now
+            const float* nxt = row + (size_t)T3_SLOTS * 4 * G * V * GN_REC_STRIDE;
+            if (nxt + GN_REC_STRIDE <= p.rec + (size_t)total_pts * V * GN_REC_STRIDE) {
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(nxt));
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(nxt + 32));
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(nxt + 64));
+            }
+        }
+#endif
         const float2 ptv = __ldg(reinterpret_cast<const float2*>(p.pt + (size_t)pidx * GN_PT_STRIDE));
         const float4 tail = ldg4(row + GN_REC_RGB);            // rgb0..2 (masked), depth
         const float4 ddv = ldg4(row + GN_REC_DD);

@@ -36,6 +36,8 @@ def test_stage_api_matches_the_reference_stage_by_stage():
             r_prj = nr.get_img_feats(ref_info, r_prj)
         r_out = nr.network_rendering(r_prj, r_dir, r_pts, r_depth, False, False, is_sdf=True)    # autograd.grad inside: grad mode on
         r_out = {k: v.detach() for k, v in r_out.items()}
+        r_pts, r_dir = r_pts.detach(), r_dir.detach()           # ibrnet.py:486 switches requires_grad on in place
+        r_prj = {k: (v.detach() if torch.is_tensor(v) else v) for k, v in r_prj.items()}
     # ---------------- the mirror, on the GPU, same calls
     net = seed0_model().to(DEV).eval()
     mnr = net.nr_net

@@ -67,10 +67,6 @@ def main():
         torch.backends.cudnn.allow_tf32 = True
         print(f'encoders eager TF32 NCHW          : {timeit(lambda: encoders(imgs)):.3f} ms')
         torch.backends.cudnn.allow_tf32 = False
-        for m in (nr.image_encoder, nr.init_net, nr.vis_encoder):
-            m.to(memory_format=torch.channels_last)
-        x_cl = imgs.contiguous(memory_format=torch.channels_last)
-        print(f'encoders eager fp32 channels_last : {timeit(lambda: encoders(x_cl)):.3f} ms')
         from torch.profiler import profile, ProfilerActivity
         for m in (nr.image_encoder, nr.init_net, nr.vis_encoder):
             m.to(memory_format=torch.contiguous_format)
