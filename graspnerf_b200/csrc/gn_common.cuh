@@ -9,12 +9,14 @@
 #define GN_POOL_STRIDE 68     // floats per point written by K2a: mean32 | var32 | wmean, nvalid, 0, 0
 #define GN_TOK_STRIDE 20      // floats per point written by K2a (tensor-core path): geometry_fc output 16 | nvalid, 0, 0, 0
 
-// record layout (floats), see DESIGN.md "Data layout in HBM"
+// record layout (floats), see DESIGN.md "Data layout in HBM".  Two halves of 36 floats = the two TMA boxes K2a stages
+// (csrc/k2a_head_tc3.cu): [ray_feats | dir_diff] is what the first GEMM rounds need, [rgb, depth | img_feats] the later ones.
 #define GN_REC_RAYF 0         // [0,32)  ray_feats * mask
-#define GN_REC_IMGF 32        // [32,64) img_feats * mask
-#define GN_REC_RGB 64         // [64,67) rgb * mask ; [67] projection depth
-#define GN_REC_DEPTH 67
-#define GN_REC_DD 68          // [68,72) dir_diff = (dir - que_dir, dir . que_dir)   (aggregate_net.py:11-17)
+#define GN_REC_DD 32          // [32,36) dir_diff = (dir - que_dir, dir . que_dir)   (aggregate_net.py:11-17)
+#define GN_REC_RGB 36         // [36,39) rgb * mask ; [39] projection depth
+#define GN_REC_DEPTH 39
+#define GN_REC_IMGF 40        // [40,72) img_feats * mask
+#define GN_REC_HALF 36        // floats per half / TMA box
 
 __device__ __forceinline__ float gn_elu(float x) {
     // nn.ELU (alpha 1): x>0 ? x : exp(x)-1.  __expf = ex2.approx(x*log2e): rel. err ~2^-21.

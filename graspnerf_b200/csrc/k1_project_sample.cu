@@ -243,9 +243,9 @@ gn_k1_kernel(const __grid_constant__ GnK1Params p)
         if (live) {
             st4_cs(row + GN_REC_RAYF + 4 * j, ray);
             st4_cs(row + GN_REC_IMGF + 4 * j, img);
-            if (j < 2) {       // tail: lanes 0 and 1 write the two adjacent 16-byte chunks [64,68) and [68,72) with ONE store instruction
+            if (j < 2) {       // lanes 0 and 1 write the two adjacent 16-byte chunks dir_diff [32,36) and rgb|depth [36,40) with ONE store instruction
                 const float4 ddq = *reinterpret_cast<const float4*>(s_misc + pair * K1_MISC);
-                st4_cs(row + GN_REC_RGB + 4 * j, j == 0 ? make_float4(cr, cg, cb, s_misc[pair * K1_MISC + 5]) : ddq);
+                st4_cs(row + GN_REC_DD + 4 * j, j == 0 ? ddq : make_float4(cr, cg, cb, s_misc[pair * K1_MISC + 5]));
             }
         }
     }

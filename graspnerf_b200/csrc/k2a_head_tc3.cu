@@ -20,6 +20,7 @@
 //   * tiles are handed out inside the CTA from a shared-memory counter (each CTA owns a contiguous range of tiles), so
 //     the three slots stay busy although a slot only sees ~7 tiles of a 40^3 volume.
 #include "k2a_tc_common.cuh"
+#include <cuda.h>          // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint, no libcuda link)
 
 #define T3_THREADS 384
 #define T3_SLOTS 3
@@ -30,8 +31,11 @@
 #define T3_SLOT 160
 #define T3_POOL_STRIDE 36                                                     // floats per row of the pooling scratch (144 B: conflict-free float4 rows)
 
+// per-warp pooling scratch [(32+G) rows][36 floats]; its first 32 rows double as the landing zone of the warp's TMA boxes
+// (a record half is 36 floats = one scratch row), so the stride is rounded up to the 128-byte alignment TMA wants
+__host__ __device__ constexpr size_t t3_warp_scratch_bytes(int G) { return (((size_t)(32 + G) * T3_POOL_STRIDE * 4) + 127) / 128 * 128; }
 __host__ __device__ constexpr size_t t3_smem_bytes(int G) {
-    return (size_t)TC_CONST_BYTES + (size_t)(T3_THREADS / 32) * (32 + G) * T3_POOL_STRIDE * 4 + 128;   // + barriers, tmem ptr, tile counter
+    return (size_t)TC_CONST_BYTES + 128 + (size_t)(T3_THREADS / 32) * t3_warp_scratch_bytes(G) + 256;   // + alignment slack, barriers, tmem ptr, tile counter
 }
 static_assert(t3_smem_bytes(5) <= 227 * 1024, "K2a-TC3 shared memory budget at V = 6");
 
@@ -239,14 +243,15 @@ __device__ __noinline__ void t3_geometry_phase(const GnK2aParams& p, uint32_t tm
 }
 
 __global__ void __launch_bounds__(T3_THREADS, 1)
-gn_k2a_tc3_kernel(const __grid_constant__ GnK2aParams p, int num_tiles, int G)
+gn_k2a_tc3_kernel(const __grid_constant__ GnK2aParams p, const __grid_constant__ CUtensorMap rec_map, int num_tiles, int G)
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __half* s_img = reinterpret_cast<__half*>(smem_raw);
     const float* sw = reinterpret_cast<const float*>(smem_raw + (size_t)TC_IMG_HALVES * 2);   // small fp32 constants, index with TS()
-    float* s_pool = reinterpret_cast<float*>(smem_raw + TC_CONST_BYTES);                       // [12 warps][(32+G)][36]
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_pool + (T3_THREADS / 32) * (32 + G) * T3_POOL_STRIDE);   // [3] slot barriers, [1] constants
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + T3_SLOTS + 1);
+    unsigned char* pool_raw = smem_raw + (((size_t)TC_CONST_BYTES + 127) / 128) * 128;         // 128-byte aligned (smem_raw is 1024-aligned)
+    const size_t wscr = t3_warp_scratch_bytes(G);                                               // [12 warps][(32+G)][36], 128-byte multiples
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(pool_raw + (T3_THREADS / 32) * wscr);        // [3] slot barriers, [1] constants, [12] per-warp TMA barriers
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + T3_SLOTS + 1 + T3_THREADS / 32);
     int* s_ctr = reinterpret_cast<int*>(s_tmem + 1);                   // next tile of this CTA's range
     int* s_tile = s_ctr + 1;                                           // [3] tile handed to each slot
 
@@ -275,6 +280,7 @@ gn_k2a_tc3_kernel(const __grid_constant__ GnK2aParams p, int num_tiles, int G)
     }
     if (tid == 0) {
         for (int s = 0; s < T3_SLOTS; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(&s_bar[s])), "r"(1));
+        for (int w = 0; w < T3_THREADS / 32; ++w) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(&s_bar[T3_SLOTS + 1 + w])), "r"(1));
         asm volatile("fence.mbarrier_init.release.cluster;");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -299,37 +305,42 @@ gn_k2a_tc3_kernel(const __grid_constant__ GnK2aParams p, int num_tiles, int G)
     const int gb = g * V;
     const long long total_pts = (long long)p.B * p.N;
     const unsigned FULL = 0xffffffffu;
-    float* scr = s_pool + warp * (32 + G) * T3_POOL_STRIDE;
+    float* scr = reinterpret_cast<float*>(pool_raw + warp * wscr);
 
-    for (;;) {
-        // ---- next tile of the CTA's range: one thread of the slot takes it, the slot's named barrier publishes it ----------
-        if ((warp & 3) == 0 && lane == 0) s_tile[slot] = atomicAdd(s_ctr, 1);
-        asm volatile("bar.sync %0, 128;" :: "r"(cx.bar_id) : "memory");
-        const int tile = s_tile[slot];
-        asm volatile("bar.sync %0, 128;" :: "r"(cx.bar_id) : "memory");     // everyone has read it before the next hand-out
-        if (tile >= tile_hi) break;
+    // ---- record staging by TMA (round 2).  A warp's G*V rows of a tile are contiguous in HBM; each row is two halves of 36
+    // floats ([ray_feats | dir_diff], [rgb, depth | img_feats]).  One cp.async.bulk.tensor box {36 floats, G*V rows} lands a
+    // half of all the warp's rows in its pooling scratch (row pitch 36 floats = the box's dense layout), where lane l reads
+    // row l.  Half A of the NEXT tile is requested at the end of the current one, half B after round 3 has consumed half A:
+    // the record's latency no longer sits in front of the first use, and no thread issues 18 strided LDG.128 per tile any more.
+    const uint32_t tma_bar = smem_u32(&s_bar[T3_SLOTS + 1 + warp]);
+    uint32_t tma_par = 0u;
+    const uint32_t scr_s = smem_u32(scr);
+    const uint32_t box_bytes = (uint32_t)(G * V) * GN_REC_HALF * 4u;
+    const float* mine = scr + lane * T3_POOL_STRIDE;
+    auto tma_rows = [&](int col, long long first_row) {           // whole warp calls; lane 0 issues
+        __syncwarp();
+        if (lane == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the scratch was last touched through the generic proxy
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(tma_bar), "r"(box_bytes) : "memory");
+            asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                         :: "r"(scr_s), "l"(&rec_map), "r"(col), "r"((int)first_row), "r"(tma_bar) : "memory");
+        }
+    };
+    auto warp_first_row = [&](int t) { return ((long long)t * 4 + (warp & 3)) * G * V; };
+    if (tile_lo + slot < tile_hi) tma_rows(0, warp_first_row(tile_lo + slot));
 
+    // tiles of the CTA's range go round-robin to the three slots (all tiles cost the same; a static order lets a slot
+    // request its next tile's rows early)
+    for (int tile = tile_lo + slot; tile < tile_hi; tile += T3_SLOTS) {
         long long pidx = ((long long)tile * 4 + (warp & 3)) * G + g;
         const bool valid = lane_active && pidx < total_pts;
         pidx = pidx < total_pts ? pidx : total_pts - 1;
         const int b = (int)(pidx / p.N);
         const int n = (int)(pidx - (long long)b * p.N);
-        const float* row = p.rec + ((size_t)pidx * V + v) * GN_REC_STRIDE;
-#ifdef GN_K2A_PREFETCH
-        {   // the slot's next tile is (most likely) three tiles ahead: pull this thread's row of it towards L2 now
-            const float* nxt = row + (size_t)T3_SLOTS * 4 * G * V * GN_REC_STRIDE;
-            if (nxt + GN_REC_STRIDE <= p.rec + (size_t)total_pts * V * GN_REC_STRIDE) {
-                asm volatile("prefetch.global.L2 [%0];" :: "l"(nxt));
-                asm volatile("prefetch.global.L2 [%0];" :: "l"(nxt + 32));
-                asm volatile("prefetch.global.L2 [%0];" :: "l"(nxt + 64));
-            }
-        }
-#endif
         const float2 ptv = __ldg(reinterpret_cast<const float2*>(p.pt + (size_t)pidx * GN_PT_STRIDE));
-        const float4 tail = ldg4(row + GN_REC_RGB);            // rgb0..2 (masked), depth
-        const float4 ddv = ldg4(row + GN_REC_DD);
+        mbar_wait(tma_bar, tma_par); tma_par ^= 1u;            // half A of this tile's rows: [ray_feats 32 | dir_diff 4] in scratch row `lane`
+        const float4 ddv = *reinterpret_cast<const float4*>(mine + GN_REC_DD);
         const float mask = (valid && ((__float_as_uint(ptv.y) >> v) & 1u)) ? 1.f : 0.f;
-        const float depth = tail.w;
         const float nvalid = ptv.x;
         const float wgt = __fdiv_rn(mask, nvalid + 1e-8f);      // ibrnet.py:466
 
@@ -338,7 +349,7 @@ gn_k2a_tc3_kernel(const __grid_constant__ GnK2aParams p, int num_tiles, int G)
             float ray[32];
 #pragma unroll
             for (int c = 0; c < 32; c += 4) {
-                const float4 t = ldg4(row + GN_REC_RAYF + c);
+                const float4 t = *reinterpret_cast<const float4*>(mine + GN_REC_RAYF + c);
                 ray[c] = t.x; ray[c + 1] = t.y; ray[c + 2] = t.z; ray[c + 3] = t.w;
             }
             t3_store_a<32>(cx.lane_addr, 0, ray);               // A[k 0..31] = ray_feats
@@ -366,11 +377,12 @@ gn_k2a_tc3_kernel(const __grid_constant__ GnK2aParams p, int num_tiles, int G)
                 float ray[32];
 #pragma unroll
                 for (int c = 0; c < 32; c += 4) {
-                    const float4 t = ldg4(row + GN_REC_RAYF + c);   // L1-resident: read a moment ago
+                    const float4 t = *reinterpret_cast<const float4*>(mine + GN_REC_RAYF + c);   // still in the scratch row
                     ray[c] = t.x; ray[c + 1] = t.y; ray[c + 2] = t.z; ray[c + 3] = t.w;
                 }
                 t3_store_a<32>(cx.lane_addr, 0, ray);               // A[k 0..31] = ray_feats again (kept for R5)
             }
+            tma_rows(GN_REC_HALF, warp_first_row(tile));            // half A is consumed: request half B [rgb, depth | img_feats] into the same rows
             TC_GEMM_BEGIN(cx) t3_issue<L_DD1, 64, 32, 0, 32>(cx, 0, 0, false); t3_issue_full<L_RD1>(cx, 32, 64, false); TC_GEMM_COMMIT(cx)
             bias_elu<32>(sw + TS(DD_MEAN_B2), hm);
             om0 = sw[TS(DD_MEAN_B4)]; om1 = sw[TS(DD_MEAN_B4) + 1];
@@ -387,12 +399,16 @@ gn_k2a_tc3_kernel(const __grid_constant__ GnK2aParams p, int num_tiles, int G)
         TC_GEMM_BEGIN(cx) t3_issue_full<L_DD2A>(cx, 0, 32, false); TC_GEMM_COMMIT(cx)
         float f[48];                                                        // D[32..79] (other columns than the running MMA's)
         tm_ld<48>(cx.lane_addr + T3_D + 32, f); bias_elu<36>(sw + TS(RD_B1), f);
+        mbar_wait(tma_bar, tma_par); tma_par ^= 1u;                         // half B has landed
+        const float4 tail = *reinterpret_cast<const float4*>(mine + (GN_REC_RGB - GN_REC_HALF));     // rgb0..2 (masked), depth
+        const float depth = tail.w;
 #pragma unroll
         for (int c = 0; c < 32; c += 4) {
-            const float4 t = ldg4(row + GN_REC_IMGF + c);
+            const float4 t = *reinterpret_cast<const float4*>(mine + (GN_REC_IMGF - GN_REC_HALF) + c);
             f[c] += t.x; f[c + 1] += t.y; f[c + 2] += t.z; f[c + 3] += t.w;     // ibrnet.py:459
         }
         f[32] += tail.x; f[33] += tail.y; f[34] += tail.z;
+        __syncwarp();                                                        // every lane has read its row: the scratch is free for the poolings
 #pragma unroll
         for (int c = 35; c < 48; ++c) f[c] = 0.f;
         TC_GEMM_WAIT(cx)
@@ -602,6 +618,7 @@ gn_k2a_tc3_kernel(const __grid_constant__ GnK2aParams p, int num_tiles, int G)
             }
             if (writer) st4(p.colors + (size_t)pidx * 4, make_float4(c0, c1, c2, 0.f));
         }
+        if (tile + T3_SLOTS < tile_hi) tma_rows(0, warp_first_row(tile + T3_SLOTS));   // next tile's half A, while this warp wraps up
     }
     if (p.tok) {            // uniform branch: phase 2, geometry_fc per point
         __syncthreads();                                                // every slot is done: all pooled rows of the CTA are written
@@ -616,6 +633,20 @@ gn_k2a_tc3_kernel(const __grid_constant__ GnK2aParams p, int num_tiles, int G)
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(*s_tmem), "r"(512));
+}
+
+typedef CUresult (*GnEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static GnEncodeTiledFn gn_encode_tiled() {
+    static GnEncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<GnEncodeTiledFn>(p);
+    }
+    return fn;
 }
 
 extern "C" int gn_k2a_forward_tc(const GnK2aParams* hp, void* stream)
@@ -633,15 +664,27 @@ extern "C" int gn_k2a_forward_tc(const GnK2aParams* hp, void* stream)
     const long long total = (long long)p.B * p.N;
     const long long per_tile = 4LL * G;
     const long long tiles = (total + per_tile - 1) / per_tile;
-    if (tiles > 0x7fffffffLL) return -6;
+    if (tiles > 0x7fffffffLL || total * p.V > 0x7fffffffLL) return -6;
     const size_t smem = t3_smem_bytes(G);
     if (smem > 227 * 1024) return -5;
+    // tensor map of the record as a 2-D fp32 tensor [B*N*V rows][72]; box = one 36-float half of a warp's G*V rows
+    GnEncodeTiledFn enc = gn_encode_tiled();
+    if (!enc) return -10;
+    CUtensorMap tmap;
+    {
+        const cuuint64_t gdim[2] = { (cuuint64_t)GN_REC_STRIDE, (cuuint64_t)(total * p.V) };
+        const cuuint64_t gstride[1] = { (cuuint64_t)GN_REC_STRIDE * 4 };
+        const cuuint32_t box[2] = { (cuuint32_t)GN_REC_HALF, (cuuint32_t)(G * p.V) };
+        const cuuint32_t estr[2] = { 1, 1 };
+        if (enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(p.rec), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return -11;
+    }
     static size_t smem_cache[16] = {0};
     cudaError_t e = gn_ensure_smem(gn_k2a_tc3_kernel, smem, smem_cache);
     if (e != cudaSuccess) return (int)e;
     const int sms = gn_sm_count();
     const long long want = (tiles + T3_SLOTS - 1) / T3_SLOTS;
     const int grid = (int)(want < sms ? want : sms);
-    gn_k2a_tc3_kernel<<<grid, T3_THREADS, smem, (cudaStream_t)stream>>>(p, (int)tiles, G);
+    gn_k2a_tc3_kernel<<<grid, T3_THREADS, smem, (cudaStream_t)stream>>>(p, tmap, (int)tiles, G);
     return (int)cudaGetLastError();
 }

@@ -95,8 +95,8 @@ def project_points_dict(ref_imgs_info, que_pts, hw=None):
         return t[0].permute(1, 0, 2).reshape(V, 1, rn, dn, -1)
     bits = pt[0, :, 1].contiguous().view(torch.int32)
     mask = ((bits[:, None] >> torch.arange(V, device=dev, dtype=torch.int32)[None]) & 1).to(torch.float32)      # [N,V]
-    d = PrjDict(dir=ref_layout(rec[..., 68:71]), depth=ref_layout(rec[..., 67:68]), mask=mask.t().reshape(V, 1, rn, dn, 1),
-                ray_feats=ref_layout(rec[..., 0:32]), rgb=ref_layout(rec[..., 64:67]), img_feats=ref_layout(rec[..., 32:64]), pts=None)
+    d = PrjDict(dir=ref_layout(rec[..., 32:35]), depth=ref_layout(rec[..., ops.REC_DEPTH:ops.REC_DEPTH + 1]), mask=mask.t().reshape(V, 1, rn, dn, 1),
+                ray_feats=ref_layout(rec[..., ops.REC_RAY]), rgb=ref_layout(rec[..., ops.REC_RGB]), img_feats=ref_layout(rec[..., ops.REC_IMG]), pts=None)
     d['_rec'], d['_pt'], d['_scene'], d['_que_pts'] = rec, pt, scene, pts
     return d
 

@@ -13,6 +13,8 @@ from . import _lib
 from .weights import DevicePacker, positional_table, voxel_axis_table
 
 REC_STRIDE, PT_STRIDE, POOL_STRIDE, TOK_STRIDE = 72, 2, 68, 20
+# record columns (csrc/gn_common.cuh): ray_feats | dir_diff | rgb, depth | img_feats
+REC_RAY, REC_DD, REC_RGB, REC_DEPTH, REC_IMG = slice(0, 32), slice(32, 36), slice(36, 39), 39, slice(40, 72)
 
 
 def _stream(dev=None):

@@ -15,7 +15,7 @@
  * Data layout in HBM:
  *   feature maps  : channels-last  [B, V, fh, fw, 32]
  *   images        : RGBA-interleaved [B, V, H, W, 4] (one bilinear tap = one 16-byte texel)
- *   record  `rec` : [B, N, V, 72]  ray_feats32 | img_feats32 | rgb3, depth | dir_diff4 ; n = ray*dn + sample
+ *   record  `rec` : [B, N, V, 72]  ray_feats32 | dir_diff4 | rgb3, depth | img_feats32 ; n = ray*dn + sample
  *   per-point `pt`: [B, N, 2]      nvalid, view bit mask
  *   `pooled`      : [B, N, 68]     K2a output: mean32 | var32 | mean_v(w), nvalid, 0, 0
  */

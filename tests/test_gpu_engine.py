@@ -34,7 +34,7 @@ def test_k1_uint8_images_give_the_same_record_as_fp32_images():
     r32, p32 = ops.k1_forward(s32, hw, resolution=40, bbox_min=bb)
     r8, p8 = ops.k1_forward(s8, hw, resolution=40, bbox_min=bb)
     assert torch.equal(r32, r8) and torch.equal(p32, p8)
-    assert float(r8[..., 64:67].abs().max()) > 0.1                       # colours are really sampled
+    assert float(r8[..., ops.REC_RGB].abs().max()) > 0.1                 # colours are really sampled
     v32, v8 = ops.sample_volume(s32, hw, bb, 40), ops.sample_volume(s8, hw, bb, 40)
     assert torch.equal(v32, v8)
 

@@ -62,11 +62,12 @@ def test_volume_path_vs_oracle_and_golden(name, impl):
     assert torch.equal(idx[0, :, :, 1].long(), orec['feat_idx'][1]), 'bilinear y0 corner indices differ'
     assert torch.equal(pt[0, :, 0], orec['mask'].sum(1)), 'nvalid'
     # ---- K1 record
-    assert_close(rec[0, :, :, 0:32], orec['ray_feats'], what='rec.ray_feats')
-    assert_close(rec[0, :, :, 32:64], orec['img_feats'], what='rec.img_feats')
-    assert_close(rec[0, :, :, 64:67], orec['rgb'], what='rec.rgb')
-    assert_close(rec[0, :, :, 67], orec['depth'], what='rec.depth')
-    assert_close(rec[0, :, :, 68:72], oagg['dir_diff'], what='rec.dir_diff')
+    from graspnerf_b200.ops import REC_RAY, REC_DD, REC_RGB, REC_DEPTH, REC_IMG
+    assert_close(rec[0, :, :, REC_RAY], orec['ray_feats'], what='rec.ray_feats')
+    assert_close(rec[0, :, :, REC_IMG], orec['img_feats'], what='rec.img_feats')
+    assert_close(rec[0, :, :, REC_RGB], orec['rgb'], what='rec.rgb')
+    assert_close(rec[0, :, :, REC_DEPTH], orec['depth'], what='rec.depth')
+    assert_close(rec[0, :, :, REC_DD], oagg['dir_diff'], what='rec.dir_diff')
     # ---- K2a rows and pooled
     assert_close(rows[0, :, :, 0], orec['hit_prob'], what='hit_prob')
     assert_close(rows[0, :, :, 1], orec['vis'], what='vis')
