@@ -14,7 +14,7 @@ class GnK1Params(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ('imgs', 'img_feats', 'ray_feats', 'KRt', 'cam', 'axis', 'bbox_min', 'pts',
                                           'que_dir', 'rec', 'pt', 'dbg_feat_idx')] + \
                [(n, C.c_int) for n in ('B', 'V', 'H', 'W', 'fh', 'fw', 'R', 'N', 'dn', 'volume_mode',
-                                       'tiles_per_scene', 'feat_stride', 'img_u8')]
+                                       'tiles_per_scene', 'feat_stride', 'img_u8')] + [('valid_count', C.c_void_p)]
 
 
 class GnK2aParams(C.Structure):

@@ -119,6 +119,9 @@ gn_k1_kernel(const __grid_constant__ GnK1Params p)
     const int npair = K1_TILE_P * V;
     K1PairInfo* s_info = reinterpret_cast<K1PairInfo*>(smem_raw);                    // [npair]
     float* s_misc  = reinterpret_cast<float*>(s_info + npair);                       // [npair][12]: dd0..3, mask, depth, pad
+    __shared__ int s_cnt[32];                                                        // valid projections per view (optional diagnostic)
+    if (p.valid_count && threadIdx.x < 32) s_cnt[threadIdx.x] = 0;
+    if (p.valid_count) __syncthreads();
 
     const int tiles_per_scene = p.tiles_per_scene;          // CTAs per scene
     const int b = blockIdx.x / tiles_per_scene;
@@ -174,8 +177,10 @@ gn_k1_kernel(const __grid_constant__ GnK1Params p)
         float* ms = s_misc + pair * K1_MISC;
         st4(ms, make_float4(o.dd[0], o.dd[1], o.dd[2], o.dd[3]));
         ms[4] = o.mask; ms[5] = o.depth;
+        if (p.valid_count && o.mask != 0.f) atomicAdd(&s_cnt[v], 1);
     }
     __syncthreads();
+    if (p.valid_count && tid < V && s_cnt[tid]) atomicAdd(p.valid_count + b * V + tid, s_cnt[tid]);
 
     const int lane = tid & 31, warp = tid >> 5;
     const int grp = lane >> 3, j = lane & 7;

@@ -340,9 +340,6 @@ gn_k2a_tc3_kernel(const __grid_constant__ GnK2aParams p, const __grid_constant__
         const float2 ptv = __ldg(reinterpret_cast<const float2*>(p.pt + (size_t)pidx * GN_PT_STRIDE));
         mbar_wait(tma_bar, tma_par); tma_par ^= 1u;            // half A of this tile's rows: [ray_feats 32 | dir_diff 4] in scratch row `lane`
         const float4 ddv = *reinterpret_cast<const float4*>(mine + GN_REC_DD);
-        const float mask = (valid && ((__float_as_uint(ptv.y) >> v) & 1u)) ? 1.f : 0.f;
-        const float nvalid = ptv.x;
-        const float wgt = __fdiv_rn(mask, nvalid + 1e-8f);      // ibrnet.py:466
 
         // ================= R1: mean / var first layers (N = 64) on ray_feats, ray_dir_fc.0 (N = 16) on dir_diff ==============
         {
@@ -399,6 +396,10 @@ gn_k2a_tc3_kernel(const __grid_constant__ GnK2aParams p, const __grid_constant__
         TC_GEMM_BEGIN(cx) t3_issue_full<L_DD2A>(cx, 0, 32, false); TC_GEMM_COMMIT(cx)
         float f[48];                                                        // D[32..79] (other columns than the running MMA's)
         tm_ld<48>(cx.lane_addr + T3_D + 32, f); bias_elu<36>(sw + TS(RD_B1), f);
+        // per-point mask word / valid count: loaded at the top of the tile, first used here (its latency sits under rounds 1-3)
+        const float mask = (valid && ((__float_as_uint(ptv.y) >> v) & 1u)) ? 1.f : 0.f;
+        const float nvalid = ptv.x;
+        const float wgt = __fdiv_rn(mask, nvalid + 1e-8f);      // ibrnet.py:466
         mbar_wait(tma_bar, tma_par); tma_par ^= 1u;                         // half B has landed
         const float4 tail = *reinterpret_cast<const float4*>(mine + (GN_REC_RGB - GN_REC_HALF));     // rgb0..2 (masked), depth
         const float depth = tail.w;

@@ -67,6 +67,7 @@ class NeuralRayRenderer(nn.Module):
         self.use_sdf = True
         self._hw = {}
         self._side = None
+        self._valid = None
         self.two_stream_encoders = True
 
     # ------------------------------------------------------------------------------------------------ plumbing
@@ -106,7 +107,32 @@ class NeuralRayRenderer(nn.Module):
             return ops.sample_volume_autograd(ref_imgs_info['imgs'], ref_imgs_info['img_feats'], ref_imgs_info['ray_feats'],
                                               ref_imgs_info['poses'], ref_imgs_info['Ks'], ref_imgs_info['depth_range'],
                                               bbox_min, named, self.cfg['volume_resolution'])
-        return ops.sample_volume(self._scene(ref_imgs_info), self._head_weights(False), bbox_min, self.cfg['volume_resolution'])
+        scene = self._scene(ref_imgs_info)
+        # the reference's "!! too low ratio" diagnostic (renderer.py:174-176) without its host synchronisation: K1 counts the
+        # valid projections per view into a device word; it is READ when the next call starts (the previous call has long
+        # finished by then) or on demand through valid_ratio()
+        capturing = torch.cuda.is_current_stream_capturing()
+        if not capturing:
+            self._report_valid_ratio()
+        if self._valid is None or self._valid[0].device != dev or self._valid[0].numel() != scene.V:
+            self._valid = [torch.zeros((1, scene.V), dtype=torch.int32, device=dev), 0, False]
+        self._valid[0].zero_()
+        self._valid[1], self._valid[2] = self.cfg['volume_resolution'] ** 3, not capturing
+        return ops.sample_volume(scene, self._head_weights(False), bbox_min, self.cfg['volume_resolution'], valid_count=self._valid[0])
+
+    def valid_ratio(self):
+        """Fraction of voxel centres that project into each reference view in the last sample_volume call ([V] tensor on the
+        host; synchronises).  renderer.py:174."""
+        if self._valid is None:
+            return None
+        return self._valid[0][0].cpu().float() / float(self._valid[1])
+
+    def _report_valid_ratio(self):
+        if self._valid is not None and self._valid[2]:
+            self._valid[2] = False
+            r = self.valid_ratio()
+            if float(r.mean()) < 0.5:
+                print("!! too low ratio", r)                     # renderer.py:175-176
 
     # ------------------------------------------------------------------------------------------------ the reference's stage API
     # renderer.py:62-162 under the reference's names.  render() / sample_volume() use the fused launch sequences in ops

@@ -178,7 +178,7 @@ def fuse_feature_maps(img_feats_cl, ray_feats_cl):
 
 
 def k1_forward(scene, hw, *, resolution=None, bbox_min=None, volume_size=0.3, pts=None, que_dir=None, dn=None,
-               debug_idx=False, ev=None):
+               debug_idx=False, ev=None, valid_count=None):
     """K1 launch.  Volume mode: resolution + bbox_min [B,3].  Ray mode: pts [B,N,3], que_dir [B,N/dn,3], dn."""
     lib = _lib.load()
     dev = scene.device
@@ -204,6 +204,9 @@ def k1_forward(scene, hw, *, resolution=None, bbox_min=None, volume_size=0.3, pt
     p.rec, p.pt, p.dbg_feat_idx = _ptr(rec).value, _ptr(pt).value, _ptr(dbg).value
     p.B, p.V, p.H, p.W, p.fh, p.fw = scene.B, scene.V, scene.H, scene.W, scene.fh, scene.fw
     p.N, p.dn, p.volume_mode, p.img_u8 = N, dn_, 1 if vol else 0, 1 if scene.img_u8 else 0
+    if valid_count is not None:                    # [B,V] int32, accumulated by the kernel (renderer.py:174-176 diagnostic, no sync)
+        assert valid_count.dtype == torch.int32 and valid_count.numel() == scene.B * scene.V
+        p.valid_count = _ptr(valid_count).value
     if ev is not None:
         ev[0].record()
     with _on(dev):
@@ -342,11 +345,11 @@ def k3_fine_depths(depth, hit_prob, depth_range_q, u, want_inds=False):
     return out, inds
 
 
-def sample_volume(scene, hw, bbox_min, resolution=40, volume_size=0.3, debug=None, impl=None):
+def sample_volume(scene, hw, bbox_min, resolution=40, volume_size=0.3, debug=None, impl=None, valid_count=None):
     """NeuralRayRenderer.sample_volume (renderer.py:164-199) for B scenes: K1 -> K2a -> K2b.  Returns [B,1,R,R,R].
     impl 'tc' (default): tcgen05 K2a emits per-point tokens, K2b is attention-only.  'simt': fp32 CUDA-core K2a + full K2b."""
     impl = 'tc' if (impl or K2A_IMPL) in ('tc', 'tc3') else 'simt'
-    rec, pt = k1_forward(scene, hw, resolution=resolution, bbox_min=bbox_min, volume_size=volume_size)
+    rec, pt = k1_forward(scene, hw, resolution=resolution, bbox_min=bbox_min, volume_size=volume_size, valid_count=valid_count)
     if impl == 'tc':
         pooled, _, dbg, tok = k2a_forward(rec, pt, hw, scene.depth_range, debug=debug is not None, impl=impl,
                                           want_pooled=debug is not None, want_tok=True, resolution=resolution,

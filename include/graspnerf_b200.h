@@ -53,6 +53,9 @@ typedef struct GnK1Params {
     int feat_stride;          /* floats per feature-map texel: 32 (two maps, 0 means 32) or 64 (fused buffer: one address per bilinear tap) */
     int img_u8;               /* 1: imgs holds uint8 texels; the kernel divides by 255 exactly as color_map_forward does (main.py:170,
                                  utils/base_utils.py:492-493), so the planner's PNG bytes cross PCIe as bytes */
+    int* valid_count;         /* optional [B,V] int32, ACCUMULATED (caller zeroes it): number of valid projections per view - the
+                                 numerator of the reference's "!! too low ratio" diagnostic (renderer.py:174-176) without a host
+                                 synchronisation; NULL = not counted */
 } GnK1Params;
 
 int gn_k1_forward(const GnK1Params* params, void* stream);

@@ -289,3 +289,23 @@ def test_k6_kernels_against_torch_ops():
         up = ops.upsample2x_pad(x, pad=1)
         want = F.pad(F.interpolate(x, scale_factor=2, mode='bilinear', align_corners=True), (1, 1, 1, 1), mode='reflect')
         assert_close(up.cpu(), want.cpu(), rtol=1e-6, atol_scale=1e-6, what='bilinear x2 + reflect pad')
+
+
+def test_low_valid_ratio_diagnostic_without_sync(capsys):
+    """renderer.py:174-176 prints "!! too low ratio" when fewer than half of the voxel centres project into the views.  K1
+    counts the valid projections per view on the device; the mirror reports them when the NEXT call starts (or on demand)."""
+    sc = make_scene(seed=42, num_views=2, h=64, w=64, radius=0.25, theta=1.0)            # close-up: most projections invalid
+    net = seed0_model().to(DEV).eval()
+    nr = net.nr_net
+    ref = {k: (torch.from_numpy(v).to(DEV) if isinstance(v, np.ndarray) else v) for k, v in sc.items()}
+    with torch.no_grad():
+        vol = nr.sample_volume(ref)
+        ratio = nr.valid_ratio()
+        from oracle import nr_oracle as O
+        sct = {k: (torch.from_numpy(v) if isinstance(v, np.ndarray) else v) for k, v in sc.items()}
+        pts = O.volume_query_points(sc['bbox3d'][0]).reshape(-1, 3)
+        want = O.project_and_sample(sct, pts)['mask'].float().mean(0)                 # mask [N,V] -> valid ratio per view
+        assert torch.allclose(ratio, want), (ratio, want)
+        assert float(ratio.mean()) < 0.5
+        nr.sample_volume(ref)                                   # the report for the first call appears now
+    assert '!! too low ratio' in capsys.readouterr().out

@@ -1,19 +1,19 @@
 #!/bin/bash
 # One GPU-box pass that produces every artefact profiles/ cites.  usage: tools/gpu_measure.sh <tag>   (run under gpurun)
 # Numbers printed by the commands running under ncu are never bench values; bench.py is run separately, un-profiled.
-TAG=${1:-r01}
+TAG=${1:-r02}
 OUT=gpurun_out
 mkdir -p $OUT
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3 > $OUT/pytest_gpu_$TAG.txt
-timeout 600 python bench.py > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err
-timeout 600 python bench.py --impl reference --steps 40 --warmup 3 > $OUT/bench_ref_$TAG.json 2> $OUT/bench_ref_$TAG.err
+( timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -6 ) > $OUT/pytest_gpu_$TAG.txt
+( timeout 300 python tools/time_k2a.py ) > $OUT/k2a_time_$TAG.txt 2>&1
+timeout 900 python bench.py > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err
+timeout 600 python bench.py --impl reference --steps 8 --warmup 1 > $OUT/bench_ref_$TAG.json 2> $OUT/bench_ref_$TAG.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_$TAG.csv \
-    python bench.py --steps 4 --warmup 3 --no-cpu --train-batch 0 > /dev/null 2>&1
+    python bench.py --steps 4 --warmup 3 --no-cpu --train-batch 0 --highres-scenes 0 --skip-full > /dev/null 2>&1
 for k in gn_k1_kernel gn_k2a_tc3_kernel gn_k2b_attn_kernel; do
   timeout 300 ncu --set full --clock-control none --import-source on -k regex:$k -s 3 -c 1 -f -o $OUT/${k}_full_$TAG \
       python tools/time_volume.py 1 2 tc > /dev/null 2>&1
 done
-if [ -x tools/tc_probe ]; then timeout 60 tools/tc_probe > $OUT/tc_probe_$TAG.txt 2>&1; fi
 nvidia-smi --query-gpu=name,clocks.max.sm,clocks.max.mem,power.limit --format=csv > $OUT/gpu_$TAG.csv
-cat $OUT/pytest_gpu_$TAG.txt $OUT/bench_$TAG.json $OUT/bench_ref_$TAG.json
-ls -la $OUT | tail -12
+cat $OUT/pytest_gpu_$TAG.txt $OUT/k2a_time_$TAG.txt; python tools/show_bench.py $OUT/bench_$TAG.json; head -c 600 $OUT/bench_ref_$TAG.json
+ls -la $OUT | tail -8
