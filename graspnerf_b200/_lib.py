@@ -70,6 +70,11 @@ class GnNormActPadParams(C.Structure):
                [(n, C.c_int) for n in ('N', 'C', 'H', 'W', 'pad', 'x_pad', 'res_pad', 'act')] + [('eps', C.c_float)]
 
 
+class GnConvParams(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ('in_', 'wimg', 'koff', 'bias', 'out')] + [('M', C.c_longlong)] + \
+               [(n, C.c_int) for n in ('Nimg', 'Cin', 'Hp', 'Wp', 'Cout', 'Npad', 'Ho', 'Wo', 'stride', 'Kpad')]
+
+
 _lib = None
 
 
@@ -87,7 +92,7 @@ def load():
     lib.gn_version.restype = C.c_char_p
     for name, st in (('gn_k1_forward', GnK1Params), ('gn_k2a_forward', GnK2aParams), ('gn_k2a_forward_tc', GnK2aParams), ('gn_k2b_forward', GnK2bParams),
                      ('gn_k3_composite', GnK3Params), ('gn_k2b_backward', GnK2bBwdParams), ('gn_k2a_backward', GnK2aBwdParams),
-                     ('gn_k1_backward', GnK1BwdParams), ('gn_k3_ray_setup', GnRaySetupParams), ('gn_k4_grasp_post', GnGraspPostParams), ('gn_vgn_forward', GnVgnParams), ('gn_k6_norm_act_pad', GnNormActPadParams)):
+                     ('gn_k1_backward', GnK1BwdParams), ('gn_k3_ray_setup', GnRaySetupParams), ('gn_k4_grasp_post', GnGraspPostParams), ('gn_vgn_forward', GnVgnParams), ('gn_k6_norm_act_pad', GnNormActPadParams), ('gn_k7_conv_forward', GnConvParams)):
         fn = getattr(lib, name)
         fn.restype = C.c_int
         fn.argtypes = [C.POINTER(st), C.c_void_p]
@@ -109,7 +114,7 @@ def load():
                      ('gn_sizeof_k2b_bwd_params', GnK2bBwdParams), ('gn_sizeof_k2a_bwd_params', GnK2aBwdParams),
                      ('gn_sizeof_k1_bwd_params', GnK1BwdParams), ('gn_sizeof_ray_setup_params', GnRaySetupParams),
                      ('gn_sizeof_grasp_post_params', GnGraspPostParams), ('gn_sizeof_vgn_params', GnVgnParams),
-                     ('gn_sizeof_norm_act_pad_params', GnNormActPadParams)):
+                     ('gn_sizeof_norm_act_pad_params', GnNormActPadParams), ('gn_sizeof_conv_params', GnConvParams)):
         got = getattr(lib, name)()
         if got != C.sizeof(st):
             raise RuntimeError(f'{name}: library says {got} bytes, ctypes mirror has {C.sizeof(st)}')

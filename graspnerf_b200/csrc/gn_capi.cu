@@ -26,3 +26,4 @@ extern "C" int gn_sizeof_ray_setup_params(void) { return (int)sizeof(GnRaySetupP
 extern "C" int gn_sizeof_grasp_post_params(void) { return (int)sizeof(GnGraspPostParams); }
 extern "C" int gn_sizeof_vgn_params(void) { return (int)sizeof(GnVgnParams); }
 extern "C" int gn_sizeof_norm_act_pad_params(void) { return (int)sizeof(GnNormActPadParams); }
+extern "C" int gn_sizeof_conv_params(void) { return (int)sizeof(GnConvParams); }

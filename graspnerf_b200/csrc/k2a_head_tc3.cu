@@ -421,9 +421,9 @@ gn_k2a_tc3_kernel(const __grid_constant__ GnK2aParams p, const __grid_constant__
             oa = sw[TS(DD_AW_B4)];
 #pragma unroll
             for (int k = 0; k < 32; ++k) oa = fmaf(h[k], sw[TS(DD_AW_W4) + k * 4], oa);
-            const float mean0 = gn_softplus(om0), mean1 = gn_softplus(om1);
-            const float var0 = gn_softplus(ov0) + 0.05f, var1 = gn_softplus(ov1) + 0.05f;
-            const float aw = gn_sigmoid(oa);
+            const float mean0 = tc_softplus(om0), mean1 = tc_softplus(om1);
+            const float var0 = tc_softplus(ov0) + 0.05f, var1 = tc_softplus(ov1) + 0.05f;
+            const float aw = tc_sigmoid(oa);
             const float* dr = p.depth_range + ((size_t)b * V + v) * 2;
             const float rnear = __fdiv_rn(-1.f, __ldg(dr)), rfar = __fdiv_rn(-1.f, __ldg(dr + 1));
             float d = __fdiv_rn(-1.f, fmaxf(depth, 1e-5f));
@@ -438,8 +438,8 @@ gn_k2a_tc3_kernel(const __grid_constant__ GnK2aParams p, const __grid_constant__
                 nearp = d - h_prev; farp = d + h_cur;
             }
             // 0.5 + 0.5*tanh(d) == sigmoid(2d)   (dist_decoder.py:129-130)
-            const float c00 = gn_sigmoid(2.f * ((nearp - mean0) * var0)), c10 = gn_sigmoid(2.f * ((farp - mean0) * var0));
-            const float c01 = gn_sigmoid(2.f * ((nearp - mean1) * var1)), c11 = gn_sigmoid(2.f * ((farp - mean1) * var1));
+            const float c00 = tc_sigmoid(2.f * ((nearp - mean0) * var0)), c10 = tc_sigmoid(2.f * ((farp - mean0) * var0));
+            const float c01 = tc_sigmoid(2.f * ((nearp - mean1) * var1)), c11 = tc_sigmoid(2.f * ((farp - mean1) * var1));
             const float mix1 = 1.f - aw;
             vis = ((1.f - c00) * aw + (1.f - c01) * mix1) * mask;
             hit = ((c10 - c00) * aw + (c11 - c01) * mix1) * mask;
@@ -471,7 +471,7 @@ gn_k2a_tc3_kernel(const __grid_constant__ GnK2aParams p, const __grid_constant__
                 float s = sw[TS(NF_B2)];
 #pragma unroll
                 for (int k = 0; k < 8; ++k) s = fmaf(tc_elu(t[k] + sw[TS(NFC_B0) + k]), sw[TS(NF_W2) + k], s);
-                w0 = gn_sigmoid(s) * wgt;                       // ibrnet.py:469
+                w0 = tc_sigmoid(s) * wgt;                       // ibrnet.py:469
             }
 #pragma unroll
             for (int c = 0; c < 36; ++c) tmp[c] = w0 * f[c];
@@ -521,7 +521,7 @@ gn_k2a_tc3_kernel(const __grid_constant__ GnK2aParams p, const __grid_constant__
             tm_ld<48>(cx.lane_addr + T3_D, xv); bias_elu<36>(sw + TS(VF_B2), xv);
 #pragma unroll
             for (int c = 0; c < 32; ++c) x[c] += xv[c];
-            const float visw = gn_sigmoid(xv[32]) * mask;       // ibrnet.py:478-479
+            const float visw = tc_sigmoid(xv[32]) * mask;       // ibrnet.py:478-479
             float xi[32];
 #pragma unroll
             for (int c = 0; c < 32; ++c) xi[c] = x[c] * visw;
@@ -536,7 +536,7 @@ gn_k2a_tc3_kernel(const __grid_constant__ GnK2aParams p, const __grid_constant__
             float s = sw[TS(V2_B2)];
 #pragma unroll
             for (int k = 0; k < 32; ++k) s = fmaf(t[k], sw[TS(V2_W2) + k], s);
-            vis2 = gn_sigmoid(s) * mask;
+            vis2 = tc_sigmoid(s) * mask;
         }
         // ================= final pooling (ibrnet.py:482-484,487) ===============================================
         float ssum = 0.f;

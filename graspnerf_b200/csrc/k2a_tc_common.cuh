@@ -151,6 +151,16 @@ template <int K, int AHI = TM_AHI, int ALO = TM_ALO> __device__ __forceinline__ 
         tm_st8(slot_lane_addr + ALO + k0 / 2 + c, lo);
     }
 }
+// sigmoid with two MUFUs (ex2, rcp): 1 / (1 + e^-x), __fdividef = rcp.approx * x (<= 2 ulp); the IEEE division of
+// gn_sigmoid costs ~10 instructions and this kernel evaluates 8 sigmoids per row
+__device__ __forceinline__ float tc_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+// nn.Softplus(beta=1, threshold=20) = log1p(e^x) without the ~30-instruction log1pf: log(u) * e / (u - 1) with u = 1 + e
+// cancels the rounding of 1 + e (error ~1e-7 relative for every e), two more MUFUs
+__device__ __forceinline__ float tc_softplus(float x) {
+    const float e = __expf(x), u = 1.f + e;
+    const float r = (u == 1.f) ? e : __logf(u) * __fdividef(e, u - 1.f);
+    return x > 20.f ? x : r;
+}
 // ELU with one MUFU: ex2.approx.ftz (rel. err 2^-22)
 __device__ __forceinline__ float tc_elu(float x) {
     float e;

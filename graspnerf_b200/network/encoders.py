@@ -14,6 +14,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 FUSED = True          # module-level switch for the fused inference path (tests compare both paths)
+TC_CONV = True        # fused path: convolutions on tcgen05 (csrc/k7_conv_tc.cu) instead of cuDNN fp32
 
 
 def use_fused(x, module):
@@ -22,7 +23,11 @@ def use_fused(x, module):
 
 
 def _conv0(xp, conv):
-    """A convolution whose (reflection) padding has already been applied by the producer of `xp`."""
+    """A convolution whose (reflection) padding has already been applied by the producer of `xp`: implicit GEMM on tcgen05
+    (K7) when the output-channel count fits its tiles, cuDNN otherwise."""
+    if TC_CONV and xp.is_cuda and conv.weight.shape[0] <= 128 and (conv.weight.shape[0] + 15) // 16 * 16 in (16, 32, 48, 64, 128):
+        from .. import ops
+        return ops.conv2d_tc(xp.contiguous(), conv)
     return F.conv2d(xp, conv.weight, conv.bias, conv.stride, 0)
 
 

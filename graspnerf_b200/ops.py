@@ -754,3 +754,69 @@ def upsample2x_pad(x, pad=0):
     with _on(x.device):
         _lib.check(lib.gn_k6_upsample2x_pad(_ptr(x), _ptr(out), N * C, H, W, int(pad), _stream(x.device)), 'gn_k6_upsample2x_pad')
     return out
+
+
+# ------------------------------------------------------------------------------------------------ encoder convolutions on tcgen05 (K7)
+class ConvWeights:
+    """fp16 hi/lo operand images of one nn.Conv2d for gn_k7_conv_forward + the k -> input-offset table for a given padded
+    input size; rebuilt when the weight tensor changed."""
+
+    def __init__(self, conv):
+        self.conv, self._version, self.wimg, self._koff = conv, None, None, {}
+        co, ci, kh, kw = conv.weight.shape
+        self.K = ci * kh * kw
+        self.Kpad = (self.K + 31) // 32 * 32
+        self.Npad = (co + 15) // 16 * 16
+
+    def images(self):
+        w = self.conv.weight
+        ver = (w._version, w.data_ptr())
+        if ver != self._version:
+            with torch.no_grad():
+                co = w.shape[0]
+                wk = torch.zeros((self.Npad, self.Kpad), dtype=torch.float32, device=w.device)
+                wk[:co, :self.K] = w.detach().reshape(co, self.K)
+                hi = wk.to(torch.float16)
+                lo = (wk - hi.float()).to(torch.float16)
+                def img(t):                                      # [Npad,Kpad] -> [Kpad/32][4][Npad][8]: element (n,k) at unit (k/8)*Npad + n
+                    return t.reshape(self.Npad, self.Kpad // 32, 4, 8).permute(1, 2, 0, 3)
+                self.wimg = torch.stack([img(hi), img(lo)], 1).contiguous()       # [chunks][2][4][Npad][8]
+            self._version = ver
+        return self.wimg
+
+    def koff(self, Hp, Wp, dev):
+        key = (Hp, Wp, str(dev))
+        if key not in self._koff:
+            _, ci, kh, kw = self.conv.weight.shape
+            k = torch.arange(self.Kpad)
+            c, r = k // (kh * kw), k % (kh * kw)
+            off = c * (Hp * Wp) + (r // kw) * Wp + (r % kw)
+            off[k >= self.K] = 0
+            self._koff[key] = off.to(torch.int32).to(dev)
+        return self._koff[key]
+
+
+_CONV_CACHE = {}
+
+
+def conv2d_tc(xp, conv):
+    """F.conv2d(xp, conv.weight, conv.bias, conv.stride, padding=0) on tcgen05 (gn_k7_conv_forward): xp [N,Cin,Hp,Wp] fp32
+    contiguous, ALREADY padded for this convolution.  fp16 hi/lo operand split, fp32 accumulation (same scheme as K2a)."""
+    lib = _lib.load()
+    dev = xp.device
+    cw = _CONV_CACHE.get(id(conv))
+    if cw is None or cw.conv is not conv:
+        cw = _CONV_CACHE[id(conv)] = ConvWeights(conv)
+    N, Cin, Hp, Wp = xp.shape
+    co, ci, kh, kw = conv.weight.shape
+    assert ci == Cin and xp.is_contiguous() and xp.dtype == torch.float32 and conv.stride[0] == conv.stride[1]
+    st = conv.stride[0]
+    Ho, Wo = (Hp - kh) // st + 1, (Wp - kw) // st + 1
+    out = torch.empty((N, co, Ho, Wo), device=dev, dtype=torch.float32)
+    p = _lib.GnConvParams()
+    p.in_, p.wimg, p.koff = _ptr(xp).value, _ptr(cw.images()).value, _ptr(cw.koff(Hp, Wp, dev)).value
+    p.bias, p.out = _ptr(conv.bias).value if conv.bias is not None else None, _ptr(out).value
+    p.Nimg, p.Cin, p.Hp, p.Wp, p.Cout, p.Npad, p.Ho, p.Wo, p.stride, p.Kpad = N, Cin, Hp, Wp, co, cw.Npad, Ho, Wo, st, cw.Kpad
+    with _on(dev):
+        _lib.check(lib.gn_k7_conv_forward(C_byref(p), _stream(dev)), 'gn_k7_conv_forward')
+    return out

@@ -224,6 +224,21 @@ int gn_k6_norm_act_pad(const GnNormActPadParams* params, void* stream);
 /* F.interpolate(scale_factor=2, bilinear, align_corners=True) (ops.py:142-150) + reflection pad: x [planes,H,W] -> out [planes,2H+2pad,2W+2pad] */
 int gn_k6_upsample2x_pad(const float* x, float* out, int planes, int H, int W, int pad, void* stream);
 
+/* K7: nn.Conv2d of the 2-D encoders (ops.py:78-230, init_net.py:21-26, vis_encoder.py:9-14) as an implicit GEMM on tcgen05,
+ * inference only.  `in` is NCHW fp32 and ALREADY padded by its producer (gn_k6_*), so this is a "valid" convolution:
+ * out[img][co][oy][ox] = bias[co] + sum_k in[img-base + (oy*stride)*Wp + ox*stride + koff[k]] * W[co][k], k = (ci, dy, dx).
+ * wimg: fp16 hi/lo operand images per 32-wide k chunk, koff: int32 [Kpad] (both built by the host, graspnerf_b200.ops). */
+typedef struct GnConvParams {
+    const float* in;           /* [Nimg,Cin,Hp,Wp] */
+    const void* wimg;          /* [Kpad/32][2 (hi,lo)][4][Npad][8] fp16 */
+    const int* koff;           /* [Kpad] input offsets of k relative to a pixel's window origin (0 for padded k) */
+    const float* bias;         /* [Cout] or NULL */
+    float* out;                /* [Nimg,Cout,Ho,Wo] */
+    long long M;               /* filled in by the launcher: Nimg*Ho*Wo */
+    int Nimg, Cin, Hp, Wp, Cout, Npad, Ho, Wo, stride, Kpad;
+} GnConvParams;
+int gn_k7_conv_forward(const GnConvParams* params, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------------------
  * Backward (training) entry points of the volume path: d volume -> d weights, d feature maps.  First order only.
  * The reference gets these from torch autograd through renderer.py:164-199; here each forward kernel has a hand-derived
@@ -283,6 +298,7 @@ int gn_sizeof_ray_setup_params(void);
 int gn_sizeof_grasp_post_params(void);
 int gn_sizeof_vgn_params(void);
 int gn_sizeof_norm_act_pad_params(void);
+int gn_sizeof_conv_params(void);
 
 #ifdef __cplusplus
 }

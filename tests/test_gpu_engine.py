@@ -309,3 +309,28 @@ def test_low_valid_ratio_diagnostic_without_sync(capsys):
         assert float(ratio.mean()) < 0.5
         nr.sample_volume(ref)                                   # the report for the first call appears now
     assert '!! too low ratio' in capsys.readouterr().out
+
+
+@pytest.mark.parametrize('cfg', [dict(cin=3, cout=16, k=7, s=2, n=2, h=70, w=102), dict(cin=16, cout=32, k=3, s=2, n=3, h=38, w=54),
+                                 dict(cin=64, cout=64, k=3, s=1, n=6, h=38, w=66), dict(cin=128, cout=128, k=3, s=1, n=6, h=20, w=34),
+                                 dict(cin=32, cout=64, k=1, s=2, n=2, h=36, w=64), dict(cin=32, cout=32, k=1, s=1, n=1, h=9, w=13, bias=True),
+                                 dict(cin=128, cout=64, k=3, s=1, n=1, h=11, w=7, bias=True)])
+def test_tcgen05_convolution_matches_cudnn_fp32(cfg):
+    """gn_k7_conv_forward (implicit GEMM on tcgen05, fp16 hi/lo operand split, fp32 accumulation) against F.conv2d in fp32 on
+    already-padded inputs: strides 1 / 2, 7x7 / 3x3 / 1x1, K not a multiple of 32, M not a multiple of 128, with / without bias."""
+    import torch.nn.functional as F
+    from graspnerf_b200 import ops
+    torch.backends.cudnn.allow_tf32 = False
+    g = torch.Generator().manual_seed(cfg['cin'] * 7 + cfg['k'])
+    conv = torch.nn.Conv2d(cfg['cin'], cfg['cout'], cfg['k'], cfg['s'], 0, bias=cfg.get('bias', False)).to(DEV)
+    x = (torch.randn(cfg['n'], cfg['cin'], cfg['h'], cfg['w'], generator=g) * 3).to(DEV)
+    with torch.no_grad():
+        want = F.conv2d(x.double(), conv.weight.double(), None if conv.bias is None else conv.bias.double(), conv.stride, 0)
+        ref32 = F.conv2d(x, conv.weight, conv.bias, conv.stride, 0)
+        got = ops.conv2d_tc(x, conv)
+    assert got.shape == ref32.shape
+    e_tc = float((got.double() - want).abs().max())
+    e_32 = float((ref32.double() - want).abs().max())
+    print(f'conv {cfg}: max |err| vs fp64: tcgen05 {e_tc:.2e}, cuDNN fp32 {e_32:.2e}')
+    assert_close(got.cpu(), want.float().cpu(), rtol=1e-5, atol_scale=2e-6, what='tcgen05 conv vs fp64 reference')
+    assert e_tc <= 4 * e_32 + 1e-6

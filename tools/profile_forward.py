@@ -36,16 +36,16 @@ def main():
         return nr.encode({'imgs': x}, None, False)
     with torch.no_grad():
         from graspnerf_b200.network import encoders as E
-        for fused in (False, True):
+        for fused, tc in ((False, False), (True, False), (True, True)):
             for two in (False, True):
-                E.FUSED, nr.two_stream_encoders = fused, two
-                print(f'encoders eager fp32 fused={fused} two_stream={two}: {timeit(lambda: encoders(imgs)):.3f} ms')
+                E.FUSED, E.TC_CONV, nr.two_stream_encoders = fused, tc, two
+                print(f'encoders eager fp32 fused={fused} tc_conv={tc} two_stream={two}: {timeit(lambda: encoders(imgs)):.3f} ms')
                 g0 = torch.cuda.CUDAGraph(); s0 = torch.cuda.Stream()
                 with torch.cuda.stream(s0):
                     encoders(imgs); torch.cuda.synchronize()
                     with torch.cuda.graph(g0, stream=s0):
                         o0 = encoders(imgs)
-                print(f'encoders GRAPH fp32 fused={fused} two_stream={two}: {timeit(lambda: g0.replay()):.3f} ms')
+                print(f'encoders GRAPH fp32 fused={fused} tc_conv={tc} two_stream={two}: {timeit(lambda: g0.replay()):.3f} ms')
                 del g0
         print(f'  image_encoder only              : {timeit(lambda: nr.image_encoder(imgs)):.3f} ms')
         print(f'  init_net only                   : {timeit(lambda: nr.init_net({"imgs": imgs}, None, False)):.3f} ms')
