@@ -38,6 +38,8 @@ __host__ __device__ constexpr size_t t3_smem_bytes(int G) {
     return (size_t)TC_CONST_BYTES + 128 + (size_t)(T3_THREADS / 32) * t3_warp_scratch_bytes(G) + 256;   // + alignment slack, barriers, tmem ptr, tile counter
 }
 static_assert(t3_smem_bytes(5) <= 227 * 1024, "K2a-TC3 shared memory budget at V = 6");
+#define T3_MAX_G 8                                                             // points per warp: min(32 / V, 8) - the scratch of 2- and 3-view scenes must fit too
+static_assert(t3_smem_bytes(T3_MAX_G) <= 227 * 1024, "K2a-TC3 shared memory budget at G = 8");
 
 template <int K> __device__ __forceinline__ void t3_store_a(uint32_t lane_addr, int k0, const float* a) { tm_store_a<K, T3_AHI, T3_ALO>(lane_addr, k0, a); }
 
@@ -661,7 +663,7 @@ extern "C" int gn_k2a_forward_tc(const GnK2aParams* hp, void* stream)
         if (!p.volume_mode && !p.pts) return -4;
         if (!p.pooled) return -9;                     // phase 2 (geometry_fc per point) reads the pooled rows back
     }
-    const int G = 32 / p.V;
+    const int G = (32 / p.V) < T3_MAX_G ? (32 / p.V) : T3_MAX_G;
     const long long total = (long long)p.B * p.N;
     const long long per_tile = 4LL * G;
     const long long tiles = (total + per_tile - 1) / per_tile;

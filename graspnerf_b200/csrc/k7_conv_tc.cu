@@ -11,10 +11,11 @@
 // SWIZZLE_NONE layout (element (m,k) at 16-byte unit (k/8)*128 + m; layout validated by tools/tc_probe.cu, SS form).  The
 // weights are prepared once per weight update (fp16 hi / lo images per k-chunk) and arrive by cp.async.bulk.  Three MMAs per
 // product (lo*hi, hi*lo, hi*hi, fp32 accumulation in TMEM) keep fp32 accuracy.  A ring of stages decouples the gather
-// (all 128 threads) from the MMAs (issued by thread 0, completion tracked by tcgen05.commit on the stage's mbarrier).
+// (all 512 threads: the gather's load latency is the cost of a chunk, 16 warps hide it) from the MMAs (issued by thread 0,
+// completion tracked by tcgen05.commit on the stage's mbarrier).  Epilogue: warp w reads TMEM lanes 32*(w%4).., column chunks w/4, w/4+4, ..
 #include "k2a_tc_common.cuh"
 
-#define K7_THREADS 128
+#define K7_THREADS 512                 // 4 threads per output pixel: thread (m, q) gathers k = 8q..8q+7 of every chunk (one 16-byte operand unit)
 #define K7_KC 32                       // k per chunk (two MMA k-steps of 16)
 #define K7_STAGES 3
 #define K7_A_BYTES (128 * K7_KC * 2)   // one half (hi or lo) of the A chunk: 8 KB
@@ -55,8 +56,9 @@ gn_k7_conv_kernel(const GnConvParams p)
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *s_tmem;
 
-    // this thread's output pixel
-    const long long gm = (long long)blockIdx.x * 128 + tid;
+    // this thread's output pixel m and its slice q of every k chunk
+    const int m = tid & 127, q = tid >> 7;
+    const long long gm = (long long)blockIdx.x * 128 + m;
     const bool live = gm < p.M;
     const long long gmc = live ? gm : p.M - 1;
     const int hw = p.Ho * p.Wo;
@@ -81,10 +83,10 @@ gn_k7_conv_kernel(const GnConvParams p)
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                          :: "r"(smem_u32(sB)), "l"(wimg + (size_t)c * B_BYTES), "r"(B_BYTES), "r"(full) : "memory");
         }
-        // ---- gather + split this row's 32 k values: 4 groups of 8 -> one 16-byte unit of the hi image and one of the lo image each
+        // ---- gather + split this thread's 8 k values of the chunk -> one 16-byte unit of the hi image and one of the lo image
         const int* ko = s_koff + c * K7_KC;
-#pragma unroll
-        for (int g8 = 0; g8 < K7_KC / 8; ++g8) {
+        {
+            const int g8 = q;
             float a[8];
             const int4 k0 = *reinterpret_cast<const int4*>(ko + g8 * 8), k1 = *reinterpret_cast<const int4*>(ko + g8 * 8 + 4);
             a[0] = __ldg(base + k0.x); a[1] = __ldg(base + k0.y); a[2] = __ldg(base + k0.z); a[3] = __ldg(base + k0.w);
@@ -98,8 +100,8 @@ gn_k7_conv_kernel(const GnConvParams p)
                     "fma.rn.f32.f16 d0, h0, m1, %2;\n\tfma.rn.f32.f16 d1, h1, m1, %3;\n\t"
                     "cvt.rn.f16x2.f32 %1, d1, d0;\n\t}" : "=&r"(hi[i]), "=r"(lo[i]) : "f"(a[2 * i]), "f"(a[2 * i + 1]));
             }
-            uint4* dh = reinterpret_cast<uint4*>(sA + ((size_t)g8 * 128 + tid) * 16);
-            uint4* dl = reinterpret_cast<uint4*>(sA + K7_A_BYTES + ((size_t)g8 * 128 + tid) * 16);
+            uint4* dh = reinterpret_cast<uint4*>(sA + ((size_t)g8 * 128 + m) * 16);
+            uint4* dl = reinterpret_cast<uint4*>(sA + K7_A_BYTES + ((size_t)g8 * 128 + m) * 16);
             *dh = make_uint4(hi[0], hi[1], hi[2], hi[3]);
             *dl = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         }
@@ -128,11 +130,11 @@ gn_k7_conv_kernel(const GnConvParams p)
     mbar_wait(smem_u32(&s_bar[2 * K7_STAGES]), 0u);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     // ---- epilogue: row m of D -> out[img][co][oy][ox] (+ bias); for a fixed co the 32 lanes of a warp write 32 consecutive pixels
-    const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+    const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     float* op = p.out + ((size_t)img * p.Cout * p.Ho + oy) * p.Wo + ox;
     const size_t cstride = (size_t)p.Ho * p.Wo;
 #pragma unroll
-    for (int c0 = 0; c0 < N; c0 += 16) {
+    for (int c0 = 16 * q; c0 < N; c0 += 64) {
         float y[16];
         tm_ld<16>(lane_addr + c0, y);
         if (live) {
