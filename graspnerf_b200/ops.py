@@ -111,6 +111,21 @@ class HeadWeights:
         return self._axis[key]
 
 
+_HW_CACHE = {}
+
+
+def _cached_head_weights(sd, agg_prefix, dd_prefix, device):
+    """HeadWeights for the autograd nodes: one object per (prefix pair, device), re-packed only when a parameter's version
+    changed - i.e. once per optimizer step, not once per scene and pass (packing + gn_k2a_tc_prepare are ~10 launches)."""
+    key = (agg_prefix, dd_prefix, str(device))
+    hw = _HW_CACHE.get(key)
+    if hw is None:
+        hw = _HW_CACHE[key] = HeadWeights(sd, agg_prefix, dd_prefix, device)
+    else:
+        hw.refresh(sd)
+    return hw
+
+
 def camera_matrices(poses, Ks):
     """[B,V,3,4] K@[R|t] and [B,V,3] camera centres -R^T t; 6 tiny matmuls, done with torch exactly as the reference
     does (render_ops.py:94,112) so that the fp32 values entering the kernel are the reference's."""
@@ -558,7 +573,7 @@ class _SampleVolumeFn(torch.autograd.Function):
     def forward(ctx, img_feats, ray_feats, static, keys, *params):
         imgs, poses, Ks, depth_range, bbox_min, R, vs, agg_prefix, dd_prefix = static
         sd = {k: p.detach() for k, p in zip(keys, params)}
-        hw = HeadWeights(sd, agg_prefix, dd_prefix, img_feats.device)
+        hw = _cached_head_weights(sd, agg_prefix, dd_prefix, img_feats.device)
         scene = Scene(imgs, img_feats.detach(), ray_feats.detach(), poses, Ks, depth_range)
         rec, pt = k1_forward(scene, hw, resolution=R, bbox_min=bbox_min, volume_size=vs)
         pooled, _, _ = k2a_forward(rec, pt, hw, scene.depth_range, impl=K2A_IMPL)      # tcgen05 kernel, pooled features kept
@@ -603,7 +618,7 @@ class _RayFeaturesFn(torch.autograd.Function):
     def forward(ctx, img_feats, ray_feats, static, keys, *params):
         imgs, poses, Ks, depth_range, pts, que_dir, inv_dists, dn, agg_prefix, dd_prefix = static
         sd = {k: p.detach() for k, p in zip(keys, params)}
-        hw = HeadWeights(sd, agg_prefix, dd_prefix, img_feats.device)
+        hw = _cached_head_weights(sd, agg_prefix, dd_prefix, img_feats.device)
         scene = Scene(imgs, img_feats.detach(), ray_feats.detach(), poses, Ks, depth_range)
         rec, pt = k1_forward(scene, hw, pts=pts, que_dir=que_dir, dn=dn)
         pooled, colors, _ = k2a_forward(rec, pt, hw, scene.depth_range, que_dists=inv_dists, dn=dn, want_colors=True)

@@ -27,8 +27,10 @@ class GradBucket:
         self.params = list(params)
         self.sizes = [p.numel() for p in self.params]
         dev = self.params[0].device
-        self.flat = torch.zeros(sum(self.sizes), dtype=torch.float32, device=dev)
-        self.views = [v.view_as(p) for v, p in zip(self.flat.split(self.sizes), self.params)]
+        # one extra trailing element carries this rank's scene count through the SAME all-reduce (uneven shards: the global mean
+        # divides by the true number of scenes, not by len(local) * world)
+        self.flat = torch.zeros(sum(self.sizes) + 1, dtype=torch.float32, device=dev)
+        self.views = [v.view_as(p) for v, p in zip(self.flat[:-1].split(self.sizes), self.params)]
         self.attach()
 
     @property
@@ -54,13 +56,18 @@ class GradBucket:
     def unpack(self):
         self.attach()
 
-    def allreduce(self, dist=None, scale=1.0):
-        """sum over ranks (if a process group is given), then scale (1 / global number of scenes)."""
+    def allreduce(self, dist=None, scale=1.0, local_count=None):
+        """sum over ranks (if a process group is given), then scale.  local_count: this rank's number of scenes; when given,
+        the scale is 1 / (sum of the counts over the ranks), computed on the device from the reduced trailing element."""
         self.pack()
+        if local_count is not None:
+            self.flat[-1] = float(local_count)
         if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
-        if scale != 1.0:
-            self.flat.mul_(scale)
+        if local_count is not None:
+            self.flat[:-1].div_(self.flat[-1].clamp_min(1.0))
+        elif scale != 1.0:
+            self.flat[:-1].mul_(scale)
         self.unpack()
 
 
@@ -148,7 +155,6 @@ class TrainStep:
             loss = self.loss_fn(self.net(data), data)
             loss.backward()
             total += loss.detach()              # no host synchronisation inside the scene loop
-        n_global = len(local_batch) * self.world
-        self.bucket.allreduce(self.dist, 1.0 / n_global)
+        self.bucket.allreduce(self.dist, local_count=len(local_batch))      # mean over the GLOBAL number of scenes (shards may be uneven)
         self.opt.step()
         return float(total) / max(len(local_batch), 1)

@@ -1,5 +1,7 @@
 """CPU, world_size 2, gloo: the N>1 bookkeeping of bench.py (scene sharding, max-over-ranks timing, whole-job throughput)."""
 import os
+
+import pytest
 import socket
 
 import torch
@@ -119,7 +121,7 @@ def _toy_batch(n):
     return [{'x': torch.randn(4, 6, generator=g), 't': torch.randn(4, 2, generator=g)} for _ in range(n)]
 
 
-def _trainstep_worker(rank, world, port, q):
+def _trainstep_worker(rank, world, port, q, nscenes=4):
     import os
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
@@ -128,30 +130,32 @@ def _trainstep_worker(rank, world, port, q):
     from graspnerf_b200.shard import shard_scenes
     net = _ToyNet()
     step = TrainStep(net, lr=1e-2, dist=dist, loss_fn=_toy_loss)
-    batch = _toy_batch(4)
-    mine = [batch[i] for i in shard_scenes(4, rank, world)]
+    batch = _toy_batch(nscenes)
+    mine = [batch[i] for i in shard_scenes(nscenes, rank, world)]
     for _ in range(3):
         step(mine)
     q.put((rank, [p.detach().numpy().copy() for p in net.parameters()]))
     dist.destroy_process_group()
 
 
-def test_trainstep_two_ranks_equals_one_rank_on_the_global_batch():
-    """Data-parallel equivalence: 2 ranks x 2 scenes with one gradient all-reduce per step == 1 process on the
-    4-scene batch, after three Adam steps; a parameter that does not require a gradient travels as zeros and stays put."""
+@pytest.mark.parametrize('nscenes', [4, 3])
+def test_trainstep_two_ranks_equals_one_rank_on_the_global_batch(nscenes):
+    """Data-parallel equivalence: 2 ranks with one gradient all-reduce per step == 1 process on the global
+    batch, after three Adam steps - for an even split (2 + 2 scenes) and an UNEVEN one (2 + 1: the mean must divide by the
+    global scene count, which travels in the same all-reduce); a parameter that does not require a gradient stays put."""
     import numpy as np
     import torch.multiprocessing as mp
     from graspnerf_b200.train import TrainStep
     ref = _ToyNet()
     step = TrainStep(ref, lr=1e-2, dist=None, loss_fn=_toy_loss)
-    batch = _toy_batch(4)
+    batch = _toy_batch(nscenes)
     for _ in range(3):
         step(batch)
     want = [p.detach().numpy() for p in ref.parameters()]
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
     port = 29800 + (os.getpid() % 150)
-    procs = [ctx.Process(target=_trainstep_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_trainstep_worker, args=(r, 2, port + nscenes, q, nscenes)) for r in range(2)]
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=180) for _ in range(2)], key=lambda t: t[0])

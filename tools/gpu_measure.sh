@@ -10,7 +10,10 @@ timeout 900 python bench.py > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err
 timeout 600 python bench.py --impl reference --steps 8 --warmup 1 > $OUT/bench_ref_$TAG.json 2> $OUT/bench_ref_$TAG.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_$TAG.csv \
     python bench.py --steps 4 --warmup 3 --no-cpu --train-batch 0 --highres-scenes 0 --skip-full > /dev/null 2>&1
-for k in gn_k1_kernel gn_k2a_tc3_kernel gn_k2b_attn_kernel; do
+# launch list of ONE eager full forward (encoders K6/K7 + hot path + VGN K5 + post K4): kernel shares of the planner's call
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 2000 -c 700 --csv --log-file $OUT/launches_forward_$TAG.csv \
+    python tools/forward_once.py > /dev/null 2>&1
+for k in gn_k1_kernel gn_k2a_tc3_kernel gn_k2b_attn_kernel gn_k7_conv_kernel; do
   timeout 300 ncu --set full --clock-control none --import-source on -k regex:$k -s 3 -c 1 -f -o $OUT/${k}_full_$TAG \
       python tools/time_volume.py 1 2 tc > /dev/null 2>&1
 done
