@@ -67,12 +67,12 @@ class GnVgnParams(C.Structure):
 
 class GnNormActPadParams(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ('x', 'gamma', 'beta', 'res', 'res_gamma', 'res_beta', 'out_padded', 'out_unpadded')] + \
-               [(n, C.c_int) for n in ('N', 'C', 'H', 'W', 'pad', 'x_pad', 'res_pad', 'act')] + [('eps', C.c_float)]
+               [(n, C.c_int) for n in ('N', 'C', 'H', 'W', 'pad', 'x_pad', 'res_pad', 'act')] + [('eps', C.c_float), ('x_splits', C.c_int), ('x_split_stride', C.c_longlong)]
 
 
 class GnConvParams(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ('in_', 'wimg', 'koff', 'bias', 'out')] + [('M', C.c_longlong)] + \
-               [(n, C.c_int) for n in ('Nimg', 'Cin', 'Hp', 'Wp', 'Cout', 'Npad', 'Ho', 'Wo', 'stride', 'Kpad')]
+               [(n, C.c_int) for n in ('Nimg', 'Cin', 'Hp', 'Wp', 'Cout', 'Npad', 'Ho', 'Wo', 'stride', 'Kpad', 'ksplit')]
 
 
 _lib = None

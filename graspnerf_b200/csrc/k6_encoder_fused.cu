@@ -27,33 +27,71 @@ __device__ __forceinline__ float k6_block_sum(float v, float* s_red)
     return t;
 }
 
-__device__ __forceinline__ void k6_plane_stats(const float* __restrict__ x, int n, int row_len, int row_stride, float eps,
-                                               float* s_red, float& mean, float& rstd)
-{
-    // x: plane of n = rows*row_len elements, row r starts at x + r*row_stride (a padded tensor's interior is such a view)
-    float s = 0.f;
-    for (int i = threadIdx.x; i < n; i += K6_THREADS) s += x[(i / row_len) * row_stride + (i % row_len)];
-    mean = k6_block_sum(s, s_red) / (float)n;
-    float q = 0.f;
-    for (int i = threadIdx.x; i < n; i += K6_THREADS) { const float d = x[(i / row_len) * row_stride + (i % row_len)] - mean; q = fmaf(d, d, q); }
-    const float var = k6_block_sum(q, s_red) / (float)n;                 // biased, like InstanceNorm
-    rstd = rsqrtf(var + eps);
-}
-
 __device__ __forceinline__ int k6_reflect(int i, int n) { return i < 0 ? -i : (i >= n ? 2 * n - 2 - i : i); }
 
+// Sum over the CLUSTER of CTAs that share a plane (cluster size CS: 1 or 8).  Large planes (the 144x256 / 72x128 maps of the
+// first stages: 6 images x 16..32 channels = only 96..192 planes for 148 SMs) are split over a thread-block cluster; the
+// partial sums meet through distributed shared memory (each CTA reads its peers' partials after a cluster barrier).
+template <int CS>
+__device__ __forceinline__ float k6_cluster_sum(float v, float* s_red, float* s_part, int phase)
+{
+    float t = k6_block_sum(v, s_red);
+    if (CS == 1) return t;
+    unsigned rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    if (threadIdx.x == 0) s_part[phase] = t;
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    float tot = 0.f;
+#pragma unroll
+    for (int r = 0; r < CS; ++r) {                        // same order in every CTA: identical mean / rstd across the cluster
+        uint32_t remote;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"((uint32_t)__cvta_generic_to_shared(&s_part[phase])), "r"(r));
+        float pv;
+        asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(pv) : "r"(remote) : "memory");
+        tot += pv;
+    }
+    return tot;
+}
+
+// statistics of rows [r0, r1) of this CTA's share of a plane, combined over the cluster
+// x as the sum of `splits` partial tensors (split-K convolution output), always added in the same order
+__device__ __forceinline__ float k6_ld(const float* __restrict__ x, int off, int splits, long long stride) {
+    float v = x[off];
+    for (int s = 1; s < splits; ++s) v += x[(long long)s * stride + off];
+    return v;
+}
+
+template <int CS>
+__device__ __forceinline__ void k6_plane_stats_cl(const float* __restrict__ x, int W, int xs, int r0, int r1, int n_total, float eps,
+                                                  float* s_red, float* s_part, int phase0, float& mean, float& rstd,
+                                                  int splits = 1, long long sstride = 0)
+{
+    const int n = (r1 - r0) * W;
+    float s = 0.f;
+    for (int i = threadIdx.x; i < n; i += K6_THREADS) s += k6_ld(x, (r0 + i / W) * xs + (i % W), splits, sstride);
+    mean = k6_cluster_sum<CS>(s, s_red, s_part, phase0) / (float)n_total;
+    float q = 0.f;
+    for (int i = threadIdx.x; i < n; i += K6_THREADS) { const float d = k6_ld(x, (r0 + i / W) * xs + (i % W), splits, sstride) - mean; q = fmaf(d, d, q); }
+    rstd = rsqrtf(k6_cluster_sum<CS>(q, s_red, s_part, phase0 + 1) / (float)n_total + eps);      // biased variance, like InstanceNorm
+}
+
+template <int CS>
 __global__ void __launch_bounds__(K6_THREADS)
 gn_k6_norm_act_pad_kernel(const GnNormActPadParams p)
 {
     __shared__ float s_red[K6_THREADS / 32];
-    const int plane = blockIdx.x;                        // n * C + c
+    __shared__ float s_part[4];
+    const int plane = blockIdx.x / CS;                   // n * C + c
+    const int rank = blockIdx.x - plane * CS;
     const int c = plane % p.C;
     const int H = p.H, W = p.W, hw = H * W;
     const int xs = W + 2 * p.x_pad;                      // row stride of the (possibly padded) input
     const float* x = p.x + (size_t)plane * (size_t)(H + 2 * p.x_pad) * xs + (size_t)p.x_pad * xs + p.x_pad;
-    float mean = 0.f, rstd = 1.f, g = 1.f, b = 0.f;
+    const int r0 = (int)((long long)H * rank / CS), r1 = (int)((long long)H * (rank + 1) / CS);     // this CTA's rows for the statistics
+    float g = 1.f, b = 0.f;
     if (p.gamma) {
-        k6_plane_stats(x, hw, W, xs, p.eps, s_red, mean, rstd);
+        float mean, rstd;
+        k6_plane_stats_cl<CS>(x, W, xs, r0, r1, hw, p.eps, s_red, s_part, 0, mean, rstd, p.x_splits, p.x_split_stride);
         g = __ldg(p.gamma + c) * rstd; b = __ldg(p.beta + c) - mean * g;          // y = (x - mean) * rstd * gamma + beta
     }
     const float* r = nullptr;
@@ -64,25 +102,47 @@ gn_k6_norm_act_pad_kernel(const GnNormActPadParams p)
         r = p.res + (size_t)plane * (size_t)(H + 2 * p.res_pad) * rs + (size_t)p.res_pad * rs + p.res_pad;
         if (p.res_gamma) {
             float rm, rr;
-            k6_plane_stats(r, hw, W, rs, p.eps, s_red, rm, rr);
+            k6_plane_stats_cl<CS>(r, W, rs, r0, r1, hw, p.eps, s_red, s_part, 2, rm, rr);
             rg = __ldg(p.res_gamma + c) * rr; rb = __ldg(p.res_beta + c) - rm * rg;
         }
     }
     const int P = p.pad, Hp = H + 2 * P, Wp = W + 2 * P;
     float* op = p.out_padded ? p.out_padded + (size_t)plane * Hp * Wp : nullptr;
     float* ou = p.out_unpadded ? p.out_unpadded + (size_t)plane * hw : nullptr;
-    const int total = Hp * Wp;
-    for (int i = threadIdx.x; i < total; i += K6_THREADS) {
+    const int o0 = (int)((long long)Hp * rank / CS) * Wp, o1 = (int)((long long)Hp * (rank + 1) / CS) * Wp;     // this CTA's padded output rows
+    for (int i = o0 + threadIdx.x; i < o1; i += K6_THREADS) {
         const int hp = i / Wp, wp = i - hp * Wp;
         const int h = k6_reflect(hp - P, H), w = k6_reflect(wp - P, W);
-        float v = fmaf(x[h * xs + w], g, b);
+        float v = fmaf(k6_ld(x, h * xs + w, p.x_splits, p.x_split_stride), g, b);
         if (r) v += fmaf(r[h * rs + w], rg, rb);
         if (p.act == 1) v = fmaxf(v, 0.f);
         else if (p.act == 2) v = v > 0.f ? v : expm1f(v);                          // F.elu
         if (op) op[i] = v;
         if (ou && hp >= P && hp < P + H && wp >= P && wp < P + W) ou[(hp - P) * W + (wp - P)] = v;
     }
-    if (!op && ou) { /* only the un-padded copy was requested and P == 0: handled by the loop above (op null) */ }
+    if (CS > 1)       // a CTA must not exit while peers may still read its partial sums
+        asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// no statistics at all (reflection pad / copy / activation / residual add only): plain grid-stride element-wise kernel
+__global__ void __launch_bounds__(K6_THREADS)
+gn_k6_pad_only_kernel(const GnNormActPadParams p)
+{
+    const int H = p.H, W = p.W, P = p.pad, Hp = H + 2 * P, Wp = W + 2 * P;
+    const int xs = W + 2 * p.x_pad, rs = W + 2 * p.res_pad;
+    const size_t xplane = (size_t)(H + 2 * p.x_pad) * xs, rplane = (size_t)(H + 2 * p.res_pad) * rs;
+    const long long total = (long long)p.N * p.C * Hp * Wp;
+    for (long long i = (long long)blockIdx.x * K6_THREADS + threadIdx.x; i < total; i += (long long)gridDim.x * K6_THREADS) {
+        const int wp = (int)(i % Wp), hp = (int)((i / Wp) % Hp);
+        const long long plane = i / ((long long)Wp * Hp);
+        const int h = k6_reflect(hp - P, H), w = k6_reflect(wp - P, W);
+        float v = p.x[plane * xplane + (size_t)(h + p.x_pad) * xs + w + p.x_pad];
+        if (p.res) v += p.res[plane * rplane + (size_t)(h + p.res_pad) * rs + w + p.res_pad];
+        if (p.act == 1) v = fmaxf(v, 0.f);
+        else if (p.act == 2) v = v > 0.f ? v : expm1f(v);
+        if (p.out_padded) p.out_padded[i] = v;
+        if (p.out_unpadded && hp >= P && hp < P + H && wp >= P && wp < P + W) p.out_unpadded[plane * H * W + (size_t)(hp - P) * W + (wp - P)] = v;
+    }
 }
 
 extern "C" int gn_k6_norm_act_pad(const GnNormActPadParams* hp, void* stream)
@@ -93,7 +153,29 @@ extern "C" int gn_k6_norm_act_pad(const GnNormActPadParams* hp, void* stream)
     if (p.res_gamma && !p.res) return -2;
     if (p.act < 0 || p.act > 2) return -3;
     if (!p.out_padded && p.pad != 0) return -3;
-    gn_k6_norm_act_pad_kernel<<<(unsigned)(p.N * p.C), K6_THREADS, 0, (cudaStream_t)stream>>>(p);
+    if (p.x_splits > 1 && (!p.gamma || p.x_pad != 0)) return -4;         // partial sums only feed a normalising stage
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!p.gamma && !p.res_gamma) {
+        const long long total = (long long)p.N * p.C * (p.H + 2 * p.pad) * (p.W + 2 * p.pad);
+        const long long blocks = (total + K6_THREADS - 1) / K6_THREADS;
+        gn_k6_pad_only_kernel<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), K6_THREADS, 0, st>>>(p);
+        return (int)cudaGetLastError();
+    }
+    const int planes = p.N * p.C;
+    if ((long long)p.H * p.W >= 4096 && p.H >= 16) {       // large planes: a cluster of 8 CTAs per plane (DSMEM reduction)
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)planes * 8, 1, 1);
+        cfg.blockDim = dim3(K6_THREADS, 1, 1);
+        cfg.dynamicSmemBytes = 0;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 8; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, gn_k6_norm_act_pad_kernel<8>, p);
+        return (int)(e != cudaSuccess ? e : cudaGetLastError());
+    }
+    gn_k6_norm_act_pad_kernel<1><<<(unsigned)planes, K6_THREADS, 0, st>>>(p);
     return (int)cudaGetLastError();
 }
 

@@ -68,8 +68,12 @@ gn_k7_conv_kernel(const GnConvParams p)
     const float* base = p.in + ((size_t)img * p.Cin * p.Hp + (size_t)oy * p.stride) * p.Wp + (size_t)ox * p.stride;
 
     constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // F32 accum, F16 x F16, M = 128
-    const int nchunk = p.Kpad / K7_KC;
-    const unsigned char* wimg = reinterpret_cast<const unsigned char*>(p.wimg);
+    // split-K: this CTA runs chunks [c_lo, c_hi) of the layer's k chunks and writes partial output `split`
+    const int nchunk_all = p.Kpad / K7_KC;
+    const int nsplit = p.ksplit > 1 ? p.ksplit : 1, split = (int)blockIdx.y;
+    const int c_lo = (int)((long long)nchunk_all * split / nsplit), c_hi = (int)((long long)nchunk_all * (split + 1) / nsplit);
+    const int nchunk = c_hi - c_lo;
+    const unsigned char* wimg = reinterpret_cast<const unsigned char*>(p.wimg) + (size_t)c_lo * (2 * N * K7_KC * 2);
     constexpr uint32_t B_BYTES = (uint32_t)(2 * N * K7_KC * 2);                          // hi + lo of one chunk
 
     for (int c = 0; c < nchunk; ++c) {
@@ -84,7 +88,7 @@ gn_k7_conv_kernel(const GnConvParams p)
                          :: "r"(smem_u32(sB)), "l"(wimg + (size_t)c * B_BYTES), "r"(B_BYTES), "r"(full) : "memory");
         }
         // ---- gather + split this thread's 8 k values of the chunk -> one 16-byte unit of the hi image and one of the lo image
-        const int* ko = s_koff + c * K7_KC;
+        const int* ko = s_koff + (c_lo + c) * K7_KC;
         {
             const int g8 = q;
             float a[8];
@@ -131,8 +135,9 @@ gn_k7_conv_kernel(const GnConvParams p)
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     // ---- epilogue: row m of D -> out[img][co][oy][ox] (+ bias); for a fixed co the 32 lanes of a warp write 32 consecutive pixels
     const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    float* op = p.out + ((size_t)img * p.Cout * p.Ho + oy) * p.Wo + ox;
+    float* op = p.out + (size_t)split * ((size_t)p.Nimg * p.Cout * p.Ho * p.Wo) + ((size_t)img * p.Cout * p.Ho + oy) * p.Wo + ox;
     const size_t cstride = (size_t)p.Ho * p.Wo;
+    const bool add_bias = p.bias != nullptr && split == 0;
 #pragma unroll
     for (int c0 = 16 * q; c0 < N; c0 += 64) {
         float y[16];
@@ -141,7 +146,7 @@ gn_k7_conv_kernel(const GnConvParams p)
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
                 const int co = c0 + i;
-                if (co < p.Cout) op[(size_t)co * cstride] = y[i] + (p.bias ? __ldg(p.bias + co) : 0.f);
+                if (co < p.Cout) op[(size_t)co * cstride] = y[i] + (add_bias ? __ldg(p.bias + co) : 0.f);
             }
         }
     }
@@ -158,7 +163,7 @@ static cudaError_t k7_launch(const GnConvParams& p, cudaStream_t st)
     cudaError_t e = gn_ensure_smem(gn_k7_conv_kernel<N>, smem, cache);
     if (e != cudaSuccess) return e;
     const long long tiles = (p.M + 127) / 128;
-    gn_k7_conv_kernel<N><<<(unsigned)tiles, K7_THREADS, smem, st>>>(p);
+    gn_k7_conv_kernel<N><<<dim3((unsigned)tiles, (unsigned)(p.ksplit > 1 ? p.ksplit : 1), 1), K7_THREADS, smem, st>>>(p);
     return cudaGetLastError();
 }
 
@@ -168,6 +173,7 @@ extern "C" int gn_k7_conv_forward(const GnConvParams* hp, void* stream)
     if (p.Nimg < 1 || p.Cin < 1 || p.Cout < 1 || p.Ho < 1 || p.Wo < 1 || p.stride < 1 || p.Kpad < K7_KC || (p.Kpad % K7_KC) != 0) return -1;
     if (!p.in || !p.wimg || !p.koff || !p.out) return -2;
     p.M = (long long)p.Nimg * p.Ho * p.Wo;
+    if (p.ksplit < 0 || p.ksplit > 8 || (p.ksplit > 1 && p.Kpad / K7_KC < p.ksplit)) return -5;
     if ((p.M + 127) / 128 > 0x7fffffffLL) return -6;
     const int npad = (p.Cout + 15) / 16 * 16;
     if (npad != p.Npad) return -3;

@@ -22,12 +22,12 @@ def use_fused(x, module):
         torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in module.parameters())))
 
 
-def _conv0(xp, conv):
+def _conv0(xp, conv, allow_split=False):
     """A convolution whose (reflection) padding has already been applied by the producer of `xp`: implicit GEMM on tcgen05
     (K7) when the output-channel count fits its tiles, cuDNN otherwise."""
     if TC_CONV and xp.is_cuda and conv.weight.shape[0] <= 128 and (conv.weight.shape[0] + 15) // 16 * 16 in (16, 32, 48, 64, 128):
         from .. import ops
-        return ops.conv2d_tc(xp.contiguous(), conv)
+        return ops.conv2d_tc(xp.contiguous(), conv, allow_split=allow_split)
     return F.conv2d(xp, conv.weight, conv.bias, conv.stride, 0)
 
 
@@ -60,8 +60,8 @@ class BasicBlock(nn.Module):                      # ops.py:86-125
         """xp: block input reflection-padded by 1; xu: the same tensor un-padded (only read by a 1x1 downsample branch).
         -> (output padded by 1 or None, output un-padded or None)."""
         from .. import ops
-        a_p, _ = ops.norm_act_pad(_conv0(xp, self.conv1), self.bn1, 'relu', pad=1)
-        raw2 = _conv0(a_p, self.conv2)
+        a_p, _ = ops.norm_act_pad(_conv0(xp, self.conv1, True), self.bn1, 'relu', pad=1)      # split-K partials are summed by the norm stage
+        raw2 = _conv0(a_p, self.conv2, True)
         if self.downsample is None:          # identity residual = interior of the padded input
             return ops.norm_act_pad(raw2, self.bn2, 'relu', pad=1, res=xp, res_pad=1, want_padded=want_padded, want_unpadded=want_unpadded)
         rawd = _conv0(xu, self.downsample[0])

@@ -730,10 +730,22 @@ def vgn_forward(volume, vw, out=None):
 _ACT = {None: 0, 'none': 0, 'relu': 1, 'elu': 2}
 
 
+class SplitK:
+    """Partial outputs [S,N,C,H,W] of a split-K convolution (conv2d_tc(..., allow_split=True)); only norm_act_pad consumes it
+    (it adds the partials in a fixed order while it reads)."""
+
+    def __init__(self, parts):
+        self.parts = parts
+
+
 def norm_act_pad(x, norm=None, act=None, pad=0, res=None, res_norm=None, x_pad=0, res_pad=0, want_padded=True, want_unpadded=False):
     """gn_k6_norm_act_pad: out = reflect_pad(act(IN(x) [+ res | + IN(res)]), pad).  x [N,C,H+2*x_pad,W+2*x_pad] (NCHW fp32,
-    contiguous); norm / res_norm: nn.InstanceNorm2d modules (affine) or None.  Returns (padded or None, un-padded or None)."""
+    contiguous) or a SplitK; norm / res_norm: nn.InstanceNorm2d modules (affine) or None.  Returns (padded or None, un-padded or None)."""
     lib = _lib.load()
+    splits = None
+    if isinstance(x, SplitK):
+        splits, x = x.parts, x.parts[0]
+        assert norm is not None and x_pad == 0
     dev = x.device
     N, C = x.shape[0], x.shape[1]
     H, W = x.shape[2] - 2 * x_pad, x.shape[3] - 2 * x_pad
@@ -754,6 +766,8 @@ def norm_act_pad(x, norm=None, act=None, pad=0, res=None, res_norm=None, x_pad=0
         if res_norm is not None:
             p.res_gamma, p.res_beta = _ptr(res_norm.weight).value, _ptr(res_norm.bias).value
     p.out_padded, p.out_unpadded = _ptr(outp).value, _ptr(outu).value
+    if splits is not None:
+        p.x_splits, p.x_split_stride = splits.shape[0], splits.stride(0)
     p.N, p.C, p.H, p.W, p.pad, p.x_pad, p.res_pad, p.act = N, C, H, W, int(pad), int(x_pad), int(res_pad), _ACT[act]
     with _on(dev):
         _lib.check(lib.gn_k6_norm_act_pad(C_byref(p), _stream(dev)), 'gn_k6_norm_act_pad')
@@ -814,9 +828,11 @@ class ConvWeights:
 _CONV_CACHE = {}
 
 
-def conv2d_tc(xp, conv):
+def conv2d_tc(xp, conv, allow_split=False):
     """F.conv2d(xp, conv.weight, conv.bias, conv.stride, padding=0) on tcgen05 (gn_k7_conv_forward): xp [N,Cin,Hp,Wp] fp32
-    contiguous, ALREADY padded for this convolution.  fp16 hi/lo operand split, fp32 accumulation (same scheme as K2a)."""
+    contiguous, ALREADY padded for this convolution.  fp16 hi/lo operand split, fp32 accumulation (same scheme as K2a).
+    allow_split: layers with few 128-pixel tiles and a long K (the 128-channel stage: 27 tiles, K = 1152) may run split-K
+    and return a SplitK of partial outputs for norm_act_pad to sum."""
     lib = _lib.load()
     dev = xp.device
     cw = _CONV_CACHE.get(id(conv))
@@ -827,11 +843,14 @@ def conv2d_tc(xp, conv):
     assert ci == Cin and xp.is_contiguous() and xp.dtype == torch.float32 and conv.stride[0] == conv.stride[1]
     st = conv.stride[0]
     Ho, Wo = (Hp - kh) // st + 1, (Wp - kw) // st + 1
-    out = torch.empty((N, co, Ho, Wo), device=dev, dtype=torch.float32)
+    tiles = (N * Ho * Wo + 127) // 128
+    S = 4 if (allow_split and tiles <= 64 and cw.Kpad // 32 >= 16) else 1
+    out = torch.empty(((S,) if S > 1 else ()) + (N, co, Ho, Wo), device=dev, dtype=torch.float32)
     p = _lib.GnConvParams()
+    p.ksplit = S
     p.in_, p.wimg, p.koff = _ptr(xp).value, _ptr(cw.images()).value, _ptr(cw.koff(Hp, Wp, dev)).value
     p.bias, p.out = _ptr(conv.bias).value if conv.bias is not None else None, _ptr(out).value
     p.Nimg, p.Cin, p.Hp, p.Wp, p.Cout, p.Npad, p.Ho, p.Wo, p.stride, p.Kpad = N, Cin, Hp, Wp, co, cw.Npad, Ho, Wo, st, cw.Kpad
     with _on(dev):
         _lib.check(lib.gn_k7_conv_forward(C_byref(p), _stream(dev)), 'gn_k7_conv_forward')
-    return out
+    return SplitK(out) if S > 1 else out

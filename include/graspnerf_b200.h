@@ -219,6 +219,9 @@ typedef struct GnNormActPadParams {
     int pad, x_pad, res_pad;
     int act;                   /* 0 none, 1 ReLU, 2 ELU */
     float eps;
+    int x_splits;              /* > 1: x is the SUM of x_splits partial tensors (split-K output of gn_k7_conv_forward), x_split_stride
+                                  floats apart; 0 / 1: a plain tensor */
+    long long x_split_stride;
 } GnNormActPadParams;
 int gn_k6_norm_act_pad(const GnNormActPadParams* params, void* stream);
 /* F.interpolate(scale_factor=2, bilinear, align_corners=True) (ops.py:142-150) + reflection pad: x [planes,H,W] -> out [planes,2H+2pad,2W+2pad] */
@@ -236,6 +239,9 @@ typedef struct GnConvParams {
     float* out;                /* [Nimg,Cout,Ho,Wo] */
     long long M;               /* filled in by the launcher: Nimg*Ho*Wo */
     int Nimg, Cin, Hp, Wp, Cout, Npad, Ho, Wo, stride, Kpad;
+    int ksplit;                /* 0 / 1: one CTA per 128-pixel tile runs all of K.  S > 1: S CTAs per tile, each a contiguous range of the
+                                  k chunks, writing S partial outputs [S][Nimg,Cout,Ho,Wo] (bias in partial 0); the consumer
+                                  (gn_k6_norm_act_pad, x_splits = S) sums them in a fixed order - deterministic, no atomics */
 } GnConvParams;
 int gn_k7_conv_forward(const GnConvParams* params, void* stream);
 

@@ -289,6 +289,21 @@ def test_k6_kernels_against_torch_ops():
         up = ops.upsample2x_pad(x, pad=1)
         want = F.pad(F.interpolate(x, scale_factor=2, mode='bilinear', align_corners=True), (1, 1, 1, 1), mode='reflect')
         assert_close(up.cpu(), want.cpu(), rtol=1e-6, atol_scale=1e-6, what='bilinear x2 + reflect pad')
+        # large planes: one 8-CTA cluster per plane, partial statistics exchanged through distributed shared memory
+        xl = (torch.randn(2, 5, 80, 96, generator=g) * 3 - 2).to(DEV)
+        rl = torch.randn(2, 5, 80, 96, generator=g).to(DEV)
+        gp, gu = ops.norm_act_pad(xl, n1, 'elu', pad=1, res=rl, res_norm=n2, want_unpadded=True)
+        assert_close(gp.cpu(), F.pad(F.elu(n1(xl) + n2(rl)), (1, 1, 1, 1), mode='reflect').cpu(), rtol=1e-5, atol_scale=1e-5, what='cluster norm_act_pad')
+        assert_close(gu.cpu(), F.elu(n1(xl) + n2(rl)).cpu(), rtol=1e-5, atol_scale=1e-5, what='cluster norm_act_pad (un-padded)')
+        # split-K convolution output (partials) summed by the normalising stage
+        conv = torch.nn.Conv2d(128, 128, 3, 1, 0, bias=False).to(DEV)
+        xc = torch.randn(2, 128, 20, 34, generator=g).to(DEV)
+        parts = ops.conv2d_tc(xc, conv, allow_split=True)
+        assert isinstance(parts, ops.SplitK) and parts.parts.shape[0] == 4
+        n3 = torch.nn.InstanceNorm2d(128, affine=True).to(DEV)
+        gp, _ = ops.norm_act_pad(parts, n3, 'relu', pad=1)
+        want = F.pad(F.relu(n3(F.conv2d(xc, conv.weight))), (1, 1, 1, 1), mode='reflect')
+        assert_close(gp.cpu(), want.cpu(), rtol=1e-4, atol_scale=2e-5, what='split-K conv + norm')
 
 
 def test_low_valid_ratio_diagnostic_without_sync(capsys):
