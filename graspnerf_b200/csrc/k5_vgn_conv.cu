@@ -33,9 +33,13 @@ gn_k5_conv_kernel(const float* __restrict__ in, const float* __restrict__ wgt, c
     const int nblk = (int)gridDim.z;
     // stage this (class, cout block)'s weights: global layout [class][cout_block][CIN*TAPS][COUT_T]
     {
-        const float4* src = reinterpret_cast<const float4*>(wgt + ((size_t)cls * nblk + cblk) * (size_t)(CIN * TAPS * COUT_T));
-        float4* dst = reinterpret_cast<float4*>(s_w);
-        for (int i = threadIdx.x; i < CIN * TAPS * COUT_T / 4; i += K5_THREADS) dst[i] = __ldg(src + i);
+        const float* src = wgt + ((size_t)cls * nblk + cblk) * (size_t)(CIN * TAPS * COUT_T);
+        if ((CIN * TAPS * COUT_T) % 4 == 0) {
+            for (int i = threadIdx.x; i < CIN * TAPS * COUT_T / 4; i += K5_THREADS)
+                reinterpret_cast<float4*>(s_w)[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
+        } else {
+            for (int i = threadIdx.x; i < CIN * TAPS * COUT_T; i += K5_THREADS) s_w[i] = __ldg(src + i);
+        }
     }
     __syncthreads();
     const int Dc = FOLD ? Din : Dout;                                // grid of "cells" the threads enumerate
@@ -66,11 +70,16 @@ gn_k5_conv_kernel(const float* __restrict__ in, const float* __restrict__ wgt, c
                     float v = 0.f;
                     if (yin && (unsigned)z < (unsigned)Din) v = __ldg(ip + ((size_t)x * Din + y) * Din + z);
                     const float* w = wp + ((dx * KD + dy) * KD + dz) * COUT_T;
+                    if (COUT_T % 4 == 0) {
 #pragma unroll
-                    for (int c = 0; c < COUT_T; c += 4) {
-                        const float4 w4 = *reinterpret_cast<const float4*>(w + c);
-                        acc[c] = fmaf(v, w4.x, acc[c]); acc[c + 1] = fmaf(v, w4.y, acc[c + 1]);
-                        acc[c + 2] = fmaf(v, w4.z, acc[c + 2]); acc[c + 3] = fmaf(v, w4.w, acc[c + 3]);
+                        for (int c = 0; c < COUT_T; c += 4) {
+                            const float4 w4 = *reinterpret_cast<const float4*>(w + c);
+                            acc[c] = fmaf(v, w4.x, acc[c]); acc[c + 1] = fmaf(v, w4.y, acc[c + 1]);
+                            acc[c + 2] = fmaf(v, w4.z, acc[c + 2]); acc[c + 3] = fmaf(v, w4.w, acc[c + 3]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < COUT_T; ++c) acc[c] = fmaf(v, w[c], acc[c]);
                     }
                 }
             }
@@ -117,9 +126,12 @@ static cudaError_t k5_launch(const float* in, const float* w, const float* b, fl
 // prepared-weight blob layout (floats), in layer order; per layer [classes][cout blocks][CIN*TAPS][COUT_T] then the biases
 // (padded to the block size).  Sizes are exported so the host packer (weights.py:pack_vgn) cannot disagree.
 struct K5Layer { int cin, cout, cout_t, taps, classes; };
+// cout_t = output channels per thread.  The coarse layers have only 125 / 1 000 output voxels: there a thread owns ONE (or 4)
+// output channel(s) and the grid's z dimension runs over the channels, otherwise 4 CTAs would do the whole layer (r02n: 117 us
+// for the 5^3 decoder convolution with 16 channels per thread).
 static const K5Layer kK5[7] = {
-    {1, 16, 16, 125, 1}, {16, 32, 16, 27, 1}, {32, 64, 16, 27, 1}, {64, 64, 16, 27, 1},
-    {64, 32, 8, 27, 8}, {32, 16, 8, 27, 8}, {16, 6, 8, 27, 8} };
+    {1, 16, 16, 125, 1}, {16, 32, 4, 27, 1}, {32, 64, 1, 27, 1}, {64, 64, 1, 27, 1},
+    {64, 32, 1, 27, 8}, {32, 16, 4, 27, 8}, {16, 6, 8, 27, 8} };
 static int k5_wfloats(int l) { const K5Layer& L = kK5[l]; const int nb = (L.cout + L.cout_t - 1) / L.cout_t; return L.classes * nb * L.cin * L.taps * L.cout_t; }
 static int k5_bfloats(int l) { const K5Layer& L = kK5[l]; const int nb = (L.cout + L.cout_t - 1) / L.cout_t; return nb * L.cout_t; }
 
@@ -159,11 +171,11 @@ extern "C" int gn_vgn_forward(const GnVgnParams* hp, void* stream)
         float* d3 = ws;
         float* out = p.out + (size_t)s * p.out_scene_stride;
         e = k5_launch<1, 16, 5, 2, false, 1>(vol, W + wo[0], W + bo[0], e1, R, a, 16, st);                 if (e) break;   // networks.py:66-67
-        e = k5_launch<16, 16, 3, 2, false, 1>(e1, W + wo[1], W + bo[1], e2, a, b, 32, st);                 if (e) break;   // 69-70
-        e = k5_launch<32, 16, 3, 2, false, 1>(e2, W + wo[2], W + bo[2], e3, b, c, 64, st);                 if (e) break;   // 72-73
-        e = k5_launch<64, 16, 3, 1, false, 1>(e3, W + wo[3], W + bo[3], d1, c, c, 64, st);                 if (e) break;   // 85-86
-        e = k5_launch<64, 8, 3, 1, true, 1>(d1, W + wo[4], W + bo[4], d2, c, b, 32, st);                   if (e) break;   // 88-90 (upsample folded)
-        e = k5_launch<32, 8, 5, 1, true, 1>(d2, W + wo[5], W + bo[5], d3, b, a, 16, st);                   if (e) break;   // 92-94
+        e = k5_launch<16, 4, 3, 2, false, 1>(e1, W + wo[1], W + bo[1], e2, a, b, 32, st);                  if (e) break;   // 69-70
+        e = k5_launch<32, 1, 3, 2, false, 1>(e2, W + wo[2], W + bo[2], e3, b, c, 64, st);                  if (e) break;   // 72-73
+        e = k5_launch<64, 1, 3, 1, false, 1>(e3, W + wo[3], W + bo[3], d1, c, c, 64, st);                  if (e) break;   // 85-86
+        e = k5_launch<64, 1, 3, 1, true, 1>(d1, W + wo[4], W + bo[4], d2, c, b, 32, st);                   if (e) break;   // 88-90 (upsample folded)
+        e = k5_launch<32, 4, 5, 1, true, 1>(d2, W + wo[5], W + bo[5], d3, b, a, 16, st);                   if (e) break;   // 92-94
         e = k5_launch<16, 8, 5, 1, true, 2>(d3, W + wo[6], W + bo[6], out, a, R, 6, st);                                   // 96 + 47-53
     }
     return (int)e;

@@ -293,7 +293,8 @@ class NeuralRayRenderer(nn.Module):
         que = data['que_imgs_info'].copy()
         is_train = 'eval' not in data
         src = data['src_imgs_info'].copy() if 'src_imgs_info' in data else None
-        ref['img_feats'], ref['ray_feats'] = self.encode(ref, src, is_train)
+        if 'img_feats' not in ref or 'ray_feats' not in ref:       # (extension) a caller that batches the encoders over several scenes
+            ref['img_feats'], ref['ray_feats'] = self.encode(ref, src, is_train)        # passes the scene's slices in (train.TrainStep)
         out = {}
         if self.cfg['render_rgb']:
             out = self.render(que, ref, is_train)

@@ -38,7 +38,9 @@ class GraspPlanner:
         key = (tuple(hs.imgs.shape),)
         if key not in self._engines:
             post = dict(tsdf_thres_high=self.tsdf_thres_high, tsdf_thres_low=self.tsdf_thres_low)
-            self._engines[key] = ForwardEngine(self.net, hs, slots=2, device=self.device, post_cfg=post, max_grasps=self.max_grasps)
+            # depth_mean=False: the depth-mean head's outputs (renderer.py:288-289) are never read by the planner (main.py:251-253)
+            self._engines[key] = ForwardEngine(self.net, hs, slots=2, device=self.device, post_cfg=post, max_grasps=self.max_grasps,
+                                               depth_mean=False)
         return self._engines[key]
 
     @staticmethod
