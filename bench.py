@@ -410,6 +410,8 @@ def main():
         raise SystemExit('bench.py needs a CUDA device: graspnerf_b200 has no CPU path (use --impl reference for the CPU arm)')
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
+    from graspnerf_b200.engine import bind_to_gpu_numa
+    numa_node = bind_to_gpu_numa(local) if world > 1 else None     # pinned staging buffers local to this rank's GPU
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -545,7 +547,7 @@ def main():
             'data': 'synthetic',
             'config': {'workload': WORKLOAD,
                        'l2': f'inputs cycle through {POOL} scenes x (28 MB inputs + 110 MB record) (> 126 MB L2); no flush kernel in the timed region',
-                       'parallelism': f'replicas x{world} (scenes sharded, no data-path collective)',
+                       'parallelism': f'replicas x{world} (scenes sharded, no data-path collective)' + (f', rank 0 bound to NUMA node {numa_node}' if numa_node is not None else ''),
                        'images': 'U[0,1) synthetic images quantised to uint8 once; both arms compute on u8/255 (main.py:170)'},
             'roofline': roof_k2 if dominant_k2 else roof_k1,
             'roofline_k1': roof_k1, 'roofline_k2': roof_k2,

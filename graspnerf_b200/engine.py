@@ -23,6 +23,42 @@ import torch
 from . import ops
 
 
+def bind_to_gpu_numa(device_index):
+    """Pin the calling process to the CPUs of the NUMA node its GPU hangs off (sysfs: /sys/bus/pci/devices/<bdf>/numa_node and
+    /sys/devices/system/node/node<N>/cpulist) BEFORE it allocates pinned host buffers, so the staging memory of every rank is
+    local to its GPU's PCIe root: with 8 ranks on a 2-socket host the H2D traffic otherwise funnels through one socket's
+    memory controllers and the inter-socket link (round 1: 7 345 volumes/s at 8 GPUs = 0.59 scaling of the end-to-end leg).
+    Returns the node number, or None when the topology is not exposed (single node, container without sysfs) - then nothing
+    changes."""
+    import ctypes
+    import os
+    try:
+        pr = torch.cuda.get_device_properties(device_index)
+        if hasattr(pr, 'pci_bus_id'):
+            bdf = '%04x:%02x:%02x.0' % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        else:                                               # ask the CUDA runtime torch has already loaded
+            buf = ctypes.create_string_buffer(32)
+            rt = ctypes.CDLL(None)
+            if rt.cudaDeviceGetPCIBusId(buf, 32, int(device_index)) != 0:
+                return None
+            dom, rest = buf.value.decode().lower().split(':', 1)
+            bdf = dom[-4:] + ':' + rest
+        node = int(open(f'/sys/bus/pci/devices/{bdf}/numa_node').read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f'/sys/devices/system/node/node{node}/cpulist').read().strip().split(','):
+            lo, _, hi = part.partition('-')
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
+
+
 def _pin(x, dtype=None):
     t = torch.as_tensor(x)
     if dtype is not None:
