@@ -66,12 +66,15 @@ __device__ __forceinline__ void k6_plane_stats_cl(const float* __restrict__ x, i
                                                   float* s_red, float* s_part, int phase0, float& mean, float& rstd,
                                                   int splits = 1, long long sstride = 0)
 {
-    const int n = (r1 - r0) * W;
+    // a warp walks a row, lanes stride over the columns: coalesced, no integer division in the loops
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float s = 0.f;
-    for (int i = threadIdx.x; i < n; i += K6_THREADS) s += k6_ld(x, (r0 + i / W) * xs + (i % W), splits, sstride);
+    for (int r = r0 + warp; r < r1; r += K6_THREADS / 32)
+        for (int c = lane; c < W; c += 32) s += k6_ld(x, r * xs + c, splits, sstride);
     mean = k6_cluster_sum<CS>(s, s_red, s_part, phase0) / (float)n_total;
     float q = 0.f;
-    for (int i = threadIdx.x; i < n; i += K6_THREADS) { const float d = k6_ld(x, (r0 + i / W) * xs + (i % W), splits, sstride) - mean; q = fmaf(d, d, q); }
+    for (int r = r0 + warp; r < r1; r += K6_THREADS / 32)
+        for (int c = lane; c < W; c += 32) { const float d = k6_ld(x, r * xs + c, splits, sstride) - mean; q = fmaf(d, d, q); }
     rstd = rsqrtf(k6_cluster_sum<CS>(q, s_red, s_part, phase0 + 1) / (float)n_total + eps);      // biased variance, like InstanceNorm
 }
 
@@ -109,16 +112,19 @@ gn_k6_norm_act_pad_kernel(const GnNormActPadParams p)
     const int P = p.pad, Hp = H + 2 * P, Wp = W + 2 * P;
     float* op = p.out_padded ? p.out_padded + (size_t)plane * Hp * Wp : nullptr;
     float* ou = p.out_unpadded ? p.out_unpadded + (size_t)plane * hw : nullptr;
-    const int o0 = (int)((long long)Hp * rank / CS) * Wp, o1 = (int)((long long)Hp * (rank + 1) / CS) * Wp;     // this CTA's padded output rows
-    for (int i = o0 + threadIdx.x; i < o1; i += K6_THREADS) {
-        const int hp = i / Wp, wp = i - hp * Wp;
-        const int h = k6_reflect(hp - P, H), w = k6_reflect(wp - P, W);
-        float v = fmaf(k6_ld(x, h * xs + w, p.x_splits, p.x_split_stride), g, b);
-        if (r) v += fmaf(r[h * rs + w], rg, rb);
-        if (p.act == 1) v = fmaxf(v, 0.f);
-        else if (p.act == 2) v = v > 0.f ? v : expm1f(v);                          // F.elu
-        if (op) op[i] = v;
-        if (ou && hp >= P && hp < P + H && wp >= P && wp < P + W) ou[(hp - P) * W + (wp - P)] = v;
+    const int h0 = (int)((long long)Hp * rank / CS), h1 = (int)((long long)Hp * (rank + 1) / CS);     // this CTA's padded output rows
+    for (int hp = h0 + (int)(threadIdx.x >> 5); hp < h1; hp += K6_THREADS / 32) {
+        const int h = k6_reflect(hp - P, H);
+        const bool hin = hp >= P && hp < P + H;
+        for (int wp = threadIdx.x & 31; wp < Wp; wp += 32) {
+            const int w = k6_reflect(wp - P, W);
+            float v = fmaf(k6_ld(x, h * xs + w, p.x_splits, p.x_split_stride), g, b);
+            if (r) v += fmaf(r[h * rs + w], rg, rb);
+            if (p.act == 1) v = fmaxf(v, 0.f);
+            else if (p.act == 2) v = v > 0.f ? v : expm1f(v);                      // F.elu
+            if (op) op[hp * Wp + wp] = v;
+            if (ou && hin && wp >= P && wp < P + W) ou[(hp - P) * W + (wp - P)] = v;
+        }
     }
     if (CS > 1)       // a CTA must not exit while peers may still read its partial sums
         asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -162,7 +168,7 @@ extern "C" int gn_k6_norm_act_pad(const GnNormActPadParams* hp, void* stream)
         return (int)cudaGetLastError();
     }
     const int planes = p.N * p.C;
-    if ((long long)p.H * p.W >= 4096 && p.H >= 16) {       // large planes: a cluster of 8 CTAs per plane (DSMEM reduction)
+    if ((long long)p.H * p.W >= 16384 && p.H >= 16) {      // large planes (>= 128x128): a cluster of 8 CTAs per plane (DSMEM reduction)
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)planes * 8, 1, 1);
         cfg.blockDim = dim3(K6_THREADS, 1, 1);

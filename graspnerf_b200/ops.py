@@ -844,7 +844,8 @@ def conv2d_tc(xp, conv, allow_split=False):
     st = conv.stride[0]
     Ho, Wo = (Hp - kh) // st + 1, (Wp - kw) // st + 1
     tiles = (N * Ho * Wo + 127) // 128
-    S = 4 if (allow_split and tiles <= 64 and cw.Kpad // 32 >= 16) else 1
+    nch = cw.Kpad // 32
+    S = (4 if tiles <= 64 else 2) if (allow_split and tiles <= 160 and nch >= 16) else 1
     out = torch.empty(((S,) if S > 1 else ()) + (N, co, Ho, Wo), device=dev, dtype=torch.float32)
     p = _lib.GnConvParams()
     p.ksplit = S

@@ -290,8 +290,8 @@ def test_k6_kernels_against_torch_ops():
         want = F.pad(F.interpolate(x, scale_factor=2, mode='bilinear', align_corners=True), (1, 1, 1, 1), mode='reflect')
         assert_close(up.cpu(), want.cpu(), rtol=1e-6, atol_scale=1e-6, what='bilinear x2 + reflect pad')
         # large planes: one 8-CTA cluster per plane, partial statistics exchanged through distributed shared memory
-        xl = (torch.randn(2, 5, 80, 96, generator=g) * 3 - 2).to(DEV)
-        rl = torch.randn(2, 5, 80, 96, generator=g).to(DEV)
+        xl = (torch.randn(2, 5, 136, 130, generator=g) * 3 - 2).to(DEV)
+        rl = torch.randn(2, 5, 136, 130, generator=g).to(DEV)
         gp, gu = ops.norm_act_pad(xl, n1, 'elu', pad=1, res=rl, res_norm=n2, want_unpadded=True)
         assert_close(gp.cpu(), F.pad(F.elu(n1(xl) + n2(rl)), (1, 1, 1, 1), mode='reflect').cpu(), rtol=1e-5, atol_scale=1e-5, what='cluster norm_act_pad')
         assert_close(gu.cpu(), F.elu(n1(xl) + n2(rl)).cpu(), rtol=1e-5, atol_scale=1e-5, what='cluster norm_act_pad (un-padded)')
