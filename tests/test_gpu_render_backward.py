@@ -131,10 +131,15 @@ def test_trainstep_batched_encoders_equal_scene_by_scene():
         step(batch)
         grads[chunk] = {k: p.grad.detach().clone() for k, p in net.named_parameters() if p.grad is not None}
     assert set(grads[1]) == set(grads[3])
+    gmax = max(float(v.double().norm()) for v in grads[1].values())
     worst = 0.0
     for k in grads[1]:
         a, b = grads[3][k].double(), grads[1][k].double()
-        rel = float((a - b).norm() / b.norm().clamp_min(1e-12))
+        if float(b.norm()) < 1e-5 * gmax:
+            # e.g. a convolution bias in front of an InstanceNorm: its true gradient is exactly zero, what is left is round-off
+            assert float(a.norm()) < 1e-4 * gmax, k
+            continue
+        rel = float((a - b).norm() / b.norm())
         worst = max(worst, rel)
-        assert rel < 1e-2, (k, rel)          # fp32 atomics in gn_k1_backward accumulate in a different order every run (measured worst 3e-3 on a bias)
+        assert rel < 1e-2, (k, rel)          # fp32 atomics in gn_k1_backward accumulate in a different order every run (measured worst 3e-3)
     print(f'batched vs scene-by-scene gradients: worst rel-L2 {worst:.2e}')
