@@ -351,8 +351,9 @@ def highres_leg(args, dist, dev, world, rank, barrier, max_over_ranks, hw, peaks
 
 def full_forward_leg(args, dist, dev, world, rank, barrier, max_over_ranks, pool_np):
     """The planner's whole network call (GraspNeRF.forward, eval, render_rgb off: main.py:150,244-247) through
-    engine.ForwardEngine: uint8 images from pinned host memory -> cuDNN encoders (fp32, TF32 off) -> K1 -> K2a -> K2b ->
-    depth-mean head -> VGN -> grasp post-processing on the device -> 7 volumes + grasp list back to pinned host memory."""
+    engine.ForwardEngine: uint8 images from pinned host memory -> 2-D encoders (K6 / K7, fp32-accurate) -> K1 -> K2a -> K2b ->
+    depth-mean head -> VGN (K5) -> grasp post-processing on the device (K4) -> 7 volumes + grasp list back to pinned host
+    memory.  Four scenes in flight, each slot's CUDA graph on a stream of its own (the scenes overlap on the GPU)."""
     from graspnerf_b200.engine import ForwardEngine, HostScene
     from graspnerf_b200.weights import seed0_model
     torch.backends.cudnn.allow_tf32 = False
@@ -361,8 +362,8 @@ def full_forward_leg(args, dist, dev, world, rank, barrier, max_over_ranks, pool
     net.nr_net.cfg['render_rgb'] = False
     hosts = [HostScene(sc['imgs_u8'], None, None, sc['poses'], sc['Ks'], sc['depth_range'], np.asarray(sc['bbox3d'][0], np.float32)) for sc in pool_np]
     post = dict(tsdf_thres_high=0.0, tsdf_thres_low=-0.85)                       # main.py:92-93
-    eng = ForwardEngine(net, hosts[0], slots=3, device=dev, post_cfg=post)
-    for i in range(4):
+    eng = ForwardEngine(net, hosts[0], slots=4, device=dev, post_cfg=post)
+    for i in range(8):
         eng.submit(hosts[i % len(hosts)])
     eng.drain()
     n = args.full_steps
@@ -378,9 +379,9 @@ def full_forward_leg(args, dist, dev, world, rank, barrier, max_over_ranks, pool
     torch.cuda.synchronize()
     ms = max_over_ranks([(time.perf_counter() - t0) * 1e3], dist, dev)[0]
     return {'value': world * n / (ms / 1e3), 'unit': 'volumes/s', 'ms_per_volume': ms / n, 'steps': n,
-            'h2d_bytes_per_step': eng.h2d_bytes, 'd2h_bytes_per_step': eng.d2h_bytes, 'cuda_graph': bool(eng.graphed), 'checksum': chk,
+            'h2d_bytes_per_step': eng.h2d_bytes, 'd2h_bytes_per_step': eng.d2h_bytes, 'cuda_graph': bool(eng.graphed), 'slots_in_flight': len(eng.slots), 'checksum': chk,
             'api': 'graspnerf_b200.engine.ForwardEngine.submit (pinned uint8 images in; tsdf/qual/rot/width volumes + grasp list out)',
-            'what': 'GraspNeRF.forward eval, render_rgb off (main.py:150): 2-D encoders (tcgen05 convolutions K7 + fused norm/act/pad K6, two streams) + K1/K2a/K2b + depth-mean head + VGN 3-D conv (K5) + process/select on the device (K4)'}
+            'what': 'GraspNeRF.forward eval, render_rgb off (main.py:150): 2-D encoders (tcgen05 convolutions K7 + fused norm/act/pad K6, two streams) + K1/K2a/K2b + depth-mean head (one launch) + VGN 3-D conv (K5) + process/select on the device (K4); one CUDA graph per slot, slots on concurrent streams'}
 
 
 def main():

@@ -55,6 +55,12 @@ class GnRaySetupParams(C.Structure):
                [(n, C.c_int) for n in ('B', 'rn', 'dn')]
 
 
+class GnDepthMeanParams(C.Structure):
+    _fields_ = [('feats', C.c_void_p), ('coords', C.c_void_p), ('w_coarse', C.c_void_p * 6), ('w_fine', C.c_void_p * 6),
+                ('mean', C.c_void_p), ('mean_fine', C.c_void_p)] + [(n, C.c_longlong) for n in ('stride_v', 'stride_c', 'stride_y', 'stride_x')] + \
+               [(n, C.c_int) for n in ('V', 'num', 'H', 'W', 'fh', 'fw', 'align_corners')]
+
+
 class GnGraspPostParams(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ('tsdf', 'qual', 'rot', 'width', 'qual_out', 'scratch', 'grasps', 'count')] + \
                [(n, C.c_float) for n in ('sigma', 'min_width', 'max_width', 'tsdf_thres_high', 'tsdf_thres_low', 'threshold')] + \
@@ -92,7 +98,7 @@ def load():
     lib.gn_version.restype = C.c_char_p
     for name, st in (('gn_k1_forward', GnK1Params), ('gn_k2a_forward', GnK2aParams), ('gn_k2a_forward_tc', GnK2aParams), ('gn_k2b_forward', GnK2bParams),
                      ('gn_k3_composite', GnK3Params), ('gn_k2b_backward', GnK2bBwdParams), ('gn_k2a_backward', GnK2aBwdParams),
-                     ('gn_k1_backward', GnK1BwdParams), ('gn_k3_ray_setup', GnRaySetupParams), ('gn_k4_grasp_post', GnGraspPostParams), ('gn_vgn_forward', GnVgnParams), ('gn_k6_norm_act_pad', GnNormActPadParams), ('gn_k7_conv_forward', GnConvParams)):
+                     ('gn_k1_backward', GnK1BwdParams), ('gn_k3_ray_setup', GnRaySetupParams), ('gn_k3_depth_mean', GnDepthMeanParams), ('gn_k4_grasp_post', GnGraspPostParams), ('gn_vgn_forward', GnVgnParams), ('gn_k6_norm_act_pad', GnNormActPadParams), ('gn_k7_conv_forward', GnConvParams)):
         fn = getattr(lib, name)
         fn.restype = C.c_int
         fn.argtypes = [C.POINTER(st), C.c_void_p]
@@ -112,7 +118,7 @@ def load():
     for name, st in (('gn_sizeof_k1_params', GnK1Params), ('gn_sizeof_k2a_params', GnK2aParams),
                      ('gn_sizeof_k2b_params', GnK2bParams), ('gn_sizeof_k3_params', GnK3Params),
                      ('gn_sizeof_k2b_bwd_params', GnK2bBwdParams), ('gn_sizeof_k2a_bwd_params', GnK2aBwdParams),
-                     ('gn_sizeof_k1_bwd_params', GnK1BwdParams), ('gn_sizeof_ray_setup_params', GnRaySetupParams),
+                     ('gn_sizeof_k1_bwd_params', GnK1BwdParams), ('gn_sizeof_ray_setup_params', GnRaySetupParams), ('gn_sizeof_depth_mean_params', GnDepthMeanParams),
                      ('gn_sizeof_grasp_post_params', GnGraspPostParams), ('gn_sizeof_vgn_params', GnVgnParams),
                      ('gn_sizeof_norm_act_pad_params', GnNormActPadParams), ('gn_sizeof_conv_params', GnConvParams)):
         got = getattr(lib, name)()

@@ -23,6 +23,7 @@ extern "C" int gn_sizeof_k2b_bwd_params(void) { return (int)sizeof(GnK2bBwdParam
 extern "C" int gn_sizeof_k2a_bwd_params(void) { return (int)sizeof(GnK2aBwdParams); }
 extern "C" int gn_sizeof_k1_bwd_params(void) { return (int)sizeof(GnK1BwdParams); }
 extern "C" int gn_sizeof_ray_setup_params(void) { return (int)sizeof(GnRaySetupParams); }
+extern "C" int gn_sizeof_depth_mean_params(void) { return (int)sizeof(GnDepthMeanParams); }
 extern "C" int gn_sizeof_grasp_post_params(void) { return (int)sizeof(GnGraspPostParams); }
 extern "C" int gn_sizeof_vgn_params(void) { return (int)sizeof(GnVgnParams); }
 extern "C" int gn_sizeof_norm_act_pad_params(void) { return (int)sizeof(GnNormActPadParams); }

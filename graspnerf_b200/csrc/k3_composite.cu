@@ -207,3 +207,108 @@ extern "C" int gn_k3_ray_setup(const GnRaySetupParams* hp, void* stream)
     gn_k3_ray_setup_kernel<<<(unsigned)((rays + 127) / 128), 128, 0, (cudaStream_t)stream>>>(p);
     return (int)cudaGetLastError();
 }
+
+// ------------------------------------------------------------------------------------------------ depth-mean head
+// renderer.py:222-266 (predict_mean_for_depth_loss) in one launch: bilinear sample of ray_feats at `num` pixels per reference
+// view (interpolate_feats -> F.grid_sample, border padding, ops.py:14-34) and the mean decoders of dist_decoder /
+// fine_dist_decoder (32 -> 32 -> 32 -> 2, ELU ELU Softplus; dist_decoder.py:64-70,148-150).  thread <-> (view, pixel); the
+// six Linear layers (17 KB) sit in shared memory and are read as broadcasts.
+#define DM_THREADS 128
+#define DM_DEC_FLOATS (32 * 32 + 32 + 32 * 32 + 32 + 2 * 32 + 2)
+
+__device__ __forceinline__ float dm_elu(float x) { return x > 0.f ? x : expm1f(x); }
+__device__ __forceinline__ float dm_softplus(float x) { return x > 20.f ? x : log1pf(expf(x)); }
+
+// grid_sampler_unnormalize + clip_coordinates (at::native GridSampler.cuh), padding_mode='border'
+__device__ __forceinline__ float dm_source_index(float g, int size, int align)
+{
+    float x = align ? ((g + 1.f) / 2.f) * (float)(size - 1) : ((g + 1.f) * (float)size - 1.f) / 2.f;
+    return fminf((float)(size - 1), fmaxf(x, 0.f));
+}
+
+__device__ __forceinline__ void dm_decode(const float* __restrict__ w, const float* x, float* out2)
+{
+    float h1[32], h2[32];
+#pragma unroll
+    for (int n = 0; n < 32; ++n) {
+        float a = w[1024 + n];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) a = fmaf(w[n * 32 + k], x[k], a);
+        h1[n] = dm_elu(a);
+    }
+    const float* w1 = w + 1056;
+#pragma unroll
+    for (int n = 0; n < 32; ++n) {
+        float a = w1[1024 + n];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) a = fmaf(w1[n * 32 + k], h1[k], a);
+        h2[n] = dm_elu(a);
+    }
+    const float* w2 = w + 2112;
+#pragma unroll
+    for (int n = 0; n < 2; ++n) {
+        float a = w2[64 + n];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) a = fmaf(w2[n * 32 + k], h2[k], a);
+        out2[n] = dm_softplus(a);
+    }
+}
+
+__global__ void __launch_bounds__(DM_THREADS)
+gn_k3_depth_mean_kernel(const GnDepthMeanParams p)
+{
+    __shared__ __align__(16) float sw[2 * DM_DEC_FLOATS];
+    const int ndec = p.w_fine[0] ? 2 : 1;
+    for (int d = 0; d < ndec; ++d) {
+        const float* const* src = d ? p.w_fine : p.w_coarse;
+        const int off[7] = {0, 1024, 1056, 2080, 2112, 2176, 2178};
+        for (int t = 0; t < 6; ++t)
+            for (int i = threadIdx.x; i < off[t + 1] - off[t]; i += DM_THREADS) sw[d * DM_DEC_FLOATS + off[t] + i] = __ldg(src[t] + i);
+    }
+    __syncthreads();
+    const long long i = (long long)blockIdx.x * DM_THREADS + threadIdx.x;
+    if (i >= (long long)p.V * p.num) return;
+    const int v = (int)(i / p.num);
+    // the reference stacks (row, col) and feeds it to interpolate_feats as (x, y) (renderer.py:229-243): kept as is
+    const float c0 = (float)p.coords[2 * i], c1 = (float)p.coords[2 * i + 1];
+    const float gx = c0 / (float)(p.W - 1) * 2.f - 1.f, gy = c1 / (float)(p.H - 1) * 2.f - 1.f;
+    const float ix = dm_source_index(gx, p.fw, p.align_corners), iy = dm_source_index(gy, p.fh, p.align_corners);
+    const float fx = floorf(ix), fy = floorf(iy);
+    const int x0 = (int)fx, y0 = (int)fy, x1 = x0 + 1, y1 = y0 + 1;
+    const float wnw = (fx + 1.f - ix) * (fy + 1.f - iy), wne = (ix - fx) * (fy + 1.f - iy);
+    const float wsw = (fx + 1.f - ix) * (iy - fy), wse = (ix - fx) * (iy - fy);
+    const bool xin = x1 < p.fw, yin = y1 < p.fh;               // (x0, y0) is always inside after the border clip
+    const float* f = p.feats + (long long)v * p.stride_v;
+    float x[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+        const float* fc = f + (long long)c * p.stride_c;
+        float a = __ldg(fc + (long long)y0 * p.stride_y + (long long)x0 * p.stride_x) * wnw;
+        if (xin) a += __ldg(fc + (long long)y0 * p.stride_y + (long long)x1 * p.stride_x) * wne;
+        if (yin) a += __ldg(fc + (long long)y1 * p.stride_y + (long long)x0 * p.stride_x) * wsw;
+        if (xin && yin) a += __ldg(fc + (long long)y1 * p.stride_y + (long long)x1 * p.stride_x) * wse;
+        x[c] = a;
+    }
+    float o[2];
+    dm_decode(sw, x, o);
+    p.mean[2 * i] = o[0]; p.mean[2 * i + 1] = o[1];
+    if (ndec == 2) {
+        dm_decode(sw + DM_DEC_FLOATS, x, o);
+        p.mean_fine[2 * i] = o[0]; p.mean_fine[2 * i + 1] = o[1];
+    }
+}
+
+extern "C" int gn_k3_depth_mean(const GnDepthMeanParams* hp, void* stream)
+{
+    const GnDepthMeanParams& p = *hp;
+    if (p.V < 1 || p.num < 1 || p.H < 2 || p.W < 2 || p.fh < 1 || p.fw < 1) return -1;
+    if (!p.feats || !p.coords || !p.mean) return -2;
+    for (int t = 0; t < 6; ++t) {
+        if (!p.w_coarse[t]) return -2;
+        if ((p.w_fine[t] == nullptr) != (p.w_fine[0] == nullptr)) return -2;
+    }
+    if (p.w_fine[0] && !p.mean_fine) return -2;
+    const long long n = (long long)p.V * p.num;
+    gn_k3_depth_mean_kernel<<<(unsigned)((n + DM_THREADS - 1) / DM_THREADS), DM_THREADS, 0, (cudaStream_t)stream>>>(p);
+    return (int)cudaGetLastError();
+}

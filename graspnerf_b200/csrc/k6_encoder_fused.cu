@@ -12,6 +12,7 @@
 #include "../../include/graspnerf_b200.h"
 
 #define K6_THREADS 256
+#define K6_CACHE_FLOATS 9216      // a CTA's share of the plane stays in shared memory between the three passes (72x128 map: 36 KB)
 
 __device__ __forceinline__ float k6_block_sum(float v, float* s_red)
 {
@@ -61,20 +62,32 @@ __device__ __forceinline__ float k6_ld(const float* __restrict__ x, int off, int
     return v;
 }
 
+// cache: optional shared-memory copy [(r1-r0)*W] of the rows read here (filled in the first pass, re-read in the second - each
+// thread re-reads exactly what it wrote - and by the caller's output pass after the block-wide barriers of the reductions)
 template <int CS>
 __device__ __forceinline__ void k6_plane_stats_cl(const float* __restrict__ x, int W, int xs, int r0, int r1, int n_total, float eps,
                                                   float* s_red, float* s_part, int phase0, float& mean, float& rstd,
-                                                  int splits = 1, long long sstride = 0)
+                                                  int splits = 1, long long sstride = 0, float* cache = nullptr)
 {
     // a warp walks a row, lanes stride over the columns: coalesced, no integer division in the loops
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float s = 0.f;
-    for (int r = r0 + warp; r < r1; r += K6_THREADS / 32)
-        for (int c = lane; c < W; c += 32) s += k6_ld(x, r * xs + c, splits, sstride);
+    if (cache) {
+        for (int r = r0 + warp; r < r1; r += K6_THREADS / 32)
+            for (int c = lane; c < W; c += 32) { const float v = k6_ld(x, r * xs + c, splits, sstride); cache[(r - r0) * W + c] = v; s += v; }
+    } else {
+        for (int r = r0 + warp; r < r1; r += K6_THREADS / 32)
+            for (int c = lane; c < W; c += 32) s += k6_ld(x, r * xs + c, splits, sstride);
+    }
     mean = k6_cluster_sum<CS>(s, s_red, s_part, phase0) / (float)n_total;
     float q = 0.f;
-    for (int r = r0 + warp; r < r1; r += K6_THREADS / 32)
-        for (int c = lane; c < W; c += 32) { const float d = k6_ld(x, r * xs + c, splits, sstride) - mean; q = fmaf(d, d, q); }
+    if (cache) {
+        for (int r = r0 + warp; r < r1; r += K6_THREADS / 32)
+            for (int c = lane; c < W; c += 32) { const float d = cache[(r - r0) * W + c] - mean; q = fmaf(d, d, q); }
+    } else {
+        for (int r = r0 + warp; r < r1; r += K6_THREADS / 32)
+            for (int c = lane; c < W; c += 32) { const float d = k6_ld(x, r * xs + c, splits, sstride) - mean; q = fmaf(d, d, q); }
+    }
     rstd = rsqrtf(k6_cluster_sum<CS>(q, s_red, s_part, phase0 + 1) / (float)n_total + eps);      // biased variance, like InstanceNorm
 }
 
@@ -84,6 +97,7 @@ gn_k6_norm_act_pad_kernel(const GnNormActPadParams p)
 {
     __shared__ float s_red[K6_THREADS / 32];
     __shared__ float s_part[4];
+    __shared__ float s_plane[K6_CACHE_FLOATS];
     const int plane = blockIdx.x / CS;                   // n * C + c
     const int rank = blockIdx.x - plane * CS;
     const int c = plane % p.C;
@@ -92,9 +106,10 @@ gn_k6_norm_act_pad_kernel(const GnNormActPadParams p)
     const float* x = p.x + (size_t)plane * (size_t)(H + 2 * p.x_pad) * xs + (size_t)p.x_pad * xs + p.x_pad;
     const int r0 = (int)((long long)H * rank / CS), r1 = (int)((long long)H * (rank + 1) / CS);     // this CTA's rows for the statistics
     float g = 1.f, b = 0.f;
+    const bool cached = p.gamma && (r1 - r0) * W <= K6_CACHE_FLOATS;
     if (p.gamma) {
         float mean, rstd;
-        k6_plane_stats_cl<CS>(x, W, xs, r0, r1, hw, p.eps, s_red, s_part, 0, mean, rstd, p.x_splits, p.x_split_stride);
+        k6_plane_stats_cl<CS>(x, W, xs, r0, r1, hw, p.eps, s_red, s_part, 0, mean, rstd, p.x_splits, p.x_split_stride, cached ? s_plane : nullptr);
         g = __ldg(p.gamma + c) * rstd; b = __ldg(p.beta + c) - mean * g;          // y = (x - mean) * rstd * gamma + beta
     }
     const float* r = nullptr;
@@ -118,7 +133,8 @@ gn_k6_norm_act_pad_kernel(const GnNormActPadParams p)
         const bool hin = hp >= P && hp < P + H;
         for (int wp = threadIdx.x & 31; wp < Wp; wp += 32) {
             const int w = k6_reflect(wp - P, W);
-            float v = fmaf(k6_ld(x, h * xs + w, p.x_splits, p.x_split_stride), g, b);
+            const float xv = (cached && h >= r0 && h < r1) ? s_plane[(h - r0) * W + w] : k6_ld(x, h * xs + w, p.x_splits, p.x_split_stride);
+            float v = fmaf(xv, g, b);
             if (r) v += fmaf(r[h * rs + w], rg, rb);
             if (p.act == 1) v = fmaxf(v, 0.f);
             else if (p.act == 2) v = v > 0.f ? v : expm1f(v);                      // F.elu

@@ -5,11 +5,13 @@ network, src/nr/main.py:225-247):
 
   VolumeEngine   the hot path alone: images + the encoders' feature maps from the host -> K1 -> K2a -> K2b -> TSDF volume.
   ForwardEngine  the whole GraspNeRF.forward of the planner (eval, render_rgb off as main.py:150): uint8 images from the
-                 host -> 2-D encoders (cuDNN) -> K1 -> K2a -> K2b -> VGN head -> (optional) grasp post-processing on the
-                 device; only the image bytes cross PCIe on the way in.
+                 host -> 2-D encoders (K6 / K7) -> K1 -> K2a -> K2b -> depth-mean head -> VGN head (K5) -> (optional) grasp
+                 post-processing on the device (K4); only the image bytes cross PCIe on the way in.
 
 `slots` scenes are kept in flight so the PCIe copies of step i+1 run under the kernels of step i (one copy stream + one
 compute stream, ordered by CUDA events; no host synchronisation inside the loop except when a slot is recycled).
+ForwardEngine gives every slot a compute stream of its own: a scene's encoders are a dependent chain of ~250 launches on
+6 small images that leaves most SMs idle, so the graphs of the scenes in flight overlap on the GPU.
 
 Images may be uint8 ([V,H,W,3] as cv2 / imread give them, or [V,H,W,4]): they cross PCIe as bytes and K1 divides by 255 in
 its gather exactly like color_map_forward (main.py:170); fp32 [V,3,H,W] images are accepted as the reference holds them.
@@ -117,12 +119,18 @@ class _Slot:
 class _Engine:
     """Slot ring shared by both engines; subclasses provide `_out_shapes()` and `_compute(slot) -> list of device tensors`."""
 
-    def __init__(self, example, slots, device):
+    def __init__(self, example, slots, device, concurrent_slots=False):
+        """concurrent_slots: every slot computes on a stream of its own, so the scenes in flight overlap on the GPU (pays when
+        a scene's work is a long chain of small launches that cannot fill 148 SMs); otherwise one compute stream, scenes in
+        submission order."""
         self.device = torch.device(device)
         self.copy_stream = torch.cuda.Stream(self.device)
         self.compute_stream = torch.cuda.Stream(self.device)
         shapes = self._out_shapes()
         self.slots = [_Slot(example, shapes, self.device) for _ in range(slots)]
+        for s in self.slots:
+            s.stream = torch.cuda.Stream(self.device) if concurrent_slots else self.compute_stream
+            s.side = torch.cuda.Stream(self.device)
         self.next = 0
         self.h2d_bytes = example.nbytes
         self.d2h_bytes = sum(int(torch.tensor(s).prod()) * torch.empty((), dtype=d).element_size() for s, d in shapes)
@@ -140,14 +148,14 @@ class _Engine:
                     dst[0].copy_(src, non_blocking=True)
             s.bbox_min.copy_(hs.bbox_min.reshape(1, 3), non_blocking=True)
             s.ev_in.record(self.copy_stream)
-        with torch.cuda.stream(self.compute_stream):
-            self.compute_stream.wait_event(s.ev_in)
+        with torch.cuda.stream(s.stream):
+            s.stream.wait_event(s.ev_in)
             outs = self._compute(s)
             s.flip ^= 1
             hosts = s.out_host[s.flip]                   # the buffer set NOT handed out by the previous collect of this slot
             for h, d in zip(hosts, outs):
                 h.copy_(d.reshape(h.shape), non_blocking=True)
-            s.ev_done.record(self.compute_stream)
+            s.ev_done.record(s.stream)
         s.busy, s.tag, s.last = True, tag, hosts
         return i, finished
 
@@ -189,20 +197,21 @@ class ForwardEngine(_Engine):
     """The planner's whole network call with host buffers (GraspNeRFPlanner.core, main.py:211-253): images in, volumes out.
 
     net: the mirror `GraspNeRF` (graspnerf_b200.network), on `device`, eval mode.  Per scene the device runs image_encoder /
-    init_net / vis_encoder (renderer.py:275-279, cuDNN fp32), sample_volume (K1 -> K2a -> K2b), the depth-mean head
+    init_net / vis_encoder (renderer.py:275-279; K6 / K7), sample_volume (K1 -> K2a -> K2b), the depth-mean head
     (renderer.py:288-289: always on in eval) and the VGN head (renderer.py:323-330), captured in ONE CUDA graph per slot
     when capture succeeds (eager otherwise; `self.graphed` says which).  Result per scene, pinned host tensors:
       [volumes [7,R,R,R] = tsdf, qual, rot0..3, width,  grasps [max_grasps,9],  count int32[1]]
     (grasps / count from gn_k4_grasp_post - main.py:23-74 - when post_cfg is given, else zeros)."""
 
-    def __init__(self, net, example, slots=3, device='cuda', post_cfg=None, max_grasps=256, depth_mean=True, use_graph=True):
+    def __init__(self, net, example, slots=3, device='cuda', post_cfg=None, max_grasps=256, depth_mean=True, use_graph=True,
+                 concurrent_slots=True):
         self.net = net.eval()
         self.R = net.nr_net.cfg['volume_resolution']
         self.post_cfg, self.max_grasps, self.depth_mean, self.use_graph = post_cfg, max_grasps, depth_mean, use_graph
         self.graphed = None
         if example.imgs.dtype != torch.uint8:
             raise ValueError('ForwardEngine takes uint8 images [V,H,W,3|4] (the planner reads PNG bytes, main.py:166-171)')
-        super().__init__(example, slots, device)
+        super().__init__(example, slots, device, concurrent_slots=concurrent_slots)
 
     def _out_shapes(self):
         R = self.R
@@ -213,10 +222,18 @@ class ForwardEngine(_Engine):
         imgs = (s.imgs[0, ..., :3].permute(0, 3, 1, 2).to(torch.float32) / 255.0).contiguous()     # color_map_forward + transpose (main.py:192)
         ref = {'imgs': imgs, 'imgs_u8': s.imgs, 'poses': s.poses[0], 'Ks': s.Ks[0], 'depth_range': s.depth_range[0],
                'bbox3d': s.bbox_min.reshape(1, 3)}
+        coords = None
+        if self.depth_mean:
+            # the depth-mean head's random pixels (a sort-based randperm, ~0.1 ms of small launches) depend on nothing: side stream
+            cur = torch.cuda.current_stream(self.device)
+            s.side.wait_stream(cur)
+            with torch.cuda.stream(s.side):
+                coords = nr.draw_depth_coords(imgs.shape[0], imgs.shape[2], imgs.shape[3], imgs.device)
         ref['img_feats'], ref['ray_feats'] = nr.encode(ref, ref, False)
         vol = nr.sample_volume(ref)
         if self.depth_mean:
-            nr.predict_mean_for_depth_loss(ref)
+            cur.wait_stream(s.side)
+            s.depth = nr.predict_mean_for_depth_loss(ref, coords=coords)     # renderer.py:288-289 (outputs stay on the device)
         R = self.R
         vols = torch.empty((7, R, R, R), device=vol.device, dtype=torch.float32)
         vols[0].copy_(vol.reshape(R, R, R))

@@ -67,6 +67,7 @@ class NeuralRayRenderer(nn.Module):
         self.use_sdf = True
         self._hw = {}
         self._side = None
+        self.fused_depth_mean = True                      # False: the torch formulation also in inference (cross-check in the GPU tests)
         self._valid = None
         self.two_stream_encoders = True
 
@@ -114,7 +115,8 @@ class NeuralRayRenderer(nn.Module):
         capturing = torch.cuda.is_current_stream_capturing()
         if not capturing:
             self._report_valid_ratio()
-        if self._valid is None or self._valid[0].device != dev or self._valid[0].numel() != scene.V:
+        if capturing or self._valid is None or self._valid[0].device != dev or self._valid[0].numel() != scene.V:
+            # (a captured graph gets a counter of its own: graphs of different engine slots may run concurrently)
             self._valid = [torch.zeros((1, scene.V), dtype=torch.int32, device=dev), 0, False]
         self._valid[0].zero_()
         self._valid[1], self._valid[2] = self.cfg['volume_resolution'] ** 3, not capturing
@@ -247,16 +249,28 @@ class NeuralRayRenderer(nn.Module):
         return {k: torch.cat(v, 1) for k, v in outs.items()}
 
     # ------------------------------------------------------------------------------------------------ torch-side heads
+    def draw_depth_coords(self, rfn, h, w, device):
+        """renderer.py:225-233: depth_loss_coords_num distinct random pixels, the same ones for every reference view ->
+        int64 [rfn,num,2].  (Independent of everything else in the forward: engine.ForwardEngine draws them on a side stream.)"""
+        idx = torch.randperm(h * w, device=device)[:self.cfg['depth_loss_coords_num']]
+        coords = torch.stack([idx // w, idx % w], -1)            # the reference stacks (row, col) of meshgrid(arange(h), arange(w))
+        return coords.unsqueeze(0).repeat(rfn, 1, 1)
+
     def predict_mean_for_depth_loss(self, ref_imgs_info, coords=None):
-        """renderer.py:222-266: depth_loss_coords_num random pixels x V -> mean_decoder (+fine).  Small; stays in torch.
-        coords (optional, [V,num,2] int64): use these pixels instead of drawing new ones (parity tests)."""
+        """renderer.py:222-266: depth_loss_coords_num random pixels x V -> mean_decoder (+fine).  Inference on the GPU: ONE
+        launch (gn_k3_depth_mean: bilinear taps + both decoders); under autograd the torch formulation below.
+        coords (optional, [V,num,2] int64): use these pixels instead of drawing new ones (parity tests, engine)."""
         ray_feats, imgs = ref_imgs_info['ray_feats'], ref_imgs_info['imgs']
         rfn, _, h, w = imgs.shape
-        num = self.cfg['depth_loss_coords_num']
         if coords is None:
-            idx = torch.randperm(h * w, device=imgs.device)[:num]
-            coords = torch.stack([idx // w, idx % w], -1)        # the reference stacks (row, col) of meshgrid(arange(h), arange(w))
-            coords = coords.unsqueeze(0).repeat(rfn, 1, 1)
+            coords = self.draw_depth_coords(rfn, h, w, imgs.device)
+        if ray_feats.is_cuda and not torch.is_grad_enabled() and self.fused_depth_mean:
+            fine = self.fine_dist_decoder.mean_decoder if self.cfg['use_hierarchical_sampling'] else None
+            m, mf = ops.depth_mean(ray_feats, coords, (h, w), self.dist_decoder.mean_decoder, fine)
+            out = {'depth_mean': m[..., 0], 'depth_coords': coords, 'depth_mean_2': m[..., 1]}
+            if mf is not None:
+                out['depth_mean_fine'], out['depth_mean_fine_2'] = mf[..., 0], mf[..., 1]
+            return out
         cf = coords.float()
         grid = torch.stack([cf[..., 0] / (w - 1) * 2 - 1, cf[..., 1] / (h - 1) * 2 - 1], -1).unsqueeze(1)   # ops.py:29-31
         feats = torch.nn.functional.grid_sample(ray_feats, grid, mode='bilinear', padding_mode='border',

@@ -407,6 +407,48 @@ class VolumeGraph:
         return self.out
 
 
+# ------------------------------------------------------------------------------------------------ depth-mean head
+def depth_mean(ray_feats, coords, img_hw, mean_decoder, fine_mean_decoder=None):
+    """predict_mean_for_depth_loss (renderer.py:222-266) in one launch (gn_k3_depth_mean): ray_feats [V,32,fh,fw] (any strides),
+    coords int64 [V,num,2], img_hw = (H, W) of the images, mean_decoder / fine_mean_decoder: the nn.Sequential
+    Linear-ELU-Linear-ELU-Linear-Softplus of MixtureLogisticsDistDecoder.  -> mean [V,num,2] (, mean_fine [V,num,2])."""
+    lib = _lib.load()
+    dev = ray_feats.device
+    if dev.type != 'cuda' or ray_feats.dtype != torch.float32:
+        raise ValueError('depth_mean: fp32 CUDA feature maps required (no CPU path)')
+    V, C_, fh, fw = ray_feats.shape
+    assert C_ == 32
+    coords = coords.to(device=dev, dtype=torch.int64).contiguous()
+    num = coords.shape[1]
+    H, W = int(img_hw[0]), int(img_hw[1])
+    p = _lib.GnDepthMeanParams()
+    keep = []
+
+    def six(dec, field):
+        lins = [dec[0], dec[2], dec[4]]
+        assert tuple(lins[0].weight.shape) == (32, 32) and tuple(lins[1].weight.shape) == (32, 32) and tuple(lins[2].weight.shape) == (2, 32)
+        for i, t in enumerate(x for l in lins for x in (l.weight, l.bias)):
+            t = t.detach()
+            if not t.is_contiguous() or t.dtype != torch.float32 or t.device != dev:
+                t = t.to(device=dev, dtype=torch.float32).contiguous()
+                keep.append(t)
+            field[i] = _ptr(t).value
+    six(mean_decoder, p.w_coarse)
+    mean = torch.empty((V, num, 2), dtype=torch.float32, device=dev)
+    mean_fine = None
+    if fine_mean_decoder is not None:
+        six(fine_mean_decoder, p.w_fine)
+        mean_fine = torch.empty((V, num, 2), dtype=torch.float32, device=dev)
+        p.mean_fine = _ptr(mean_fine).value
+    p.feats, p.coords, p.mean = _ptr(ray_feats).value, _ptr(coords).value, _ptr(mean).value
+    p.stride_v, p.stride_c, p.stride_y, p.stride_x = (int(s) for s in ray_feats.stride())
+    p.V, p.num, p.H, p.W, p.fh, p.fw = V, num, H, W, fh, fw
+    p.align_corners = 1 if (fh, fw) == (H, W) else 0                              # ops.py:25-33
+    with _on(dev):
+        _lib.check(lib.gn_k3_depth_mean(C.byref(p), _stream(dev)), 'gn_k3_depth_mean')
+    return mean, mean_fine
+
+
 # ------------------------------------------------------------------------------------------------ RGB head
 def ray_setup(coords, poses, Ks, depth_range_q, que_depth, want_rays=False):
     """coords2rays + depth2points + depth2inv_dists (render_ops.py:4-52) in one launch (gn_k3_ray_setup): coords [B,rn,2]
@@ -689,7 +731,7 @@ class VgnWeights:
     """Prepared weights of the VGN ConvNet for gn_vgn_forward; re-packed when a source tensor changed (like HeadWeights)."""
 
     def __init__(self, module):
-        self.module, self._versions, self.blob, self._ws = module, None, None, {}
+        self.module, self._versions, self.blob = module, None, None
 
     def refresh(self):
         sd = dict(self.module.named_parameters())
@@ -702,9 +744,9 @@ class VgnWeights:
         return self.blob
 
     def workspace(self, R, dev):
-        if (R, dev) not in self._ws:
-            self._ws[(R, dev)] = torch.empty(_lib.load().gn_vgn_workspace_floats(R), dtype=torch.float32, device=dev)
-        return self._ws[(R, dev)]
+        """Scratch of one gn_vgn_forward call.  A fresh allocation per call (the caching allocator / a capturing graph's private
+        pool make it cheap): calls on different streams - engine slots that overlap on the GPU - must not share it."""
+        return torch.empty(_lib.load().gn_vgn_workspace_floats(R), dtype=torch.float32, device=dev)
 
 
 def vgn_forward(volume, vw, out=None):

@@ -163,6 +163,23 @@ typedef struct GnRaySetupParams {
 } GnRaySetupParams;
 int gn_k3_ray_setup(const GnRaySetupParams* params, void* stream);
 
+/* Depth-mean head (renderer.py:222-266, predict_mean_for_depth_loss; runs in every eval forward, renderer.py:288-289):
+ * bilinear sample of ray_feats at `num` pixels per reference view (ops.py:14-34: grid_sample, border padding) and
+ * MixtureLogisticsDistDecoder.predict_mean (dist_decoder.py:148-150) of the coarse and, optionally, the fine decoder.
+ * feats is addressed through element strides, so NCHW [V,32,fh,fw] and channels-last maps both work.
+ * w_*: the six tensors of mean_decoder in nn.Linear layout: W0 [32,32], b0 [32], W1 [32,32], b1 [32], W2 [2,32], b2 [2]. */
+typedef struct GnDepthMeanParams {
+    const float* feats;            /* ray_feats of the reference views */
+    const long long* coords;       /* [V,num,2] int64, the reference's (row, col) pairs used as (x, y) */
+    const float* w_coarse[6];
+    const float* w_fine[6];        /* all NULL: coarse decoder only */
+    float* mean;                   /* out [V,num,2] */
+    float* mean_fine;              /* out [V,num,2] (with w_fine) */
+    long long stride_v, stride_c, stride_y, stride_x;
+    int V, num, H, W, fh, fw, align_corners;
+} GnDepthMeanParams;
+int gn_k3_depth_mean(const GnDepthMeanParams* params, void* stream);
+
 /* Grasp post-processing on the device (the step after the path in GraspNeRFPlanner.__call__, main.py:23-84,202-203):
  * `process` = gaussian_filter(qual, sigma 1, 'nearest') + TSDF band mask (binary_dilation of the outside voxels, 2
  * iterations, restricted to the band) + width limits; `select` = threshold, 4^3 maximum-filter NMS ('reflect'), ordered
@@ -301,6 +318,7 @@ int gn_sizeof_k2b_bwd_params(void);
 int gn_sizeof_k2a_bwd_params(void);
 int gn_sizeof_k1_bwd_params(void);
 int gn_sizeof_ray_setup_params(void);
+int gn_sizeof_depth_mean_params(void);
 int gn_sizeof_grasp_post_params(void);
 int gn_sizeof_vgn_params(void);
 int gn_sizeof_norm_act_pad_params(void);

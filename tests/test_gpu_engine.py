@@ -113,6 +113,34 @@ def test_mirror_depth_mean_values_with_injected_coords():
     assert_close(out['depth_mean'].cpu(), g['depth_mean'], rtol=2e-3, atol_scale=2e-3, what='depth_mean vs reference')
 
 
+@pytest.mark.parametrize('same_size', [False, True])
+def test_depth_mean_kernel_matches_the_torch_formulation(same_size):
+    """gn_k3_depth_mean (one launch) vs the torch formulation of renderer.py:222-266 in the mirror (grid_sample + the two
+    mean decoders' nn.Linear layers): NCHW and channels-last feature maps, border pixels included, and the
+    align_corners=True branch the reference takes when the feature map has the image's size (ops.py:25-33)."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    net = seed0_model().to(DEV).eval()
+    nr = net.nr_net
+    V, h, w = 3, 96, 160
+    fh, fw = (h, w) if same_size else (h // 4, w // 4)
+    gen = torch.Generator().manual_seed(5)
+    ray_feats = torch.randn(V, 32, fh, fw, generator=gen).to(DEV)
+    imgs = torch.zeros(V, 3, h, w, device=DEV)
+    idx = torch.randperm(h * w, generator=gen)[:500]
+    coords = torch.stack([idx // w, idx % w], -1)
+    corners = torch.tensor([[0, 0], [h - 1, w - 1], [0, w - 1], [h - 1, 0], [h - 1, h - 1], [w - 1 if w - 1 < h else h - 1, 0]])
+    coords = torch.cat([coords, corners], 0).unsqueeze(0).repeat(V, 1, 1).to(DEV)
+    with torch.no_grad():
+        nr.fused_depth_mean = False
+        want = nr.predict_mean_for_depth_loss({'imgs': imgs, 'ray_feats': ray_feats}, coords=coords)
+        nr.fused_depth_mean = True
+        got = nr.predict_mean_for_depth_loss({'imgs': imgs, 'ray_feats': ray_feats}, coords=coords)
+        got_cl = nr.predict_mean_for_depth_loss({'imgs': imgs, 'ray_feats': ray_feats.contiguous(memory_format=torch.channels_last)}, coords=coords)
+    for k in ('depth_mean', 'depth_mean_2', 'depth_mean_fine', 'depth_mean_fine_2'):
+        assert_close(got[k].cpu(), want[k].cpu().numpy(), rtol=1e-5, atol_scale=1e-5, what=f'{k} kernel vs torch (same_size={same_size})')
+        assert torch.equal(got[k], got_cl[k])
+
+
 def test_ray_setup_kernel_matches_the_reference_formulas():
     """gn_k3_ray_setup vs coords2rays / depth2points / depth2inv_dists written with torch exactly as render_ops.py:4-52."""
     from graspnerf_b200 import ops

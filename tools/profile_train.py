@@ -12,19 +12,19 @@ def main():
     torch.manual_seed(0)
     net = name2network['grasp_nerf'](dict(NRVGN_SDF_CFG)).to(dev).train()
     step = TrainStep(net, lr=1e-4)
-    batch = [bench.make_train_data(i, dev) for i in range(2)]
+    batch = [bench.make_train_data(i, dev) for i in range(8)]
     step(batch)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     step(batch)
     torch.cuda.synchronize()
-    print(f'wall per scene: {(time.perf_counter() - t0) / 2 * 1e3:.1f} ms')
+    print(f'wall per scene: {(time.perf_counter() - t0) / 8 * 1e3:.1f} ms')
     from torch.profiler import profile, ProfilerActivity
     with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
         step(batch)
         torch.cuda.synchronize()
-    print(prof.key_averages().table(sort_by='cuda_time_total', row_limit=18, max_name_column_width=60))
-    print(prof.key_averages().table(sort_by='self_cpu_time_total', row_limit=18, max_name_column_width=60))
+    print(prof.key_averages().table(sort_by='cuda_time_total', row_limit=40, max_name_column_width=60))
+    print(prof.key_averages().table(sort_by='self_cpu_time_total', row_limit=40, max_name_column_width=60))
 
 
 if __name__ == '__main__':
