@@ -281,10 +281,11 @@ def train_leg(args, dist, dev, world, rank, barrier, max_over_ranks):
     cfg = dict(NRVGN_SDF_CFG)
     torch.manual_seed(0)
     net = name2network[cfg['network']](cfg).to(dev).train()
-    step = TrainStep(net, lr=1e-4, dist=dist)
+    step = TrainStep(net, lr=1e-4, dist=dist, graph=True)
     nb = args.train_batch
     batch = [make_train_data(rank * nb + i, dev) for i in range(nb)]
     step(batch)                                               # warm-up: cuDNN autotune, allocator pools, kernel attributes
+    step(batch)                                               # second step: captures the CUDA graph of one 8-scene group
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
@@ -293,8 +294,8 @@ def train_leg(args, dist, dev, world, rank, barrier, max_over_ranks):
     barrier()
     ms = max_over_ranks([ev0.elapsed_time(ev1)], dist, dev)[0] / args.train_steps
     return {'value': world * nb / (ms / 1e3), 'unit': 'scenes/s', 'ms_per_step': ms, 'scenes_per_gpu': nb, 'global_batch': world * nb,
-            'steps': args.train_steps, 'allreduce_bytes': step.bucket.nbytes if world > 1 else 0, 'loss': losses[-1],
-            'what': 'GraspNeRF mirror fwd+bwd, shipped config (render_rgb on, 512 rays coarse+fine, 40^3 volume) + render/depth/sdf/eikonal/vgn losses + 1 NCCL all-reduce + Adam; 6x288x512'}
+            'steps': args.train_steps, 'allreduce_bytes': step.bucket.nbytes if world > 1 else 0, 'loss': losses[-1], 'cuda_graph': step._g is not None,
+            'what': 'GraspNeRF mirror fwd+bwd, shipped config (render_rgb on, 512 rays coarse+fine, 40^3 volume) + render/depth/sdf/eikonal/vgn losses + 1 NCCL all-reduce + Adam; 6x288x512; forward+backward of each 8-scene group replayed as one CUDA graph'}
 
 
 def highres_leg(args, dist, dev, world, rank, barrier, max_over_ranks, hw, peaks):

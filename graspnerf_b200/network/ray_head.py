@@ -79,10 +79,28 @@ def neus_alpha(sdf, grad, que_dir, dists, inv_s, cos_anneal_ratio=1.0):
     return ((prev_cdf - next_cdf + 1e-5) / (prev_cdf + 1e-5)).clip(0.0, 1.0)
 
 
+class _CumprodPositive(torch.autograd.Function):
+    """torch.cumprod along the last axis for strictly positive inputs.  Same forward; the backward is the formula
+    at::cumprod_backward uses when the input has no zero, reversed_cumsum(grad * out) / x - WITHOUT its `(x == 0).any()` test,
+    which synchronises with the host on every call (and cannot be captured in a CUDA graph)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        out = torch.cumprod(x, -1)
+        ctx.save_for_backward(x, out)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        x, out = ctx.saved_tensors
+        return torch.flip(torch.cumsum(torch.flip(g * out, [-1]), -1), [-1]) / x
+
+
 def alpha_to_hit_prob(alpha):
-    """render_ops.py:72-80."""
+    """render_ops.py:72-80.  (alpha is clipped to [0,1], so every factor 1 - alpha + 1e-10 is >= 1e-10 > 0.)"""
     no_hit = torch.cat([torch.ones_like(alpha[..., :1]), 1.0 - alpha + 1e-10], -1)
-    return alpha * torch.cumprod(no_hit, -1)[..., :-1]
+    return alpha * _CumprodPositive.apply(no_hit)[..., :-1]
 
 
 def render_by_depth_autograd(nr, ref, que, que_depth, is_fine, is_train=True):

@@ -101,7 +101,11 @@ class NeuralRayRenderer(nn.Module):
             raise NotImplementedError("volume_type other than ['sdf'] is not implemented")
         dev = ref_imgs_info['imgs'].device
         # bbox3d is a python list in training (train_dataset.py) and an fp32 tensor [2,3] in inference (main.py:231)
-        bbox_min = torch.as_tensor(ref_imgs_info['bbox3d'][0], dtype=torch.float32).to(dev).reshape(1, 3)
+        bbox = ref_imgs_info['bbox3d']
+        if torch.is_tensor(bbox) and bbox.device == dev and bbox.dtype == torch.float32:
+            bbox_min = bbox.reshape(-1, 3)[0:1]               # already on the device: no pageable H2D copy (which synchronises)
+        else:
+            bbox_min = torch.as_tensor(bbox[0], dtype=torch.float32).to(dev).reshape(1, 3)
         if torch.is_grad_enabled() and (ref_imgs_info['img_feats'].requires_grad or ref_imgs_info['ray_feats'].requires_grad
                                         or any(p.requires_grad for p in self.agg_net.parameters())):
             named = {k: v for k, v in self.named_parameters() if k.startswith(('agg_net.', 'dist_decoder.'))}
@@ -337,7 +341,7 @@ class GraspNeRF(nn.Module):
 
     def select(self, out, index):                                                         # renderer.py:305-311
         qual, rot, width = out
-        bi = torch.arange(qual.shape[0])
+        bi = torch.arange(qual.shape[0], device=qual.device)       # (on the device: a host index tensor makes every gather synchronise)
         return (qual[bi, :, index[:, 0], index[:, 1], index[:, 2]].squeeze(), rot[bi, :, index[:, 0], index[:, 1], index[:, 2]],
                 width[bi, :, index[:, 0], index[:, 1], index[:, 2]].squeeze())
 

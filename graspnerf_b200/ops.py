@@ -126,6 +126,14 @@ def _cached_head_weights(sd, agg_prefix, dd_prefix, device):
     return hw
 
 
+def invalidate_weight_caches():
+    """Forget which parameter versions the cached HeadWeights were packed from: the next use re-packs.  train.TrainStep calls
+    this right before it captures a CUDA graph, so that the packing kernels are PART of the graph (a replay must pack the
+    weights the optimizer has just updated, not find the blob of the capture-time weights)."""
+    for hw in _HW_CACHE.values():
+        hw._versions = None
+
+
 def camera_matrices(poses, Ks):
     """[B,V,3,4] K@[R|t] and [B,V,3] camera centres -R^T t; 6 tiny matmuls, done with torch exactly as the reference
     does (render_ops.py:94,112) so that the fp32 values entering the kernel are the reference's."""

@@ -61,7 +61,7 @@ class GradBucket:
         the scale is 1 / (sum of the counts over the ranks), computed on the device from the reduced trailing element."""
         self.pack()
         if local_count is not None:
-            self.flat[-1] = float(local_count)
+            self.flat[-1:].fill_(float(local_count))          # (a kernel argument; `flat[-1] = x` copies from the host and synchronises)
         if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
         if local_count is not None:
@@ -139,36 +139,157 @@ def volume_losses(out, data):
     return loss
 
 
+def _static_like(x, dev):
+    """Device-resident copy of a (nested) sample: tensors / arrays / lists of numbers become device tensors that keep their
+    address from step to step (CUDA-graph inputs); ints, strings, None stay as they are."""
+    if torch.is_tensor(x):
+        return x.detach().to(dev).clone()
+    if isinstance(x, dict):
+        return {k: _static_like(v, dev) for k, v in x.items()}
+    if isinstance(x, (list, tuple)):
+        if len(x) and all(torch.is_tensor(v) or isinstance(v, dict) for v in x):
+            return [_static_like(v, dev) for v in x]
+        try:
+            return torch.as_tensor(x, dtype=torch.float32).to(dev)           # e.g. bbox3d, a list of lists in the dataset
+        except (TypeError, ValueError):
+            return x
+    return x
+
+
+def _copy_into(static, new):
+    if torch.is_tensor(static):
+        if not torch.is_tensor(new):
+            new = torch.as_tensor(new, dtype=static.dtype)
+        static.copy_(new.reshape(static.shape), non_blocking=True)
+    elif isinstance(static, dict):
+        for k in static:
+            _copy_into(static[k], new[k])
+    elif isinstance(static, list):
+        for s, n in zip(static, new):
+            _copy_into(s, n)
+
+
 class TrainStep:
     """One optimizer step over a global batch of scenes, this rank's share passed in as a list of `data` dicts."""
 
-    def __init__(self, net, lr=1e-4, dist=None, loss_fn=training_losses, encoder_chunk=8):
+    def __init__(self, net, lr=1e-4, dist=None, loss_fn=training_losses, encoder_chunk=8, graph=False):
         """encoder_chunk: the 2-D encoders of up to this many scenes run as ONE batched forward / backward (InstanceNorm is per
         image, so batching is exact): the encoders are ~60 % of the ~6 400 launches of a training scene and the step is
-        host-launch bound.  1 = scene by scene (the reference's order of operations)."""
+        host-launch bound.  1 = scene by scene (the reference's order of operations).
+        graph: capture forward + losses + backward of one group of `encoder_chunk` scenes in ONE CUDA graph (inputs staged into
+        static device buffers, gradients accumulate into the flat bucket, random draws through the graph-safe generator) and
+        replay it for every full group of a step: ~25 000 launches per group become one cudaGraphLaunch.  The step counters the
+        reference keeps on the host (cos_anneal_ratio, fix_s: aggregate_net.py:135-137) are frozen in a captured graph, so graph
+        mode is refused (eager step instead) while the configuration makes values depend on them (cos_anneal_end_iter != 0;
+        before the variance of SingleVarianceNetwork has started to train, neus.py:16-19)."""
         self.net, self.dist, self.loss_fn, self.encoder_chunk = net, dist, loss_fn, max(1, int(encoder_chunk))
         self.bucket = GradBucket(net.parameters())
         self.opt = torch.optim.Adam(self.bucket.params, lr=lr)
         self.world = dist.get_world_size() if (dist is not None and dist.is_initialized()) else 1
+        self.graph = bool(graph)
+        self.graph_error = None                          # why graph mode was abandoned (None: not abandoned)
+        self._g = None                                   # (signature, static group, CUDAGraph)
+        self._total = None
+        self.steps_done = 0
+
+    def _group_loss(self, group):
+        """One encoder pass for the whole group, then scene by scene through the hot path; the caller runs ONE backward."""
+        nr = self.net.nr_net
+        imgs = torch.cat([d['ref_imgs_info']['imgs'] for d in group], 0)
+        img_f, ray_f = nr.encode({'imgs': imgs}, None, True)
+        V = group[0]['ref_imgs_info']['imgs'].shape[0]
+        loss = 0.0
+        for i, data in enumerate(group):
+            d2 = dict(data)
+            d2['ref_imgs_info'] = dict(data['ref_imgs_info'], img_feats=img_f[i * V:(i + 1) * V], ray_feats=ray_f[i * V:(i + 1) * V])
+            loss = loss + self.loss_fn(self.net(d2), d2)
+        return loss
+
+    def _graph_allowed(self):
+        nr = getattr(self.net, 'nr_net', None)
+        if nr is None or self.steps_done < 1:            # the first step runs eagerly (deviation_network.variance starts to
+            return False                                  # require a gradient after the first training forward, neus.py:16-19)
+        for agg in (getattr(nr, 'agg_net', None), getattr(nr, 'fine_agg_net', None)):
+            if agg is None:
+                continue
+            if agg.cfg.get('cos_anneal_end_iter'):
+                self.graph_error = 'cos_anneal_ratio follows a host-side step counter (cos_anneal_end_iter != 0)'
+                return False
+            dn = agg.deviation_network
+            if dn.fix_s != -1 and not dn.variance.requires_grad:
+                return False                              # not yet past fix_s (neus.py:16-19): eager for now, graph later
+        return True
+
+    @staticmethod
+    def _signature(group):
+        def sig(x):
+            if torch.is_tensor(x):
+                return (tuple(x.shape), str(x.dtype))
+            if isinstance(x, dict):
+                return tuple((k, sig(v)) for k, v in sorted(x.items()))
+            if isinstance(x, (list, tuple)):
+                return tuple(sig(v) for v in x) if len(x) and (torch.is_tensor(x[0]) or isinstance(x[0], dict)) else ('list', len(x))
+            return type(x).__name__
+        return tuple(sig(d) for d in group)
+
+    def _run_group_graphed(self, group):
+        dev = self.bucket.flat.device
+        sg = self._signature(group)
+        if self._g is None or self._g[0] != sg:
+            static = []
+            for d in group:
+                sd = {k: _static_like(v, dev) for k, v in d.items() if k != 'src_imgs_info'}
+                if 'src_imgs_info' in d:                  # the dataset passes the reference views again under this key
+                    sd['src_imgs_info'] = sd['ref_imgs_info'] if d['src_imgs_info'] is d['ref_imgs_info'] else _static_like(d['src_imgs_info'], dev)
+                static.append(sd)
+            keep = self.bucket.flat.clone()
+            keep_total = self._total.clone()
+            try:
+                side = torch.cuda.Stream(dev)
+                side.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(side):             # warm-up off the capture: allocator pools, cuDNN plans, kernel attributes
+                    for _ in range(2):
+                        self._group_loss(static).backward()
+                torch.cuda.current_stream(dev).wait_stream(side)
+                from . import ops
+                ops.invalidate_weight_caches()            # the weight packing must be captured too (replays follow optimizer steps)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    loss = self._group_loss(static)
+                    loss.backward()
+                    self._total += loss.detach()
+            finally:
+                torch.cuda.synchronize(dev)
+                self.bucket.flat.copy_(keep)              # the warm-up passes accumulated into the bucket: restore it
+                self._total.copy_(keep_total)
+            self._g = (sg, static, g)
+        _, static, g = self._g
+        for s, d in zip(static, group):
+            for k in s:
+                if k == 'src_imgs_info' and s[k] is s.get('ref_imgs_info'):
+                    continue
+                _copy_into(s[k], d[k])
+        g.replay()
 
     def __call__(self, local_batch):
         self.bucket.zero()
-        total = torch.zeros((), device=self.bucket.flat.device)
+        dev = self.bucket.flat.device
+        if self._total is None:
+            self._total = torch.zeros((), device=dev)
+        self._total.zero_()
+        total = self._total
         nr = getattr(self.net, 'nr_net', None)
         chunk = self.encoder_chunk if nr is not None else 1
+        use_graph = self.graph and self.graph_error is None and dev.type == 'cuda' and self._graph_allowed()
         for c0 in range(0, len(local_batch), chunk):
             group = local_batch[c0:c0 + chunk]
             same = len({tuple(d['ref_imgs_info']['imgs'].shape) for d in group}) == 1 if chunk > 1 else False
             if chunk > 1 and len(group) > 1 and same:
-                # one encoder pass for the whole group, then scene by scene through the hot path; ONE backward for the group
-                imgs = torch.cat([d['ref_imgs_info']['imgs'] for d in group], 0)
-                img_f, ray_f = nr.encode({'imgs': imgs}, None, True)
-                V = group[0]['ref_imgs_info']['imgs'].shape[0]
-                loss = 0.0
-                for i, data in enumerate(group):
-                    d2 = dict(data)
-                    d2['ref_imgs_info'] = dict(data['ref_imgs_info'], img_feats=img_f[i * V:(i + 1) * V], ray_feats=ray_f[i * V:(i + 1) * V])
-                    loss = loss + self.loss_fn(self.net(d2), d2)
+                if use_graph and len(group) == chunk:
+                    # (a failed capture is raised, not papered over: it leaves the CUDA generator in capture state)
+                    self._run_group_graphed(group)
+                    continue
+                loss = self._group_loss(group)
                 loss.backward()
                 total += loss.detach()
             else:
@@ -178,4 +299,5 @@ class TrainStep:
                     total += loss.detach()              # no host synchronisation inside the scene loop
         self.bucket.allreduce(self.dist, local_count=len(local_batch))      # mean over the GLOBAL number of scenes (shards may be uneven)
         self.opt.step()
+        self.steps_done += 1
         return float(total) / max(len(local_batch), 1)

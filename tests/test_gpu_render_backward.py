@@ -143,3 +143,56 @@ def test_trainstep_batched_encoders_equal_scene_by_scene():
         worst = max(worst, rel)
         assert rel < 1e-2, (k, rel)          # fp32 atomics in gn_k1_backward accumulate in a different order every run (measured worst 3e-3)
     print(f'batched vs scene-by-scene gradients: worst rel-L2 {worst:.2e}')
+
+
+def _small_train_batch(dev, seeds, with_rays):
+    batch = []
+    for s in seeds:
+        scene = make_scene(seed=50 + s, num_views=4, h=96, w=160, radius=0.45)
+        ref = {k: (torch.from_numpy(v).to(dev) if isinstance(v, np.ndarray) else v) for k, v in scene.items() if k not in ('img_feats', 'ray_feats')}
+        ref['sdf_gt'] = torch.from_numpy(np.random.default_rng(s).uniform(-1, 1, (40, 40, 40)).astype(np.float32)).to(dev)
+        q = {k: torch.from_numpy(v).to(dev) for k, v in make_query(scene, 24, 7 + s).items() if isinstance(v, np.ndarray)}
+        batch.append({'step': 0, 'full_vol': True, 'ref_imgs_info': ref, 'que_imgs_info': q, 'src_imgs_info': ref})
+    return batch
+
+
+@pytest.mark.parametrize('render_rgb', [False, True])
+def test_trainstep_cuda_graph_mode(render_rgb):
+    """TrainStep(graph=True): forward + losses + backward of a group of scenes replayed as ONE CUDA graph on inputs staged into
+    static buffers.  render_rgb off (no random draws in the forward): the graphed step must reproduce the eager step on NEW
+    inputs - losses, and at frozen weights the whole gradient bucket - to the noise of the reverse kernels' atomics.  render_rgb on (shipped
+    configuration: random fine-sampling offsets and depth-loss pixels come from the graph-safe generator, so the draws differ
+    from the eager run): same losses to the sampling noise."""
+    import copy
+    from graspnerf_b200.train import TrainStep
+    dev = torch.device('cuda:0')
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    A, B = _small_train_batch(dev, (0, 1), render_rgb), _small_train_batch(dev, (2, 3), render_rgb)
+    net_e = _mirror_with_golden_weights(dev).train()
+    net_e.nr_net.cfg['render_rgb'] = render_rgb
+    if not render_rgb:
+        net_e.nr_net.cfg['use_depth_loss'] = False
+        for agg in (net_e.nr_net.agg_net, net_e.nr_net.fine_agg_net):          # no RGB head: nothing flips the variance's flag
+            agg.deviation_network.fix_s = -1
+    net_g = copy.deepcopy(net_e)
+    eager, graphed = TrainStep(net_e, lr=1e-3, encoder_chunk=2), TrainStep(net_g, lr=1e-3, encoder_chunk=2, graph=True)
+    losses = {}
+    for name, step in (('eager', eager), ('graph', graphed)):
+        torch.manual_seed(3)
+        losses[name] = [step(A), step(B), step(A), step(B)]
+    assert graphed.graph_error is None and graphed._g is not None, graphed.graph_error        # the graph was captured and used
+    assert all(np.isfinite(losses['graph']))
+    tol = 2e-2 if render_rgb else 1e-4
+    for le, lg in zip(losses['eager'], losses['graph']):
+        assert abs(le - lg) <= tol * max(abs(le), 1e-3), (losses, render_rgb)
+    if not render_rgb:
+        # gradients of a REPLAY on inputs the graph was not captured with, against the eager step, at identical weights (lr 0)
+        ne, ng = copy.deepcopy(net_e), copy.deepcopy(net_e)
+        se, sg = TrainStep(ne, lr=0.0, encoder_chunk=2), TrainStep(ng, lr=0.0, encoder_chunk=2, graph=True)
+        for step in (se, sg):
+            step(A); step(B); step(A)                                   # graph mode: eager, capture on B, replay on A
+        assert sg._g is not None
+        a, b = sg.bucket.flat[:-1].double(), se.bucket.flat[:-1].double()
+        rel = float((a - b).norm() / b.norm())
+        assert rel < 2e-3, rel                                          # fp32 atomics of the reverse kernels (order differs run to run)
