@@ -271,13 +271,18 @@ def make_train_data(seed, dev):
     return {'step': 0, 'ref_imgs_info': ref, 'que_imgs_info': que, 'src_imgs_info': ref, 'grasp_info': grasp}
 
 
-def train_leg(args, dist, dev, world, rank, barrier, max_over_ranks):
+def train_leg(args, dist, dev, world, rank, barrier, max_over_ranks, tf32=False):
     """configs[2]/[3]-style optimizer step (an extra key, not the headline metric): `train_batch` scenes per GPU, GraspNeRF
     mirror forward with the SHIPPED configuration (render_rgb on: 512 rays x 40 coarse + 40 fine samples, 40^3 volume,
     depth-mean head, cuDNN encoders, VGN), the four losses of nrvgn_sdf.yaml (render, depth, sdf + eikonal, vgn), backward
-    through the hand-written reverse kernels, ONE all-reduce of the flat gradient bucket over the ranks, Adam."""
+    through the hand-written reverse kernels, ONE all-reduce of the flat gradient bucket over the ranks, Adam.
+    tf32: what cuDNN / cuBLAS may do in the torch-side encoders, VGN and per-ray head.  False (the reported value): plain fp32,
+    like the CPU reference arm; True: PyTorch's default for convolutions on this GPU (what the reference itself would run
+    with on an Ampere+ GPU), reported beside it as `tf32_convs`."""
     from graspnerf_b200.network import name2network, NRVGN_SDF_CFG
     from graspnerf_b200.train import TrainStep
+    torch.backends.cudnn.allow_tf32 = bool(tf32)
+    torch.backends.cuda.matmul.allow_tf32 = False
     cfg = dict(NRVGN_SDF_CFG)
     torch.manual_seed(0)
     net = name2network[cfg['network']](cfg).to(dev).train()
@@ -294,7 +299,7 @@ def train_leg(args, dist, dev, world, rank, barrier, max_over_ranks):
     barrier()
     ms = max_over_ranks([ev0.elapsed_time(ev1)], dist, dev)[0] / args.train_steps
     return {'value': world * nb / (ms / 1e3), 'unit': 'scenes/s', 'ms_per_step': ms, 'scenes_per_gpu': nb, 'global_batch': world * nb,
-            'steps': args.train_steps, 'allreduce_bytes': step.bucket.nbytes if world > 1 else 0, 'loss': losses[-1], 'cuda_graph': step._g is not None,
+            'steps': args.train_steps, 'allreduce_bytes': step.bucket.nbytes if world > 1 else 0, 'loss': losses[-1], 'cuda_graph': step._g is not None, 'cudnn_tf32': bool(tf32),
             'what': 'GraspNeRF mirror fwd+bwd, shipped config (render_rgb on, 512 rays coarse+fine, 40^3 volume) + render/depth/sdf/eikonal/vgn losses + 1 NCCL all-reduce + Adam; 6x288x512; forward+backward of each 8-scene group replayed as one CUDA graph'}
 
 
@@ -526,6 +531,11 @@ def main():
     highres = guarded(highres_leg, args, dist, dev, world, rank, barrier, max_over_ranks, hw, peaks) if args.highres_scenes > 0 else None
     torch.cuda.empty_cache()
     train = guarded(train_leg, args, dist, dev, world, rank, barrier, max_over_ranks) if args.train_batch > 0 else None
+    if train is not None and 'error' not in train:
+        torch.cuda.empty_cache()
+        t32 = guarded(train_leg, args, dist, dev, world, rank, barrier, max_over_ranks, True)
+        train['tf32_convs'] = {k: t32.get(k) for k in ('value', 'ms_per_step', 'loss', 'error') if k in t32}
+        torch.backends.cudnn.allow_tf32 = False
     if rank == 0:
         traffic = load_traffic()
         value = world * K / (total_ms / 1e3)
@@ -558,7 +568,7 @@ def main():
             'kernel_us': {'k1': kt[0] * 1e3, 'k2a': kt[1] * 1e3, 'k2b': kt[2] * 1e3},
             'e2e': {'value': world * KE / (e2e_ms / 1e3), 'unit': 'volumes/s', 'h2d_bytes_per_step': h2d_bytes,
                     'd2h_bytes_per_step': d2h_bytes, 'steps': KE,
-                    'api': 'graspnerf_b200.engine.VolumeEngine.submit (pinned host buffers: uint8 RGBA images + fp32 fused feature maps in, fp32 volume out)'},
+                    'api': 'graspnerf_b200.engine.VolumeEngine.submit (pinned host buffers: uint8 RGB images + fp32 fused feature maps in, fp32 volume out)'},
             'gpu_launches': 3 * K, 'launch_mode': 'CUDA graph of the 3 kernels per scene (cudaGraphLaunch per step); kernel_us: each kernel launched 16x back to back over 8 scenes between one event pair (event clock ticks at 4.096 us)',
             'clocks': sampler.summary(),
             'checksum': checksum,

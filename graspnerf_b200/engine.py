@@ -13,8 +13,9 @@ compute stream, ordered by CUDA events; no host synchronisation inside the loop 
 ForwardEngine gives every slot a compute stream of its own: a scene's encoders are a dependent chain of ~250 launches on
 6 small images that leaves most SMs idle, so the graphs of the scenes in flight overlap on the GPU.
 
-Images may be uint8 ([V,H,W,3] as cv2 / imread give them, or [V,H,W,4]): they cross PCIe as bytes and K1 divides by 255 in
-its gather exactly like color_map_forward (main.py:170); fp32 [V,3,H,W] images are accepted as the reference holds them.
+Images may be uint8 ([V,H,W,3] as cv2 / imread give them, or [V,H,W,4]): they cross PCIe as bytes (3 per pixel for RGB; the
+slot's graph expands them to 4-byte RGBA texels on the device) and K1 divides by 255 in its gather exactly like
+color_map_forward (main.py:170); fp32 [V,3,H,W] images are accepted as the reference holds them.
 
 Result lifetime: a result handed back by submit()/collect()/drain() is a pinned buffer owned by the engine.  Each slot
 alternates between TWO output buffers, so a returned buffer stays untouched until the SAME slot has been submitted to twice
@@ -76,8 +77,8 @@ class HostScene:
     def __init__(self, imgs, img_feats_cl=None, ray_feats_cl=None, poses=None, Ks=None, depth_range=None, bbox_min=None):
         imgs = torch.as_tensor(imgs)
         if imgs.dtype == torch.uint8:
-            if imgs.shape[-1] == 3:                       # pad to RGBA once on the host: one 4-byte texel per bilinear tap
-                imgs = torch.cat([imgs, torch.zeros(imgs.shape[:-1] + (1,), dtype=torch.uint8)], -1)
+            # RGB bytes cross PCIe as they are (3 bytes per pixel); the slot expands them to the 4-byte RGBA texels K1 gathers
+            # (one bilinear tap = one aligned 32-bit load) with one strided copy on the device
             self.imgs = _pin(imgs)
         else:
             self.imgs = _pin(imgs, torch.float32)
@@ -100,7 +101,9 @@ class _Slot:
     def __init__(self, hs, out_shapes, device):
         def dev(t):
             return torch.empty(t.shape, dtype=t.dtype, device=device)
-        self.imgs = dev(hs.imgs)[None]
+        self.imgs_in = dev(hs.imgs)[None]                 # as shipped: uint8 RGB / RGBA or fp32 [V,3,H,W]
+        self.rgb = hs.imgs.dtype == torch.uint8 and hs.imgs.shape[-1] == 3
+        self.imgs = torch.zeros(self.imgs_in.shape[:-1] + (4,), dtype=torch.uint8, device=device) if self.rgb else self.imgs_in
         self.feats = dev(hs.feats)[None] if hs.feats is not None else None
         self.poses, self.Ks, self.depth_range = dev(hs.poses)[None], dev(hs.Ks)[None], dev(hs.depth_range)[None]
         self.bbox_min = dev(hs.bbox_min).reshape(1, 3)
@@ -114,6 +117,11 @@ class _Slot:
         self.busy = False
         self.tag = None
         self.last = None
+
+    def expand_rgb(self):
+        """uint8 RGB as shipped -> the RGBA texel buffer (alpha stays 0); part of the slot's CUDA graph."""
+        if self.rgb:
+            self.imgs[..., :3].copy_(self.imgs_in)
 
 
 class _Engine:
@@ -143,7 +151,7 @@ class _Engine:
         s = self.slots[i]
         finished = self.collect(i) if s.busy else None
         with torch.cuda.stream(self.copy_stream):
-            for dst, src in ((s.imgs, hs.imgs), (s.feats, hs.feats), (s.poses, hs.poses), (s.Ks, hs.Ks), (s.depth_range, hs.depth_range)):
+            for dst, src in ((s.imgs_in, hs.imgs), (s.feats, hs.feats), (s.poses, hs.poses), (s.Ks, hs.Ks), (s.depth_range, hs.depth_range)):
                 if dst is not None:
                     dst[0].copy_(src, non_blocking=True)
             s.bbox_min.copy_(hs.bbox_min.reshape(1, 3), non_blocking=True)
@@ -188,6 +196,7 @@ class VolumeEngine(_Engine):
     def _compute(self, s):
         if s.graph is None:                   # first use of the slot: capture (layout prep + K1 + K2a + K2b) once
             def prologue(s=s):
+                s.expand_rgb()
                 return ops.Scene(s.imgs, None, None, s.poses, s.Ks, s.depth_range, feats_fused=s.feats)
             s.graph = ops.VolumeGraph(None, self.hw, s.bbox_min, self.R, self.vs, prologue=prologue)
         return [s.graph.replay()]
@@ -219,6 +228,7 @@ class ForwardEngine(_Engine):
 
     def _body(self, s):
         nr = self.net.nr_net
+        s.expand_rgb()
         imgs = (s.imgs[0, ..., :3].permute(0, 3, 1, 2).to(torch.float32) / 255.0).contiguous()     # color_map_forward + transpose (main.py:192)
         ref = {'imgs': imgs, 'imgs_u8': s.imgs, 'poses': s.poses[0], 'Ks': s.Ks[0], 'depth_range': s.depth_range[0],
                'bbox3d': s.bbox_min.reshape(1, 3)}
