@@ -138,15 +138,23 @@ gn_k7_conv_kernel(const GnConvParams p)
     float* op = p.out + (size_t)split * ((size_t)p.Nimg * p.Cout * p.Ho * p.Wo) + ((size_t)img * p.Cout * p.Ho + oy) * p.Wo + ox;
     const size_t cstride = (size_t)p.Ho * p.Wo;
     const bool add_bias = p.bias != nullptr && split == 0;
+    const bool full_n = p.Cout == N;                       // no padded output channels: no per-element channel test
 #pragma unroll
     for (int c0 = 16 * q; c0 < N; c0 += 64) {
         float y[16];
         tm_ld<16>(lane_addr + c0, y);
-        if (live) {
+        if (add_bias) {                                    // CTA-uniform branch; the bias has Cout entries (not Npad): the tail is guarded
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const int co = c0 + i;
-                if (co < p.Cout) op[(size_t)co * cstride] = y[i] + (add_bias ? __ldg(p.bias + co) : 0.f);
+            for (int i = 0; i < 16; ++i) if (full_n || c0 + i < p.Cout) y[i] += __ldg(p.bias + c0 + i);
+        }
+        if (live) {
+            float* o = op + (size_t)c0 * cstride;
+            if (full_n) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) { *o = y[i]; o += cstride; }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) { if (c0 + i < p.Cout) *o = y[i]; o += cstride; }
             }
         }
     }
