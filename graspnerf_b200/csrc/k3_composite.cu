@@ -280,6 +280,24 @@ gn_k3_depth_mean_kernel(const GnDepthMeanParams p)
     const bool xin = x1 < p.fw, yin = y1 < p.fh;               // (x0, y0) is always inside after the border clip
     const float* f = p.feats + (long long)v * p.stride_v;
     float x[32];
+    if (p.stride_c == 1 && (p.stride_x & 3) == 0 && (p.stride_y & 3) == 0 && (p.stride_v & 3) == 0 && (reinterpret_cast<uintptr_t>(p.feats) & 15) == 0) {
+        // channels-last map (the fused K1 feature buffer): a tap's 32 channels are one 128-byte run -> 8 float4 loads per tap
+        const float4* t00 = reinterpret_cast<const float4*>(f + (long long)y0 * p.stride_y + (long long)x0 * p.stride_x);
+        const float4* t01 = reinterpret_cast<const float4*>(f + (long long)y0 * p.stride_y + (long long)(xin ? x1 : x0) * p.stride_x);
+        const float4* t10 = reinterpret_cast<const float4*>(f + (long long)(yin ? y1 : y0) * p.stride_y + (long long)x0 * p.stride_x);
+        const float4* t11 = reinterpret_cast<const float4*>(f + (long long)(yin ? y1 : y0) * p.stride_y + (long long)(xin ? x1 : x0) * p.stride_x);
+        const float w01 = xin ? wne : 0.f, w10 = yin ? wsw : 0.f, w11 = (xin && yin) ? wse : 0.f;
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) {
+            const float4 a = __ldg(t00 + c4), b = __ldg(t01 + c4), c = __ldg(t10 + c4), d = __ldg(t11 + c4);
+            // same order of operations as the scalar path: a*wnw (+ b*wne) (+ c*wsw) (+ d*wse); a skipped tap has weight 0 there
+            float r0 = a.x * wnw, r1 = a.y * wnw, r2 = a.z * wnw, r3 = a.w * wnw;
+            if (xin) { r0 += b.x * w01; r1 += b.y * w01; r2 += b.z * w01; r3 += b.w * w01; }
+            if (yin) { r0 += c.x * w10; r1 += c.y * w10; r2 += c.z * w10; r3 += c.w * w10; }
+            if (xin && yin) { r0 += d.x * w11; r1 += d.y * w11; r2 += d.z * w11; r3 += d.w * w11; }
+            x[4 * c4] = r0; x[4 * c4 + 1] = r1; x[4 * c4 + 2] = r2; x[4 * c4 + 3] = r3;
+        }
+    } else
 #pragma unroll
     for (int c = 0; c < 32; ++c) {
         const float* fc = f + (long long)c * p.stride_c;

@@ -17,9 +17,19 @@
 #include "../../include/graspnerf_b200.h"
 
 #define K5_THREADS 128
+#ifndef K5_SPLIT_D3
+#define K5_SPLIT_D3 1          // lanes per output of the 20^3 -> 40^3 decoder layer / of the heads (A/B knobs, see KSPLIT below)
+#endif
+#ifndef K5_SPLIT_HEADS
+#define K5_SPLIT_HEADS 1
+#endif
 
 // ACT: 0 none, 1 ReLU, 2 VGN heads (channel 0 sigmoid, 1..4 L2-normalised, 5 identity)
-template <int CIN, int COUT_T, int KS, int STRIDE, bool FOLD, int ACT>
+// KSPLIT: the input channels of one output are split over KSPLIT ADJACENT LANES (each runs CIN/KSPLIT channels, the partial sums
+// meet in xor-shuffles, always in the same order).  The coarse layers have 125 / 1 000 output cells and a reduction of 864 / 1 728
+// terms per output: with one thread per output that is a serial chain of ~1 700 dependent load+FMA steps on a handful of warps
+// (45-65 us per layer, r02z launch list); split 8 ways the chain is ~200 steps and the layer has 8x the threads.
+template <int CIN, int COUT_T, int KS, int STRIDE, bool FOLD, int ACT, int KSPLIT>
 __global__ void __launch_bounds__(K5_THREADS)
 gn_k5_conv_kernel(const float* __restrict__ in, const float* __restrict__ wgt, const float* __restrict__ bias, float* __restrict__ out,
                   int Din, int Dout, int cout_total)
@@ -43,17 +53,23 @@ gn_k5_conv_kernel(const float* __restrict__ in, const float* __restrict__ wgt, c
     }
     __syncthreads();
     const int Dc = FOLD ? Din : Dout;                                // grid of "cells" the threads enumerate
-    const int cell = blockIdx.x * K5_THREADS + threadIdx.x;
-    if (cell >= Dc * Dc * Dc) return;
+    const int gt = blockIdx.x * K5_THREADS + threadIdx.x;
+    const int ks = gt % KSPLIT;                                      // this lane's slice of the input channels
+    const int ncell = Dc * Dc * Dc;
+    // lanes past the last cell still take part in the shuffles (KSPLIT > 1): they compute on the last cell and do not store
+    const bool live = gt / KSPLIT < ncell;
+    if (KSPLIT == 1 && !live) return;
+    const int cell = live ? gt / KSPLIT : ncell - 1;
     const int cz = cell % Dc, cy = (cell / Dc) % Dc, cx = cell / (Dc * Dc);
     // first input coordinate of the window
     const int bx = (FOLD ? cx : cx * STRIDE) - PAD, by = (FOLD ? cy : cy * STRIDE) - PAD, bz = (FOLD ? cz : cz * STRIDE) - PAD;
     float acc[COUT_T];
 #pragma unroll
-    for (int c = 0; c < COUT_T; ++c) acc[c] = __ldg(bias + cblk * COUT_T + c);
+    for (int c = 0; c < COUT_T; ++c) acc[c] = ks == 0 ? __ldg(bias + cblk * COUT_T + c) : 0.f;
     const size_t plane = (size_t)Din * Din * Din;
+    static_assert(CIN % KSPLIT == 0 && (KSPLIT & (KSPLIT - 1)) == 0 && KSPLIT <= 32, "KSPLIT: power of two dividing CIN");
 #pragma unroll 1
-    for (int ci = 0; ci < CIN; ++ci) {
+    for (int ci = ks * (CIN / KSPLIT); ci < (ks + 1) * (CIN / KSPLIT); ++ci) {
         const float* ip = in + (size_t)ci * plane;
         const float* wp = s_w + (size_t)ci * TAPS * COUT_T;
 #pragma unroll 1
@@ -85,6 +101,14 @@ gn_k5_conv_kernel(const float* __restrict__ in, const float* __restrict__ wgt, c
             }
         }
     }
+    if (KSPLIT > 1) {
+#pragma unroll
+        for (int o = 1; o < KSPLIT; o <<= 1) {
+#pragma unroll
+            for (int c = 0; c < COUT_T; ++c) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+        }
+        if (ks != 0 || !live) return;
+    }
     // output voxel
     int ox = cx, oy = cy, oz = cz;
     if (FOLD) { ox = 2 * cx + ((cls >> 2) & 1); oy = 2 * cy + ((cls >> 1) & 1); oz = 2 * cz + (cls & 1); }
@@ -107,19 +131,19 @@ gn_k5_conv_kernel(const float* __restrict__ in, const float* __restrict__ wgt, c
     }
 }
 
-template <int CIN, int COUT_T, int KS, int STRIDE, bool FOLD, int ACT>
+template <int CIN, int COUT_T, int KS, int STRIDE, bool FOLD, int ACT, int KSPLIT = 1>
 static cudaError_t k5_launch(const float* in, const float* w, const float* b, float* out, int Din, int Dout, int cout_total,
                              cudaStream_t st)
 {
     constexpr int TAPS = FOLD ? 27 : KS * KS * KS;
     const size_t smem = (size_t)CIN * TAPS * COUT_T * sizeof(float);
     static size_t cache[16] = {0};
-    cudaError_t e = gn_ensure_smem(gn_k5_conv_kernel<CIN, COUT_T, KS, STRIDE, FOLD, ACT>, smem, cache);
+    cudaError_t e = gn_ensure_smem(gn_k5_conv_kernel<CIN, COUT_T, KS, STRIDE, FOLD, ACT, KSPLIT>, smem, cache);
     if (e != cudaSuccess) return e;
     const int Dc = FOLD ? Din : Dout;
     const int cells = Dc * Dc * Dc;
-    dim3 grid((cells + K5_THREADS - 1) / K5_THREADS, FOLD ? 8 : 1, (cout_total + COUT_T - 1) / COUT_T);
-    gn_k5_conv_kernel<CIN, COUT_T, KS, STRIDE, FOLD, ACT><<<grid, K5_THREADS, smem, st>>>(in, w, b, out, Din, Dout, cout_total);
+    dim3 grid((cells * KSPLIT + K5_THREADS - 1) / K5_THREADS, FOLD ? 8 : 1, (cout_total + COUT_T - 1) / COUT_T);
+    gn_k5_conv_kernel<CIN, COUT_T, KS, STRIDE, FOLD, ACT, KSPLIT><<<grid, K5_THREADS, smem, st>>>(in, w, b, out, Din, Dout, cout_total);
     return cudaGetLastError();
 }
 
@@ -171,12 +195,12 @@ extern "C" int gn_vgn_forward(const GnVgnParams* hp, void* stream)
         float* d3 = ws;
         float* out = p.out + (size_t)s * p.out_scene_stride;
         e = k5_launch<1, 16, 5, 2, false, 1>(vol, W + wo[0], W + bo[0], e1, R, a, 16, st);                 if (e) break;   // networks.py:66-67
-        e = k5_launch<16, 4, 3, 2, false, 1>(e1, W + wo[1], W + bo[1], e2, a, b, 32, st);                  if (e) break;   // 69-70
-        e = k5_launch<32, 1, 3, 2, false, 1>(e2, W + wo[2], W + bo[2], e3, b, c, 64, st);                  if (e) break;   // 72-73
-        e = k5_launch<64, 1, 3, 1, false, 1>(e3, W + wo[3], W + bo[3], d1, c, c, 64, st);                  if (e) break;   // 85-86
-        e = k5_launch<64, 1, 3, 1, true, 1>(d1, W + wo[4], W + bo[4], d2, c, b, 32, st);                   if (e) break;   // 88-90 (upsample folded)
-        e = k5_launch<32, 4, 5, 1, true, 1>(d2, W + wo[5], W + bo[5], d3, b, a, 16, st);                   if (e) break;   // 92-94
-        e = k5_launch<16, 8, 5, 1, true, 2>(d3, W + wo[6], W + bo[6], out, a, R, 6, st);                                   // 96 + 47-53
+        e = k5_launch<16, 4, 3, 2, false, 1, 4>(e1, W + wo[1], W + bo[1], e2, a, b, 32, st);               if (e) break;   // 69-70
+        e = k5_launch<32, 1, 3, 2, false, 1, 8>(e2, W + wo[2], W + bo[2], e3, b, c, 64, st);               if (e) break;   // 72-73
+        e = k5_launch<64, 1, 3, 1, false, 1, 8>(e3, W + wo[3], W + bo[3], d1, c, c, 64, st);               if (e) break;   // 85-86
+        e = k5_launch<64, 1, 3, 1, true, 1, 8>(d1, W + wo[4], W + bo[4], d2, c, b, 32, st);                if (e) break;   // 88-90 (upsample folded)
+        e = k5_launch<32, 4, 5, 1, true, 1, K5_SPLIT_D3>(d2, W + wo[5], W + bo[5], d3, b, a, 16, st);      if (e) break;   // 92-94
+        e = k5_launch<16, 8, 5, 1, true, 2, K5_SPLIT_HEADS>(d3, W + wo[6], W + bo[6], out, a, R, 6, st);                   // 96 + 47-53
     }
     return (int)e;
 }

@@ -104,7 +104,9 @@ gn_k6_norm_act_pad_kernel(const GnNormActPadParams p)
     const int H = p.H, W = p.W, hw = H * W;
     const int xs = W + 2 * p.x_pad;                      // row stride of the (possibly padded) input
     const float* x = p.x + (size_t)plane * (size_t)(H + 2 * p.x_pad) * xs + (size_t)p.x_pad * xs + p.x_pad;
-    const int r0 = (int)((long long)H * rank / CS), r1 = (int)((long long)H * (rank + 1) / CS);     // this CTA's rows for the statistics
+    // this CTA's rows for the statistics (32-bit arithmetic: H * CS < 2^31; a 64-bit division costs ~100 instructions and these
+    // kernels run 2-40 elements per thread)
+    const int r0 = CS == 1 ? 0 : (H * rank) / CS, r1 = CS == 1 ? H : (H * (rank + 1)) / CS;
     float g = 1.f, b = 0.f;
     const bool cached = p.gamma && (r1 - r0) * W <= K6_CACHE_FLOATS;
     if (p.gamma) {
@@ -127,7 +129,7 @@ gn_k6_norm_act_pad_kernel(const GnNormActPadParams p)
     const int P = p.pad, Hp = H + 2 * P, Wp = W + 2 * P;
     float* op = p.out_padded ? p.out_padded + (size_t)plane * Hp * Wp : nullptr;
     float* ou = p.out_unpadded ? p.out_unpadded + (size_t)plane * hw : nullptr;
-    const int h0 = (int)((long long)Hp * rank / CS), h1 = (int)((long long)Hp * (rank + 1) / CS);     // this CTA's padded output rows
+    const int h0 = CS == 1 ? 0 : (Hp * rank) / CS, h1 = CS == 1 ? Hp : (Hp * (rank + 1)) / CS;        // this CTA's padded output rows
     for (int hp = h0 + (int)(threadIdx.x >> 5); hp < h1; hp += K6_THREADS / 32) {
         const int h = k6_reflect(hp - P, H);
         const bool hin = hp >= P && hp < P + H;
@@ -153,17 +155,23 @@ gn_k6_pad_only_kernel(const GnNormActPadParams p)
     const int H = p.H, W = p.W, P = p.pad, Hp = H + 2 * P, Wp = W + 2 * P;
     const int xs = W + 2 * p.x_pad, rs = W + 2 * p.res_pad;
     const size_t xplane = (size_t)(H + 2 * p.x_pad) * xs, rplane = (size_t)(H + 2 * p.res_pad) * rs;
-    const long long total = (long long)p.N * p.C * Hp * Wp;
-    for (long long i = (long long)blockIdx.x * K6_THREADS + threadIdx.x; i < total; i += (long long)gridDim.x * K6_THREADS) {
-        const int wp = (int)(i % Wp), hp = (int)((i / Wp) % Hp);
-        const long long plane = i / ((long long)Wp * Hp);
-        const int h = k6_reflect(hp - P, H), w = k6_reflect(wp - P, W);
-        float v = p.x[plane * xplane + (size_t)(h + p.x_pad) * xs + w + p.x_pad];
-        if (p.res) v += p.res[plane * rplane + (size_t)(h + p.res_pad) * rs + w + p.res_pad];
-        if (p.act == 1) v = fmaxf(v, 0.f);
-        else if (p.act == 2) v = v > 0.f ? v : expm1f(v);
-        if (p.out_padded) p.out_padded[i] = v;
-        if (p.out_unpadded && hp >= P && hp < P + H && wp >= P && wp < P + W) p.out_unpadded[plane * H * W + (size_t)(hp - P) * W + (wp - P)] = v;
+    // grid: x covers one padded plane (32-bit index, one 32-bit division per element), y strides over the planes
+    const int per_plane = Hp * Wp, planes = p.N * p.C;
+    for (int plane = blockIdx.y; plane < planes; plane += gridDim.y) {
+        const float* xp = p.x + (size_t)plane * xplane + (size_t)p.x_pad * xs + p.x_pad;
+        const float* rp = p.res ? p.res + (size_t)plane * rplane + (size_t)p.res_pad * rs + p.res_pad : nullptr;
+        float* op = p.out_padded ? p.out_padded + (size_t)plane * per_plane : nullptr;
+        float* ou = p.out_unpadded ? p.out_unpadded + (size_t)plane * H * W : nullptr;
+        for (int i = blockIdx.x * K6_THREADS + threadIdx.x; i < per_plane; i += gridDim.x * K6_THREADS) {
+            const int hp = i / Wp, wp = i - hp * Wp;
+            const int h = k6_reflect(hp - P, H), w = k6_reflect(wp - P, W);
+            float v = xp[h * xs + w];
+            if (rp) v += rp[h * rs + w];
+            if (p.act == 1) v = fmaxf(v, 0.f);
+            else if (p.act == 2) v = v > 0.f ? v : expm1f(v);
+            if (op) op[i] = v;
+            if (ou && hp >= P && hp < P + H && wp >= P && wp < P + W) ou[(hp - P) * W + (wp - P)] = v;
+        }
     }
 }
 
@@ -178,9 +186,11 @@ extern "C" int gn_k6_norm_act_pad(const GnNormActPadParams* hp, void* stream)
     if (p.x_splits > 1 && (!p.gamma || p.x_pad != 0)) return -4;         // partial sums only feed a normalising stage
     cudaStream_t st = (cudaStream_t)stream;
     if (!p.gamma && !p.res_gamma) {
-        const long long total = (long long)p.N * p.C * (p.H + 2 * p.pad) * (p.W + 2 * p.pad);
-        const long long blocks = (total + K6_THREADS - 1) / K6_THREADS;
-        gn_k6_pad_only_kernel<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), K6_THREADS, 0, st>>>(p);
+        const long long per_plane = (long long)(p.H + 2 * p.pad) * (p.W + 2 * p.pad);
+        if (per_plane > 0x7fffffffLL) return -6;
+        const long long planes = (long long)p.N * p.C;
+        const unsigned bx = (unsigned)((per_plane + K6_THREADS - 1) / K6_THREADS < 64 ? (per_plane + K6_THREADS - 1) / K6_THREADS : 64);
+        gn_k6_pad_only_kernel<<<dim3(bx, (unsigned)(planes < 65535 ? planes : 65535), 1), K6_THREADS, 0, st>>>(p);
         return (int)cudaGetLastError();
     }
     const int planes = p.N * p.C;
@@ -207,26 +217,29 @@ __global__ void __launch_bounds__(K6_THREADS)
 gn_k6_upsample2x_pad_kernel(const float* __restrict__ x, float* __restrict__ out, int planes, int H, int W, int pad)
 {
     const int Ho = 2 * H, Wo = 2 * W, Hp = Ho + 2 * pad, Wp = Wo + 2 * pad;
-    const long long total = (long long)planes * Hp * Wp;
+    const int per_plane = Hp * Wp;
     const float sh = Ho > 1 ? (float)(H - 1) / (float)(Ho - 1) : 0.f, sw = Wo > 1 ? (float)(W - 1) / (float)(Wo - 1) : 0.f;
-    for (long long i = (long long)blockIdx.x * K6_THREADS + threadIdx.x; i < total; i += (long long)gridDim.x * K6_THREADS) {
-        const int wp = (int)(i % Wp), hp = (int)((i / Wp) % Hp);
-        const long long pl = i / ((long long)Wp * Hp);
-        const int ho = k6_reflect(hp - pad, Ho), wo = k6_reflect(wp - pad, Wo);
-        const float fh = sh * (float)ho, fw = sw * (float)wo;
-        const int h0 = (int)fh, w0 = (int)fw;
-        const int h1 = h0 + (h0 < H - 1 ? 1 : 0), w1 = w0 + (w0 < W - 1 ? 1 : 0);
-        const float lh1 = fh - (float)h0, lw1 = fw - (float)w0, lh0 = 1.f - lh1, lw0 = 1.f - lw1;
-        const float* xp = x + pl * (long long)H * W;
-        out[i] = lh0 * (lw0 * __ldg(xp + h0 * W + w0) + lw1 * __ldg(xp + h0 * W + w1)) + lh1 * (lw0 * __ldg(xp + h1 * W + w0) + lw1 * __ldg(xp + h1 * W + w1));
+    for (int pl = blockIdx.y; pl < planes; pl += gridDim.y) {                  // x: inside one padded plane (32-bit index math), y: planes
+        const float* xp = x + (size_t)pl * H * W;
+        float* op = out + (size_t)pl * per_plane;
+        for (int i = blockIdx.x * K6_THREADS + threadIdx.x; i < per_plane; i += gridDim.x * K6_THREADS) {
+            const int hp = i / Wp, wp = i - hp * Wp;
+            const int ho = k6_reflect(hp - pad, Ho), wo = k6_reflect(wp - pad, Wo);
+            const float fh = sh * (float)ho, fw = sw * (float)wo;
+            const int h0 = (int)fh, w0 = (int)fw;
+            const int h1 = h0 + (h0 < H - 1 ? 1 : 0), w1 = w0 + (w0 < W - 1 ? 1 : 0);
+            const float lh1 = fh - (float)h0, lw1 = fw - (float)w0, lh0 = 1.f - lh1, lw0 = 1.f - lw1;
+            op[i] = lh0 * (lw0 * __ldg(xp + h0 * W + w0) + lw1 * __ldg(xp + h0 * W + w1)) + lh1 * (lw0 * __ldg(xp + h1 * W + w0) + lw1 * __ldg(xp + h1 * W + w1));
+        }
     }
 }
 
 extern "C" int gn_k6_upsample2x_pad(const float* x, float* out, int planes, int H, int W, int pad, void* stream)
 {
     if (!x || !out || planes < 1 || H < 1 || W < 1 || pad < 0 || pad >= 2 * H || pad >= 2 * W) return -1;
-    const long long total = (long long)planes * (2 * H + 2 * pad) * (2 * W + 2 * pad);
-    const long long blocks = (total + K6_THREADS - 1) / K6_THREADS;
-    gn_k6_upsample2x_pad_kernel<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), K6_THREADS, 0, (cudaStream_t)stream>>>(x, out, planes, H, W, pad);
+    const long long per_plane = (long long)(2 * H + 2 * pad) * (2 * W + 2 * pad);
+    if (per_plane > 0x7fffffffLL) return -6;
+    const long long nb = (per_plane + K6_THREADS - 1) / K6_THREADS;
+    gn_k6_upsample2x_pad_kernel<<<dim3((unsigned)(nb < 64 ? nb : 64), (unsigned)(planes < 65535 ? planes : 65535), 1), K6_THREADS, 0, (cudaStream_t)stream>>>(x, out, planes, H, W, pad);
     return (int)cudaGetLastError();
 }

@@ -62,7 +62,7 @@ gn_k7_conv_kernel(const GnConvParams p)
     const bool live = gm < p.M;
     const long long gmc = live ? gm : p.M - 1;
     const int hw = p.Ho * p.Wo;
-    const int img = (int)(gmc / hw);
+    const int img = p.M <= 0x7fffffffLL ? (int)gmc / hw : (int)(gmc / hw);          // (a 64-bit division is ~100 instructions per thread)
     const int r = (int)(gmc - (long long)img * hw);
     const int oy = r / p.Wo, ox = r - oy * p.Wo;
     const float* base = p.in + ((size_t)img * p.Cin * p.Hp + (size_t)oy * p.stride) * p.Wp + (size_t)ox * p.stride;
@@ -71,7 +71,7 @@ gn_k7_conv_kernel(const GnConvParams p)
     // split-K: this CTA runs chunks [c_lo, c_hi) of the layer's k chunks and writes partial output `split`
     const int nchunk_all = p.Kpad / K7_KC;
     const int nsplit = p.ksplit > 1 ? p.ksplit : 1, split = (int)blockIdx.y;
-    const int c_lo = (int)((long long)nchunk_all * split / nsplit), c_hi = (int)((long long)nchunk_all * (split + 1) / nsplit);
+    const int c_lo = nchunk_all * split / nsplit, c_hi = nchunk_all * (split + 1) / nsplit;     // nchunk_all * 8 fits an int by far
     const int nchunk = c_hi - c_lo;
     const unsigned char* wimg = reinterpret_cast<const unsigned char*>(p.wimg) + (size_t)c_lo * (2 * N * K7_KC * 2);
     constexpr uint32_t B_BYTES = (uint32_t)(2 * N * K7_KC * 2);                          // hi + lo of one chunk

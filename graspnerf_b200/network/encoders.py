@@ -162,7 +162,7 @@ class ResUNetLight(nn.Module):                    # ops.py:150-230
         y = self._skip(x1u, self.upconv2.forward_fused(y))
         yp, _ = ops.norm_act_pad(y.contiguous(), None, None, pad=1)
         y = self.iconv2.forward_fused(yp)[1]
-        return self.out_conv(y)
+        return _conv0(y, self.out_conv)                    # 1x1 + bias (as a module call: cuDNN + its index pre-computation kernel)
 
 
 class ResidualBlock(nn.Module):                   # ops.py:43-76 (use_norm branch)
@@ -200,7 +200,8 @@ class CostVolumeInitNet(nn.Module):               # init_net.py:8-35 (no cost vo
         if use_fused(x, self):
             from .. import ops
             xp, _ = ops.norm_act_pad(x.contiguous(), None, None, pad=1)
-            return self.out_conv[2](self.out_conv[1].forward_fused(_conv0(xp, self.out_conv[0])))
+            # (the 1x1 module has padding_mode='reflect' with padding 0: nn.Conv2d would still launch a pad kernel that copies)
+            return _conv0(self.out_conv[1].forward_fused(_conv0(xp, self.out_conv[0])), self.out_conv[2])
         return self.out_conv(x)
 
 
@@ -216,7 +217,7 @@ class DefaultVisEncoder(nn.Module):               # vis_encoder.py:6-21
             from .. import ops
             xp, _ = ops.norm_act_pad(x, None, None, pad=1)
             y = self.out_conv[1].forward_fused(_conv0(xp, self.out_conv[0]))
-            return self.out_conv[3](self.out_conv[2].forward_fused(y))
+            return _conv0(self.out_conv[2].forward_fused(y), self.out_conv[3])
         return self.out_conv(x)
 
 
