@@ -18,7 +18,7 @@
 
 #define K5_THREADS 128
 #ifndef K5_SPLIT_D3
-#define K5_SPLIT_D3 1          // lanes per output of the 20^3 -> 40^3 decoder layer / of the heads (A/B knobs, see KSPLIT below)
+#define K5_SPLIT_D3 2          // lanes per output of the 20^3 -> 40^3 decoder layer / of the heads (A/B knobs, see KSPLIT below)
 #endif
 #ifndef K5_SPLIT_HEADS
 #define K5_SPLIT_HEADS 1
