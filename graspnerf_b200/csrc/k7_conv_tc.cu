@@ -18,6 +18,9 @@
 #define K7_THREADS 512                 // 4 threads per output pixel: thread (m, q) gathers k = 8q..8q+7 of every chunk (one 16-byte operand unit)
 #define K7_KC 32                       // k per chunk (two MMA k-steps of 16)
 #define K7_STAGES 3
+#ifndef K7_WPREFETCH
+#define K7_WPREFETCH 1
+#endif
 #define K7_A_BYTES (128 * K7_KC * 2)   // one half (hi or lo) of the A chunk: 8 KB
 
 __host__ __device__ constexpr size_t k7_stage_bytes(int N) { return (size_t)2 * K7_A_BYTES + (size_t)2 * N * K7_KC * 2; }
@@ -76,6 +79,19 @@ gn_k7_conv_kernel(const GnConvParams p)
     const unsigned char* wimg = reinterpret_cast<const unsigned char*>(p.wimg) + (size_t)c_lo * (2 * N * K7_KC * 2);
     constexpr uint32_t B_BYTES = (uint32_t)(2 * N * K7_KC * 2);                          // hi + lo of one chunk
 
+    // weight chunk k -> the B half of stage k % STAGES; issued ONE CHUNK AHEAD (K7_WPREFETCH) so that its L2 -> shared-memory
+    // latency is not exposed in every chunk
+    auto load_weights = [&](int k) {
+        const int s1 = k % K7_STAGES;
+        const uint32_t fb = smem_u32(&s_bar[s1]);
+        if (k >= K7_STAGES) mbar_wait(smem_u32(&s_bar[K7_STAGES + s1]), (uint32_t)((k / K7_STAGES - 1) & 1));   // MMAs of chunk k - STAGES are done
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(fb), "r"(B_BYTES) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     :: "r"(smem_u32(smem + s1 * STAGE + 2 * K7_A_BYTES)), "l"(wimg + (size_t)k * B_BYTES), "r"(B_BYTES), "r"(fb) : "memory");
+    };
+#if K7_WPREFETCH
+    if (tid == 0 && nchunk > 0) load_weights(0);
+#endif
     for (int c = 0; c < nchunk; ++c) {
         const int st = c % K7_STAGES;
         unsigned char* sA = smem + st * STAGE;                                           // A hi | A lo | B hi | B lo
@@ -83,9 +99,11 @@ gn_k7_conv_kernel(const GnConvParams p)
         const uint32_t full = smem_u32(&s_bar[st]), empty = smem_u32(&s_bar[K7_STAGES + st]);
         if (c >= K7_STAGES) mbar_wait(empty, (uint32_t)((c / K7_STAGES - 1) & 1));       // the MMAs that read this stage have completed
         if (tid == 0) {
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(full), "r"(B_BYTES) : "memory");
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         :: "r"(smem_u32(sB)), "l"(wimg + (size_t)c * B_BYTES), "r"(B_BYTES), "r"(full) : "memory");
+#if K7_WPREFETCH
+            if (c + 1 < nchunk) load_weights(c + 1);
+#else
+            load_weights(c);
+#endif
         }
         // ---- gather + split this thread's 8 k values of the chunk -> one 16-byte unit of the hi image and one of the lo image
         const int* ko = s_koff + (c_lo + c) * K7_KC;
