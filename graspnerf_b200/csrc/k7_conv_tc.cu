@@ -11,16 +11,15 @@
 // SWIZZLE_NONE layout (element (m,k) at 16-byte unit (k/8)*128 + m; layout validated by tools/tc_probe.cu, SS form).  The
 // weights are prepared once per weight update (fp16 hi / lo images per k-chunk) and arrive by cp.async.bulk.  Three MMAs per
 // product (lo*hi, hi*lo, hi*hi, fp32 accumulation in TMEM) keep fp32 accuracy.  A ring of stages decouples the gather
-// (all 512 threads: the gather's load latency is the cost of a chunk, 16 warps hide it) from the MMAs (issued by thread 0,
-// completion tracked by tcgen05.commit on the stage's mbarrier).  Epilogue: warp w reads TMEM lanes 32*(w%4).., column chunks w/4, w/4+4, ..
+// (512 threads = 16 gather warps, which signal a per-stage `ready` mbarrier) from the MMAs and the weight TMA (a 17th, issuer
+// warp; completion tracked by tcgen05.commit on the stage's `empty` mbarrier): no block-wide barrier inside the chunk loop - with
+// thread 0 issuing between two __syncthreads, 33 % of the stall samples were the other 15 warps waiting for it (r02zc capture).  Epilogue: warp w reads TMEM lanes 32*(w%4).., column chunks w/4, w/4+4, ..
 #include "k2a_tc_common.cuh"
 
-#define K7_THREADS 512                 // 4 threads per output pixel: thread (m, q) gathers k = 8q..8q+7 of every chunk (one 16-byte operand unit)
+#define K7_THREADS 512                 // gather threads, 4 per output pixel: thread (m, q) gathers k = 8q..8q+7 of every chunk (one 16-byte operand unit)
+#define K7_BLOCK (K7_THREADS + 32)     // + one issuer warp: weight TMA + tcgen05.mma + commits (lane 0); the gather warps never wait for it
 #define K7_KC 32                       // k per chunk (two MMA k-steps of 16)
 #define K7_STAGES 3
-#ifndef K7_WPREFETCH
-#define K7_WPREFETCH 1
-#endif
 #define K7_A_BYTES (128 * K7_KC * 2)   // one half (hi or lo) of the A chunk: 8 KB
 
 __host__ __device__ constexpr size_t k7_stage_bytes(int N) { return (size_t)2 * K7_A_BYTES + (size_t)2 * N * K7_KC * 2; }
@@ -35,23 +34,25 @@ __device__ __forceinline__ void k7_mma_ss(uint32_t d_tmem, uint32_t adesc_lo, ui
 }
 
 template <int N>
-__global__ void __launch_bounds__(K7_THREADS)
+__global__ void __launch_bounds__(K7_BLOCK)
 gn_k7_conv_kernel(const GnConvParams p)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
     constexpr size_t STAGE = k7_stage_bytes(N);
     int* s_koff = reinterpret_cast<int*>(smem + K7_STAGES * STAGE);                    // [Kpad]
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_koff + p.Kpad);                      // full[S] | empty[S] | done
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 2 * K7_STAGES + 1);
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_koff + p.Kpad);                      // full[S] | empty[S] | done | ready[S]
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 3 * K7_STAGES + 1);
     const int tid = threadIdx.x, warp = tid >> 5;
 
-    for (int i = tid; i < p.Kpad; i += K7_THREADS) s_koff[i] = __ldg(p.koff + i);
+    for (int i = tid; i < p.Kpad; i += K7_BLOCK) s_koff[i] = __ldg(p.koff + i);
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(s_tmem)), "r"(k7_tmem_cols(N)));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     if (tid == 0) {
         for (int s = 0; s < 2 * K7_STAGES + 1; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(&s_bar[s])), "r"(1));
+        for (int s = 0; s < K7_STAGES; ++s)              // ready[s]: one arrival per gather warp
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(&s_bar[2 * K7_STAGES + 1 + s])), "r"(K7_THREADS / 32));
         asm volatile("fence.mbarrier_init.release.cluster;");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -79,33 +80,53 @@ gn_k7_conv_kernel(const GnConvParams p)
     const unsigned char* wimg = reinterpret_cast<const unsigned char*>(p.wimg) + (size_t)c_lo * (2 * N * K7_KC * 2);
     constexpr uint32_t B_BYTES = (uint32_t)(2 * N * K7_KC * 2);                          // hi + lo of one chunk
 
-    // weight chunk k -> the B half of stage k % STAGES; issued ONE CHUNK AHEAD (K7_WPREFETCH) so that its L2 -> shared-memory
-    // latency is not exposed in every chunk
-    auto load_weights = [&](int k) {
-        const int s1 = k % K7_STAGES;
-        const uint32_t fb = smem_u32(&s_bar[s1]);
-        if (k >= K7_STAGES) mbar_wait(smem_u32(&s_bar[K7_STAGES + s1]), (uint32_t)((k / K7_STAGES - 1) & 1));   // MMAs of chunk k - STAGES are done
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(fb), "r"(B_BYTES) : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     :: "r"(smem_u32(smem + s1 * STAGE + 2 * K7_A_BYTES)), "l"(wimg + (size_t)k * B_BYTES), "r"(B_BYTES), "r"(fb) : "memory");
-    };
-#if K7_WPREFETCH
-    if (tid == 0 && nchunk > 0) load_weights(0);
-#endif
+    // ---- issuer warp: weight chunks by TMA (two chunks ahead of the MMAs), MMAs as soon as a stage's A image is ready
+    if (warp == K7_THREADS / 32) {
+        if ((tid & 31) == 0) {
+            auto load_weights = [&](int k) {              // chunk k -> the B half of stage k % STAGES (its previous MMAs must be done)
+                const int s1 = k % K7_STAGES;
+                const uint32_t fb = smem_u32(&s_bar[s1]);
+                if (k >= K7_STAGES) mbar_wait(smem_u32(&s_bar[K7_STAGES + s1]), (uint32_t)((k / K7_STAGES - 1) & 1));
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(fb), "r"(B_BYTES) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             :: "r"(smem_u32(smem + s1 * STAGE + 2 * K7_A_BYTES)), "l"(wimg + (size_t)k * B_BYTES), "r"(B_BYTES), "r"(fb) : "memory");
+            };
+            for (int k = 0; k < K7_STAGES - 1 && k < nchunk; ++k) load_weights(k);
+            for (int c = 0; c < nchunk; ++c) {
+                const int st = c % K7_STAGES;
+                if (c + K7_STAGES - 1 < nchunk) load_weights(c + K7_STAGES - 1);         // into the stage chunk c-1 has just been issued from
+                unsigned char* sA = smem + st * STAGE;                                   // A hi | A lo | B hi | B lo
+                unsigned char* sB = sA + 2 * K7_A_BYTES;
+                mbar_wait(smem_u32(&s_bar[2 * K7_STAGES + 1 + st]), (uint32_t)((c / K7_STAGES) & 1));     // the 16 gather warps have written A
+                mbar_wait(smem_u32(&s_bar[st]), (uint32_t)((c / K7_STAGES) & 1));                          // the weight chunk has landed
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t a_hi = smem_u32(sA) >> 4, a_lo = a_hi + (K7_A_BYTES >> 4);
+                const uint32_t b_hi = smem_u32(sB) >> 4, b_lo = b_hi + ((N * K7_KC * 2) >> 4);
+                constexpr uint32_t lboA = (uint32_t)((128 * 16) >> 4) << 16, lboB = (uint32_t)((N * 16) >> 4) << 16;
+#pragma unroll
+                for (int pass = 0; pass < 3; ++pass) {                                   // small terms first: lo*hi, hi*lo, hi*hi
+                    const uint32_t ao = pass == 0 ? a_lo : a_hi, bo = pass == 1 ? b_lo : b_hi;
+#pragma unroll
+                    for (int ks = 0; ks < K7_KC / 16; ++ks)
+                        k7_mma_ss(tmem, ((ao + (uint32_t)(ks * 2 * 128)) & 0x3FFF) | lboA, ((bo + (uint32_t)(ks * 2 * N)) & 0x3FFF) | lboB, idesc,
+                                  (c > 0 || pass > 0 || ks > 0) ? 1u : 0u);
+                }
+                // completion of everything issued so far -> this stage may be overwritten; after the last chunk -> accumulator ready
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(&s_bar[K7_STAGES + st])) : "memory");
+                if (c == nchunk - 1)
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(&s_bar[2 * K7_STAGES])) : "memory");
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();                                                                 // (the gather warps' final barrier, below)
+        return;
+    }
+    // ---- gather warps: chunk after chunk into the ring; they only wait for a stage's previous MMAs (empty), never for the issuer
     for (int c = 0; c < nchunk; ++c) {
         const int st = c % K7_STAGES;
-        unsigned char* sA = smem + st * STAGE;                                           // A hi | A lo | B hi | B lo
-        unsigned char* sB = sA + 2 * K7_A_BYTES;
-        const uint32_t full = smem_u32(&s_bar[st]), empty = smem_u32(&s_bar[K7_STAGES + st]);
-        if (c >= K7_STAGES) mbar_wait(empty, (uint32_t)((c / K7_STAGES - 1) & 1));       // the MMAs that read this stage have completed
-        if (tid == 0) {
-#if K7_WPREFETCH
-            if (c + 1 < nchunk) load_weights(c + 1);
-#else
-            load_weights(c);
-#endif
-        }
-        // ---- gather + split this thread's 8 k values of the chunk -> one 16-byte unit of the hi image and one of the lo image
+        unsigned char* sA = smem + st * STAGE;
+        if (c >= K7_STAGES) mbar_wait(smem_u32(&s_bar[K7_STAGES + st]), (uint32_t)((c / K7_STAGES - 1) & 1));   // the MMAs that read this stage have completed
+        // gather + split this thread's 8 k values of the chunk -> one 16-byte unit of the hi image and one of the lo image
         const int* ko = s_koff + (c_lo + c) * K7_KC;
         {
             const int g8 = q;
@@ -128,26 +149,9 @@ gn_k7_conv_kernel(const GnConvParams p)
             *dl = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");                    // generic-proxy writes -> visible to the MMA (async proxy)
-        __syncthreads();
-        if (tid == 0) {
-            mbar_wait(full, (uint32_t)((c / K7_STAGES) & 1));                            // the weight chunk has landed
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t a_hi = smem_u32(sA) >> 4, a_lo = a_hi + (K7_A_BYTES >> 4);
-            const uint32_t b_hi = smem_u32(sB) >> 4, b_lo = b_hi + ((N * K7_KC * 2) >> 4);
-            constexpr uint32_t lboA = (uint32_t)((128 * 16) >> 4) << 16, lboB = (uint32_t)((N * 16) >> 4) << 16;
-#pragma unroll
-            for (int pass = 0; pass < 3; ++pass) {                                       // small terms first: lo*hi, hi*lo, hi*hi
-                const uint32_t ao = pass == 0 ? a_lo : a_hi, bo = pass == 1 ? b_lo : b_hi;
-#pragma unroll
-                for (int ks = 0; ks < K7_KC / 16; ++ks)
-                    k7_mma_ss(tmem, ((ao + (uint32_t)(ks * 2 * 128)) & 0x3FFF) | lboA, ((bo + (uint32_t)(ks * 2 * N)) & 0x3FFF) | lboB, idesc,
-                              (c > 0 || pass > 0 || ks > 0) ? 1u : 0u);
-            }
-            // completion of everything issued so far -> this stage may be overwritten; after the last chunk -> accumulator ready
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(empty) : "memory");
-            if (c == nchunk - 1)
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(&s_bar[2 * K7_STAGES])) : "memory");
-        }
+        __syncwarp();
+        if ((tid & 31) == 0)
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(&s_bar[2 * K7_STAGES + 1 + st])) : "memory");
     }
     mbar_wait(smem_u32(&s_bar[2 * K7_STAGES]), 0u);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -184,12 +188,12 @@ gn_k7_conv_kernel(const GnConvParams p)
 template <int N>
 static cudaError_t k7_launch(const GnConvParams& p, cudaStream_t st)
 {
-    const size_t smem = K7_STAGES * k7_stage_bytes(N) + (size_t)p.Kpad * 4 + (2 * K7_STAGES + 1) * 8 + 16;
+    const size_t smem = K7_STAGES * k7_stage_bytes(N) + (size_t)p.Kpad * 4 + (3 * K7_STAGES + 1) * 8 + 16;
     static size_t cache[16] = {0};
     cudaError_t e = gn_ensure_smem(gn_k7_conv_kernel<N>, smem, cache);
     if (e != cudaSuccess) return e;
     const long long tiles = (p.M + 127) / 128;
-    gn_k7_conv_kernel<N><<<dim3((unsigned)tiles, (unsigned)(p.ksplit > 1 ? p.ksplit : 1), 1), K7_THREADS, smem, st>>>(p);
+    gn_k7_conv_kernel<N><<<dim3((unsigned)tiles, (unsigned)(p.ksplit > 1 ? p.ksplit : 1), 1), K7_BLOCK, smem, st>>>(p);
     return cudaGetLastError();
 }
 
