@@ -19,7 +19,9 @@
 #define K7_THREADS 512                 // gather threads, 4 per output pixel: thread (m, q) gathers k = 8q..8q+7 of every chunk (one 16-byte operand unit)
 #define K7_BLOCK (K7_THREADS + 32)     // + one issuer warp: weight TMA + tcgen05.mma + commits (lane 0); the gather warps never wait for it
 #define K7_KC 32                       // k per chunk (two MMA k-steps of 16)
+#ifndef K7_STAGES
 #define K7_STAGES 3
+#endif
 #define K7_A_BYTES (128 * K7_KC * 2)   // one half (hi or lo) of the A chunk: 8 KB
 
 __host__ __device__ constexpr size_t k7_stage_bytes(int N) { return (size_t)2 * K7_A_BYTES + (size_t)2 * N * K7_KC * 2; }
