@@ -110,6 +110,10 @@ def load():
     lib.gn_k2a_tc_prepare.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.gn_k6_upsample2x_pad.restype = C.c_int
     lib.gn_k6_upsample2x_pad.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    lib.gn_k6_fuse_features.restype = C.c_int
+    lib.gn_k6_fuse_features.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    lib.gn_k6_images_u8.restype = C.c_int
+    lib.gn_k6_images_u8.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
     lib.gn_vgn_layer_info.restype = C.c_int
     lib.gn_vgn_layer_info.argtypes = [C.c_int] + [C.POINTER(C.c_int)] * 7
     lib.gn_vgn_workspace_floats.argtypes = [C.c_int]

@@ -243,3 +243,59 @@ extern "C" int gn_k6_upsample2x_pad(const float* x, float* out, int planes, int 
     gn_k6_upsample2x_pad_kernel<<<dim3((unsigned)(nb < 64 ? nb : 64), (unsigned)(planes < 65535 ? planes : 65535), 1), K6_THREADS, 0, (cudaStream_t)stream>>>(x, out, planes, H, W, pad);
     return (int)cudaGetLastError();
 }
+
+// ------------------------------------------------------------------------------------------------ layout glue around the encoders
+// gn_k6_fuse_features: the encoders' two NCHW maps [P,32,h,w] -> the fused channels-last buffer [P,h,w,64] (ray | img) K1 gathers
+// from (ops.Scene).  A 64-channel x 32-pixel tile goes through shared memory: reads coalesced along w, writes along the channels.
+__global__ void __launch_bounds__(256)
+gn_k6_fuse_features_kernel(const float* __restrict__ ray, const float* __restrict__ img, float* __restrict__ out, int hw)
+{
+    __shared__ float tile[64][33];
+    const int plane = blockIdx.y, p0 = blockIdx.x * 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t src = (size_t)plane * 32 * hw;
+#pragma unroll
+    for (int c = warp; c < 64; c += 8) {
+        const float* s = (c < 32 ? ray + src + (size_t)c * hw : img + src + (size_t)(c - 32) * hw);
+        tile[c][lane] = p0 + lane < hw ? __ldg(s + p0 + lane) : 0.f;
+    }
+    __syncthreads();
+    float* o = out + ((size_t)plane * hw + p0) * 64;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int idx = threadIdx.x + 256 * i, px = idx >> 6, ch = idx & 63;
+        if (p0 + px < hw) o[idx] = tile[ch][px];
+    }
+}
+
+extern "C" int gn_k6_fuse_features(const float* ray_feats, const float* img_feats, float* out, int planes, int hw, void* stream)
+{
+    if (!ray_feats || !img_feats || !out || planes < 1 || planes > 65535 || hw < 1) return -1;
+    gn_k6_fuse_features_kernel<<<dim3((unsigned)((hw + 31) / 32), (unsigned)planes, 1), 256, 0, (cudaStream_t)stream>>>(ray_feats, img_feats, out, hw);
+    return (int)cudaGetLastError();
+}
+
+// gn_k6_images_u8: uint8 images [V,H,W,C] (C = 3 or 4, as imread gives them) -> fp32 [V,3,H,W] = u8 / 255 (color_map_forward,
+// main.py:170: a true division, like numpy's) for the encoders and, optionally, the uint8 RGBA texel buffer [V,H,W,4] of K1.
+__global__ void __launch_bounds__(256)
+gn_k6_images_u8_kernel(const unsigned char* __restrict__ in, float* __restrict__ out_f, unsigned char* __restrict__ out_rgba, int V, int HW, int C)
+{
+    const int v = blockIdx.y;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < HW; i += gridDim.x * 256) {
+        const unsigned char* px = in + ((size_t)v * HW + i) * C;
+        const unsigned char r = px[0], g = px[1], b = px[2];
+        float* o = out_f + (size_t)v * 3 * HW + i;
+        o[0] = __fdiv_rn((float)r, 255.f); o[HW] = __fdiv_rn((float)g, 255.f); o[2 * (size_t)HW] = __fdiv_rn((float)b, 255.f);
+        if (out_rgba) reinterpret_cast<uchar4*>(out_rgba)[(size_t)v * HW + i] = make_uchar4(r, g, b, 0);
+    }
+}
+
+extern "C" int gn_k6_images_u8(const unsigned char* in, float* out_f, unsigned char* out_rgba, int V, int H, int W, int C, void* stream)
+{
+    if (!in || !out_f || V < 1 || V > 65535 || H < 1 || W < 1 || (C != 3 && C != 4)) return -1;
+    const long long hw = (long long)H * W;
+    if (hw > 0x7fffffffLL) return -6;
+    const long long nb = (hw + 255) / 256;
+    gn_k6_images_u8_kernel<<<dim3((unsigned)(nb < 1024 ? nb : 1024), (unsigned)V, 1), 256, 0, (cudaStream_t)stream>>>(in, out_f, out_rgba, V, (int)hw, C);
+    return (int)cudaGetLastError();
+}

@@ -228,8 +228,8 @@ class ForwardEngine(_Engine):
 
     def _body(self, s):
         nr = self.net.nr_net
-        s.expand_rgb()
-        imgs = (s.imgs[0, ..., :3].permute(0, 3, 1, 2).to(torch.float32) / 255.0).contiguous()     # color_map_forward + transpose (main.py:192)
+        # color_map_forward + transpose (main.py:170,192) and the RGBA texels of K1 in one launch
+        imgs = ops.images_u8_to_float(s.imgs_in[0], s.imgs if s.rgb else None)
         ref = {'imgs': imgs, 'imgs_u8': s.imgs, 'poses': s.poses[0], 'Ks': s.Ks[0], 'depth_range': s.depth_range[0],
                'bbox3d': s.bbox_min.reshape(1, 3)}
         coords = None

@@ -186,7 +186,7 @@ class Scene:
                 img_feats, ray_feats = img_feats.permute(0, 1, 3, 4, 2), ray_feats.permute(0, 1, 3, 4, 2)
             if img_feats.shape[-1] != 32 or ray_feats.shape != img_feats.shape:
                 raise ValueError('feature maps must be [B,V,fh,fw,32]')
-            self.feats = torch.cat([ray_feats.to(dev, torch.float32), img_feats.to(dev, torch.float32)], -1).contiguous()
+            self.feats = fuse_feature_maps(img_feats.to(dev, torch.float32), ray_feats.to(dev, torch.float32))
         if self.feats.dim() != 5 or self.feats.shape[-1] != 64:
             raise ValueError('fused feature buffer must be [B,V,fh,fw,64]')
         _, _, self.fh, self.fw, _ = self.feats.shape
@@ -196,8 +196,34 @@ class Scene:
 
 
 def fuse_feature_maps(img_feats_cl, ray_feats_cl):
-    """Two channels-last maps [...,fh,fw,32] -> the fused buffer [...,fh,fw,64] (ray_feats | img_feats) K1 consumes."""
+    """Two channels-last maps [...,fh,fw,32] -> the fused buffer [...,fh,fw,64] (ray_feats | img_feats) K1 consumes.  When the
+    arguments are channels-last VIEWS of contiguous NCHW tensors on the GPU (what the encoders produce), one tiled-transpose
+    launch (gn_k6_fuse_features); otherwise torch.cat."""
+    a, b = ray_feats_cl, img_feats_cl
+    if a.is_cuda and b.is_cuda and a.dim() >= 4 and a.shape == b.shape and a.dtype == b.dtype == torch.float32:
+        an, bn = a.movedim(-1, -3), b.movedim(-1, -3)                 # back to [...,32,fh,fw]
+        if an.is_contiguous() and bn.is_contiguous() and a.shape[-1] == 32:
+            fh, fw = a.shape[-3], a.shape[-2]
+            planes = an.numel() // (32 * fh * fw)
+            if planes <= 65535:
+                out = torch.empty(a.shape[:-1] + (64,), dtype=torch.float32, device=a.device)
+                with _on(a.device):
+                    _lib.check(_lib.load().gn_k6_fuse_features(_ptr(an), _ptr(bn), _ptr(out), planes, fh * fw, _stream(a.device)), 'gn_k6_fuse_features')
+                return out
     return torch.cat([ray_feats_cl, img_feats_cl], -1).contiguous()
+
+
+def images_u8_to_float(imgs_u8, rgba_out=None):
+    """uint8 images [V,H,W,3|4] on the GPU -> fp32 [V,3,H,W] = u8 / 255 (color_map_forward, main.py:170) in one launch
+    (gn_k6_images_u8); rgba_out (optional uint8 [V,H,W,4]) also receives the RGBA texels K1's uint8 mode gathers."""
+    V, H, W, C_ = imgs_u8.shape
+    assert imgs_u8.is_cuda and imgs_u8.dtype == torch.uint8 and imgs_u8.is_contiguous() and C_ in (3, 4)
+    out = torch.empty((V, 3, H, W), dtype=torch.float32, device=imgs_u8.device)
+    if rgba_out is not None:
+        assert rgba_out.dtype == torch.uint8 and rgba_out.is_contiguous() and rgba_out.numel() == V * H * W * 4
+    with _on(imgs_u8.device):
+        _lib.check(_lib.load().gn_k6_images_u8(_ptr(imgs_u8), _ptr(out), _ptr(rgba_out), V, H, W, C_, _stream(imgs_u8.device)), 'gn_k6_images_u8')
+    return out
 
 
 def k1_forward(scene, hw, *, resolution=None, bbox_min=None, volume_size=0.3, pts=None, que_dir=None, dn=None,

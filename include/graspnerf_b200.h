@@ -163,6 +163,14 @@ typedef struct GnRaySetupParams {
 } GnRaySetupParams;
 int gn_k3_ray_setup(const GnRaySetupParams* params, void* stream);
 
+/* Layout glue around the encoders (one launch each instead of 2-4 strided torch copies):
+ * gn_k6_fuse_features: the two NCHW maps the encoders produce, [planes,32,h*w] each, -> the fused channels-last buffer
+ *   [planes,h*w,64] (ray_feats | img_feats per texel) that gn_k1_forward gathers from (ray_feats / img_feats / feat_stride = 64).
+ * gn_k6_images_u8: uint8 images [V,H,W,C] (C = 3 or 4) -> fp32 [V,3,H,W] = u8 / 255 (color_map_forward, main.py:170, a true
+ *   division) and, if out_rgba is not NULL, the uint8 RGBA texels [V,H,W,4] for gn_k1_forward's img_u8 mode. */
+int gn_k6_fuse_features(const float* ray_feats, const float* img_feats, float* out, int planes, int hw, void* stream);
+int gn_k6_images_u8(const unsigned char* in, float* out_f, unsigned char* out_rgba, int V, int H, int W, int C, void* stream);
+
 /* Depth-mean head (renderer.py:222-266, predict_mean_for_depth_loss; runs in every eval forward, renderer.py:288-289):
  * bilinear sample of ray_feats at `num` pixels per reference view (ops.py:14-34: grid_sample, border padding) and
  * MixtureLogisticsDistDecoder.predict_mean (dist_decoder.py:148-150) of the coarse and, optionally, the fine decoder.

@@ -413,3 +413,26 @@ def test_tcgen05_convolution_matches_cudnn_fp32(cfg):
     print(f'conv {cfg}: max |err| vs fp64: tcgen05 {e_tc:.2e}, cuDNN fp32 {e_32:.2e}')
     assert_close(got.cpu(), want.float().cpu(), rtol=1e-5, atol_scale=1e-5, what='tcgen05 conv vs fp64 reference')
     assert e_tc <= 4 * e_32 + 1e-6
+
+
+def test_layout_glue_kernels_are_exact():
+    """gn_k6_fuse_features = torch.cat of the two channels-last views (bit-equal; odd plane sizes included) and gn_k6_images_u8 =
+    numpy's uint8 -> float32 / 255 of color_map_forward (main.py:170; a TRUE division - torch's tensor / 255.0 on the GPU
+    multiplies by the rounded reciprocal and differs in the last bit for some bytes) + the RGBA texels."""
+    gen = torch.Generator().manual_seed(3)
+    for shape in ((1, 4, 32, 24, 40), (2, 3, 32, 7, 13)):
+        img_f, ray_f = torch.randn(shape, generator=gen).to(DEV), torch.randn(shape, generator=gen).to(DEV)
+        a, b = img_f.permute(0, 1, 3, 4, 2), ray_f.permute(0, 1, 3, 4, 2)
+        got = ops.fuse_feature_maps(a, b)
+        assert got.shape == shape[:2] + shape[3:] + (64,) and got.is_contiguous()
+        assert torch.equal(got, torch.cat([b, a], -1))
+    u8 = torch.randint(0, 256, (3, 20, 36, 3), generator=gen, dtype=torch.uint8)
+    u8[0, 0, :, 0] = torch.arange(36, dtype=torch.uint8) * 7
+    u8[0, 1] = torch.arange(256, dtype=torch.uint8)[:108].reshape(36, 3)
+    want = (u8.numpy().astype(np.float32) / 255).transpose(0, 3, 1, 2)                     # color_map_forward + transpose
+    rgba = torch.full((3, 20, 36, 4), 9, dtype=torch.uint8, device=DEV)
+    got = ops.images_u8_to_float(u8.to(DEV), rgba)
+    assert np.array_equal(got.cpu().numpy(), want)
+    assert torch.equal(rgba[..., :3].cpu(), u8) and int(rgba[..., 3].max()) == 0
+    u8a = torch.cat([u8, torch.full_like(u8[..., :1], 77)], -1)                            # RGBA in: alpha ignored
+    assert torch.equal(ops.images_u8_to_float(u8a.to(DEV)), got)
