@@ -419,6 +419,7 @@ def test_layout_glue_kernels_are_exact():
     """gn_k6_fuse_features = torch.cat of the two channels-last views (bit-equal; odd plane sizes included) and gn_k6_images_u8 =
     numpy's uint8 -> float32 / 255 of color_map_forward (main.py:170; a TRUE division - torch's tensor / 255.0 on the GPU
     multiplies by the rounded reciprocal and differs in the last bit for some bytes) + the RGBA texels."""
+    from graspnerf_b200 import ops
     gen = torch.Generator().manual_seed(3)
     for shape in ((1, 4, 32, 24, 40), (2, 3, 32, 7, 13)):
         img_f, ray_f = torch.randn(shape, generator=gen).to(DEV), torch.randn(shape, generator=gen).to(DEV)
