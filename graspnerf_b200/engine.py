@@ -70,6 +70,15 @@ def _pin(x, dtype=None):
     return t.pin_memory() if torch.cuda.is_available() else t
 
 
+def _small_layout(parts):
+    """Offsets (in floats, 16-byte aligned) of the small tensors inside their shared block, and the block's size."""
+    offs, o = [], 0
+    for p in parts:
+        offs.append(o)
+        o += (p.numel() + 3) // 4 * 4
+    return offs, o
+
+
 class HostScene:
     """Pinned host buffers of one scene.  imgs: uint8 [V,H,W,3|4] or fp32 [V,3,H,W]; feature maps (VolumeEngine only):
     the two channels-last maps [V,fh,fw,32], interleaved per texel into the fused [V,fh,fw,64] buffer K1 consumes."""
@@ -86,11 +95,18 @@ class HostScene:
         if img_feats_cl is not None:
             self.feats = _pin(ops.fuse_feature_maps(torch.as_tensor(img_feats_cl, dtype=torch.float32),
                                                     torch.as_tensor(ray_feats_cl, dtype=torch.float32)))
-        self.poses, self.Ks = _pin(poses, torch.float32), _pin(Ks, torch.float32)
-        self.depth_range, self.bbox_min = _pin(depth_range, torch.float32), _pin(bbox_min, torch.float32)
+        # the four small camera tensors live in ONE pinned block (poses | Ks | depth_range | bbox_min: 564 bytes at V = 6) and
+        # cross PCIe as one copy: every cudaMemcpyAsync is a DMA job of its own with a fixed cost of a few microseconds
+        parts = [torch.as_tensor(x).to(torch.float32).contiguous() for x in (poses, Ks, depth_range, bbox_min)]
+        offs, total = _small_layout(parts)
+        block = torch.zeros(total, dtype=torch.float32)
+        for p, o in zip(parts, offs):
+            block[o:o + p.numel()] = p.reshape(-1)
+        self.small = _pin(block)
+        self.poses, self.Ks, self.depth_range, self.bbox_min = (self.small[o:o + p.numel()].view(p.shape) for p, o in zip(parts, offs))
 
     def tensors(self):
-        return [t for t in (self.imgs, self.feats, self.poses, self.Ks, self.depth_range, self.bbox_min) if t is not None]
+        return [t for t in (self.imgs, self.feats, self.small) if t is not None]
 
     @property
     def nbytes(self):
@@ -105,8 +121,11 @@ class _Slot:
         self.rgb = hs.imgs.dtype == torch.uint8 and hs.imgs.shape[-1] == 3
         self.imgs = torch.zeros(self.imgs_in.shape[:-1] + (4,), dtype=torch.uint8, device=device) if self.rgb else self.imgs_in
         self.feats = dev(hs.feats)[None] if hs.feats is not None else None
-        self.poses, self.Ks, self.depth_range = dev(hs.poses)[None], dev(hs.Ks)[None], dev(hs.depth_range)[None]
-        self.bbox_min = dev(hs.bbox_min).reshape(1, 3)
+        self.small = dev(hs.small)                        # poses | Ks | depth_range | bbox_min, one H2D copy
+        parts = (hs.poses, hs.Ks, hs.depth_range, hs.bbox_min)
+        views = [self.small[o:o + t.numel()].view(t.shape) for t, o in zip(parts, _small_layout(parts)[0])]
+        self.poses, self.Ks, self.depth_range = views[0][None], views[1][None], views[2][None]
+        self.bbox_min = views[3].reshape(1, 3)
         # two pinned output sets per slot, alternating (see "Result lifetime" in the module docstring)
         self.out_host = [[torch.empty(s, dtype=d).pin_memory() for s, d in out_shapes] for _ in range(2)]
         self.flip = 0
@@ -151,10 +170,10 @@ class _Engine:
         s = self.slots[i]
         finished = self.collect(i) if s.busy else None
         with torch.cuda.stream(self.copy_stream):
-            for dst, src in ((s.imgs_in, hs.imgs), (s.feats, hs.feats), (s.poses, hs.poses), (s.Ks, hs.Ks), (s.depth_range, hs.depth_range)):
+            for dst, src in ((s.imgs_in, hs.imgs), (s.feats, hs.feats)):
                 if dst is not None:
                     dst[0].copy_(src, non_blocking=True)
-            s.bbox_min.copy_(hs.bbox_min.reshape(1, 3), non_blocking=True)
+            s.small.copy_(hs.small, non_blocking=True)
             s.ev_in.record(self.copy_stream)
         with torch.cuda.stream(s.stream):
             s.stream.wait_event(s.ev_in)
