@@ -113,7 +113,9 @@ class NeuralRayRenderer(nn.Module):
                                               ref_imgs_info['poses'], ref_imgs_info['Ks'], ref_imgs_info['depth_range'],
                                               bbox_min, named, self.cfg['volume_resolution'])
         scene = self._scene(ref_imgs_info)
-        ref_imgs_info['_fused_feats'] = scene.feats           # [1,V,fh,fw,64] channels-last ray|img map (the depth-mean head samples it too)
+        # [1,V,fh,fw,64] channels-last ray|img map: the depth-mean head samples it too (keyed to the tensor it was built from)
+        rf = ref_imgs_info['ray_feats']
+        ref_imgs_info['_fused_feats'] = (scene.feats, rf.data_ptr(), rf._version)
         # the reference's "!! too low ratio" diagnostic (renderer.py:174-176) without its host synchronisation: K1 counts the
         # valid projections per view into a device word; it is READ when the next call starts (the previous call has long
         # finished by then) or on demand through valid_ratio()
@@ -271,8 +273,9 @@ class NeuralRayRenderer(nn.Module):
             coords = self.draw_depth_coords(rfn, h, w, imgs.device)
         if ray_feats.is_cuda and not torch.is_grad_enabled() and self.fused_depth_mean:
             fine = self.fine_dist_decoder.mean_decoder if self.cfg['use_hierarchical_sampling'] else None
-            fused = ref_imgs_info.get('_fused_feats')
-            if fused is not None and fused.shape[0] == 1 and tuple(fused.shape[1:4]) == (ray_feats.shape[0],) + tuple(ray_feats.shape[2:]):
+            fused, ptr, ver = ref_imgs_info.get('_fused_feats', (None, 0, 0))
+            if (fused is not None and ptr == ray_feats.data_ptr() and ver == ray_feats._version and fused.shape[0] == 1
+                    and tuple(fused.shape[1:4]) == (ray_feats.shape[0],) + tuple(ray_feats.shape[2:])):
                 ray_feats = fused[0, ..., :32].permute(0, 3, 1, 2)       # same values, channels-last: one 128-byte run per tap
             m, mf = ops.depth_mean(ray_feats, coords, (h, w), self.dist_decoder.mean_decoder, fine)
             out = {'depth_mean': m[..., 0], 'depth_coords': coords, 'depth_mean_2': m[..., 1]}
