@@ -907,6 +907,15 @@ _CONV_CACHE = {}
 K7_SPLIT_POLICY = ((64, 16, 4), (160, 16, 2))       # the 18x32 / 128-channel stage: 4 CTAs per tile; the 36x64 stage: 2
 
 
+def k7_splits(tiles, nchunks):
+    """Split-K factor of a K7 launch: K7_SPLIT_POLICY rows are (max tiles, min k chunks, splits), first match wins; the partial
+    outputs cost a pass in the K6 launch that sums them, so only layers with few 128-pixel tiles and a long reduction split."""
+    for max_tiles, min_chunks, splits in K7_SPLIT_POLICY:
+        if tiles <= max_tiles and nchunks >= min_chunks:
+            return splits
+    return 1
+
+
 def conv2d_tc(xp, conv, allow_split=False):
     """F.conv2d(xp, conv.weight, conv.bias, conv.stride, padding=0) on tcgen05 (gn_k7_conv_forward): xp [N,Cin,Hp,Wp] fp32
     contiguous, ALREADY padded for this convolution.  fp16 hi/lo operand split, fp32 accumulation (same scheme as K2a).
@@ -924,13 +933,7 @@ def conv2d_tc(xp, conv, allow_split=False):
     Ho, Wo = (Hp - kh) // st + 1, (Wp - kw) // st + 1
     tiles = (N * Ho * Wo + 127) // 128
     nch = cw.Kpad // 32
-    # split-K: (max tiles, min k chunks, splits) rows, first match wins (K7_SPLIT_POLICY; the partial outputs cost a pass in K6)
-    S = 1
-    if allow_split:
-        for max_tiles, min_chunks, splits in K7_SPLIT_POLICY:
-            if tiles <= max_tiles and nch >= min_chunks:
-                S = splits
-                break
+    S = k7_splits(tiles, nch) if allow_split else 1
     out = torch.empty(((S,) if S > 1 else ()) + (N, co, Ho, Wo), device=dev, dtype=torch.float32)
     p = _lib.GnConvParams()
     p.ksplit = S
